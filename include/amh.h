@@ -1,0 +1,181 @@
+/* amh.h -- C ABI of libamh_b200.so, the B200-native many-chain
+ * Metropolis-Hastings engine.  This is the drop-in boundary for the multi-chain
+ * `sample(model, sampler, parallel, N, nchains; kw...)` path of AdvancedMH.jl
+ * (SURVEY.md 8b).  A Julia shim `ccall`s exactly these entry points
+ * (INTEGRATION.md shows the binding); tests drive them through Python ctypes.
+ *
+ * Conventions
+ *   - every function returns an int32 status (AMH_OK == 0); on failure the
+ *     text is available from amh_last_error() (thread-local, library owned).
+ *     AMH_ERR_INVALID maps to Julia's ArgumentError / ErrorException.
+ *   - no C++ exception and no callback crosses the boundary.
+ *   - handles are opaque and owned by the library; caller buffers are plain
+ *     pointers + sizes and are only read/written during the call.
+ *   - one process (or one handle set) per GPU; a handle must not be used from
+ *     two host threads at once.  Multi-GPU = one amh_ctx per device, chains
+ *     sharded by (chain_offset, nchains_local); no per-step collective.
+ *   - there is NO CPU fallback: without a CUDA device amh_ctx_create fails.
+ *
+ * The CPU oracle (oracle/amh_oracle.cpp) exports the same functions with the
+ * prefix amho_ so that one harness drives both.
+ */
+#ifndef AMH_H
+#define AMH_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMH_VERSION_MAJOR 0
+#define AMH_VERSION_MINOR 1
+
+/* ---- status codes ---- */
+#define AMH_OK               0
+#define AMH_ERR_INVALID      1   /* bad argument (Julia: ArgumentError) */
+#define AMH_ERR_CUDA         2   /* CUDA runtime failure, or no device */
+#define AMH_ERR_UNSUPPORTED  3   /* representable in the reference, not on the device */
+#define AMH_ERR_STATE        4   /* call out of order (e.g. MALA without initial params) */
+
+/* ---- device target catalogue ------------------------
+ * Replaces the opaque closure of DensityModel(f) (src/AdvancedMH.jl:52-54) and
+ * LogDensityProblems.logdensity[_and_gradient] (src/AdvancedMH.jl:74-77,
+ * MALA.jl:100-105) by a fixed catalogue.  `blob` layouts (all float64):        */
+#define AMH_TARGET_IID_NORMAL  1 /* theta=(mu,sigma); blob=[y_1..y_n]; dim==2.
+                                    lp = sigma>=0 ? sum_i logpdf(Normal(mu,sigma),y_i) : -Inf
+                                    (README.md:26-31, test/runtests.jl:23-31)            */
+#define AMH_TARGET_MVNORMAL    2 /* blob=[c0, mu[d], U[d(d+1)/2]] ; U lower-triangular
+                                    packed by rows, U'U = inv(Sigma);
+                                    lp = c0 - 0.5*|U(x-mu)|^2
+                                    (test/RobustAdaptiveMetropolis.jl:1-9 `Gaussian`)     */
+#define AMH_TARGET_ROSENBROCK  3 /* blob=[a, b, s]; lp = -sum_{i<d-1}[b(x_{i+1}-x_i^2)^2+(a-x_i)^2]/s */
+#define AMH_TARGET_LOGISTIC    4 /* blob=[tau, X[n*d] row-major, y[n]];
+                                    lp = sum_i[y_i eta_i - log1pexp(eta_i)] - |beta|^2/(2 tau^2)  */
+#define AMH_TARGET_GAUSS_PREC  5 /* blob=A[d*d] row-major symmetric; lp = -x'Ax/2, grad = -Ax
+                                    (test/runtests.jl:335-347 `TheNormalLogDensity`)      */
+#define AMH_TARGET_NIG_TOY     6 /* theta=(s,m); blob=[alpha, beta, y_1..y_n]; dim==2;
+                                    s>0 ? logpdf(InverseGamma(alpha,beta),s)+logpdf(Normal(0,sqrt s),m)
+                                          + sum_i logpdf(Normal(m,sqrt s),y_i) : -Inf
+                                    (test/emcee.jl:5-15)                                   */
+#define AMH_TARGET_NIG_TOY_LOG 7 /* same in (log s, m) with the Jacobian term (test/emcee.jl:46-56) */
+
+/* ---- sampler kinds: the reference constructors they stand for ---- */
+#define AMH_SAMPLER_STATIC   1  /* MetropolisHastings(StaticProposal(..)), StaticMH   mh-core.jl:44-49, proposal.jl:70-85 */
+#define AMH_SAMPLER_RW       2  /* MetropolisHastings(RandomWalkProposal(..)), RWMH   mh-core.jl:50-51, proposal.jl:41-64 */
+#define AMH_SAMPLER_STRETCH  3  /* Ensemble(n_walkers, StretchProposal(p, a))         emcee.jl:1-102                      */
+#define AMH_SAMPLER_MALA     4  /* MALA(g -> MvNormal(drift*g, sigma2*I))             MALA.jl:1-93                        */
+#define AMH_SAMPLER_RAM      5  /* RobustAdaptiveMetropolis(alpha, gamma, S, lo, hi)  RobustAdaptiveMetropolis.jl:75-278  */
+
+/* proposal covariance representation (Distributions' ScalMat / PDiagMat / PDMat) */
+#define AMH_COV_SCALAR 1   /* scale[0]   = sigma                                      */
+#define AMH_COV_DIAG   2   /* scale[dim] = sigma_i  (also: array of Normal(mu_i,sigma_i), proposal.jl:26-35) */
+#define AMH_COV_FULL   3   /* scale[dim(dim+1)/2] = lower Cholesky factor L, packed by rows */
+
+typedef struct amh_sampler_desc {
+    int32_t kind;            /* AMH_SAMPLER_*                                                   */
+    int32_t dim;
+    int32_t symmetric;       /* the `issymmetric` type parameter (proposal.jl:1-21): 1 => the
+                                Hastings term is the literal 0 (proposal.jl:195-196)            */
+    int32_t cov_kind;        /* AMH_COV_*  (STATIC / RW; also the initial-draw law of STRETCH)  */
+    const double* mean;      /* proposal mean[dim], NULL = zeros                                */
+    const double* scale;     /* see AMH_COV_*                                                   */
+    double  stretch_a;       /* StretchProposal.stretch_length, default 2.0 (emcee.jl:68)       */
+    int64_t n_walkers;       /* Ensemble.n_walkers (emcee.jl:2)                                 */
+    double  mala_sigma2;     /* MALA proposal g -> MvNormal(mala_drift*g, mala_sigma2*I)        */
+    double  mala_drift;      /*   canonical: mala_drift = sigma2/2 (README.md:180)              */
+    double  ram_alpha;       /* RAM.alpha  = 0.234 (RobustAdaptiveMetropolis.jl:78)             */
+    double  ram_gamma;       /* RAM.gamma  = 0.6   (:80)                                        */
+    double  ram_eig_lo;      /* RAM.eigenvalue_lower_bound = 0   (:84)                          */
+    double  ram_eig_hi;      /* RAM.eigenvalue_upper_bound = Inf (:86)                          */
+    const double* ram_S0;    /* RAM.S: dense dim x dim row-major (lower triangle used), NULL = I (:82,198-207) */
+} amh_sampler_desc;
+
+/* pooled and per-chain summaries accumulated on the device over SAVED samples */
+typedef struct amh_summary {
+    int64_t n_saved;         /* samples accumulated per chain                                   */
+    int64_t n_steps;         /* stateful steps taken per chain                                  */
+    double  accept_rate;     /* accepted moves / steps, pooled over local chains                */
+    double* mean;            /* [dim]   pooled posterior mean  (caller buffer, may be NULL)     */
+    double* var;             /* [dim]   pooled posterior variance (population, /n)              */
+    double* chain_mean;      /* [dim][nchains_local] per-chain means (may be NULL)              */
+} amh_summary;
+
+typedef struct amh_ctx     amh_ctx;
+typedef struct amh_target  amh_target;
+typedef struct amh_sampler amh_sampler;
+typedef struct amh_run     amh_run;
+
+/* handshake, diagnostics */
+int32_t     amh_version(int32_t* major, int32_t* minor);
+const char* amh_last_error(void);
+int32_t     amh_contract_version(void);
+
+/* one context per GPU: device selection + the stream all work is ordered on */
+int32_t amh_ctx_create(int32_t device, amh_ctx** out);
+int32_t amh_ctx_destroy(amh_ctx* ctx);
+int32_t amh_ctx_sync(amh_ctx* ctx);
+
+/* model: stands for DensityModel / LogDensityModel of a catalogue target */
+int32_t amh_target_create(amh_ctx* ctx, int32_t kind, int32_t dim,
+                          const double* blob, int64_t nblob, amh_target** out);
+int32_t amh_target_destroy(amh_target* t);
+
+/* sampler: POD image of the unchanged AdvancedMH constructor */
+int32_t amh_sampler_create(amh_ctx* ctx, const amh_sampler_desc* desc, amh_sampler** out);
+int32_t amh_sampler_destroy(amh_sampler* s);
+
+/* run = the state of `nchains_local` chains [chain_offset, chain_offset+nchains_local)
+ * of a job with global seeds.  Performs the FIRST step of AbstractMCMC
+ * (mh-core.jl:76-86, emcee.jl:29-34, MALA.jl:37-40, RAM :175-214):
+ *   init == NULL : draw from the proposal (STATIC/RW/STRETCH) or randn (RAM);
+ *                  MALA -> AMH_ERR_STATE "please specify initial parameters" (MALA.jl:37)
+ *   init != NULL : [dim][nchains_local] float64, chains fastest.
+ * seeds: one uint64 per local chain (MH/MALA/RAM) or per local ENSEMBLE (STRETCH,
+ * nchains_local = n_ensembles * n_walkers), i.e. rand(rng, UInt, nchains). */
+int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler,
+                       int64_t nchains_local, int64_t chain_offset,
+                       const uint64_t* seeds, const double* init, amh_run** out);
+int32_t amh_run_destroy(amh_run* run);
+
+/* `nsteps` stateful steps for every chain, asynchronously on the ctx stream
+ * (AbstractMCMC.step / step_warmup: mh-core.jl:92-117, emcee.jl:14-24,
+ * MALA.jl:54-93, RAM :216-278).  warmup != 0 selects step_warmup (RAM adapts).
+ * steps_per_launch <= 0 lets the library choose how many steps one kernel
+ * launch fuses; 1 gives exactly one kernel per MCMC step. */
+int32_t amh_run_steps(amh_run* run, int64_t nsteps, int32_t warmup, int32_t steps_per_launch);
+int32_t amh_run_sync(amh_run* run);
+
+/* The AbstractMCMC.mcmcsample schedule:
+ *   discard_initial steps, save, then (N-1) x { thinning steps, save };
+ *   stateful step s (1-based) is a warm-up step iff s <= num_warmup.
+ * out (may be NULL): [N][dim+1][nchains_local] float64 = params..., lp
+ *   (ext/AdvancedMHMCMCChainsExt.jl:24-38,93-106 layout, chains fastest);
+ * accepted_out (may be NULL): [N][nchains_local] uint8 Transition.accepted;
+ * summary (may be NULL): filled with moments over the N saved samples. */
+int32_t amh_run_sample(amh_run* run, int64_t N, int64_t discard_initial, int64_t thinning,
+                       int64_t num_warmup, double* out, uint8_t* accepted_out,
+                       amh_summary* summary);
+
+/* state introspection / resume (getparams/setparams!!: src/AdvancedMH.jl:146-157,
+ * MALA.jl:23-35, RAM :116-121; StatesExtractor: test/RobustAdaptiveMetropolis.jl:11-28).
+ * Any pointer may be NULL.  x:[dim][n] lp:[n] grad:[dim][n] (MALA)
+ * S:[dim(dim+1)/2][n] packed rows (RAM) accepted:[n] naccept:[n] */
+int32_t amh_run_get_state(amh_run* run, double* x, double* lp, double* grad, double* S,
+                          uint8_t* accepted, int64_t* naccept, int64_t* step_counter);
+/* setparams!!: replaces x and recomputes lp (and the gradient for MALA) on the device */
+int32_t amh_run_set_params(amh_run* run, const double* x);
+
+int32_t amh_run_dim(amh_run* run);
+int64_t amh_run_nchains(amh_run* run);
+/* number of kernel launches issued by this run so far (bench.py's gpu_launches) */
+int64_t amh_run_launch_count(amh_run* run);
+/* device time of the stepping kernels since the last reset, measured with CUDA
+ * events on the ctx stream (milliseconds); reset != 0 zeroes the accumulator */
+int32_t amh_run_kernel_time_ms(amh_run* run, int32_t reset, double* ms, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMH_H */
