@@ -1,0 +1,279 @@
+"""ctypes binding of the C ABI declared in include/amh.h.
+
+`Engine()` loads the product library `libamh_b200.so` (hand-written sm_100a
+kernels) that sits next to this file and fails loudly when it is missing or
+when no CUDA device is present -- there is no CPU fallback.  The same binding
+class can be pointed at another library exporting the same ABI under another
+prefix; only the test-suite does that (with the CPU oracle, prefix ``amho_``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PRODUCT_LIB = os.path.join(_HERE, "libamh_b200.so")
+
+AMH_OK, AMH_ERR_INVALID, AMH_ERR_CUDA, AMH_ERR_UNSUPPORTED, AMH_ERR_STATE = 0, 1, 2, 3, 4
+
+TARGET_IID_NORMAL, TARGET_MVNORMAL, TARGET_ROSENBROCK, TARGET_LOGISTIC = 1, 2, 3, 4
+TARGET_GAUSS_PREC, TARGET_NIG_TOY, TARGET_NIG_TOY_LOG = 5, 6, 7
+SAMPLER_STATIC, SAMPLER_RW, SAMPLER_STRETCH, SAMPLER_MALA, SAMPLER_RAM = 1, 2, 3, 4, 5
+COV_SCALAR, COV_DIAG, COV_FULL = 1, 2, 3
+
+_dp = C.POINTER(C.c_double)
+_u8p = C.POINTER(C.c_uint8)
+_u64p = C.POINTER(C.c_uint64)
+_i64p = C.POINTER(C.c_int64)
+
+
+class SamplerDesc(C.Structure):
+    """struct amh_sampler_desc (include/amh.h)"""
+    _fields_ = [
+        ("kind", C.c_int32), ("dim", C.c_int32), ("symmetric", C.c_int32), ("cov_kind", C.c_int32),
+        ("mean", _dp), ("scale", _dp),
+        ("stretch_a", C.c_double), ("n_walkers", C.c_int64),
+        ("mala_sigma2", C.c_double), ("mala_drift", C.c_double),
+        ("ram_alpha", C.c_double), ("ram_gamma", C.c_double),
+        ("ram_eig_lo", C.c_double), ("ram_eig_hi", C.c_double),
+        ("ram_S0", _dp),
+    ]
+
+
+class Summary(C.Structure):
+    """struct amh_summary (include/amh.h)"""
+    _fields_ = [
+        ("n_saved", C.c_int64), ("n_steps", C.c_int64), ("accept_rate", C.c_double),
+        ("mean", _dp), ("var", _dp), ("chain_mean", _dp),
+    ]
+
+
+class AMHError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+class AMHArgumentError(AMHError, ValueError):
+    """AMH_ERR_INVALID / AMH_ERR_UNSUPPORTED -- Julia's ArgumentError"""
+
+
+class AMHStateError(AMHError):
+    """AMH_ERR_STATE -- e.g. MALA without initial parameters (MALA.jl:37)"""
+
+
+# every symbol include/amh.h declares (tests check that the library exports all of them)
+ABI_SYMBOLS = [
+    "version", "last_error", "contract_version", "ctx_create", "ctx_destroy", "ctx_sync",
+    "target_create", "target_destroy", "sampler_create", "sampler_destroy",
+    "run_create", "run_destroy", "run_steps", "run_sync", "run_sample",
+    "run_get_state", "run_set_params", "run_dim", "run_nchains", "run_launch_count",
+    "run_kernel_time_ms",
+]
+
+
+def _as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Engine:
+    """One library + one device context."""
+
+    def __init__(self, lib_path: str | None = None, prefix: str = "amh_", device: int = 0):
+        path = lib_path or PRODUCT_LIB
+        if not os.path.exists(path):
+            raise ImportError(
+                f"{path} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
+                "advancedmh.jl_b200 has no CPU fallback.")
+        self.path = path
+        self.prefix = prefix
+        self.lib = C.CDLL(path)
+        self._bind()
+        ctx = C.c_void_p()
+        self._check(self._f("ctx_create")(C.c_int32(device), C.byref(ctx)))
+        self.ctx = ctx
+        self.device = device
+
+    # -- plumbing ---------------------------------------------------------
+    def _f(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def _bind(self):
+        f = self._f
+        f("last_error").restype = C.c_char_p
+        f("run_nchains").restype = C.c_int64
+        f("run_launch_count").restype = C.c_int64
+        for n in ("run_nchains", "run_launch_count", "run_dim", "run_sync", "run_destroy", "ctx_sync",
+                  "ctx_destroy", "target_destroy", "sampler_destroy"):
+            f(n).argtypes = [C.c_void_p]
+        f("ctx_create").argtypes = [C.c_int32, C.POINTER(C.c_void_p)]
+        f("target_create").argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, C.c_int64, C.POINTER(C.c_void_p)]
+        f("sampler_create").argtypes = [C.c_void_p, C.POINTER(SamplerDesc), C.POINTER(C.c_void_p)]
+        f("run_create").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, _u64p, _dp,
+                                    C.POINTER(C.c_void_p)]
+        f("run_steps").argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32]
+        f("run_sample").argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _dp, _u8p,
+                                    C.POINTER(Summary)]
+        f("run_get_state").argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _u8p, _i64p, _i64p]
+        f("run_set_params").argtypes = [C.c_void_p, _dp]
+        f("run_kernel_time_ms").argtypes = [C.c_void_p, C.c_int32, _dp, _i64p]
+
+    def _check(self, rc):
+        if rc == AMH_OK:
+            return
+        msg = (self._f("last_error")() or b"").decode()
+        if rc in (AMH_ERR_INVALID, AMH_ERR_UNSUPPORTED):
+            raise AMHArgumentError(rc, msg)
+        if rc == AMH_ERR_STATE:
+            raise AMHStateError(rc, msg)
+        raise AMHError(rc, msg)
+
+    def version(self):
+        a, b = C.c_int32(), C.c_int32()
+        self._f("version")(C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def contract_version(self):
+        return int(self._f("contract_version")())
+
+    def sync(self):
+        self._check(self._f("ctx_sync")(self.ctx))
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self._f("ctx_destroy")(self.ctx)
+            self.ctx = None
+
+    # -- objects ----------------------------------------------------------
+    def target(self, kind: int, dim: int, blob) -> "TargetHandle":
+        blob = _as_f64(blob).ravel()
+        h = C.c_void_p()
+        self._check(self._f("target_create")(self.ctx, kind, dim, blob.ctypes.data_as(_dp), blob.size, C.byref(h)))
+        return TargetHandle(self, h, kind, dim)
+
+    def sampler(self, *, kind, dim, symmetric=False, cov_kind=COV_SCALAR, mean=None, scale=None,
+                stretch_a=2.0, n_walkers=0, mala_sigma2=0.0, mala_drift=0.0,
+                ram_alpha=0.234, ram_gamma=0.6, ram_eig_lo=0.0, ram_eig_hi=float("inf"), ram_S0=None) -> "SamplerHandle":
+        keep = []
+        def ptr(a):
+            if a is None:
+                return None
+            a = _as_f64(a).ravel()
+            keep.append(a)
+            return a.ctypes.data_as(_dp)
+        d = SamplerDesc(kind, dim, int(bool(symmetric)), cov_kind, ptr(mean), ptr(scale), float(stretch_a),
+                        int(n_walkers), float(mala_sigma2), float(mala_drift), float(ram_alpha), float(ram_gamma),
+                        float(ram_eig_lo), float(ram_eig_hi), ptr(ram_S0))
+        h = C.c_void_p()
+        self._check(self._f("sampler_create")(self.ctx, C.byref(d), C.byref(h)))
+        return SamplerHandle(self, h, kind, dim, int(n_walkers))
+
+    def run(self, target: "TargetHandle", sampler: "SamplerHandle", nchains: int, seeds, init=None,
+            chain_offset: int = 0) -> "Run":
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64).ravel()
+        init_p = None
+        if init is not None:
+            init = _as_f64(init)
+            if init.shape != (target.dim, nchains):
+                raise AMHArgumentError(AMH_ERR_INVALID, f"init must have shape (dim, nchains) = {(target.dim, nchains)}, got {init.shape}")
+            init_p = init.ctypes.data_as(_dp)
+        h = C.c_void_p()
+        self._check(self._f("run_create")(self.ctx, target.h, sampler.h, nchains, chain_offset,
+                                          seeds.ctypes.data_as(_u64p), init_p, C.byref(h)))
+        return Run(self, h, target, sampler, nchains)
+
+
+@dataclass
+class TargetHandle:
+    eng: Engine
+    h: C.c_void_p
+    kind: int
+    dim: int
+
+    def close(self):
+        if self.h:
+            self.eng._f("target_destroy")(self.h)
+            self.h = None
+
+
+@dataclass
+class SamplerHandle:
+    eng: Engine
+    h: C.c_void_p
+    kind: int
+    dim: int
+    n_walkers: int
+
+    def close(self):
+        if self.h:
+            self.eng._f("sampler_destroy")(self.h)
+            self.h = None
+
+
+class Run:
+    def __init__(self, eng, h, target, sampler, n):
+        self.eng, self.h, self.target, self.sampler, self.n = eng, h, target, sampler, n
+        self.dim = target.dim
+
+    def steps(self, nsteps: int, warmup: bool = False, steps_per_launch: int = 0):
+        self.eng._check(self.eng._f("run_steps")(self.h, nsteps, int(warmup), steps_per_launch))
+
+    def sync(self):
+        self.eng._check(self.eng._f("run_sync")(self.h))
+
+    def sample(self, N, discard_initial=0, thinning=1, num_warmup=0, store=True, store_accepted=True,
+               summary=True, chain_means=False):
+        d, n = self.dim, self.n
+        out = np.empty((N, d + 1, n), dtype=np.float64) if store else None
+        acc = np.empty((N, n), dtype=np.uint8) if store_accepted else None
+        summ = None
+        s = None
+        if summary:
+            mean = np.zeros(d); var = np.zeros(d)
+            cm = np.zeros((d, n)) if chain_means else None
+            s = Summary(0, 0, 0.0, mean.ctypes.data_as(_dp), var.ctypes.data_as(_dp),
+                        cm.ctypes.data_as(_dp) if cm is not None else None)
+        self.eng._check(self.eng._f("run_sample")(
+            self.h, N, discard_initial, thinning, num_warmup,
+            out.ctypes.data_as(_dp) if out is not None else None,
+            acc.ctypes.data_as(_u8p) if acc is not None else None,
+            C.byref(s) if s is not None else None))
+        if s is not None:
+            summ = dict(n_saved=s.n_saved, n_steps=s.n_steps, accept_rate=s.accept_rate, mean=mean, var=var,
+                        chain_mean=cm)
+        return out, acc, summ
+
+    def state(self, grad=False, S=False):
+        d, n = self.dim, self.n
+        x = np.empty((d, n)); lp = np.empty(n)
+        g = np.empty((d, n)) if grad else None
+        Sm = np.empty((d * (d + 1) // 2, n)) if S else None
+        acc = np.empty(n, dtype=np.uint8); nacc = np.empty(n, dtype=np.int64)
+        step = C.c_int64()
+        self.eng._check(self.eng._f("run_get_state")(
+            self.h, x.ctypes.data_as(_dp), lp.ctypes.data_as(_dp),
+            g.ctypes.data_as(_dp) if g is not None else None,
+            Sm.ctypes.data_as(_dp) if Sm is not None else None,
+            acc.ctypes.data_as(_u8p), nacc.ctypes.data_as(_i64p), C.byref(step)))
+        return dict(x=x, lp=lp, grad=g, S=Sm, accepted=acc, naccept=nacc, step=step.value)
+
+    def set_params(self, x):
+        x = _as_f64(x)
+        assert x.shape == (self.dim, self.n)
+        self.eng._check(self.eng._f("run_set_params")(self.h, x.ctypes.data_as(_dp)))
+
+    def launch_count(self):
+        return int(self.eng._f("run_launch_count")(self.h))
+
+    def kernel_time_ms(self, reset=False):
+        ms = C.c_double(); nl = C.c_int64()
+        self.eng._check(self.eng._f("run_kernel_time_ms")(self.h, int(reset), C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value
+
+    def close(self):
+        if self.h:
+            self.eng._f("run_destroy")(self.h)
+            self.h = None

@@ -1,0 +1,546 @@
+/* amh_api.cu -- host runtime behind the C ABI of include/amh.h: contexts,
+ * target / sampler objects, run state in HBM, the AbstractMCMC sampling
+ * schedule and sample / summary read-back.  There is no CPU code path for the
+ * MCMC arithmetic in this library: without a CUDA device amh_ctx_create fails.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include "amh_host.h"
+
+namespace amhh {
+
+static thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    return AMH_ERR_CUDA;
+}
+
+amhd::ChainState chain_state(amh_run& r) {
+    amhd::ChainState st;
+    st.X = r.X; st.lp = r.lp; st.lq = r.lq; st.G = r.G;
+    st.acc = r.acc; st.nacc = r.nacc; st.seeds = r.seeds;
+    st.n = r.n; st.pitch = r.pitch;
+    return st;
+}
+
+int default_steps_per_launch(const amh_run& r) {
+    switch (r.sampler->d.kind) {
+    case AMH_SAMPLER_STRETCH: return 16;
+    case AMH_SAMPLER_RAM: return 1;      /* HBM-streaming: nothing to keep resident */
+    default: return 64;
+    }
+}
+
+template <class T>
+static int dev_alloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) return AMH_OK;
+    AMH_CUDA_TRY(cudaMalloc((void**)p, count * sizeof(T)));
+    return AMH_OK;
+}
+
+static int upload(double** dptr, const std::vector<double>& h, cudaStream_t st) {
+    *dptr = nullptr;
+    if (h.empty()) return AMH_OK;
+    AMH_CUDA_TRY(cudaMalloc((void**)dptr, h.size() * sizeof(double)));
+    AMH_CUDA_TRY(cudaMemcpyAsync(*dptr, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    AMH_CUDA_TRY(cudaStreamSynchronize(st));
+    return AMH_OK;
+}
+
+static int get_events(amh_run& r, cudaEvent_t* a, cudaEvent_t* b) {
+    if (!r.pool.empty()) {
+        *a = r.pool.back().first; *b = r.pool.back().second;
+        r.pool.pop_back();
+        return AMH_OK;
+    }
+    AMH_CUDA_TRY(cudaEventCreate(a));
+    AMH_CUDA_TRY(cudaEventCreate(b));
+    return AMH_OK;
+}
+
+static int resolve_events(amh_run& r) {
+    if (r.pending.empty()) return AMH_OK;
+    AMH_CUDA_TRY(cudaEventSynchronize(r.pending.back().second));
+    for (auto& pr : r.pending) {
+        float ms = 0;
+        AMH_CUDA_TRY(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        r.kernel_ms += ms;
+        r.pool.push_back(pr);
+    }
+    r.pending.clear();
+    r.timed_launches += r.pending_launches;
+    r.pending_launches = 0;
+    return AMH_OK;
+}
+
+/* enqueue `nsteps` stateful steps; the last launch carries the save epilogue */
+static int enqueue_steps(amh_run& r, long long nsteps, bool warmup, int spl, const amhd::SaveArgs* sv_last) {
+    if (spl <= 0) spl = default_steps_per_launch(r);
+    amhd::SaveArgs none;
+    std::memset(&none, 0, sizeof(none));
+    AMH_CUDA_TRY(cudaSetDevice(r.ctx->device));
+    cudaEvent_t e0, e1;
+    int rc = get_events(r, &e0, &e1);
+    if (rc) return rc;
+    AMH_CUDA_TRY(cudaEventRecord(e0, r.ctx->stream));
+    long long left = nsteps;
+    bool first = true;
+    while (left > 0 || (first && sv_last)) {
+        const int m = (int)std::min<long long>(left, spl);
+        const bool last = (left - m) == 0;
+        const amhd::SaveArgs& sv = (last && sv_last) ? *sv_last : none;
+        switch (r.sampler->d.kind) {
+        case AMH_SAMPLER_STATIC:
+        case AMH_SAMPLER_RW: rc = launch_mh(r, m, sv); break;
+        case AMH_SAMPLER_MALA: rc = launch_mala(r, m, sv); break;
+        case AMH_SAMPLER_RAM: rc = launch_ram(r, m, warmup, sv); break;
+        case AMH_SAMPLER_STRETCH: rc = launch_stretch(r, m, sv); break;
+        default: rc = fail(AMH_ERR_INVALID, "unknown sampler kind");
+        }
+        if (rc) return rc;
+        r.step += m;
+        left -= m;
+        first = false;
+    }
+    AMH_CUDA_TRY(cudaEventRecord(e1, r.ctx->stream));
+    r.pending.emplace_back(e0, e1);
+    if (r.pending.size() > 2048) {
+        rc = resolve_events(r);
+        if (rc) return rc;
+    }
+    return AMH_OK;
+}
+
+static void free_run(amh_run* r) {
+    if (!r) return;
+    cudaSetDevice(r->ctx->device);
+    cudaStreamSynchronize(r->ctx->stream);
+    void* ptrs[] = {r->X, r->X2, r->lp, r->lp2, r->lq, r->G, r->S, r->S2, r->logalpha, r->eta, r->acc, r->failed,
+                    r->sflag, r->nacc, r->seeds, r->sum, r->sumsq, r->scratch};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    for (auto& pr : r->pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto& pr : r->pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    delete r;
+}
+
+}  // namespace amhh
+
+using namespace amhh;
+
+extern "C" {
+
+int32_t amh_version(int32_t* major, int32_t* minor) {
+    if (major) *major = AMH_VERSION_MAJOR;
+    if (minor) *minor = AMH_VERSION_MINOR;
+    return AMH_OK;
+}
+const char* amh_last_error(void) { return g_err.c_str(); }
+int32_t amh_contract_version(void) { return AMH_CONTRACT_VERSION; }
+
+int32_t amh_ctx_create(int32_t device, amh_ctx** out) {
+    if (!out) return fail(AMH_ERR_INVALID, "out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(AMH_ERR_CUDA, std::string("no CUDA device available (this library has no CPU fallback): ") +
+                                      cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(AMH_ERR_INVALID, "device index out of range");
+    AMH_CUDA_TRY(cudaSetDevice(device));
+    amh_ctx* c = new amh_ctx();
+    c->device = device;
+    AMH_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    AMH_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    AMH_CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    *out = c;
+    return AMH_OK;
+}
+int32_t amh_ctx_destroy(amh_ctx* c) {
+    if (!c) return AMH_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->copy_stream);
+    delete c;
+    return AMH_OK;
+}
+int32_t amh_ctx_sync(amh_ctx* c) {
+    if (!c) return fail(AMH_ERR_INVALID, "ctx is NULL");
+    AMH_CUDA_TRY(cudaSetDevice(c->device));
+    AMH_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return AMH_OK;
+}
+
+int32_t amh_target_create(amh_ctx* ctx, int32_t kind, int32_t dim, const double* blob, int64_t nblob,
+                          amh_target** out) {
+    if (!ctx || !out) return fail(AMH_ERR_INVALID, "ctx/out is NULL");
+    if (dim < 1) return fail(AMH_ERR_INVALID, "dim must be >= 1");
+    if (nblob < 0 || (nblob > 0 && !blob)) return fail(AMH_ERR_INVALID, "blob is NULL");
+    const long long d = dim;
+    bool ok = true;
+    long long ndata = 0;
+    double inv2tau2 = 0, invtau2 = 0;
+    switch (kind) {
+    case AMH_TARGET_IID_NORMAL: ok = (dim == 2 && nblob >= 1); ndata = nblob; break;
+    case AMH_TARGET_MVNORMAL: ok = (nblob == 1 + d + d * (d + 1) / 2); break;
+    case AMH_TARGET_ROSENBROCK: ok = (nblob == 3 && dim >= 2); break;
+    case AMH_TARGET_GAUSS_PREC: ok = (nblob == d * d); break;
+    case AMH_TARGET_NIG_TOY:
+    case AMH_TARGET_NIG_TOY_LOG: ok = (dim == 2 && nblob >= 3); ndata = nblob - 3; break;
+    case AMH_TARGET_LOGISTIC:
+        ok = (nblob >= 1 + d + 1) && ((nblob - 1) % (d + 1) == 0);
+        if (ok) {
+            ndata = (nblob - 1) / (d + 1);
+            const double tau = blob[0];
+            inv2tau2 = 1.0 / (2.0 * tau * tau);
+            invtau2 = 1.0 / (tau * tau);
+        }
+        break;
+    default: ok = false;
+    }
+    if (!ok) return fail(AMH_ERR_INVALID, "target kind/dim/blob size mismatch");
+    AMH_CUDA_TRY(cudaSetDevice(ctx->device));
+    amh_target* t = new amh_target();
+    t->ctx = ctx; t->kind = kind; t->dim = dim; t->ndata = ndata;
+    t->inv2tau2 = inv2tau2; t->invtau2 = invtau2;
+    t->blob.assign(blob, blob + nblob);
+    const int rc = upload(&t->dblob, t->blob, ctx->stream);
+    if (rc) { delete t; return rc; }
+    *out = t;
+    return AMH_OK;
+}
+int32_t amh_target_destroy(amh_target* t) {
+    if (!t) return AMH_OK;
+    cudaSetDevice(t->ctx->device);
+    if (t->dblob) cudaFree(t->dblob);
+    delete t;
+    return AMH_OK;
+}
+
+int32_t amh_sampler_create(amh_ctx* ctx, const amh_sampler_desc* desc, amh_sampler** out) {
+    if (!ctx || !desc || !out) return fail(AMH_ERR_INVALID, "ctx/desc/out is NULL");
+    const int d = desc->dim;
+    if (d < 1) return fail(AMH_ERR_INVALID, "dim must be >= 1");
+    amh_sampler* s = new amh_sampler();
+    s->ctx = ctx;
+    s->d = *desc;
+    const long long nt = (long long)d * (d + 1) / 2;
+    auto bad = [&](const char* m) { delete s; return fail(AMH_ERR_INVALID, m); };
+    switch (desc->kind) {
+    case AMH_SAMPLER_STATIC:
+    case AMH_SAMPLER_RW:
+    case AMH_SAMPLER_STRETCH: {
+        if (desc->kind == AMH_SAMPLER_STRETCH) {
+            if (desc->n_walkers < 2) return bad("Ensemble needs n_walkers >= 2");
+            if (!(desc->stretch_a > 1.0)) return bad("stretch_length must be > 1");
+        }
+        const bool need_cov = desc->kind != AMH_SAMPLER_STRETCH || desc->scale != nullptr;
+        if (need_cov) {
+            if (!desc->scale) return bad("proposal scale is NULL");
+            const long long ns = desc->cov_kind == AMH_COV_FULL ? nt : desc->cov_kind == AMH_COV_DIAG ? d
+                                 : desc->cov_kind == AMH_COV_SCALAR ? 1 : -1;
+            if (ns < 0) return bad("unknown cov_kind");
+            s->scale.assign(desc->scale, desc->scale + ns);
+            for (int i = 0; i < d; ++i) {
+                const double dg = desc->cov_kind == AMH_COV_FULL ? s->scale[tri_h(i, i)]
+                                  : desc->cov_kind == AMH_COV_DIAG ? s->scale[i] : s->scale[0];
+                if (!(dg > 0.0)) return bad("proposal scale must have a positive diagonal");
+            }
+        }
+        if (desc->mean) { s->mean.assign(desc->mean, desc->mean + d); s->has_mean = true; }
+        break;
+    }
+    case AMH_SAMPLER_MALA:
+        if (!(desc->mala_sigma2 > 0.0)) return bad("MALA sigma2 must be > 0");
+        s->mala_sigma = std::sqrt(desc->mala_sigma2);
+        break;
+    case AMH_SAMPLER_RAM:
+        if (desc->ram_S0) {
+            s->S0.resize(nt);
+            for (int i = 0; i < d; ++i)
+                for (int j = 0; j <= i; ++j) s->S0[tri_h(i, j)] = desc->ram_S0[(long long)i * d + j];
+        }
+        break;
+    default:
+        return bad("unknown sampler kind");
+    }
+    s->d.mean = nullptr; s->d.scale = nullptr; s->d.ram_S0 = nullptr;
+    cudaSetDevice(ctx->device);
+    int rc = upload(&s->dmean, s->mean, ctx->stream);
+    if (!rc) rc = upload(&s->dscale, s->scale, ctx->stream);
+    if (!rc) rc = upload(&s->dS0, s->S0, ctx->stream);
+    if (rc) { amh_sampler_destroy(s); return rc; }
+    *out = s;
+    return AMH_OK;
+}
+int32_t amh_sampler_destroy(amh_sampler* s) {
+    if (!s) return AMH_OK;
+    cudaSetDevice(s->ctx->device);
+    if (s->dmean) cudaFree(s->dmean);
+    if (s->dscale) cudaFree(s->dscale);
+    if (s->dS0) cudaFree(s->dS0);
+    delete s;
+    return AMH_OK;
+}
+
+int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, int64_t n, int64_t off,
+                       const uint64_t* seeds, const double* init, amh_run** out) {
+    if (!ctx || !target || !sampler || !out || !seeds) return fail(AMH_ERR_INVALID, "NULL argument");
+    if (target->dim != sampler->d.dim) return fail(AMH_ERR_INVALID, "target and sampler dimensions differ");
+    if (target->ctx != ctx || sampler->ctx != ctx) return fail(AMH_ERR_INVALID, "target/sampler belong to another ctx");
+    if (n < 1) return fail(AMH_ERR_INVALID, "nchains_local must be >= 1");
+    const int kind = sampler->d.kind;
+    const int d = target->dim;
+    if (d > amhd::kGenericCap) return fail(AMH_ERR_UNSUPPORTED, "device samplers support dim <= 128");
+    long long nseeds = n;
+    if (kind == AMH_SAMPLER_STRETCH) {
+        if (n % sampler->d.n_walkers) return fail(AMH_ERR_INVALID, "nchains_local must be a multiple of n_walkers");
+        nseeds = n / sampler->d.n_walkers;
+    }
+    if (kind == AMH_SAMPLER_MALA) {
+        /* propose(::MALA) = error("please specify initial parameters")  (MALA.jl:37) */
+        if (!init) return fail(AMH_ERR_STATE, "please specify initial parameters");
+        /* check_capabilities (MALA.jl:42-52) */
+        if (!target->has_grad()) return fail(AMH_ERR_INVALID, "The gradient of the log density function is not defined");
+    }
+    if (kind == AMH_SAMPLER_STRETCH && !init && sampler->scale.empty())
+        return fail(AMH_ERR_INVALID, "stretch move without init needs an initial-draw proposal");
+    AMH_CUDA_TRY(cudaSetDevice(ctx->device));
+    amh_run* r = new amh_run();
+    r->ctx = ctx; r->target = target; r->sampler = sampler;
+    r->n = n; r->off = off; r->dim = d; r->nseeds = nseeds;
+    r->pitch = (n + 15) / 16 * 16;          /* rows start 128-byte aligned */
+    const size_t np = (size_t)r->pitch;
+    const size_t nt = (size_t)d * (d + 1) / 2;
+    int rc = AMH_OK;
+    auto chk = [&](int c) { if (!rc) rc = c; };
+    chk(dev_alloc(&r->X, (size_t)d * np));
+    chk(dev_alloc(&r->lp, np));
+    chk(dev_alloc(&r->lq, np));
+    chk(dev_alloc(&r->acc, np));
+    chk(dev_alloc(&r->failed, np));
+    chk(dev_alloc(&r->nacc, np));
+    chk(dev_alloc(&r->seeds, (size_t)nseeds));
+    chk(dev_alloc(&r->sum, (size_t)d * np));
+    chk(dev_alloc(&r->sumsq, (size_t)d * np));
+    if (kind == AMH_SAMPLER_MALA) chk(dev_alloc(&r->G, (size_t)d * np));
+    if (kind == AMH_SAMPLER_STRETCH) {
+        chk(dev_alloc(&r->X2, (size_t)d * np));
+        chk(dev_alloc(&r->lp2, np));
+    }
+    if (kind == AMH_SAMPLER_RAM) {
+        chk(dev_alloc(&r->S, nt * np));
+        chk(dev_alloc(&r->logalpha, np));
+        chk(dev_alloc(&r->eta, np));
+        const bool bounds = !(sampler->d.ram_eig_lo == 0.0 && sampler->d.ram_eig_hi == INFINITY);
+        if (bounds) chk(dev_alloc(&r->S2, nt * np));
+    }
+    if (rc) { free_run(r); return rc; }
+    cudaStream_t st = ctx->stream;
+    auto cu = [&](cudaError_t e, const char* w) { if (!rc && e != cudaSuccess) rc = cuda_fail(e, w); };
+    cu(cudaMemsetAsync(r->X, 0, sizeof(double) * d * np, st), "memset X");
+    cu(cudaMemsetAsync(r->lp, 0, sizeof(double) * np, st), "memset lp");
+    cu(cudaMemsetAsync(r->lq, 0, sizeof(double) * np, st), "memset lq");
+    cu(cudaMemsetAsync(r->acc, 0, np, st), "memset acc");
+    cu(cudaMemsetAsync(r->failed, 0, np, st), "memset failed");
+    cu(cudaMemsetAsync(r->nacc, 0, sizeof(unsigned long long) * np, st), "memset nacc");
+    cu(cudaMemsetAsync(r->sum, 0, sizeof(double) * d * np, st), "memset sum");
+    cu(cudaMemsetAsync(r->sumsq, 0, sizeof(double) * d * np, st), "memset sumsq");
+    if (r->logalpha) cu(cudaMemsetAsync(r->logalpha, 0, sizeof(double) * np, st), "memset logalpha");
+    if (r->eta) cu(cudaMemsetAsync(r->eta, 0, sizeof(double) * np, st), "memset eta");
+    cu(cudaMemcpyAsync(r->seeds, seeds, sizeof(uint64_t) * nseeds, cudaMemcpyHostToDevice, st), "copy seeds");
+    int mode;
+    if (init) {
+        cu(cudaMemcpy2DAsync(r->X, sizeof(double) * np, init, sizeof(double) * n, sizeof(double) * n, d,
+                             cudaMemcpyHostToDevice, st), "copy init");
+        mode = 0;
+    } else {
+        mode = kind == AMH_SAMPLER_RAM ? 2 : kind == AMH_SAMPLER_STRETCH ? 3 : 1;
+    }
+    if (!rc) rc = launch_init(*r, mode);
+    cu(cudaStreamSynchronize(st), "init sync");       /* host buffers are only read during the call */
+    if (rc) { free_run(r); return rc; }
+    *out = r;
+    return AMH_OK;
+}
+int32_t amh_run_destroy(amh_run* r) {
+    free_run(r);
+    return AMH_OK;
+}
+
+int32_t amh_run_steps(amh_run* run, int64_t nsteps, int32_t warmup, int32_t steps_per_launch) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    if (nsteps < 0) return fail(AMH_ERR_INVALID, "nsteps must be >= 0");
+    if (nsteps == 0) return AMH_OK;
+    return enqueue_steps(*run, nsteps, warmup != 0, steps_per_launch, nullptr);
+}
+int32_t amh_run_sync(amh_run* run) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    AMH_CUDA_TRY(cudaSetDevice(run->ctx->device));
+    AMH_CUDA_TRY(cudaStreamSynchronize(run->ctx->stream));
+    return AMH_OK;
+}
+
+int32_t amh_run_sample(amh_run* run, int64_t N, int64_t discard_initial, int64_t thinning, int64_t num_warmup,
+                       double* out, uint8_t* accepted_out, amh_summary* summary) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    if (N < 1 || thinning < 1 || discard_initial < 0 || num_warmup < 0)
+        return fail(AMH_ERR_INVALID, "need N >= 1, thinning >= 1, discard_initial >= 0, num_warmup >= 0");
+    amh_run& r = *run;
+    const long long n = r.n, np = r.pitch;
+    const int d = r.dim;
+    cudaStream_t st = r.ctx->stream;
+    AMH_CUDA_TRY(cudaSetDevice(r.ctx->device));
+    AMH_CUDA_TRY(cudaMemsetAsync(r.sum, 0, sizeof(double) * d * np, st));
+    AMH_CUDA_TRY(cudaMemsetAsync(r.sumsq, 0, sizeof(double) * d * np, st));
+    r.nsaved = 0;
+    /* device sample ring: `chunk` slabs of [(d+1)][pitch] doubles (+ accepted flags) */
+    const size_t slab = (size_t)(d + 1) * np;
+    long long chunk = 0;
+    double* dsamp = nullptr;
+    unsigned char* dacc = nullptr;
+    if (out || accepted_out) {
+        chunk = std::max<long long>(1, std::min<long long>(N, (long long)((256ull << 20) / (slab * sizeof(double)))));
+        if (out) AMH_CUDA_TRY(cudaMalloc((void**)&dsamp, sizeof(double) * slab * chunk));
+        if (accepted_out) AMH_CUDA_TRY(cudaMalloc((void**)&dacc, (size_t)np * chunk));
+    }
+    int rc = AMH_OK;
+    long long filled = 0, base = 0;
+    auto flush = [&]() -> int {
+        if (filled == 0) return AMH_OK;
+        if (out)
+            AMH_CUDA_TRY(cudaMemcpy2DAsync(out + (size_t)base * (d + 1) * n, sizeof(double) * n, dsamp, sizeof(double) * np,
+                                           sizeof(double) * n, (size_t)filled * (d + 1), cudaMemcpyDeviceToHost, st));
+        if (accepted_out)
+            AMH_CUDA_TRY(cudaMemcpy2DAsync(accepted_out + (size_t)base * n, (size_t)n, dacc, (size_t)np, (size_t)n,
+                                           (size_t)filled, cudaMemcpyDeviceToHost, st));
+        AMH_CUDA_TRY(cudaStreamSynchronize(st));
+        base += filled;
+        filled = 0;
+        return AMH_OK;
+    };
+    for (long long i = 0; i < N && !rc; ++i) {
+        long long k = (i == 0) ? discard_initial : thinning;
+        amhd::SaveArgs sv;
+        std::memset(&sv, 0, sizeof(sv));
+        sv.out = dsamp ? dsamp + (size_t)filled * slab : nullptr;
+        sv.out_pitch = np;
+        sv.acc_out = dacc ? dacc + (size_t)filled * np : nullptr;
+        sv.sum = r.sum;
+        sv.sumsq = r.sumsq;
+        /* stateful step s (1-based, cumulative) is step_warmup iff s <= num_warmup */
+        bool done = false;
+        while (!done && !rc) {
+            const bool wu = k > 0 && r.step < num_warmup;
+            const long long m = wu ? std::min<long long>(k, num_warmup - r.step) : k;
+            rc = enqueue_steps(r, m, wu, 0, (m == k) ? &sv : nullptr);
+            k -= m;
+            done = (k == 0);
+        }
+        r.nsaved += 1;
+        if (dsamp || dacc) {
+            filled += 1;
+            if (filled == chunk && !rc) rc = flush();
+        }
+    }
+    if (!rc) rc = flush();
+    if (dsamp) cudaFree(dsamp);
+    if (dacc) cudaFree(dacc);
+    if (rc) return rc;
+    AMH_CUDA_TRY(cudaStreamSynchronize(st));
+    if (summary) {
+        std::vector<double> hs((size_t)d * np), hq((size_t)d * np);
+        std::vector<unsigned long long> ha((size_t)np);
+        AMH_CUDA_TRY(cudaMemcpy(hs.data(), r.sum, sizeof(double) * d * np, cudaMemcpyDeviceToHost));
+        AMH_CUDA_TRY(cudaMemcpy(hq.data(), r.sumsq, sizeof(double) * d * np, cudaMemcpyDeviceToHost));
+        AMH_CUDA_TRY(cudaMemcpy(ha.data(), r.nacc, sizeof(unsigned long long) * np, cudaMemcpyDeviceToHost));
+        summary->n_saved = r.nsaved;
+        summary->n_steps = r.step;
+        double na = 0;
+        for (long long c = 0; c < n; ++c) na += (double)ha[c];
+        summary->accept_rate = r.step > 0 ? na / ((double)n * (double)r.step) : 0.0;
+        for (int i = 0; i < d; ++i) {
+            double s1 = 0, s2 = 0;
+            for (long long c = 0; c < n; ++c) {
+                s1 += hs[(size_t)i * np + c];
+                s2 += hq[(size_t)i * np + c];
+                if (summary->chain_mean) summary->chain_mean[(size_t)i * n + c] = hs[(size_t)i * np + c] / (double)r.nsaved;
+            }
+            const double tot = (double)n * (double)r.nsaved;
+            const double m = s1 / tot;
+            if (summary->mean) summary->mean[i] = m;
+            if (summary->var) summary->var[i] = s2 / tot - m * m;
+        }
+    }
+    return AMH_OK;
+}
+
+int32_t amh_run_get_state(amh_run* run, double* x, double* lp, double* grad, double* S, uint8_t* accepted,
+                          int64_t* naccept, int64_t* step_counter) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    amh_run& r = *run;
+    const long long n = r.n, np = r.pitch;
+    const int d = r.dim;
+    AMH_CUDA_TRY(cudaSetDevice(r.ctx->device));
+    AMH_CUDA_TRY(cudaStreamSynchronize(r.ctx->stream));
+    if (x) AMH_CUDA_TRY(cudaMemcpy2D(x, sizeof(double) * n, r.X, sizeof(double) * np, sizeof(double) * n, d, cudaMemcpyDeviceToHost));
+    if (lp) AMH_CUDA_TRY(cudaMemcpy(lp, r.lp, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (grad) {
+        if (!r.G) return fail(AMH_ERR_INVALID, "sampler keeps no gradient");
+        AMH_CUDA_TRY(cudaMemcpy2D(grad, sizeof(double) * n, r.G, sizeof(double) * np, sizeof(double) * n, d, cudaMemcpyDeviceToHost));
+    }
+    if (S) {
+        if (!r.S) return fail(AMH_ERR_INVALID, "sampler keeps no Cholesky factor");
+        const size_t nt = (size_t)d * (d + 1) / 2;
+        AMH_CUDA_TRY(cudaMemcpy2D(S, sizeof(double) * n, r.S, sizeof(double) * np, sizeof(double) * n, nt, cudaMemcpyDeviceToHost));
+    }
+    if (accepted) AMH_CUDA_TRY(cudaMemcpy(accepted, r.acc, (size_t)n, cudaMemcpyDeviceToHost));
+    if (naccept) AMH_CUDA_TRY(cudaMemcpy(naccept, r.nacc, sizeof(int64_t) * n, cudaMemcpyDeviceToHost));
+    if (step_counter) *step_counter = r.step;
+    return AMH_OK;
+}
+
+int32_t amh_run_set_params(amh_run* run, const double* x) {
+    if (!run || !x) return fail(AMH_ERR_INVALID, "NULL argument");
+    amh_run& r = *run;
+    AMH_CUDA_TRY(cudaSetDevice(r.ctx->device));
+    AMH_CUDA_TRY(cudaMemcpy2DAsync(r.X, sizeof(double) * r.pitch, x, sizeof(double) * r.n, sizeof(double) * r.n, r.dim,
+                                   cudaMemcpyHostToDevice, r.ctx->stream));
+    int rc = AMH_OK;
+    /* setparams!! recomputes lp (src/AdvancedMH.jl:151-157) and the gradient (MALA.jl:27-35);
+     * RAM's setparams!! keeps logprob and S (RobustAdaptiveMetropolis.jl:117-121) */
+    if (r.sampler->d.kind != AMH_SAMPLER_RAM) {
+        double* Ssave = r.S;
+        r.S = nullptr;
+        rc = launch_init(r, 0);
+        r.S = Ssave;
+    }
+    AMH_CUDA_TRY(cudaStreamSynchronize(r.ctx->stream));
+    return rc;
+}
+
+int32_t amh_run_dim(amh_run* run) { return run ? run->dim : -1; }
+int64_t amh_run_nchains(amh_run* run) { return run ? run->n : -1; }
+int64_t amh_run_launch_count(amh_run* run) { return run ? run->launches : -1; }
+
+int32_t amh_run_kernel_time_ms(amh_run* run, int32_t reset, double* ms, int64_t* launches) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    AMH_CUDA_TRY(cudaSetDevice(run->ctx->device));
+    const int rc = resolve_events(*run);
+    if (rc) return rc;
+    if (ms) *ms = run->kernel_ms;
+    if (launches) *launches = run->timed_launches;
+    if (reset) { run->kernel_ms = 0; run->timed_launches = 0; }
+    return AMH_OK;
+}
+
+}  /* extern "C" */

@@ -1,0 +1,97 @@
+/* amh_host.h -- host-side objects behind the opaque handles of include/amh.h. */
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/amh.h"
+#include "amh_device.cuh"
+
+struct amh_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    int sm_count = 0;
+};
+
+struct amh_target {
+    amh_ctx* ctx = nullptr;
+    int kind = 0, dim = 0;
+    std::vector<double> blob;      /* host copy */
+    double* dblob = nullptr;       /* device copy of the whole blob */
+    long long ndata = 0;
+    double inv2tau2 = 0, invtau2 = 0;
+    bool has_grad() const {
+        return kind == AMH_TARGET_MVNORMAL || kind == AMH_TARGET_GAUSS_PREC || kind == AMH_TARGET_IID_NORMAL ||
+               kind == AMH_TARGET_LOGISTIC || kind == AMH_TARGET_ROSENBROCK;
+    }
+};
+
+struct amh_sampler {
+    amh_ctx* ctx = nullptr;
+    amh_sampler_desc d{};
+    std::vector<double> mean, scale, S0;   /* host copies (S0 packed lower) */
+    bool has_mean = false;
+    double mala_sigma = 0;
+    double* dmean = nullptr;
+    double* dscale = nullptr;
+    double* dS0 = nullptr;
+};
+
+struct amh_run {
+    amh_ctx* ctx = nullptr;
+    amh_target* target = nullptr;
+    amh_sampler* sampler = nullptr;
+    long long n = 0, off = 0, pitch = 0;
+    int dim = 0;
+    long long nseeds = 0;
+    /* device state */
+    double* X = nullptr;
+    double* X2 = nullptr;          /* second walker buffer (stretch) / second S buffer flagging (RAM) */
+    double* lp = nullptr;
+    double* lp2 = nullptr;
+    double* lq = nullptr;
+    double* G = nullptr;
+    double* S = nullptr;
+    double* S2 = nullptr;
+    double* logalpha = nullptr;
+    double* eta = nullptr;
+    unsigned char* acc = nullptr;
+    unsigned char* failed = nullptr;
+    unsigned char* sflag = nullptr;
+    unsigned long long* nacc = nullptr;
+    unsigned long long* seeds = nullptr;
+    double* sum = nullptr;
+    double* sumsq = nullptr;
+    void* scratch = nullptr;       /* sampler specific (stretch: done flags ...) */
+    long long step = 0;
+    long long nsaved = 0;
+    long long launches = 0;
+    /* kernel timing */
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+    double kernel_ms = 0;
+    long long timed_launches = 0;
+    long long pending_launches = 0;
+};
+
+namespace amhh {
+inline int tri_h(int i, int j) { return i * (i + 1) / 2 + j; }
+int fail(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+#define AMH_CUDA_TRY(expr)                                   \
+    do {                                                     \
+        cudaError_t _e = (expr);                             \
+        if (_e != cudaSuccess) return amhh::cuda_fail(_e, #expr); \
+    } while (0)
+
+amhd::ChainState chain_state(amh_run& r);
+
+/* per-sampler launchers; each enqueues kernels on r.ctx->stream and bumps r.launches */
+int launch_mh(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
+int launch_mala(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
+int launch_ram(amh_run& r, int nsteps, bool warmup, const amhd::SaveArgs& sv);
+int launch_stretch(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
+int launch_init(amh_run& r, int mode);
+int default_steps_per_launch(const amh_run& r);
+}  // namespace amhh

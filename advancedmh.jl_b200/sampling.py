@@ -1,0 +1,256 @@
+"""`sample` -- the AbstractMCMC call surface of the multi-chain path
+(README.md:135-148, test/runtests.jl:96-110; loop semantics SURVEY.md A.1):
+
+    sample([rng,] model, sampler, N; kw...)
+    sample([rng,] model, sampler, parallel, N, nchains; kw...)
+
+All chains advance in lock-step on the GPU(s); `parallel` only says how many.
+Keyword arguments keep the reference's names: initial_params, discard_initial,
+thinning, num_warmup, chain_type, param_names, progress (ignored), callback."""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _capi as K
+from .models import as_target
+from .samplers import Ensemble, MALA, MHSampler, RobustAdaptiveMetropolis
+
+
+# ------------------------------------------------------------------ parallel
+class MCMCSerial:
+    pass
+
+
+class MCMCThreads:
+    pass
+
+
+class MCMCDistributed:
+    pass
+
+
+@dataclass
+class MCMCB200:
+    """The ensemble type the Julia shim adds (`MCMCB200 <: AbstractMCMCEnsemble`): run all chains on
+    B200s.  Under torchrun (one process per GPU) the chains are sharded in contiguous blocks
+    across ranks; there is no per-step collective."""
+    device: int | None = None
+    gather: bool = True
+
+
+# ---------------------------------------------------------------- chain types
+class Transition:
+    """Transition(params, lp, accepted)  (src/AdvancedMH.jl:61-65)"""
+    __slots__ = ("params", "lp", "accepted")
+    def __init__(self, params, lp, accepted):
+        self.params, self.lp, self.accepted = params, lp, accepted
+
+
+class Chains:
+    """MCMCChains.Chains look-alike: value[iter, param..+lp, chain]
+    (ext/AdvancedMHMCMCChainsExt.jl:24-38, 93-121)."""
+    def __init__(self, value, names, start=1, thin=1, accepted=None, info=None):
+        self.value = value
+        self.names = list(names)
+        self.start, self.thin = start, thin
+        self.accepted = accepted
+        self.info = info or {}
+    def range(self):
+        n = self.value.shape[0]
+        return range(self.start, self.start + self.thin * n, self.thin)
+    def __getitem__(self, name):
+        return self.value[:, self.names.index(name), :]
+    @property
+    def parameters(self):
+        return self.names[:-1]
+    def array(self):
+        """Array(chain): iterations x parameters, chains stacked, internals (lp) dropped"""
+        v = self.value[:, :-1, :]
+        return np.concatenate([v[:, :, c] for c in range(v.shape[2])], axis=0)
+
+
+class StructArray(dict):
+    """StructArrays look-alike (ext/AdvancedMHStructArraysExt.jl:12-27): one array per field"""
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+class TransitionVector:
+    """Vector{Transition} view over the stored samples of ONE chain (or, for Ensemble, of the walkers)"""
+    def __init__(self, value, accepted):
+        self.value, self.accepted = value, accepted
+    def __len__(self):
+        return self.value.shape[0]
+    def __getitem__(self, i):
+        v = self.value[i]
+        if v.shape[1] == 1:
+            return Transition(v[:-1, 0].copy(), float(v[-1, 0]), bool(self.accepted[i, 0]))
+        return [Transition(v[:-1, c].copy(), float(v[-1, c]), bool(self.accepted[i, c])) for c in range(v.shape[1])]
+
+
+# --------------------------------------------------------------------- engine
+_ENGINES: dict = {}
+
+
+def default_engine(device: int | None = None) -> K.Engine:
+    """The CUDA engine of this process (LOCAL_RANK selects the GPU under torchrun)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _ENGINES:
+        _ENGINES[device] = K.Engine(device=device)
+    return _ENGINES[device]
+
+
+def _dist_info():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size(), dist
+    except Exception:
+        pass
+    return 0, 1, None
+
+
+def shard_bounds(nunits: int, rank: int, world: int):
+    """contiguous block partition of `nunits` chains (or ensembles) over `world` ranks"""
+    base, rem = divmod(nunits, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _initial_matrix(initial_params, sampler, dim, nchains, multi):
+    """-> (dim, nchains_total) float64 or None; mirrors AbstractMCMC: a multi-chain call takes one entry per chain"""
+    if initial_params is None:
+        return None
+    nw = sampler.n_walkers if isinstance(sampler, Ensemble) else 1
+    ip = initial_params
+    if not multi:
+        ip = [ip]
+    if len(ip) != nchains:
+        raise ValueError("initial_params must have one entry per chain")
+    cols = []
+    for entry in ip:
+        e = np.asarray(entry, dtype=np.float64)
+        if nw == 1:
+            e = e.reshape(-1)
+            if e.size != dim:
+                raise ValueError(f"initial_params entry has length {e.size}, model dimension is {dim}")
+            cols.append(e[:, None])
+        else:
+            e = e.reshape(nw, dim)
+            cols.append(e.T)
+    return np.ascontiguousarray(np.concatenate(cols, axis=1))
+
+
+def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None, thinning=1, num_warmup=0,
+           chain_type=None, param_names=None, progress=False, callback=None, engine=None, store=True,
+           summary=False, steps_per_launch=0):
+    """See module docstring.  Extra device-side keywords (never on the samplers): `engine`
+    (a _capi.Engine; default = the CUDA library), `store=False` + `summary=True` for runs whose
+    samples cannot be stored (SURVEY.md 7 hard part 7)."""
+    args = list(args)
+    if args and isinstance(args[0], np.random.Generator):
+        rng = args.pop(0)
+    if len(args) == 3:
+        model, sampler, N = args
+        parallel, nchains, multi = None, 1, False
+    elif len(args) == 5:
+        model, sampler, parallel, N, nchains = args
+        multi = True
+    else:
+        raise TypeError("sample(model, sampler, N) or sample(model, sampler, parallel, N, nchains)")
+    if not isinstance(sampler, MHSampler):
+        raise TypeError("sampler must be an AdvancedMH sampler")
+    target = as_target(model)
+    dim = target.dim
+    N, nchains = int(N), int(nchains)
+    if discard_initial is None:
+        discard_initial = num_warmup          # AbstractMCMC default (RAM docstring :41-44)
+    if isinstance(sampler, RobustAdaptiveMetropolis) and not hasattr(target, "kind"):
+        raise ValueError("RobustAdaptiveMetropolis needs a LogDensityProblems-style target")
+    if rng is None:
+        rng = np.random.default_rng(seed)
+    nw = sampler.n_walkers if isinstance(sampler, Ensemble) else 1
+    # seeds = rand(rng, UInt, nchains): drawn for ALL chains so results do not depend on the sharding
+    seeds = rng.integers(0, 2 ** 64, size=nchains, dtype=np.uint64)
+    init = _initial_matrix(initial_params, sampler, dim, nchains, multi)
+
+    rank, world, dist = (0, 1, None)
+    if isinstance(parallel, MCMCB200):
+        rank, world, dist = _dist_info()
+    lo, hi = shard_bounds(nchains, rank, world)
+    eng = engine or default_engine(parallel.device if isinstance(parallel, MCMCB200) else None)
+
+    th = eng.target(target.kind, dim, target.blob())
+    sh = sampler.lower(eng, dim)
+    n_local = (hi - lo) * nw
+    run = None
+    try:
+        if n_local > 0:
+            run = eng.run(th, sh, n_local, seeds[lo:hi], None if init is None else init[:, lo * nw:hi * nw],
+                          chain_offset=lo * nw)
+            out, acc, summ = run.sample(N, discard_initial, thinning, num_warmup, store=store,
+                                        store_accepted=store, summary=summary or not store, chain_means=False)
+            info = dict(summary=summ, launches=run.launch_count(), rank=rank, world=world,
+                        chains=(lo * nw, hi * nw))
+            if callback is not None and store:
+                for i in range(N):
+                    callback(rng, model, sampler, out[i], None, i + 1)
+        else:
+            out = np.empty((N, dim + 1, 0)) if store else None
+            acc = np.empty((N, 0), dtype=np.uint8) if store else None
+            info = dict(summary=None, launches=0, rank=rank, world=world, chains=(0, 0))
+    finally:
+        if run is not None:
+            run.close()
+        sh.close()
+        th.close()
+
+    if world > 1 and isinstance(parallel, MCMCB200) and parallel.gather and store:
+        out, acc = _gather_samples(dist, out, acc, nchains * nw, world, nw)
+
+    if not store:
+        return info
+    names = list(param_names) if param_names is not None else [f"param_{i + 1}" for i in range(dim)]
+    if len(names) != dim:
+        raise ValueError("param_names must have one entry per parameter")
+    if chain_type is None:
+        return TransitionVector(out, acc) if not multi else [TransitionVector(out[:, :, c * nw:(c + 1) * nw], acc[:, c * nw:(c + 1) * nw]) for c in range(out.shape[2] // nw)]
+    if chain_type is Chains or chain_type == "Chains":
+        return Chains(out, names + ["lp"], start=discard_initial + 1, thin=thinning, accepted=acc, info=info)
+    if chain_type is StructArray or chain_type == "StructArray":
+        sa = StructArray({nm: out[:, i, :].reshape(-1, order="F") if out.shape[2] > 1 else out[:, i, 0] for i, nm in enumerate(names)})
+        sa["lp"] = out[:, dim, :].reshape(-1, order="F") if out.shape[2] > 1 else out[:, dim, 0]
+        return sa
+    if chain_type == "namedtuples":
+        keys = names + ["lp"]
+        return [dict(zip(keys, out[i, :, 0])) for i in range(out.shape[0])]
+    raise ValueError("chain_type must be None, Chains, StructArray or 'namedtuples'")
+
+
+def _gather_samples(dist, out, acc, ntotal, world, nw):
+    """final gather of every rank's chains to all ranks (NCCL all_gather over NVLink when the
+    tensors live on the GPUs; gloo on CPU in the tests)."""
+    import torch
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    N, dp1 = out.shape[0], out.shape[1]
+    counts = [(shard_bounds(ntotal // nw, r, world)[1] - shard_bounds(ntotal // nw, r, world)[0]) * nw for r in range(world)]
+    cmax = max(counts)
+    buf = torch.zeros((N, dp1, cmax), dtype=torch.float64, device=dev)
+    buf[:, :, :out.shape[2]] = torch.from_numpy(out).to(dev)
+    abuf = torch.zeros((N, cmax), dtype=torch.uint8, device=dev)
+    abuf[:, :acc.shape[1]] = torch.from_numpy(acc).to(dev)
+    outs = [torch.empty_like(buf) for _ in range(world)]
+    accs = [torch.empty_like(abuf) for _ in range(world)]
+    dist.all_gather(outs, buf)
+    dist.all_gather(accs, abuf)
+    full = np.concatenate([o[:, :, :c].cpu().numpy() for o, c in zip(outs, counts)], axis=2)
+    facc = np.concatenate([a[:, :c].cpu().numpy() for a, c in zip(accs, counts)], axis=1)
+    return full, facc
