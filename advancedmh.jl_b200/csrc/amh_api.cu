@@ -341,8 +341,9 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
         chk(dev_alloc(&r->S, nt * np));
         chk(dev_alloc(&r->logalpha, np));
         chk(dev_alloc(&r->eta, np));
-        const bool bounds = !(sampler->d.ram_eig_lo == 0.0 && sampler->d.ram_eig_hi == INFINITY);
-        if (bounds) chk(dev_alloc(&r->S2, nt * np));
+        /* second factor buffer + per-chain selector: the non-mutating lowrankupdate/downdate (RAM :167,:170) */
+        chk(dev_alloc(&r->S2, nt * np));
+        chk(dev_alloc(&r->sflag, np));
     }
     if (rc) { free_run(r); return rc; }
     cudaStream_t st = ctx->stream;
@@ -357,6 +358,8 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
     cu(cudaMemsetAsync(r->sumsq, 0, sizeof(double) * d * np, st), "memset sumsq");
     if (r->logalpha) cu(cudaMemsetAsync(r->logalpha, 0, sizeof(double) * np, st), "memset logalpha");
     if (r->eta) cu(cudaMemsetAsync(r->eta, 0, sizeof(double) * np, st), "memset eta");
+    if (r->sflag) cu(cudaMemsetAsync(r->sflag, 0, np, st), "memset sflag");
+    if (r->S2) cu(cudaMemsetAsync(r->S2, 0, sizeof(double) * nt * np, st), "memset S2");
     cu(cudaMemcpyAsync(r->seeds, seeds, sizeof(uint64_t) * nseeds, cudaMemcpyHostToDevice, st), "copy seeds");
     int mode;
     if (init) {
@@ -501,7 +504,17 @@ int32_t amh_run_get_state(amh_run* run, double* x, double* lp, double* grad, dou
     if (S) {
         if (!r.S) return fail(AMH_ERR_INVALID, "sampler keeps no Cholesky factor");
         const size_t nt = (size_t)d * (d + 1) / 2;
-        AMH_CUDA_TRY(cudaMemcpy2D(S, sizeof(double) * n, r.S, sizeof(double) * np, sizeof(double) * n, nt, cudaMemcpyDeviceToHost));
+        double* tmp = nullptr;
+        AMH_CUDA_TRY(cudaMalloc((void**)&tmp, sizeof(double) * nt * np));
+        int rc = ram_gather_S(r, tmp);
+        if (!rc) {
+            cudaError_t e = cudaStreamSynchronize(r.ctx->stream);
+            if (e == cudaSuccess)
+                e = cudaMemcpy2D(S, sizeof(double) * n, tmp, sizeof(double) * np, sizeof(double) * n, nt, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) rc = cuda_fail(e, "copy S");
+        }
+        cudaFree(tmp);
+        if (rc) return rc;
     }
     if (accepted) AMH_CUDA_TRY(cudaMemcpy(accepted, r.acc, (size_t)n, cudaMemcpyDeviceToHost));
     if (naccept) AMH_CUDA_TRY(cudaMemcpy(naccept, r.nacc, sizeof(int64_t) * n, cudaMemcpyDeviceToHost));

@@ -93,5 +93,6 @@ int launch_mala(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_ram(amh_run& r, int nsteps, bool warmup, const amhd::SaveArgs& sv);
 int launch_stretch(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_init(amh_run& r, int mode);
+int ram_gather_S(amh_run& r, double* dst);   /* current factor of every chain -> dst [tri][pitch] */
 int default_steps_per_launch(const amh_run& r);
 }  // namespace amhh

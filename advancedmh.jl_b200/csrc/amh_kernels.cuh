@@ -44,7 +44,7 @@ mh_step_kernel(const __grid_constant__ MhArgs<DMAX> a,
     const int tid = threadIdx.x;
     const long long ch = (long long)blockIdx.x * BLOCK + tid;
     if (ch >= a.st.n) return;
-    const int d = a.d;
+    const int d = D::fixed ? DMAX : a.d;      /* fixed path: launched only with dim == DMAX, every `i < d` folds */
     const int top = D::fixed ? DMAX : d;
     const unsigned long long seed = a.st.seeds[ch];
     double lp = a.st.lp[ch];

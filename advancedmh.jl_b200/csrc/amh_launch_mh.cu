@@ -56,11 +56,19 @@ static bool needs_generic(const amh_run& r) {
 template <class T>
 int launch_mh_full(amh_run& r, int nsteps, const SaveArgs& sv) {
     if (needs_generic(r)) return launch_mh_t<0, T>(r, nsteps, sv);
-    switch (dim_bucket(r.dim)) {
+    switch (r.dim) {          /* exact-dimension instantiations; everything else is generic */
+    case 1: return launch_mh_t<1, T>(r, nsteps, sv);
     case 2: return launch_mh_t<2, T>(r, nsteps, sv);
+    case 3: return launch_mh_t<3, T>(r, nsteps, sv);
     case 4: return launch_mh_t<4, T>(r, nsteps, sv);
+    case 5: return launch_mh_t<5, T>(r, nsteps, sv);
+    case 6: return launch_mh_t<6, T>(r, nsteps, sv);
     case 8: return launch_mh_t<8, T>(r, nsteps, sv);
+    case 10: return launch_mh_t<10, T>(r, nsteps, sv);
+    case 12: return launch_mh_t<12, T>(r, nsteps, sv);
     case 16: return launch_mh_t<16, T>(r, nsteps, sv);
+    case 20: return launch_mh_t<20, T>(r, nsteps, sv);
+    case 24: return launch_mh_t<24, T>(r, nsteps, sv);
     case 32: return launch_mh_t<32, T>(r, nsteps, sv);
     }
     return launch_mh_t<0, T>(r, nsteps, sv);

@@ -62,14 +62,4 @@ typename T::template Params<DMAX> make_tp(const amh_target& t) {
     return p;
 }
 
-/* dimension bucket of the fully unrolled, constant-bank kernels; 0 = generic */
-inline int dim_bucket(int d) {
-    if (d <= 2) return 2;
-    if (d <= 4) return 4;
-    if (d <= 8) return 8;
-    if (d <= 16) return 16;
-    if (d <= 32) return 32;
-    return 0;
-}
-
 }  // namespace amhh

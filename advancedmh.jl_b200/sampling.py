@@ -125,11 +125,14 @@ def shard_bounds(nunits: int, rank: int, world: int):
 
 
 def _initial_matrix(initial_params, sampler, dim, nchains, multi):
-    """-> (dim, nchains_total) float64 or None; mirrors AbstractMCMC: a multi-chain call takes one entry per chain"""
+    """-> (dim, nchains_total) float64 or None; mirrors AbstractMCMC: a multi-chain call takes one entry per
+    chain.  Fast path: a (dim, nchains_total) float64 array in the device layout is used as is."""
     if initial_params is None:
         return None
     nw = sampler.n_walkers if isinstance(sampler, Ensemble) else 1
     ip = initial_params
+    if isinstance(ip, np.ndarray) and ip.ndim == 2 and ip.shape == (dim, nchains * nw) and (multi or nw > 1 or dim == 1):
+        return ip if (ip.dtype == np.float64 and ip.flags.c_contiguous) else np.ascontiguousarray(ip, dtype=np.float64)
     if not multi:
         ip = [ip]
     if len(ip) != nchains:

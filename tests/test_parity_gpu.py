@@ -166,3 +166,135 @@ def test_large_config2_shape_bit_exact_and_moments(amh, cuda, oracle):
     # pooled over 65 536 x 20 draws: relative error of the variances ~ 1e-3
     assert np.allclose(s["var"], np.diag(Sigma), rtol=0.01)
     assert np.all(np.abs(s["mean"]) < 0.01 * np.sqrt(np.diag(Sigma)) * 3)
+
+
+# ----------------------------------------------------------------------------- MALA (K3)
+@pytest.mark.parametrize("kind,d", [("gaussprec", 2), ("mvnormal", 5), ("mvnormal", 16), ("mvnormal", 24),
+                                    ("rosenbrock", 10), ("iid", 2), ("logistic", 7)])
+def test_mala_bit_exact(amh, cuda, oracle, kind, d):
+    rng = np.random.default_rng(5)
+    sigma2 = 0.05
+    if kind == "gaussprec":
+        # TheNormalLogDensity of test/runtests.jl:335-365
+        target = amh.GaussianPrecisionTarget(np.linalg.inv(np.array([[1.5, 0.35], [0.35, 1.0]])))
+        sigma2 = 0.5
+    elif kind == "mvnormal":
+        target = amh.MvNormalTarget(np.linspace(-0.5, 0.5, d), make_spd(d, seed=d, lo=0.5, hi=4.0))
+    elif kind == "rosenbrock":
+        target = amh.RosenbrockTarget(d)
+        sigma2 = 1e-3
+    elif kind == "iid":
+        target = amh.IIDNormalTarget(rng.normal(0, 1, 30))
+        sigma2 = 1e-3
+    else:
+        X = rng.normal(size=(40, d)) / np.sqrt(d)
+        y = (rng.random(40) < 0.5).astype(float)
+        target = amh.LogisticRegressionTarget(X, y, tau=3.0)
+    spl = amh.MALA(lambda g: amh.MvNormal((sigma2 / 2) * g, sigma2 * amh.I))
+    n = 300
+    init = np.ones((d, n)) + 0.05 * rng.normal(size=(d, n))
+    rg, ro = _pair(amh, cuda, oracle, target, spl, n, _seeds(n, 40 + d), init)
+    _assert_same_state(rg, ro, grad=True)
+    for k, spl_ in [(1, 1), (9, 4), (40, 0)]:
+        rg.steps(k, steps_per_launch=spl_)
+        ro.steps(k)
+        _assert_same_state(rg, ro, grad=True)
+    acc = rg.state()["naccept"].sum() / (n * 50)
+    assert 0.05 < acc <= 1.0
+
+
+def test_mala_requires_initial_params_and_gradient(amh, cuda):
+    target = amh.GaussianPrecisionTarget(np.eye(2))
+    spl = amh.MALA(lambda g: amh.MvNormal(0.25 * g, 0.5 * amh.I))
+    th = cuda.target(target.kind, 2, target.blob()); sh = spl.lower(cuda, 2)
+    with pytest.raises(amh.AMHStateError, match="please specify initial parameters"):      # MALA.jl:37
+        cuda.run(th, sh, 4, _seeds(4))
+    nig = amh.NormalInverseGammaToy()
+    with pytest.raises(amh.AMHArgumentError, match="gradient"):                            # MALA.jl:42-52
+        cuda.run(cuda.target(nig.kind, 2, nig.blob()), sh, 4, _seeds(4), np.ones((2, 4)))
+
+
+# ------------------------------------------------------------------------------ RAM (K4)
+@pytest.mark.parametrize("d,bounds", [(2, None), (2, (0.9, 1.1)), (5, None), (16, (0.1, 2.0)), (33, None), (64, None)])
+def test_ram_bit_exact(amh, cuda, oracle, d, bounds):
+    Sigma = make_spd(d, seed=60 + d, lo=1e-2, hi=1.0)
+    target = amh.MvNormalTarget(None, Sigma)
+    kw = {} if bounds is None else dict(eigenvalue_lower_bound=bounds[0], eigenvalue_upper_bound=bounds[1])
+    spl = amh.RobustAdaptiveMetropolis(**kw)
+    n = 200 if d < 64 else 96
+    rg, ro = _pair(amh, cuda, oracle, target, spl, n, _seeds(n, 70 + d))
+    _assert_same_state(rg, ro, S=True)                    # x = randn(d), S = I, accepted = true (:175-214)
+    assert rg.state()["accepted"].all()
+    for k, wu in [(1, True), (30, True), (5, False), (12, True)]:
+        rg.steps(k, warmup=wu)
+        ro.steps(k, warmup=wu)
+        _assert_same_state(rg, ro, S=True)
+    S = rg.state(S=True)["S"]
+    diag = np.array([S[i * (i + 1) // 2 + i] for i in range(d)])
+    assert np.all(diag > 0)
+    if bounds is not None:
+        assert np.all(diag >= bounds[0]) and np.all(diag <= bounds[1])
+
+
+def test_ram_user_S_and_init(amh, cuda, oracle):
+    d = 3
+    target = amh.GaussianPrecisionTarget(np.linalg.inv(make_spd(d, 3, 0.5, 3.0)))
+    S0 = np.linalg.cholesky(make_spd(d, 4, 0.2, 1.0))
+    spl = amh.RobustAdaptiveMetropolis(alpha=0.3, gamma=0.51, S=S0)
+    n = 64
+    init = np.random.default_rng(3).normal(size=(d, n))
+    rg, ro = _pair(amh, cuda, oracle, target, spl, n, _seeds(n, 5), init)
+    rg.steps(25, warmup=True); ro.steps(25, warmup=True)
+    _assert_same_state(rg, ro, S=True)
+    with pytest.raises(ValueError, match="wrong dimensionality"):          # RAM :202-204
+        amh.RobustAdaptiveMetropolis(S=np.eye(4)).lower(cuda, d)
+
+
+def test_ram_sample_schedule_warmup_bit_exact(amh, cuda, oracle):
+    d = 4
+    target = amh.MvNormalTarget(None, make_spd(d, 8, 0.1, 2.0))
+    spl = amh.RobustAdaptiveMetropolis()
+    n = 77
+    rg, ro = _pair(amh, cuda, oracle, target, spl, n, _seeds(n, 6))
+    og, ag, sg = rg.sample(11, discard_initial=30, thinning=3, num_warmup=37)
+    oo, ao, so = ro.sample(11, discard_initial=30, thinning=3, num_warmup=37)
+    assert np.array_equal(og, oo) and np.array_equal(ag, ao)
+    _assert_same_state(rg, ro, S=True)
+
+
+# -------------------------------------------------------------------------- stretch (K2)
+@pytest.mark.parametrize("kind,d,nw,ne", [("rosenbrock", 10, 64, 3), ("nig", 2, 100, 2), ("niglog", 2, 37, 2),
+                                          ("mvnormal", 5, 1024, 2), ("rosenbrock", 10, 4096, 1), ("mvnormal", 20, 50, 2)])
+def test_stretch_bit_exact_sequential_sweep(amh, cuda, oracle, kind, d, nw, ne):
+    if kind == "rosenbrock":
+        target = amh.RosenbrockTarget(d)
+    elif kind == "nig":
+        target = amh.NormalInverseGammaToy()
+    elif kind == "niglog":
+        target = amh.NormalInverseGammaToy(log_space=True)
+    else:
+        target = amh.MvNormalTarget(None, make_spd(d, seed=d, lo=0.5, hi=4.0))
+    spl = amh.Ensemble(nw, amh.StretchProposal(amh.MvNormal(np.zeros(d), amh.I)))
+    n = nw * ne
+    init = None
+    if kind == "nig":
+        init = np.abs(np.random.default_rng(2).normal(size=(d, n))) + 0.5
+    rg, ro = _pair(amh, cuda, oracle, target, spl, n, _seeds(ne, 90 + d), init)
+    _assert_same_state(rg, ro)
+    for k, spl_ in [(1, 1), (3, 2), (8, 0)]:
+        rg.steps(k, steps_per_launch=spl_)
+        ro.steps(k)
+        _assert_same_state(rg, ro)
+    acc = rg.state()["naccept"].sum() / (n * 12)
+    assert 0.05 < acc < 0.99
+
+
+def test_stretch_sample_bit_exact(amh, cuda, oracle):
+    d, nw, ne = 2, 50, 2
+    target = amh.NormalInverseGammaToy(log_space=True)
+    spl = amh.Ensemble(nw, amh.StretchProposal(amh.MvNormal(np.zeros(d), amh.I)))
+    rg, ro = _pair(amh, cuda, oracle, target, spl, nw * ne, _seeds(ne, 8))
+    og, ag, sg = rg.sample(13, discard_initial=5, thinning=2)
+    oo, ao, so = ro.sample(13, discard_initial=5, thinning=2)
+    assert np.array_equal(og, oo) and np.array_equal(ag, ao)
+    assert np.array_equal(sg["mean"], so["mean"])
