@@ -1,0 +1,168 @@
+"""Host-side mirror of the reference interface (constructors, `sample` keywords, chain types, errors),
+exercised on the CPU oracle engine so that it runs without a GPU.  Mirrors test/runtests.jl:37-54,
+112-213, 288-303 of the reference."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import make_spd
+
+
+@pytest.fixture(scope="module")
+def model(amh):
+    data = np.random.default_rng(1234).normal(0, 1, 30)
+    return amh.DensityModel(amh.IIDNormalTarget(data))
+
+
+def test_constructor_lowering(amh, oracle):
+    for spl, cov in [(amh.RWMH(3), "scalar"), (amh.StaticMH([amh.Normal(0, 1)] * 3), "diag"),
+                     (amh.RWMH(amh.MvNormal(np.zeros(3), make_spd(3, 1))), "full")]:
+        assert spl.dim == 3
+        spl.lower(oracle, 3).close()
+    assert amh.RWMH(2).proposal.issymmetric is False                      # proposal.jl:18 default
+    assert amh.SymmetricRandomWalkProposal(amh.Normal()).issymmetric is True
+    with pytest.raises(ValueError, match="dimension"):
+        amh.RWMH(3).lower(oracle, 2)
+    with pytest.raises(ValueError, match="function-valued"):
+        amh.MetropolisHastings(amh.RandomWalkProposal(lambda x: amh.Normal(x, 1)))
+    with pytest.raises(ValueError):
+        amh.MetropolisHastings([amh.Normal(0, 1)])                        # bare containers are host-only
+    with pytest.raises(ValueError, match="catalogue"):
+        amh.DensityModel(lambda x: -0.5 * x @ x)                         # closures cannot run on the device
+
+
+def test_mvnormal_forms(amh):
+    I = amh.I
+    a = amh.MvNormal(np.zeros(4), I)
+    assert a.kind == "scalar" and a.scale[0] == 1.0 and a.zero_mean
+    b = amh.MvNormal(np.ones(2), 0.25 * I)
+    assert b.scale[0] == 0.5 and not b.zero_mean
+    c = amh.MvNormal(np.zeros(2), np.array([4.0, 9.0]))
+    assert c.kind == "diag" and np.array_equal(c.scale, [2.0, 3.0])
+    S = make_spd(3, 2)
+    d = amh.MvNormal(np.zeros(3), S)
+    L = np.zeros((3, 3)); L[np.tril_indices(3)] = d.scale
+    assert np.allclose(L @ L.T, S)
+    with pytest.raises(ValueError):
+        amh.MvNormal(np.zeros(2), -1.0 * I)
+
+
+def test_mala_closure_probing(amh, oracle):
+    s2 = 0.3
+    spl = amh.MALA(lambda g: amh.MvNormal((s2 / 2) * g, s2 * amh.I))
+    assert spl.probe(3) == (pytest.approx(s2), pytest.approx(s2 / 2))
+    # MALA wraps a RandomWalkProposal too (MALA.jl:8-11)
+    spl2 = amh.MALA(amh.RandomWalkProposal(lambda g: amh.MvNormal(0.1 * g, s2 * amh.I)))
+    assert spl2.probe(2) == (pytest.approx(s2), pytest.approx(0.1))
+    with pytest.raises(ValueError):
+        amh.MALA(lambda g: amh.MvNormal(g * g, s2 * amh.I)).probe(2)        # not linear in g
+    with pytest.raises(ValueError):
+        amh.MALA(lambda g: amh.MvNormal(0.1 * g, np.array([1.0, 2.0]))).probe(2)   # not sigma2 * I
+    with pytest.raises(ValueError):
+        amh.MALA(amh.Normal())
+
+
+def test_sample_single_chain_and_chain_types(amh, oracle, model):
+    ch = amh.sample(model, amh.RWMH(2), 50, engine=oracle, seed=1)
+    assert len(ch) == 50 and ch[3].params.shape == (2,) and isinstance(ch[3].lp, float)
+    c2 = amh.sample(model, amh.RWMH(2), 50, engine=oracle, seed=1, chain_type=amh.Chains)
+    assert c2.value.shape == (50, 3, 1) and c2.names == ["param_1", "param_2", "lp"]
+    assert np.array_equal(c2.value[3, :2, 0], ch[3].params)             # same seed, same chain
+    sa = amh.sample(model, amh.RWMH(2), 50, engine=oracle, seed=1, chain_type=amh.StructArray, param_names=["a", "b"])
+    assert set(sa.keys()) == {"a", "b", "lp"} and np.array_equal(sa.a, c2["param_1"][:, 0])
+    nt = amh.sample(model, amh.RWMH(2), 5, engine=oracle, seed=1, chain_type="namedtuples")
+    assert list(nt[0].keys()) == ["param_1", "param_2", "lp"]
+    with pytest.raises(ValueError, match="param_names"):
+        amh.sample(model, amh.RWMH(2), 5, engine=oracle, param_names=["a"], chain_type=amh.Chains)
+
+
+def test_sample_multi_chain_matches_single_chains(amh, oracle, model):
+    """chains are independent streams: chain c of a 4-chain call equals a 1-chain run seeded with seeds[c]"""
+    rng = np.random.default_rng(5)
+    ch = amh.sample(rng, model, amh.RWMH(2), amh.MCMCThreads(), 40, 4, chain_type=amh.Chains, engine=oracle,
+                    initial_params=[[0.0, 1.0]] * 4)
+    assert ch.value.shape == (40, 3, 4)
+    assert np.array_equal(ch.value[0, :2, :], np.tile([[0.0], [1.0]], (1, 4)))
+    seeds = np.random.default_rng(5).integers(0, 2 ** 64, size=4, dtype=np.uint64)
+    t = model.logdensity
+    for c in range(4):
+        run = oracle.run(oracle.target(t.kind, 2, t.blob()), amh.RWMH(2).lower(oracle, 2), 1, seeds[c:c + 1],
+                         np.array([[0.0], [1.0]]))
+        out, _, _ = run.sample(40)
+        assert np.array_equal(out[:, :, 0], ch.value[:, :, c])
+    with pytest.raises(ValueError, match="one entry per chain"):
+        amh.sample(model, amh.RWMH(2), amh.MCMCSerial(), 10, 4, engine=oracle, initial_params=[[0.0, 1.0]] * 3)
+    assert ch.array().shape == (160, 2)
+
+
+def test_discard_thinning_warmup_defaults(amh, oracle):
+    target = amh.MvNormalTarget(None, np.eye(2))
+    ch = amh.sample(target, amh.RobustAdaptiveMetropolis(), 20, num_warmup=30, chain_type=amh.Chains, engine=oracle,
+                    summary=True)
+    assert ch.start == 31 and ch.info["summary"]["n_steps"] == 30 + 19       # discard_initial defaults to num_warmup
+    ch = amh.sample(target, amh.RWMH(2), 7, discard_initial=3, thinning=5, chain_type=amh.Chains, engine=oracle,
+                    summary=True)
+    assert list(ch.range()) == [4 + 5 * i for i in range(7)] and ch.info["summary"]["n_steps"] == 3 + 30
+
+
+def test_mala_errors_match_reference(amh, oracle):
+    target = amh.GaussianPrecisionTarget(np.eye(2))
+    spl = amh.MALA(lambda g: amh.MvNormal(0.25 * g, 0.5 * amh.I))
+    with pytest.raises(amh.AMHStateError, match="please specify initial parameters"):      # MALA.jl:37
+        amh.sample(target, spl, 10, engine=oracle)
+    with pytest.raises(amh.AMHArgumentError, match="gradient"):                            # MALA.jl:42-52
+        amh.sample(amh.NormalInverseGammaToy(), spl, 10, engine=oracle, initial_params=np.ones(2))
+    st = amh.sample(target, spl, 10, engine=oracle, initial_params=np.ones(2))
+    assert np.array_equal(st[0].params, np.ones(2))
+
+
+def test_getparams_setparams_roundtrip(amh, oracle):
+    """test/runtests.jl:37-54: setparams!! recomputes lp (and the gradient for MALA); RAM keeps logprob"""
+    target = amh.GaussianPrecisionTarget(np.array([[2.0, 0.3], [0.3, 1.0]]))
+    th = oracle.target(target.kind, 2, target.blob())
+    x0 = np.ones((2, 3)); x1 = np.array([[0.5, -1.0, 2.0], [0.1, 0.2, 0.3]])
+    run = oracle.run(th, amh.MALA(lambda g: amh.MvNormal(0.05 * g, 0.1 * amh.I)).lower(oracle, 2), 3, np.arange(3, dtype=np.uint64), x0)
+    run.set_params(x1)
+    st = run.state(grad=True)
+    A = target.A
+    assert np.array_equal(st["x"], x1)
+    assert np.allclose(st["lp"], [-0.5 * x1[:, c] @ A @ x1[:, c] for c in range(3)])
+    assert np.allclose(st["grad"], -A @ x1)
+    run = oracle.run(th, amh.RobustAdaptiveMetropolis().lower(oracle, 2), 3, np.arange(3, dtype=np.uint64), x0)
+    lp0 = run.state()["lp"].copy()
+    run.set_params(x1)
+    assert np.array_equal(run.state()["lp"], lp0)                          # RAM :117-121
+
+
+def test_ensemble_layout_and_errors(amh, oracle):
+    target = amh.RosenbrockTarget(4)
+    spl = amh.Ensemble(16, amh.StretchProposal(amh.MvNormal(np.zeros(4), amh.I)))
+    ch = amh.sample(target, spl, 12, chain_type=amh.Chains, engine=oracle)
+    assert ch.value.shape == (12, 5, 16)        # nsamples x (d+1) x n_walkers  (ext/AdvancedMHMCMCChainsExt.jl:93-106)
+    tv = amh.sample(target, spl, 12, engine=oracle)
+    assert len(tv[0]) == 16 and tv[0][0].params.shape == (4,)
+    with pytest.raises(ValueError):
+        amh.Ensemble(16, amh.MvNormal(np.zeros(4), amh.I))
+    with pytest.raises(amh.AMHArgumentError, match="n_walkers"):
+        amh.sample(target, amh.Ensemble(1, amh.StretchProposal(amh.MvNormal(np.zeros(4), amh.I))), 3, engine=oracle)
+    ch2 = amh.sample(target, spl, amh.MCMCSerial(), 5, 3, chain_type=amh.Chains, engine=oracle)
+    assert ch2.value.shape == (5, 5, 48)
+
+
+def test_callback_and_summary_only(amh, oracle, model):
+    seen = []
+    amh.sample(model, amh.RWMH(2), 6, engine=oracle, callback=lambda rng, m, s, sample, state, i: seen.append(i))
+    assert seen == [1, 2, 3, 4, 5, 6]
+    info = amh.sample(model, amh.RWMH(2), amh.MCMCSerial(), 100, 8, engine=oracle, store=False, summary=True)
+    assert info["summary"]["n_saved"] == 100 and info["summary"]["mean"].shape == (2,)
+    assert 0 < info["summary"]["accept_rate"] < 1
+
+
+def test_shard_bounds_partition(amh):
+    for n, w in [(10, 3), (8, 8), (5, 8), (262144, 8), (64, 8)]:
+        parts = [amh.shard_bounds(n, r, w) for r in range(w)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+        sizes = [b - a for a, b in parts]
+        assert max(sizes) - min(sizes) <= 1
