@@ -60,7 +60,14 @@ mh_step_kernel(const __grid_constant__ MhArgs<DMAX> a,
     for (int s = 0; s < a.nsteps; ++s) {
         const unsigned long long k = a.step0 + (unsigned long long)s + 1ull;
         const unsigned long long blk0 = k * B;
-        step_normals<DMAX>(seed, blk0, d, z);
+        double e;
+        if constexpr (D::fixed) {
+            step_noise_fixed<DMAX>(seed, blk0, z, e);
+        } else {
+            step_normals<DMAX>(seed, blk0, d, z);
+            const amh::Block be = amh::stream_block(seed, blk0 + (unsigned long long)((d + 1) / 2), 0u);
+            e = amh::exponential(be.v[0], be.v[1]);
+        }
         draw_inplace<DMAX>(z, d, a.prop);
         if (a.is_rw) {
 #pragma unroll UNR
@@ -84,8 +91,6 @@ mh_step_kernel(const __grid_constant__ MhArgs<DMAX> a,
             }
         }
         const double loga = (lp_c - lp) + logratio;
-        const amh::Block be = amh::stream_block(seed, blk0 + (unsigned long long)((d + 1) / 2), 0u);
-        const double e = amh::exponential(be.v[0], be.v[1]);
         if (-e < loga) {
 #pragma unroll UNR
             for (int i = 0; i < top; ++i)

@@ -52,7 +52,14 @@ mala_step_kernel(const __grid_constant__ MalaArgs a, const __grid_constant__ typ
     for (int s = 0; s < a.nsteps; ++s) {
         const unsigned long long k = a.step0 + (unsigned long long)s + 1ull;
         const unsigned long long blk0 = k * B;
-        step_normals<DMAX>(seed, blk0, d, c);
+        double e;
+        if constexpr (D::fixed) {
+            step_noise_fixed<DMAX>(seed, blk0, c, e);
+        } else {
+            step_normals<DMAX>(seed, blk0, d, c);
+            const amh::Block be = amh::stream_block(seed, blk0 + (unsigned long long)((d + 1) / 2), 0u);
+            e = amh::exponential(be.v[0], be.v[1]);
+        }
         /* candidate = state + rand(MvNormal(drift*grad, sigma2*I))  (MALA.jl:70 -> proposal.jl:49-56) */
 #pragma unroll UNR
         for (int i = 0; i < top; ++i)
@@ -72,8 +79,6 @@ mala_step_kernel(const __grid_constant__ MalaArgs a, const __grid_constant__ typ
             }
         const double logratio = (-0.5 * (A / a.sigma2)) - (-0.5 * (Bq / a.sigma2));
         const double loga = (lp_c - lp) + logratio;
-        const amh::Block be = amh::stream_block(seed, blk0 + (unsigned long long)((d + 1) / 2), 0u);
-        const double e = amh::exponential(be.v[0], be.v[1]);
         if (-e < loga) {                                   /* MALA.jl:86 */
 #pragma unroll UNR
             for (int i = 0; i < top; ++i)

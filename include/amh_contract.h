@@ -102,7 +102,7 @@ AMH_HD double u01(uint32_t wlo, uint32_t whi) {
  * Table-driven: z = x / 2^k in [0.6875, 1.375), r = z/c_i - 1 with |r| < 2^-7,
  * ln x = k ln2 - ln(1/c_i) + ln(1+r).  The two intervals adjacent to 1 use
  * c = 1 exactly, so ln(u) keeps full relative accuracy for u -> 1. */
-struct LogTabEntry { double invc, nlogc; };
+struct alignas(16) LogTabEntry { double invc, nlogc; };
 
 #if defined(__CUDACC__)
 static __device__ const LogTabEntry amh_log_tab_dev[128] = { AMH_LOG_TABLE_ENTRIES };
