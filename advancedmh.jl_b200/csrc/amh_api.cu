@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
 #include "amh_host.h"
 
@@ -318,7 +319,12 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
     amh_run* r = new amh_run();
     r->ctx = ctx; r->target = target; r->sampler = sampler;
     r->n = n; r->off = off; r->dim = d; r->nseeds = nseeds;
-    r->pitch = (n + 15) / 16 * 16;          /* rows start 128-byte aligned */
+    r->pitch = (n + 31) / 32 * 32;          /* rows start 256-byte aligned; a warp's 32 chains never straddle a row end */
+    {
+        const char* ev = std::getenv("AMH_MH_PATH");     /* developer switch for A/B measurements: "dfma" forces K1 */
+        if (ev && std::strcmp(ev, "dfma") == 0) r->mh_path = 1;
+        if (ev && std::strcmp(ev, "tc32") == 0) r->mh_path = 2;
+    }
     const size_t np = (size_t)r->pitch;
     const size_t nt = (size_t)d * (d + 1) / 2;
     int rc = AMH_OK;

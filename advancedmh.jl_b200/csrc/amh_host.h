@@ -67,6 +67,7 @@ struct amh_run {
     long long step = 0;
     long long nsaved = 0;
     long long launches = 0;
+    int mh_path = 0;               /* 0 = choose (tensor-core K1T when eligible), 1 = force the per-thread DFMA kernel K1 */
     /* kernel timing */
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
@@ -89,6 +90,8 @@ amhd::ChainState chain_state(amh_run& r);
 
 /* per-sampler launchers; each enqueues kernels on r.ctx->stream and bumps r.launches */
 int launch_mh(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
+bool mh_tc_eligible(const amh_run& r);        /* K1T: both mat-vecs on the FP64 tensor cores */
+int launch_mh_tc(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_mala(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_ram(amh_run& r, int nsteps, bool warmup, const amhd::SaveArgs& sv);
 int launch_stretch(amh_run& r, int nsteps, const amhd::SaveArgs& sv);

@@ -1,0 +1,426 @@
+/* amh_launch_mh_tc.cu -- K1T: the random-walk / static MH step with both triangular mat-vecs
+ * (proposal L z, target U (c - mu)) on the FP64 tensor cores (mma.sync m8n8k4 = DMMA).
+ *
+ * Why (tools/ubench/dmma_probe.cu, measured on B200): DMMA and DFMA share ONE FP64 datapath of
+ * 64 FMA/clk/SM, so tensor cores add no FP64 throughput -- but one DMMA retires 256 FMAs for one
+ * issue slot and takes its L/U operand from a register fragment, where the per-thread DFMA form
+ * needs 1056 DFMA + 528 constant loads per chain-step, 64+ live registers for z and c, and ~70 KB
+ * of straight-line code.  The warp is the natural tile: its 32 chains are the N dimension,
+ *     Y[32 x 32 chains] = L[32 x 32] * Z[32 x 32 chains].
+ * DMMA accumulates k = 0..3 as a sequential IEEE fma chain (verified by the probe), so the result is
+ * bit-identical to the contract's row dot products (include/amh_contract.h, oracle `draw` / `logp`).
+ *
+ * Per warp and MCMC step (mh-core.jl:92-117, proposal.jl:41-56):
+ *   phase 0  every lane = one chain: batched Philox / Box-Muller -> Z[k][lane] in shared memory
+ *   phase 1  row blocks 3..0: DMMA chains over the lower-triangular tiles of L; c = x + y in the
+ *            accumulator layout (x is re-read from global/L2: 528 B per chain-step is exactly the
+ *            algorithmic traffic); C overwrites Z in place (descending row blocks make that safe)
+ *   phase 2  row blocks 0..3: W = U (C - mu) by DMMA; each 8 x 32 slab of W goes through a 2.5 KB
+ *            staging tile back to the chain lanes, which accumulate q = sum w_i^2 in index order
+ *   accept   chain lanes: -randexp < lp_c - lp (strict); accepted lanes copy their column of C to X.
+ * Shared memory: 11.6 KB per warp -> 14 warps/SM = the whole 65 536-chain problem in one wave.
+ */
+#include "amh_params.cuh"
+
+namespace amhh {
+using namespace amhd;
+
+struct MhTcArgs {
+    ChainState st;
+    SaveArgs sv;
+    int nsteps;
+    int is_rw;
+    int mu_zero;
+    unsigned long long step0;
+    const double* Lf;          /* [NT][32] A fragments of the proposal factor   */
+    const double* Uf;          /* [NT][32] A fragments of the target factor     */
+    const double* mu;          /* [D]                                           */
+    double c0;
+};
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+constexpr int kPZ = 36;        /* row pitch (doubles) of the Z/C tile: conflict-free B-fragment loads */
+constexpr int kPW = 40;        /* row pitch of the W staging tile: conflict-free 128-bit stores       */
+
+template <int D>
+__host__ __device__ constexpr int tc_smem_doubles_per_warp() { return D * kPZ + 8 * kPW; }
+
+template <int D, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 14 / WARPS)
+mh_step_tc_kernel(const __grid_constant__ MhTcArgs a) {
+    static_assert(D % 8 == 0 && D >= 8 && D <= 32, "row blocks of 8");
+    constexpr int NB = D / 8;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    double* __restrict__ ZC = smem + warp * tc_smem_doubles_per_warp<D>();
+    double* __restrict__ WB = ZC + D * kPZ;
+    const long long cbase = ((long long)blockIdx.x * WARPS + warp) * 32;     /* first chain of this warp */
+    if (cbase >= a.st.n) return;                                              /* whole warp idle */
+    const long long ch = cbase + lane;
+    const bool active = ch < a.st.n;
+    const long long pitch = a.st.pitch;
+    const int fr = lane >> 2, fc = lane & 3;                                  /* fragment row / column ids */
+    double* __restrict__ X = a.st.X;
+
+    const unsigned long long seed = active ? a.st.seeds[ch] : 0ull;
+    double lp = active ? a.st.lp[ch] : 0.0;
+    unsigned long long nacc = active ? a.st.nacc[ch] : 0ull;
+    unsigned char accepted = active ? a.st.acc[ch] : (unsigned char)0;
+    constexpr unsigned long long B = (unsigned long long)((D + 1) / 2 + 1);
+
+    for (int s = 0; s < a.nsteps; ++s) {
+        const unsigned long long k = a.step0 + (unsigned long long)s + 1ull;
+        /* ---- phase 0: noise of this step, one chain per lane -> Z[k][lane] ---- */
+        double e;
+        {
+            double z[D];
+            step_noise_fixed<D>(seed, k * B, z, e);
+#pragma unroll
+            for (int i = 0; i < D; ++i) ZC[i * kPZ + lane] = z[i];
+        }
+        /* x in accumulator-fragment layout: rows 8mb+fr, chains cbase + 8nb + 2fc + {0,1} (L2 resident) */
+        double2 xf[NB][4];
+        if (a.is_rw) {
+#pragma unroll
+            for (int mb = 0; mb < NB; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb)
+                    xf[mb][nb] = __ldcg(reinterpret_cast<const double2*>(X + (long long)(8 * mb + fr) * pitch + cbase + 8 * nb + 2 * fc));
+        }
+        __syncwarp();
+        /* ---- phase 1: C = X + L Z, row blocks in descending order, in place ---- */
+#pragma unroll
+        for (int mbi = 0; mbi < NB; ++mbi) {
+            const int mb = NB - 1 - mbi;
+            double acc[4][2];
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) { acc[nb][0] = 0.0; acc[nb][1] = 0.0; }
+#pragma unroll
+            for (int kb = 0; kb <= 2 * mb + 1; ++kb) {
+                const double af = __ldg(a.Lf + (mb * (mb + 1) + kb) * 32 + lane);
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    const double bf = ZC[(4 * kb + fc) * kPZ + 8 * nb + fr];
+                    dmma(acc[nb][0], acc[nb][1], af, bf);
+                }
+            }
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                double2 c;
+                if (a.is_rw) { c.x = xf[mb][nb].x + acc[nb][0]; c.y = xf[mb][nb].y + acc[nb][1]; }
+                else { c.x = acc[nb][0]; c.y = acc[nb][1]; }
+                *reinterpret_cast<double2*>(ZC + (8 * mb + fr) * kPZ + 8 * nb + 2 * fc) = c;
+            }
+        }
+        __syncwarp();
+        /* ---- phase 2: W = U (C - mu), q = sum_i w_i^2 in index order ---- */
+        double q = 0.0;
+#pragma unroll
+        for (int mb = 0; mb < NB; ++mb) {
+            double acc[4][2];
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) { acc[nb][0] = 0.0; acc[nb][1] = 0.0; }
+#pragma unroll
+            for (int kb = 0; kb <= 2 * mb + 1; ++kb) {
+                const double af = __ldg(a.Uf + (mb * (mb + 1) + kb) * 32 + lane);
+                const double muk = a.mu_zero ? 0.0 : __ldg(a.mu + 4 * kb + fc);
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    const double cv = ZC[(4 * kb + fc) * kPZ + 8 * nb + fr];
+                    const double bf = a.mu_zero ? cv : cv - muk;
+                    dmma(acc[nb][0], acc[nb][1], af, bf);
+                }
+            }
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb)
+                *reinterpret_cast<double2*>(WB + fr * kPW + 8 * nb + 2 * fc) = make_double2(acc[nb][0], acc[nb][1]);
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const double w = WB[r * kPW + lane];
+                q = (mb == 0 && r == 0) ? w * w : fma(w, w, q);
+            }
+            __syncwarp();
+        }
+        const double lp_c = fma(-0.5, q, a.c0);
+        /* ---- accept / reject (mh-core.jl:104-114); the Hastings term is exactly 0 on this path ---- */
+        const double loga = (lp_c - lp) + 0.0;
+        if (active && -e < loga) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) X[(long long)i * pitch + ch] = ZC[i * kPZ + lane];
+            lp = lp_c;
+            accepted = 1;
+            ++nacc;
+        } else {
+            accepted = 0;
+        }
+        __syncwarp();
+    }
+
+    if (!active) return;
+    if (a.sv.out || a.sv.sum) {
+#pragma unroll 4
+        for (int i = 0; i < D; ++i) {
+            const long long o = (long long)i * pitch + ch;
+            const double v = X[o];
+            if (a.sv.out) a.sv.out[(long long)i * a.sv.out_pitch + ch] = v;
+            if (a.sv.sum) {
+                a.sv.sum[o] = a.sv.sum[o] + v;
+                a.sv.sumsq[o] = fma(v, v, a.sv.sumsq[o]);
+            }
+        }
+    }
+    a.st.lp[ch] = lp;
+    a.st.nacc[ch] = nacc;
+    a.st.acc[ch] = accepted;
+    if (a.sv.out) a.sv.out[(long long)D * a.sv.out_pitch + ch] = lp;
+    if (a.sv.acc_out) a.sv.acc_out[ch] = accepted;
+}
+
+/* ---------------------------------------------------------------------------
+ * K1T16: same algorithm, 16 chains per warp.  Two lanes share a chain: lane = (half, cl); each half
+ * generates 8 of the 16 Philox/Box-Muller blocks of the chain's step, the DMMA tiles cover N = 16
+ * chains (2 n-tiles), and both lanes of a chain carry the same q / lp / accept decision (no shuffles).
+ * Twice the warps for the same problem: 28 resident warps per SM instead of 14, which is what hides
+ * the integer / FP64 dependency latency of the noise phase (ncu: issue slots 34% busy with 14 warps). */
+constexpr int kPZ16 = 20;
+constexpr int kPW16 = 24;
+template <int D>
+__host__ __device__ constexpr int tc16_smem_doubles_per_warp() { return D * kPZ16 + 8 * kPW16; }
+
+template <int D, int WARPS, bool MU_ZERO>
+__global__ void __launch_bounds__(32 * WARPS, 28 / WARPS)
+mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
+    static_assert(D == 32, "the half split assumes 16 noise blocks per chain");
+    constexpr int NB = D / 8;
+    extern __shared__ double smem[];
+    __shared__ amh::LogTabEntry slog[128];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 128; i += 32 * WARPS) slog[i] = amh::amh_log_tab_dev[i];
+    __syncthreads();
+    double* __restrict__ ZC = smem + warp * tc16_smem_doubles_per_warp<D>();
+    double* __restrict__ WB = ZC + D * kPZ16;
+    const long long cbase = ((long long)blockIdx.x * WARPS + warp) * 16;
+    if (cbase >= a.st.n) return;
+    const int cl = lane & 15, half = lane >> 4;
+    const long long ch = cbase + cl;
+    const bool active = ch < a.st.n;
+    const long long pitch = a.st.pitch;
+    const int fr = lane >> 2, fc = lane & 3;
+    double* __restrict__ X = a.st.X;
+
+    const unsigned long long seed = active ? a.st.seeds[ch] : 0ull;
+    double lp = active ? a.st.lp[ch] : 0.0;
+    unsigned long long nacc = active ? a.st.nacc[ch] : 0ull;
+    unsigned char accepted = active ? a.st.acc[ch] : (unsigned char)0;
+    constexpr unsigned long long B = (unsigned long long)((D + 1) / 2 + 1);
+
+    for (int s = 0; s < a.nsteps; ++s) {
+        const unsigned long long k = a.step0 + (unsigned long long)s + 1ull;
+        double e;
+        {
+            double z[16];
+            noise_group<8, true>(seed, k * B + (unsigned long long)(8 * half), k * B + (unsigned long long)(D / 2), z, e, slog);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ZC[(16 * half + i) * kPZ16 + cl] = z[i];
+        }
+        double2 xf[NB][2];
+        if (a.is_rw) {
+#pragma unroll
+            for (int mb = 0; mb < NB; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb)
+                    xf[mb][nb] = __ldcg(reinterpret_cast<const double2*>(X + (long long)(8 * mb + fr) * pitch + cbase + 8 * nb + 2 * fc));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int mbi = 0; mbi < NB; ++mbi) {
+            const int mb = NB - 1 - mbi;
+            double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+            for (int kb = 0; kb <= 2 * mb + 1; ++kb) {
+                const double af = __ldg(a.Lf + (mb * (mb + 1) + kb) * 32 + lane);
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb) {
+                    const double bf = ZC[(4 * kb + fc) * kPZ16 + 8 * nb + fr];
+                    dmma(acc[nb][0], acc[nb][1], af, bf);
+                }
+            }
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) {
+                double2 c;
+                if (a.is_rw) { c.x = xf[mb][nb].x + acc[nb][0]; c.y = xf[mb][nb].y + acc[nb][1]; }
+                else { c.x = acc[nb][0]; c.y = acc[nb][1]; }
+                *reinterpret_cast<double2*>(ZC + (8 * mb + fr) * kPZ16 + 8 * nb + 2 * fc) = c;
+            }
+        }
+        __syncwarp();
+        double q = 0.0;
+#pragma unroll
+        for (int mb = 0; mb < NB; ++mb) {
+            double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+            for (int kb = 0; kb <= 2 * mb + 1; ++kb) {
+                const double af = __ldg(a.Uf + (mb * (mb + 1) + kb) * 32 + lane);
+                double muk = 0.0;
+                if (!MU_ZERO) muk = __ldg(a.mu + 4 * kb + fc);
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb) {
+                    double bf = ZC[(4 * kb + fc) * kPZ16 + 8 * nb + fr];
+                    if (!MU_ZERO) bf = bf - muk;
+                    dmma(acc[nb][0], acc[nb][1], af, bf);
+                }
+            }
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb)
+                *reinterpret_cast<double2*>(WB + fr * kPW16 + 8 * nb + 2 * fc) = make_double2(acc[nb][0], acc[nb][1]);
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const double w = WB[r * kPW16 + cl];
+                q = (mb == 0 && r == 0) ? w * w : fma(w, w, q);
+            }
+            __syncwarp();
+        }
+        const double lp_c = fma(-0.5, q, a.c0);
+        const double loga = (lp_c - lp) + 0.0;
+        if (active && -e < loga) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) X[(long long)(16 * half + i) * pitch + ch] = ZC[(16 * half + i) * kPZ16 + cl];
+            lp = lp_c;
+            accepted = 1;
+            ++nacc;
+        } else {
+            accepted = 0;
+        }
+        __syncwarp();
+    }
+
+    if (!active) return;
+    if (a.sv.out || a.sv.sum) {
+#pragma unroll 4
+        for (int ii = 0; ii < 16; ++ii) {
+            const int i = 16 * half + ii;
+            const long long o = (long long)i * pitch + ch;
+            const double v = X[o];
+            if (a.sv.out) a.sv.out[(long long)i * a.sv.out_pitch + ch] = v;
+            if (a.sv.sum) {
+                a.sv.sum[o] = a.sv.sum[o] + v;
+                a.sv.sumsq[o] = fma(v, v, a.sv.sumsq[o]);
+            }
+        }
+    }
+    if (half == 0) {
+        a.st.lp[ch] = lp;
+        a.st.nacc[ch] = nacc;
+        a.st.acc[ch] = accepted;
+        if (a.sv.out) a.sv.out[(long long)D * a.sv.out_pitch + ch] = lp;
+        if (a.sv.acc_out) a.sv.acc_out[ch] = accepted;
+    }
+}
+
+/* A fragments of a packed lower-triangular factor: frag[tile(mb,kb)][lane] = M[8mb + lane/4][4kb + lane%4] */
+static void build_frags(const double* tri_packed, int d, std::vector<double>& out) {
+    const int nb = d / 8;
+    out.assign((size_t)nb * (nb + 1) * 32, 0.0);
+    for (int mb = 0; mb < nb; ++mb)
+        for (int kb = 0; kb <= 2 * mb + 1; ++kb)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int row = 8 * mb + lane / 4, col = 4 * kb + lane % 4;
+                if (col <= row) out[((size_t)(mb * (mb + 1) + kb)) * 32 + lane] = tri_packed[tri_h(row, col)];
+            }
+}
+
+bool mh_tc_eligible(const amh_run& r) {
+    const amh_sampler& s = *r.sampler;
+    const int d = r.dim;
+    if (r.target->kind != AMH_TARGET_MVNORMAL) return false;
+    if (!(d == 16 || d == 24 || d == 32)) return false;
+    if (s.d.cov_kind != AMH_COV_FULL || s.has_mean) return false;
+    if (s.d.kind == AMH_SAMPLER_STATIC && !s.d.symmetric) return false;      /* needs logq: generic path */
+    if (r.pitch % 32) return false;
+    return true;
+}
+
+template <int D>
+static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
+    constexpr int WARPS = 2;
+    const amh_sampler& s = *r.sampler;
+    const amh_target& t = *r.target;
+    if (!r.scratch) {
+        std::vector<double> lf, uf, all;
+        build_frags(s.scale.data(), D, lf);
+        build_frags(t.blob.data() + 1 + D, D, uf);
+        all = lf;
+        all.insert(all.end(), uf.begin(), uf.end());
+        all.insert(all.end(), t.blob.begin() + 1, t.blob.begin() + 1 + D);
+        AMH_CUDA_TRY(cudaMalloc(&r.scratch, all.size() * sizeof(double)));
+        AMH_CUDA_TRY(cudaMemcpyAsync(r.scratch, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice, r.ctx->stream));
+        AMH_CUDA_TRY(cudaStreamSynchronize(r.ctx->stream));     /* `all` is a stack temporary */
+    }
+    constexpr int NT = (D / 8) * (D / 8 + 1);
+    MhTcArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.st = chain_state(r);
+    a.sv = sv;
+    a.nsteps = nsteps;
+    a.is_rw = s.d.kind == AMH_SAMPLER_RW;
+    a.mu_zero = 1;
+    for (int i = 0; i < D; ++i)
+        if (t.blob[1 + i] != 0.0) a.mu_zero = 0;
+    a.step0 = (unsigned long long)r.step;
+    a.Lf = (const double*)r.scratch;
+    a.Uf = a.Lf + (size_t)NT * 32;
+    a.mu = a.Uf + (size_t)NT * 32;
+    a.c0 = t.blob[0];
+    if constexpr (D == 32) {
+        if (r.mh_path != 2) {
+            constexpr int W16 = 4;
+            const size_t smem16 = (size_t)W16 * tc16_smem_doubles_per_warp<D>() * sizeof(double);
+            const unsigned grid16 = (unsigned)((r.n + 16 * W16 - 1) / (16 * W16));
+            static bool attr16 = false;
+            if (!attr16) {
+                AMH_CUDA_TRY(cudaFuncSetAttribute(mh_step_tc16_kernel<D, W16, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                AMH_CUDA_TRY(cudaFuncSetAttribute(mh_step_tc16_kernel<D, W16, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                attr16 = true;
+            }
+            if (a.mu_zero) mh_step_tc16_kernel<D, W16, true><<<grid16, 32 * W16, smem16, r.ctx->stream>>>(a);
+            else mh_step_tc16_kernel<D, W16, false><<<grid16, 32 * W16, smem16, r.ctx->stream>>>(a);
+            AMH_CUDA_TRY(cudaGetLastError());
+            r.launches += 1;
+            r.pending_launches += 1;
+            return AMH_OK;
+        }
+    }
+    const size_t smem = (size_t)WARPS * tc_smem_doubles_per_warp<D>() * sizeof(double);
+    auto kern = mh_step_tc_kernel<D, WARPS>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        AMH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_set = true;
+    }
+    const unsigned grid = (unsigned)((r.n + 32 * WARPS - 1) / (32 * WARPS));
+    kern<<<grid, 32 * WARPS, smem, r.ctx->stream>>>(a);
+    AMH_CUDA_TRY(cudaGetLastError());
+    r.launches += 1;
+    r.pending_launches += 1;
+    return AMH_OK;
+}
+
+int launch_mh_tc(amh_run& r, int nsteps, const SaveArgs& sv) {
+    switch (r.dim) {
+    case 16: return launch_mh_tc_t<16>(r, nsteps, sv);
+    case 24: return launch_mh_tc_t<24>(r, nsteps, sv);
+    case 32: return launch_mh_tc_t<32>(r, nsteps, sv);
+    }
+    return fail(AMH_ERR_INVALID, "tensor-core MH path: unsupported dimension");
+}
+
+}  // namespace amhh

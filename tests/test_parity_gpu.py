@@ -31,7 +31,7 @@ def _seeds(n, s=0):
 
 
 @pytest.mark.parametrize("d,cov", [(1, "scalar"), (2, "scalar"), (2, "diag"), (3, "full"), (8, "full"), (13, "full"),
-                                   (32, "full"), (32, "scalar"), (40, "full")])
+                                   (16, "full"), (24, "full"), (32, "full"), (32, "scalar"), (40, "full")])
 def test_rwmh_mvnormal_bit_exact(amh, cuda, oracle, d, cov):
     Sigma = make_spd(d, seed=d)
     target = amh.MvNormalTarget(np.linspace(-1, 1, d), Sigma)
@@ -298,3 +298,19 @@ def test_stretch_sample_bit_exact(amh, cuda, oracle):
     oo, ao, so = ro.sample(13, discard_initial=5, thinning=2)
     assert np.array_equal(og, oo) and np.array_equal(ag, ao)
     assert np.array_equal(sg["mean"], so["mean"])
+
+
+def test_tensor_core_path_static_symmetric_and_sample(amh, cuda, oracle):
+    """K1T (DMMA mat-vecs) with a symmetric StaticProposal and through the sample schedule / save epilogue"""
+    d = 16
+    Sigma = make_spd(d, seed=77, lo=0.5, hi=4.0)
+    target = amh.MvNormalTarget(np.linspace(0.5, -0.5, d), Sigma)
+    spl = amh.MetropolisHastings(amh.SymmetricStaticProposal(amh.MvNormal(np.zeros(d), 1.2 * Sigma)))
+    n = 100
+    rg, ro = _pair(amh, cuda, oracle, target, spl, n, _seeds(n, 78))
+    og, ag, sg = rg.sample(12, discard_initial=3, thinning=2, chain_means=True)
+    oo, ao, so = ro.sample(12, discard_initial=3, thinning=2, chain_means=True)
+    assert np.array_equal(og, oo) and np.array_equal(ag, ao)
+    for k in ("mean", "var", "chain_mean"):
+        assert np.array_equal(sg[k], so[k])
+    _assert_same_state(rg, ro)
