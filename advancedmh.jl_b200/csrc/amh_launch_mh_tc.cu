@@ -20,6 +20,7 @@
  *   accept   chain lanes: -randexp < lp_c - lp (strict); accepted lanes copy their column of C to X.
  * Shared memory: 11.6 KB per warp -> 14 warps/SM = the whole 65 536-chain problem in one wave.
  */
+#include <cstdlib>
 #include "amh_params.cuh"
 
 namespace amhh {
@@ -41,6 +42,40 @@ struct MhTcArgs {
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
         : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+/* x fragment load pinned in program order (volatile): ptxas otherwise hoists all of them to the top of the
+ * step and then spills the values, which exposes the full L2 latency on the spill store (ncu, round 1) */
+__device__ __forceinline__ double2 ld_x_frag(const double* p) {
+    double2 v;
+    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+/* A-fragment load pinned in program order (explicit software pipeline, see ld_x_frag) */
+__device__ __forceinline__ double ld_a_frag(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+/* flattened lower-triangular tile sequences: row block mb has k-tiles 0 .. 2mb+1 */
+__host__ __device__ constexpr int tseq_mb(int nb, int t, bool desc) {
+    for (int i = 0; i < nb; ++i) {
+        const int mb = desc ? nb - 1 - i : i;
+        const int cnt = 2 * mb + 2;
+        if (t < cnt) return mb;
+        t -= cnt;
+    }
+    return -1;
+}
+__host__ __device__ constexpr int tseq_kb(int nb, int t, bool desc) {
+    for (int i = 0; i < nb; ++i) {
+        const int mb = desc ? nb - 1 - i : i;
+        const int cnt = 2 * mb + 2;
+        if (t < cnt) return t;
+        t -= cnt;
+    }
+    return -1;
 }
 
 constexpr int kPZ = 36;        /* row pitch (doubles) of the Z/C tile: conflict-free B-fragment loads */
@@ -193,17 +228,14 @@ constexpr int kPW16 = 24;
 template <int D>
 __host__ __device__ constexpr int tc16_smem_doubles_per_warp() { return D * kPZ16 + 8 * kPW16; }
 
-template <int D, int WARPS, bool MU_ZERO>
+template <int D, int WARPS, bool MU_ZERO, int NG1, bool IS_RW>
 __global__ void __launch_bounds__(32 * WARPS, 28 / WARPS)
 mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
     static_assert(D == 32, "the half split assumes 16 noise blocks per chain");
     constexpr int NB = D / 8;
     extern __shared__ double smem[];
-    __shared__ amh::LogTabEntry slog[128];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 128; i += 32 * WARPS) slog[i] = amh::amh_log_tab_dev[i];
-    __syncthreads();
     double* __restrict__ ZC = smem + warp * tc16_smem_doubles_per_warp<D>();
     double* __restrict__ WB = ZC + D * kPZ16;
     const long long cbase = ((long long)blockIdx.x * WARPS + warp) * 16;
@@ -217,7 +249,7 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
 
     const unsigned long long seed = active ? a.st.seeds[ch] : 0ull;
     double lp = active ? a.st.lp[ch] : 0.0;
-    unsigned long long nacc = active ? a.st.nacc[ch] : 0ull;
+    unsigned nacc = 0u;                         /* accepted moves of this launch */
     unsigned char accepted = active ? a.st.acc[ch] : (unsigned char)0;
     constexpr unsigned long long B = (unsigned long long)((D + 1) / 2 + 1);
 
@@ -225,68 +257,102 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
         const unsigned long long k = a.step0 + (unsigned long long)s + 1ull;
         double e;
         {
-            double z[16];
-            noise_group<8, true>(seed, k * B + (unsigned long long)(8 * half), k * B + (unsigned long long)(D / 2), z, e, slog);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) ZC[(16 * half + i) * kPZ16 + cl] = z[i];
+            const unsigned long long b0 = k * B + (unsigned long long)(8 * half);
+            double* zt = ZC + (16 * half) * kPZ16 + cl;            /* Z[16 half + j][cl] */
+            if constexpr (NG1 > 0) noise_group<(NG1 > 0 ? NG1 : 1), false>(seed, b0, 0ull, zt, e, amh::amh_log_tab_dev, kPZ16);
+            noise_group<8 - NG1, true>(seed, b0 + NG1, k * B + (unsigned long long)(D / 2), zt + 2 * NG1 * kPZ16, e,
+                                       amh::amh_log_tab_dev, kPZ16);
         }
+        /* x in accumulator-fragment layout, software-pipelined two row blocks ahead of its use */
         double2 xf[NB][2];
-        if (a.is_rw) {
+        const double* xp = X + (long long)fr * pitch + cbase + 2 * fc;
+        if (IS_RW) {
 #pragma unroll
-            for (int mb = 0; mb < NB; ++mb)
+            for (int mb = NB - 1; mb >= (NB >= 2 ? NB - 2 : 0); --mb)
 #pragma unroll
-                for (int nb = 0; nb < 2; ++nb)
-                    xf[mb][nb] = __ldcg(reinterpret_cast<const double2*>(X + (long long)(8 * mb + fr) * pitch + cbase + 8 * nb + 2 * fc));
+                for (int nb = 0; nb < 2; ++nb) xf[mb][nb] = ld_x_frag(xp + (long long)(8 * mb) * pitch + 8 * nb);
         }
         __syncwarp();
+        {
+            constexpr int NT = NB * (NB + 1);
+            constexpr int P = 4;                       /* A-fragment prefetch distance (tiles) */
+            double aq[NT];
+            double acc[2][2];
 #pragma unroll
-        for (int mbi = 0; mbi < NB; ++mbi) {
-            const int mb = NB - 1 - mbi;
-            double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            for (int j = 0; j < P && j < NT; ++j) {
+                constexpr bool DESC = true;
+                const int mbj = tseq_mb(NB, j, DESC), kbj = tseq_kb(NB, j, DESC);
+                aq[j] = ld_a_frag(a.Lf + (mbj * (mbj + 1) + kbj) * 32 + lane);
+            }
 #pragma unroll
-            for (int kb = 0; kb <= 2 * mb + 1; ++kb) {
-                const double af = __ldg(a.Lf + (mb * (mb + 1) + kb) * 32 + lane);
+            for (int t = 0; t < NT; ++t) {
+                const int mb = tseq_mb(NB, t, true), kb = tseq_kb(NB, t, true);
+                if (t + P < NT) {
+                    const int mbj = tseq_mb(NB, t + P, true), kbj = tseq_kb(NB, t + P, true);
+                    aq[t + P] = ld_a_frag(a.Lf + (mbj * (mbj + 1) + kbj) * 32 + lane);
+                }
+                if (kb == 0) { acc[0][0] = 0.0; acc[0][1] = 0.0; acc[1][0] = 0.0; acc[1][1] = 0.0; }
 #pragma unroll
                 for (int nb = 0; nb < 2; ++nb) {
                     const double bf = ZC[(4 * kb + fc) * kPZ16 + 8 * nb + fr];
-                    dmma(acc[nb][0], acc[nb][1], af, bf);
+                    dmma(acc[nb][0], acc[nb][1], aq[t], bf);
                 }
-            }
+                if (kb == 2 * mb + 1) {
 #pragma unroll
-            for (int nb = 0; nb < 2; ++nb) {
-                double2 c;
-                if (a.is_rw) { c.x = xf[mb][nb].x + acc[nb][0]; c.y = xf[mb][nb].y + acc[nb][1]; }
-                else { c.x = acc[nb][0]; c.y = acc[nb][1]; }
-                *reinterpret_cast<double2*>(ZC + (8 * mb + fr) * kPZ16 + 8 * nb + 2 * fc) = c;
+                    for (int nb = 0; nb < 2; ++nb) {
+                        double2 c;
+                        if (IS_RW) { c.x = xf[mb][nb].x + acc[nb][0]; c.y = xf[mb][nb].y + acc[nb][1]; }
+                        else { c.x = acc[nb][0]; c.y = acc[nb][1]; }
+                        *reinterpret_cast<double2*>(ZC + (8 * mb + fr) * kPZ16 + 8 * nb + 2 * fc) = c;
+                    }
+                    if (IS_RW && mb >= 2) {
+#pragma unroll
+                        for (int nb = 0; nb < 2; ++nb) xf[mb - 2][nb] = ld_x_frag(xp + (long long)(8 * (mb - 2)) * pitch + 8 * nb);
+                    }
+                }
             }
         }
         __syncwarp();
         double q = 0.0;
+        {
+            constexpr int NT = NB * (NB + 1);
+            constexpr int P = 4;
+            double aq[NT];
+            double acc[2][2];
 #pragma unroll
-        for (int mb = 0; mb < NB; ++mb) {
-            double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            for (int j = 0; j < P && j < NT; ++j) {
+                const int mbj = tseq_mb(NB, j, false), kbj = tseq_kb(NB, j, false);
+                aq[j] = ld_a_frag(a.Uf + (mbj * (mbj + 1) + kbj) * 32 + lane);
+            }
 #pragma unroll
-            for (int kb = 0; kb <= 2 * mb + 1; ++kb) {
-                const double af = __ldg(a.Uf + (mb * (mb + 1) + kb) * 32 + lane);
+            for (int t = 0; t < NT; ++t) {
+                const int mb = tseq_mb(NB, t, false), kb = tseq_kb(NB, t, false);
+                if (t + P < NT) {
+                    const int mbj = tseq_mb(NB, t + P, false), kbj = tseq_kb(NB, t + P, false);
+                    aq[t + P] = ld_a_frag(a.Uf + (mbj * (mbj + 1) + kbj) * 32 + lane);
+                }
+                if (kb == 0) { acc[0][0] = 0.0; acc[0][1] = 0.0; acc[1][0] = 0.0; acc[1][1] = 0.0; }
                 double muk = 0.0;
                 if (!MU_ZERO) muk = __ldg(a.mu + 4 * kb + fc);
 #pragma unroll
                 for (int nb = 0; nb < 2; ++nb) {
                     double bf = ZC[(4 * kb + fc) * kPZ16 + 8 * nb + fr];
                     if (!MU_ZERO) bf = bf - muk;
-                    dmma(acc[nb][0], acc[nb][1], af, bf);
+                    dmma(acc[nb][0], acc[nb][1], aq[t], bf);
+                }
+                if (kb == 2 * mb + 1) {
+#pragma unroll
+                    for (int nb = 0; nb < 2; ++nb)
+                        *reinterpret_cast<double2*>(WB + fr * kPW16 + 8 * nb + 2 * fc) = make_double2(acc[nb][0], acc[nb][1]);
+                    __syncwarp();
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const double w = WB[r * kPW16 + cl];
+                        q = (mb == 0 && r == 0) ? w * w : fma(w, w, q);
+                    }
+                    __syncwarp();
                 }
             }
-#pragma unroll
-            for (int nb = 0; nb < 2; ++nb)
-                *reinterpret_cast<double2*>(WB + fr * kPW16 + 8 * nb + 2 * fc) = make_double2(acc[nb][0], acc[nb][1]);
-            __syncwarp();
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const double w = WB[r * kPW16 + cl];
-                q = (mb == 0 && r == 0) ? w * w : fma(w, w, q);
-            }
-            __syncwarp();
         }
         const double lp_c = fma(-0.5, q, a.c0);
         const double loga = (lp_c - lp) + 0.0;
@@ -318,7 +384,7 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
     }
     if (half == 0) {
         a.st.lp[ch] = lp;
-        a.st.nacc[ch] = nacc;
+        a.st.nacc[ch] = a.st.nacc[ch] + (unsigned long long)nacc;
         a.st.acc[ch] = accepted;
         if (a.sv.out) a.sv.out[(long long)D * a.sv.out_pitch + ch] = lp;
         if (a.sv.acc_out) a.sv.acc_out[ch] = accepted;
@@ -386,12 +452,26 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
             const unsigned grid16 = (unsigned)((r.n + 16 * W16 - 1) / (16 * W16));
             static bool attr16 = false;
             if (!attr16) {
-                AMH_CUDA_TRY(cudaFuncSetAttribute(mh_step_tc16_kernel<D, W16, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-                AMH_CUDA_TRY(cudaFuncSetAttribute(mh_step_tc16_kernel<D, W16, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                /* 7 CTAs x 27 KB = 189 KB of shared memory; the rest of the 256 KB stays L1 for the L/U fragments */
+                const char* cv = std::getenv("AMH_TC_CARVEOUT");
+                const int carve = cv ? std::atoi(cv) : 84;
+#define AMH_TC16_ATTR(...) AMH_CUDA_TRY(cudaFuncSetAttribute(mh_step_tc16_kernel<D, W16, __VA_ARGS__>, cudaFuncAttributePreferredSharedMemoryCarveout, carve))
+                AMH_TC16_ATTR(true, 4, true); AMH_TC16_ATTR(false, 4, true); AMH_TC16_ATTR(true, 4, false); AMH_TC16_ATTR(false, 4, false);
+                AMH_TC16_ATTR(true, 0, true);
+#undef AMH_TC16_ATTR
                 attr16 = true;
             }
-            if (a.mu_zero) mh_step_tc16_kernel<D, W16, true><<<grid16, 32 * W16, smem16, r.ctx->stream>>>(a);
-            else mh_step_tc16_kernel<D, W16, false><<<grid16, 32 * W16, smem16, r.ctx->stream>>>(a);
+            static const int variant = std::getenv("AMH_TC_VARIANT") ? std::atoi(std::getenv("AMH_TC_VARIANT")) : 0;
+#define AMH_TC16_GO(...) mh_step_tc16_kernel<D, W16, __VA_ARGS__><<<grid16, 32 * W16, smem16, r.ctx->stream>>>(a)
+            if (a.is_rw) {
+                if (!a.mu_zero) AMH_TC16_GO(false, 4, true);
+                else if (variant == 1) AMH_TC16_GO(true, 0, true);
+                else AMH_TC16_GO(true, 4, true);
+            } else {
+                if (!a.mu_zero) AMH_TC16_GO(false, 4, false);
+                else AMH_TC16_GO(true, 4, false);
+            }
+#undef AMH_TC16_GO
             AMH_CUDA_TRY(cudaGetLastError());
             r.launches += 1;
             r.pending_launches += 1;
