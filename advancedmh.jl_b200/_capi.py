@@ -71,7 +71,7 @@ ABI_SYMBOLS = [
     "target_create", "target_destroy", "sampler_create", "sampler_destroy",
     "run_create", "run_destroy", "run_steps", "run_sync", "run_sample",
     "run_get_state", "run_set_params", "run_dim", "run_nchains", "run_launch_count",
-    "run_kernel_time_ms",
+    "run_kernel_time_ms", "host_alloc", "host_free",
 ]
 
 
@@ -120,6 +120,8 @@ class Engine:
         f("run_get_state").argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _u8p, _i64p, _i64p]
         f("run_set_params").argtypes = [C.c_void_p, _dp]
         f("run_kernel_time_ms").argtypes = [C.c_void_p, C.c_int32, _dp, _i64p]
+        f("host_alloc").argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+        f("host_free").argtypes = [C.c_void_p]
 
     def _check(self, rc):
         if rc == AMH_OK:
@@ -146,6 +148,19 @@ class Engine:
         if getattr(self, "ctx", None):
             self._f("ctx_destroy")(self.ctx)
             self.ctx = None
+
+    def pinned_empty(self, shape, dtype=np.float64):
+        """numpy array over page-locked host memory (amh_host_alloc): use it for `initial_params` and for the
+        `out=` buffers of `sample` to get full-speed asynchronous host<->device copies.  Freed with the array."""
+        import weakref
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        self._check(self._f("host_alloc")(C.c_size_t(max(nbytes, 1)), C.byref(p)))
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        weakref.finalize(buf, self._f("host_free"), p)
+        return arr
 
     # -- objects ----------------------------------------------------------
     def target(self, kind: int, dim: int, blob) -> "TargetHandle":
@@ -225,10 +240,20 @@ class Run:
         self.eng._check(self.eng._f("run_sync")(self.h))
 
     def sample(self, N, discard_initial=0, thinning=1, num_warmup=0, store=True, store_accepted=True,
-               summary=True, chain_means=False):
+               summary=True, chain_means=False, out=None, acc=None):
+        """`out` / `acc`: optional caller buffers ((N, d+1, n) float64 / (N, n) uint8, C-contiguous), e.g. pinned
+        ones from Engine.pinned_empty; otherwise pageable numpy arrays are allocated."""
         d, n = self.dim, self.n
-        out = np.empty((N, d + 1, n), dtype=np.float64) if store else None
-        acc = np.empty((N, n), dtype=np.uint8) if store_accepted else None
+        if out is not None:
+            if out.shape != (N, d + 1, n) or out.dtype != np.float64 or not out.flags.c_contiguous:
+                raise AMHArgumentError(AMH_ERR_INVALID, f"out must be a C-contiguous float64 array of shape {(N, d + 1, n)}")
+        elif store:
+            out = np.empty((N, d + 1, n), dtype=np.float64)
+        if acc is not None:
+            if acc.shape != (N, n) or acc.dtype != np.uint8 or not acc.flags.c_contiguous:
+                raise AMHArgumentError(AMH_ERR_INVALID, f"acc must be a C-contiguous uint8 array of shape {(N, n)}")
+        elif store_accepted:
+            acc = np.empty((N, n), dtype=np.uint8)
         summ = None
         s = None
         if summary:

@@ -40,20 +40,28 @@ int default_steps_per_launch(const amh_run& r) {
     }
 }
 
-template <class T>
-static int dev_alloc(T** p, size_t count) {
+int dmalloc(amh_ctx* ctx, void** p, size_t bytes) {
     *p = nullptr;
-    if (count == 0) return AMH_OK;
-    AMH_CUDA_TRY(cudaMalloc((void**)p, count * sizeof(T)));
+    if (bytes == 0) return AMH_OK;
+    AMH_CUDA_TRY(cudaMallocAsync(p, bytes, ctx->stream));
     return AMH_OK;
 }
+void dfree(amh_ctx* ctx, void* p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
 
-static int upload(double** dptr, const std::vector<double>& h, cudaStream_t st) {
+template <class T>
+static int dev_alloc(amh_ctx* ctx, T** p, size_t count) {
+    return dmalloc(ctx, (void**)p, count * sizeof(T));
+}
+
+static int upload(amh_ctx* ctx, double** dptr, const std::vector<double>& h) {
     *dptr = nullptr;
     if (h.empty()) return AMH_OK;
-    AMH_CUDA_TRY(cudaMalloc((void**)dptr, h.size() * sizeof(double)));
-    AMH_CUDA_TRY(cudaMemcpyAsync(*dptr, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    AMH_CUDA_TRY(cudaStreamSynchronize(st));
+    int rc = dmalloc(ctx, (void**)dptr, h.size() * sizeof(double));
+    if (rc) return rc;
+    AMH_CUDA_TRY(cudaMemcpyAsync(*dptr, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    AMH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return AMH_OK;
 }
 
@@ -89,10 +97,13 @@ static int enqueue_steps(amh_run& r, long long nsteps, bool warmup, int spl, con
     amhd::SaveArgs none;
     std::memset(&none, 0, sizeof(none));
     AMH_CUDA_TRY(cudaSetDevice(r.ctx->device));
-    cudaEvent_t e0, e1;
-    int rc = get_events(r, &e0, &e1);
-    if (rc) return rc;
-    AMH_CUDA_TRY(cudaEventRecord(e0, r.ctx->stream));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = AMH_OK;
+    if (r.timing) {
+        rc = get_events(r, &e0, &e1);
+        if (rc) return rc;
+        AMH_CUDA_TRY(cudaEventRecord(e0, r.ctx->stream));
+    }
     long long left = nsteps;
     bool first = true;
     while (left > 0 || (first && sv_last)) {
@@ -112,11 +123,15 @@ static int enqueue_steps(amh_run& r, long long nsteps, bool warmup, int spl, con
         left -= m;
         first = false;
     }
-    AMH_CUDA_TRY(cudaEventRecord(e1, r.ctx->stream));
-    r.pending.emplace_back(e0, e1);
-    if (r.pending.size() > 2048) {
-        rc = resolve_events(r);
-        if (rc) return rc;
+    if (r.timing) {
+        AMH_CUDA_TRY(cudaEventRecord(e1, r.ctx->stream));
+        r.pending.emplace_back(e0, e1);
+        if (r.pending.size() > 2048) {
+            rc = resolve_events(r);
+            if (rc) return rc;
+        }
+    } else {
+        r.pending_launches = 0;
     }
     return AMH_OK;
 }
@@ -127,8 +142,7 @@ static void free_run(amh_run* r) {
     cudaStreamSynchronize(r->ctx->stream);
     void* ptrs[] = {r->X, r->X2, r->lp, r->lp2, r->lq, r->G, r->S, r->S2, r->logalpha, r->eta, r->acc, r->failed,
                     r->sflag, r->nacc, r->seeds, r->sum, r->sumsq, r->scratch};
-    for (void* p : ptrs)
-        if (p) cudaFree(p);
+    for (void* p : ptrs) dfree(r->ctx, p);
     for (auto& pr : r->pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto& pr : r->pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     delete r;
@@ -162,6 +176,12 @@ int32_t amh_ctx_create(int32_t device, amh_ctx** out) {
     AMH_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     AMH_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     AMH_CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    {   /* keep freed blocks cached in the stream-ordered pool instead of returning them to the driver */
+        cudaMemPool_t pool;
+        AMH_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;
+        AMH_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     *out = c;
     return AMH_OK;
 }
@@ -214,7 +234,7 @@ int32_t amh_target_create(amh_ctx* ctx, int32_t kind, int32_t dim, const double*
     t->ctx = ctx; t->kind = kind; t->dim = dim; t->ndata = ndata;
     t->inv2tau2 = inv2tau2; t->invtau2 = invtau2;
     t->blob.assign(blob, blob + nblob);
-    const int rc = upload(&t->dblob, t->blob, ctx->stream);
+    const int rc = upload(ctx, &t->dblob, t->blob);
     if (rc) { delete t; return rc; }
     *out = t;
     return AMH_OK;
@@ -222,7 +242,7 @@ int32_t amh_target_create(amh_ctx* ctx, int32_t kind, int32_t dim, const double*
 int32_t amh_target_destroy(amh_target* t) {
     if (!t) return AMH_OK;
     cudaSetDevice(t->ctx->device);
-    if (t->dblob) cudaFree(t->dblob);
+    dfree(t->ctx, t->dblob);
     delete t;
     return AMH_OK;
 }
@@ -276,9 +296,9 @@ int32_t amh_sampler_create(amh_ctx* ctx, const amh_sampler_desc* desc, amh_sampl
     }
     s->d.mean = nullptr; s->d.scale = nullptr; s->d.ram_S0 = nullptr;
     cudaSetDevice(ctx->device);
-    int rc = upload(&s->dmean, s->mean, ctx->stream);
-    if (!rc) rc = upload(&s->dscale, s->scale, ctx->stream);
-    if (!rc) rc = upload(&s->dS0, s->S0, ctx->stream);
+    int rc = upload(ctx, &s->dmean, s->mean);
+    if (!rc) rc = upload(ctx, &s->dscale, s->scale);
+    if (!rc) rc = upload(ctx, &s->dS0, s->S0);
     if (rc) { amh_sampler_destroy(s); return rc; }
     *out = s;
     return AMH_OK;
@@ -286,9 +306,9 @@ int32_t amh_sampler_create(amh_ctx* ctx, const amh_sampler_desc* desc, amh_sampl
 int32_t amh_sampler_destroy(amh_sampler* s) {
     if (!s) return AMH_OK;
     cudaSetDevice(s->ctx->device);
-    if (s->dmean) cudaFree(s->dmean);
-    if (s->dscale) cudaFree(s->dscale);
-    if (s->dS0) cudaFree(s->dS0);
+    dfree(s->ctx, s->dmean);
+    dfree(s->ctx, s->dscale);
+    dfree(s->ctx, s->dS0);
     delete s;
     return AMH_OK;
 }
@@ -329,27 +349,27 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
     const size_t nt = (size_t)d * (d + 1) / 2;
     int rc = AMH_OK;
     auto chk = [&](int c) { if (!rc) rc = c; };
-    chk(dev_alloc(&r->X, (size_t)d * np));
-    chk(dev_alloc(&r->lp, np));
-    chk(dev_alloc(&r->lq, np));
-    chk(dev_alloc(&r->acc, np));
-    chk(dev_alloc(&r->failed, np));
-    chk(dev_alloc(&r->nacc, np));
-    chk(dev_alloc(&r->seeds, (size_t)nseeds));
-    chk(dev_alloc(&r->sum, (size_t)d * np));
-    chk(dev_alloc(&r->sumsq, (size_t)d * np));
-    if (kind == AMH_SAMPLER_MALA) chk(dev_alloc(&r->G, (size_t)d * np));
+    chk(dev_alloc(ctx, &r->X, (size_t)d * np));
+    chk(dev_alloc(ctx, &r->lp, np));
+    chk(dev_alloc(ctx, &r->lq, np));
+    chk(dev_alloc(ctx, &r->acc, np));
+    chk(dev_alloc(ctx, &r->failed, np));
+    chk(dev_alloc(ctx, &r->nacc, np));
+    chk(dev_alloc(ctx, &r->seeds, (size_t)nseeds));
+    chk(dev_alloc(ctx, &r->sum, (size_t)d * np));
+    chk(dev_alloc(ctx, &r->sumsq, (size_t)d * np));
+    if (kind == AMH_SAMPLER_MALA) chk(dev_alloc(ctx, &r->G, (size_t)d * np));
     if (kind == AMH_SAMPLER_STRETCH) {
-        chk(dev_alloc(&r->X2, (size_t)d * np));
-        chk(dev_alloc(&r->lp2, np));
+        chk(dev_alloc(ctx, &r->X2, (size_t)d * np));
+        chk(dev_alloc(ctx, &r->lp2, np));
     }
     if (kind == AMH_SAMPLER_RAM) {
-        chk(dev_alloc(&r->S, nt * np));
-        chk(dev_alloc(&r->logalpha, np));
-        chk(dev_alloc(&r->eta, np));
+        chk(dev_alloc(ctx, &r->S, nt * np));
+        chk(dev_alloc(ctx, &r->logalpha, np));
+        chk(dev_alloc(ctx, &r->eta, np));
         /* second factor buffer + per-chain selector: the non-mutating lowrankupdate/downdate (RAM :167,:170) */
-        chk(dev_alloc(&r->S2, nt * np));
-        chk(dev_alloc(&r->sflag, np));
+        chk(dev_alloc(ctx, &r->S2, nt * np));
+        chk(dev_alloc(ctx, &r->sflag, np));
     }
     if (rc) { free_run(r); return rc; }
     cudaStream_t st = ctx->stream;
@@ -419,8 +439,8 @@ int32_t amh_run_sample(amh_run* run, int64_t N, int64_t discard_initial, int64_t
     unsigned char* dacc = nullptr;
     if (out || accepted_out) {
         chunk = std::max<long long>(1, std::min<long long>(N, (long long)((256ull << 20) / (slab * sizeof(double)))));
-        if (out) AMH_CUDA_TRY(cudaMalloc((void**)&dsamp, sizeof(double) * slab * chunk));
-        if (accepted_out) AMH_CUDA_TRY(cudaMalloc((void**)&dacc, (size_t)np * chunk));
+        if (out) { const int rca = dmalloc(r.ctx, (void**)&dsamp, sizeof(double) * slab * chunk); if (rca) return rca; }
+        if (accepted_out) { const int rca = dmalloc(r.ctx, (void**)&dacc, (size_t)np * chunk); if (rca) return rca; }
     }
     int rc = AMH_OK;
     long long filled = 0, base = 0;
@@ -462,8 +482,8 @@ int32_t amh_run_sample(amh_run* run, int64_t N, int64_t discard_initial, int64_t
         }
     }
     if (!rc) rc = flush();
-    if (dsamp) cudaFree(dsamp);
-    if (dacc) cudaFree(dacc);
+    dfree(r.ctx, dsamp);
+    dfree(r.ctx, dacc);
     if (rc) return rc;
     AMH_CUDA_TRY(cudaStreamSynchronize(st));
     if (summary) {
@@ -511,15 +531,16 @@ int32_t amh_run_get_state(amh_run* run, double* x, double* lp, double* grad, dou
         if (!r.S) return fail(AMH_ERR_INVALID, "sampler keeps no Cholesky factor");
         const size_t nt = (size_t)d * (d + 1) / 2;
         double* tmp = nullptr;
-        AMH_CUDA_TRY(cudaMalloc((void**)&tmp, sizeof(double) * nt * np));
-        int rc = ram_gather_S(r, tmp);
+        int rc = dmalloc(r.ctx, (void**)&tmp, sizeof(double) * nt * np);
+        if (rc) return rc;
+        rc = ram_gather_S(r, tmp);
         if (!rc) {
             cudaError_t e = cudaStreamSynchronize(r.ctx->stream);
             if (e == cudaSuccess)
                 e = cudaMemcpy2D(S, sizeof(double) * n, tmp, sizeof(double) * np, sizeof(double) * n, nt, cudaMemcpyDeviceToHost);
             if (e != cudaSuccess) rc = cuda_fail(e, "copy S");
         }
-        cudaFree(tmp);
+        dfree(r.ctx, tmp);
         if (rc) return rc;
     }
     if (accepted) AMH_CUDA_TRY(cudaMemcpy(accepted, r.acc, (size_t)n, cudaMemcpyDeviceToHost));
@@ -547,6 +568,18 @@ int32_t amh_run_set_params(amh_run* run, const double* x) {
     return rc;
 }
 
+int32_t amh_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(AMH_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (bytes == 0) return AMH_OK;
+    AMH_CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return AMH_OK;
+}
+int32_t amh_host_free(void* p) {
+    if (p) AMH_CUDA_TRY(cudaFreeHost(p));
+    return AMH_OK;
+}
+
 int32_t amh_run_dim(amh_run* run) { return run ? run->dim : -1; }
 int64_t amh_run_nchains(amh_run* run) { return run ? run->n : -1; }
 int64_t amh_run_launch_count(amh_run* run) { return run ? run->launches : -1; }
@@ -554,6 +587,7 @@ int64_t amh_run_launch_count(amh_run* run) { return run ? run->launches : -1; }
 int32_t amh_run_kernel_time_ms(amh_run* run, int32_t reset, double* ms, int64_t* launches) {
     if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
     AMH_CUDA_TRY(cudaSetDevice(run->ctx->device));
+    run->timing = true;           /* from now on step launches are bracketed by CUDA events */
     const int rc = resolve_events(*run);
     if (rc) return rc;
     if (ms) *ms = run->kernel_ms;

@@ -74,6 +74,7 @@ struct amh_run {
     double kernel_ms = 0;
     long long timed_launches = 0;
     long long pending_launches = 0;
+    bool timing = false;           /* record CUDA events around step launches (enabled by amh_run_kernel_time_ms) */
 };
 
 namespace amhh {
@@ -87,6 +88,10 @@ int cuda_fail(cudaError_t e, const char* what);
     } while (0)
 
 amhd::ChainState chain_state(amh_run& r);
+/* device memory from the context's stream-ordered pool (cudaMallocAsync): run handles are created and
+ * destroyed per `sample` call, and the pool makes that cheap */
+int dmalloc(amh_ctx* ctx, void** p, size_t bytes);
+void dfree(amh_ctx* ctx, void* p);
 
 /* per-sampler launchers; each enqueues kernels on r.ctx->stream and bumps r.launches */
 int launch_mh(amh_run& r, int nsteps, const amhd::SaveArgs& sv);

@@ -426,7 +426,7 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
         all = lf;
         all.insert(all.end(), uf.begin(), uf.end());
         all.insert(all.end(), t.blob.begin() + 1, t.blob.begin() + 1 + D);
-        AMH_CUDA_TRY(cudaMalloc(&r.scratch, all.size() * sizeof(double)));
+        { const int rca = dmalloc(r.ctx, &r.scratch, all.size() * sizeof(double)); if (rca) return rca; }
         AMH_CUDA_TRY(cudaMemcpyAsync(r.scratch, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice, r.ctx->stream));
         AMH_CUDA_TRY(cudaStreamSynchronize(r.ctx->stream));     /* `all` is a stack temporary */
     }

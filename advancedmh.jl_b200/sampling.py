@@ -153,10 +153,11 @@ def _initial_matrix(initial_params, sampler, dim, nchains, multi):
 
 def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None, thinning=1, num_warmup=0,
            chain_type=None, param_names=None, progress=False, callback=None, engine=None, store=True,
-           summary=False, steps_per_launch=0):
+           summary=False, steps_per_launch=0, out=None):
     """See module docstring.  Extra device-side keywords (never on the samplers): `engine`
     (a _capi.Engine; default = the CUDA library), `store=False` + `summary=True` for runs whose
-    samples cannot be stored (SURVEY.md 7 hard part 7)."""
+    samples cannot be stored (SURVEY.md 7 hard part 7), `out=(values, accepted)` caller-owned (ideally
+    pinned, Engine.pinned_empty) buffers of this rank's shard: (N, dim+1, n_local) float64, (N, n_local) uint8."""
     args = list(args)
     if args and isinstance(args[0], np.random.Generator):
         rng = args.pop(0)
@@ -199,7 +200,8 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
             run = eng.run(th, sh, n_local, seeds[lo:hi], None if init is None else init[:, lo * nw:hi * nw],
                           chain_offset=lo * nw)
             out, acc, summ = run.sample(N, discard_initial, thinning, num_warmup, store=store,
-                                        store_accepted=store, summary=summary or not store, chain_means=False)
+                                        store_accepted=store, summary=summary or not store, chain_means=False,
+                                        out=None if out is None else out[0], acc=None if out is None else out[1])
             info = dict(summary=summ, launches=run.launch_count(), rank=rank, world=world,
                         chains=(lo * nw, hi * nw))
             if callback is not None and store:

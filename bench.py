@@ -6,8 +6,11 @@ Workload (BASELINE.json configs[1], "C2"): RWMH on a d=32 full-covariance MvNorm
 MvNormal(0, 2.38^2/d * Sigma) through its full Cholesky factor, fp64 throughout.
 
 A bench "step" is ONE launch of the fused step kernel over all local chains; it advances every
-chain by `--mcmc-steps-per-launch` MCMC steps (the library's amh_run_steps call).  Between timed
-steps L2 is flushed (a 512 MB buffer is rewritten) because the 17 MB chain state is L2 resident.
+chain by `--mcmc-steps-per-launch` MCMC steps (default 500 = 0.5 % of the 100 000-iteration C2 job; the
+library's amh_run_steps call).  Between timed steps L2 is flushed (a 512 MB buffer is rewritten) because
+the 17 MB chain state is L2 resident.  `e2e` is the same step through the public `sample()` call with
+HOST buffers: initial parameters, seeds and target go host->device, two saved samples of every chain
+come device->host, handle creation and destruction included.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # this engine
   python bench.py --impl reference ...                           # the CPU arm (oracle port; Julia is not installed)
@@ -81,7 +84,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
     def result(self):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
@@ -145,13 +148,13 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dim", type=int, default=32)
     ap.add_argument("--chains", type=int, default=65536, help="chains per GPU")
-    ap.add_argument("--mcmc-steps-per-launch", type=int, default=100)
-    ap.add_argument("--ref-chains", type=int, default=2048)
+    ap.add_argument("--mcmc-steps-per-launch", type=int, default=500)
+    ap.add_argument("--ref-chains", type=int, default=16384)
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
@@ -235,13 +238,18 @@ def main():
     e2e = None
     if args.e2e_steps > 0:
         init_all = np.concatenate([L @ np.random.default_rng(100 + r).normal(size=(d, n)) for r in range(world)], axis=1)
-        hinit = torch.from_numpy(np.ascontiguousarray(init_all)).pin_memory().numpy()
+        hinit = eng.pinned_empty((d, n * world))
+        hinit[...] = init_all
+        pout = eng.pinned_empty((2, d + 1, n))          # this rank's shard of the two saved samples
+        pacc = eng.pinned_empty((2, n), dtype=np.uint8)
         model = amh.DensityModel(target)
+        amh.sample(model, sampler, amh.MCMCB200(device=local, gather=False), 2, n * world, initial_params=hinit,
+                   thinning=spl, chain_type=amh.Chains, seed=99, out=(pout, pacc))          # warm-up call
         barrier()
         t0 = time.perf_counter()
         for i in range(args.e2e_steps):
             ch = amh.sample(model, sampler, amh.MCMCB200(device=local, gather=False), 2, n * world,
-                            initial_params=hinit, thinning=spl, chain_type=amh.Chains, seed=i)
+                            initial_params=hinit, thinning=spl, chain_type=amh.Chains, seed=i, out=(pout, pacc))
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -251,9 +259,9 @@ def main():
         h2d = 8 * d * n + 8 * n + target.blob().nbytes + 8 * (d * (d + 1) // 2)       # per rank: init, seeds, target, L
         d2h = 2 * (d + 1) * n * 8 + 2 * n                                             # per rank: 2 samples + accepted flags
         e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "call": "sample(model, RWMH(MvNormal), MCMCB200(), N=2, nchains; thinning=spl) incl. handle creation, "
-                       "H2D of initial_params/seeds/target from pinned host memory, D2H of 2 samples"}
-        del hinit, ch
+               "call": "sample(model, RWMH(MvNormal), MCMCB200(), N=2, nchains; thinning=spl, out=pinned) incl. handle "
+                       "creation, H2D of initial_params/seeds/target from pinned host memory, D2H of 2 samples into pinned memory"}
+        del hinit, ch, pout, pacc
 
     B = algorithmic_bytes_per_chain_step(d)
     peaks = {}
@@ -273,9 +281,10 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "kernel": "mh_step_kernel<32,TMvNormal,64,7>", "algorithmic_bytes_per_chain_step": B,
+                "kernel": "mh_step_tc16_kernel<32,4,true,4,true> (K1T16: DMMA mat-vecs, 16 chains per warp)",
+                "algorithmic_bytes_per_chain_step": B,
                 "chain_steps_per_launch": n * spl,
-                "note": "state (17 MB) is L2 resident and the kernel is fp64-ALU bound; the HBM figure is the contractual denominator (SURVEY.md 8d)"}
+                "note": "state (17 MB) is L2 resident and the kernel is bound by the shared FP64 datapath (DFMA + DMMA, 64 FMA/clk/SM); the HBM figure is the contractual denominator (SURVEY.md 8d)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

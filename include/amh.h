@@ -167,12 +167,19 @@ int32_t amh_run_get_state(amh_run* run, double* x, double* lp, double* grad, dou
 /* setparams!!: replaces x and recomputes lp (and the gradient for MALA) on the device */
 int32_t amh_run_set_params(amh_run* run, const double* x);
 
+/* page-locked host memory for initial_params / sample buffers: host<->device copies of pinned buffers run at
+ * full PCIe/C2C speed and asynchronously (Julia: unsafe_wrap(Array, Ptr{Float64}(p), dims)) */
+int32_t amh_host_alloc(size_t bytes, void** out);
+int32_t amh_host_free(void* p);
+
 int32_t amh_run_dim(amh_run* run);
 int64_t amh_run_nchains(amh_run* run);
 /* number of kernel launches issued by this run so far (bench.py's gpu_launches) */
 int64_t amh_run_launch_count(amh_run* run);
 /* device time of the stepping kernels since the last reset, measured with CUDA
- * events on the ctx stream (milliseconds); reset != 0 zeroes the accumulator */
+ * events on the ctx stream (milliseconds); reset != 0 zeroes the accumulator.
+ * The first call switches event recording on for this run (off by default: two
+ * event records per amh_run_steps call are not free at one launch per step). */
 int32_t amh_run_kernel_time_ms(amh_run* run, int32_t reset, double* ms, int64_t* launches);
 
 #ifdef __cplusplus

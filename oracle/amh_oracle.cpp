@@ -914,6 +914,13 @@ int32_t amho_run_set_params(amh_run* run, const double* x) {
     return AMH_OK;
 }
 
+int32_t amho_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(AMH_ERR_INVALID, "out is NULL");
+    *out = bytes ? std::malloc(bytes) : nullptr;
+    return AMH_OK;
+}
+int32_t amho_host_free(void* p) { std::free(p); return AMH_OK; }
+
 int32_t amho_run_dim(amh_run* run) { return run ? ((Run*)run)->dim : -1; }
 int64_t amho_run_nchains(amh_run* run) { return run ? ((Run*)run)->n : -1; }
 int64_t amho_run_launch_count(amh_run*) { return 0; }
