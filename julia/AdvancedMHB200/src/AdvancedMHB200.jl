@@ -1,0 +1,242 @@
+# AdvancedMHB200.jl -- thin Julia shim over libamh_b200.so (include/amh.h).
+#
+# STATUS: written against the C ABI and the AbstractMCMC >= 5.6 interface, but NEVER EXECUTED: there is no Julia
+# toolchain in the build container nor on the GPU box.  The tested equivalent of every call below is the Python
+# ctypes mirror (advancedmh.jl_b200/_capi.py, sampling.py).  Treat this file as the reference-side binding a
+# maintainer would review, not as verified code.
+#
+# What it adds to an unmodified AdvancedMH.jl:
+#   * `MCMCB200 <: AbstractMCMC.AbstractMCMCEnsemble`: sample(model, sampler, MCMCB200(), N, nchains; kw...)
+#   * catalogue targets (`MvNormalTarget`, ...) that ALSO implement LogDensityProblems, so the same object runs
+#     through stock MCMCThreads() for CPU comparison
+#   * `PhiloxRNG <: Random.AbstractRNG`: makes stock AdvancedMH consume the contract stream (include/amh_contract.h)
+#     so a CPU run can be compared step by step with the GPU (parity tier T3 of SURVEY.md 8c)
+module AdvancedMHB200
+
+using AbstractMCMC, AdvancedMH, Distributions, LinearAlgebra, LogDensityProblems, Random
+
+const libamh = get(ENV, "AMH_B200_LIB", "libamh_b200")
+
+# ---------------------------------------------------------------- ABI constants (include/amh.h)
+const AMH_OK = Int32(0)
+const TARGET_IID_NORMAL, TARGET_MVNORMAL, TARGET_ROSENBROCK, TARGET_LOGISTIC, TARGET_GAUSS_PREC = Int32.(1:5)
+const SAMPLER_STATIC, SAMPLER_RW, SAMPLER_STRETCH, SAMPLER_MALA, SAMPLER_RAM = Int32.(1:5)
+const COV_SCALAR, COV_DIAG, COV_FULL = Int32.(1:3)
+
+struct SamplerDesc            # struct amh_sampler_desc, field for field
+    kind::Int32; dim::Int32; symmetric::Int32; cov_kind::Int32
+    mean::Ptr{Float64}; scale::Ptr{Float64}
+    stretch_a::Float64; n_walkers::Int64
+    mala_sigma2::Float64; mala_drift::Float64
+    ram_alpha::Float64; ram_gamma::Float64; ram_eig_lo::Float64; ram_eig_hi::Float64
+    ram_S0::Ptr{Float64}
+end
+
+function check(rc::Int32)
+    rc == AMH_OK && return nothing
+    msg = unsafe_string(ccall((:amh_last_error, libamh), Cstring, ()))
+    rc == 1 || rc == 3 ? throw(ArgumentError(msg)) : error(msg)      # AMH_ERR_INVALID/UNSUPPORTED -> ArgumentError
+end
+
+# ---------------------------------------------------------------- device-target catalogue
+abstract type DeviceTarget end
+
+"""logpdf(MvNormal(mu, Sigma), x); blob = [c0, mu, U packed by rows], U'U = inv(Sigma)"""
+struct MvNormalTarget <: DeviceTarget
+    mu::Vector{Float64}
+    Sigma::Matrix{Float64}
+end
+kind(::MvNormalTarget) = TARGET_MVNORMAL
+function blob(t::MvNormalTarget)
+    d = length(t.mu)
+    C = cholesky(Symmetric(t.Sigma)).L
+    U = inv(C)                                   # lower triangular
+    c0 = -0.5 * (d * log(2pi) + 2sum(log, diag(C)))
+    vcat(c0, t.mu, [U[i, j] for i in 1:d for j in 1:i])
+end
+LogDensityProblems.logdensity(t::MvNormalTarget, x) = logpdf(MvNormal(t.mu, t.Sigma), x)
+LogDensityProblems.dimension(t::MvNormalTarget) = length(t.mu)
+LogDensityProblems.capabilities(::Type{MvNormalTarget}) = LogDensityProblems.LogDensityOrder{1}()
+LogDensityProblems.logdensity_and_gradient(t::MvNormalTarget, x) =
+    (LogDensityProblems.logdensity(t, x), -(t.Sigma \ (x - t.mu)))
+
+"""-x'Ax/2 (test/runtests.jl:335-347 `TheNormalLogDensity`)"""
+struct GaussianPrecisionTarget <: DeviceTarget
+    A::Matrix{Float64}
+end
+kind(::GaussianPrecisionTarget) = TARGET_GAUSS_PREC
+blob(t::GaussianPrecisionTarget) = vec(permutedims(t.A))        # row-major
+LogDensityProblems.logdensity(t::GaussianPrecisionTarget, x) = -dot(x, t.A, x) / 2
+LogDensityProblems.dimension(t::GaussianPrecisionTarget) = size(t.A, 1)
+LogDensityProblems.capabilities(::Type{GaussianPrecisionTarget}) = LogDensityProblems.LogDensityOrder{1}()
+LogDensityProblems.logdensity_and_gradient(t::GaussianPrecisionTarget, x) = (-dot(x, t.A, x) / 2, -t.A * x)
+
+"""sum(logpdf.(Normal(mu, sigma), data)) on sigma >= 0 (README.md:26-31)"""
+struct IIDNormalTarget <: DeviceTarget
+    data::Vector{Float64}
+end
+kind(::IIDNormalTarget) = TARGET_IID_NORMAL
+blob(t::IIDNormalTarget) = t.data
+LogDensityProblems.logdensity(t::IIDNormalTarget, th) = th[2] >= 0 ? sum(logpdf.(Normal(th[1], th[2]), t.data)) : -Inf
+LogDensityProblems.dimension(::IIDNormalTarget) = 2
+LogDensityProblems.capabilities(::Type{IIDNormalTarget}) = LogDensityProblems.LogDensityOrder{0}()
+
+struct RosenbrockTarget <: DeviceTarget
+    dim::Int; a::Float64; b::Float64; s::Float64
+end
+RosenbrockTarget(d) = RosenbrockTarget(d, 1.0, 100.0, 20.0)
+kind(::RosenbrockTarget) = TARGET_ROSENBROCK
+blob(t::RosenbrockTarget) = [t.a, t.b, t.s]
+LogDensityProblems.logdensity(t::RosenbrockTarget, x) =
+    -sum(t.b * (x[i + 1] - x[i]^2)^2 + (t.a - x[i])^2 for i in 1:(t.dim - 1)) / t.s
+LogDensityProblems.dimension(t::RosenbrockTarget) = t.dim
+LogDensityProblems.capabilities(::Type{RosenbrockTarget}) = LogDensityProblems.LogDensityOrder{0}()
+
+# a DensityModel / LogDensityModel must wrap a catalogue target; anything else cannot run on the device
+unwrap(m::AdvancedMH.DensityModel) = unwrap(m.logdensity)
+unwrap(m::AbstractMCMC.LogDensityModel) = unwrap(m.logdensity)
+unwrap(t::DeviceTarget) = t
+unwrap(x) = throw(ArgumentError("MCMCB200 needs a catalogue device target, got $(typeof(x)); arbitrary closures cannot run in a CUDA kernel and there is no CPU fallback"))
+
+# ---------------------------------------------------------------- sampler lowering (unchanged AdvancedMH constructors)
+function gaussian(p)      # -> (cov_kind, mean or nothing, scale)
+    if p isa MvNormal
+        S = p.Σ
+        mu = all(iszero, mean(p)) ? nothing : collect(Float64, mean(p))
+        S isa Distributions.PDMats.ScalMat && return (COV_SCALAR, mu, [sqrt(S.value)])
+        S isa Distributions.PDMats.PDiagMat && return (COV_DIAG, mu, sqrt.(S.diag))
+        L = cholesky(Symmetric(Matrix(S))).L
+        return (COV_FULL, mu, [L[i, j] for i in 1:size(L, 1) for j in 1:i])
+    elseif p isa Normal
+        return (COV_SCALAR, iszero(p.μ) ? nothing : [p.μ], [p.σ])
+    elseif p isa AbstractVector{<:Normal}
+        mu = [q.μ for q in p]
+        return (COV_DIAG, all(iszero, mu) ? nothing : mu, [q.σ for q in p])
+    end
+    throw(ArgumentError("unsupported proposal on the device path: $(typeof(p))"))
+end
+
+issym(::AdvancedMH.Proposal{S}) where {S} = S       # the `issymmetric` type parameter (proposal.jl:1-21)
+
+struct Lowered
+    desc::SamplerDesc
+    keep::Vector{Any}       # arrays the desc points into
+end
+
+function lower(spl::AdvancedMH.MetropolisHastings, d)
+    p = spl.proposal
+    p isa Union{AdvancedMH.StaticProposal,AdvancedMH.RandomWalkProposal} ||
+        throw(ArgumentError("container / function-valued proposals are host-only"))
+    ck, mu, sc = gaussian(p.proposal)
+    k = p isa AdvancedMH.RandomWalkProposal ? SAMPLER_RW : SAMPLER_STATIC
+    keep = Any[mu, sc]
+    Lowered(SamplerDesc(k, d, issym(p), ck, mu === nothing ? C_NULL : pointer(mu), pointer(sc), 2.0, 0, 0.0, 0.0,
+                        0.234, 0.6, 0.0, Inf, C_NULL), keep)
+end
+
+function lower(spl::AdvancedMH.Ensemble, d)
+    sp = spl.proposal::AdvancedMH.StretchProposal
+    ck, mu, sc = try gaussian(sp.proposal) catch; (COV_SCALAR, nothing, nothing) end
+    keep = Any[mu, sc]
+    Lowered(SamplerDesc(SAMPLER_STRETCH, d, 0, ck, mu === nothing ? C_NULL : pointer(mu),
+                        sc === nothing ? C_NULL : pointer(sc), sp.stretch_length, spl.n_walkers, 0.0, 0.0,
+                        0.234, 0.6, 0.0, Inf, C_NULL), keep)
+end
+
+function lower(spl::AdvancedMH.MALA, d)
+    # recover (sigma2, drift) of g -> MvNormal(drift*g, sigma2*I) by probing the closure on the host
+    f = spl.proposal.proposal
+    p0 = f(zeros(d)); e1 = zeros(d); e1[1] = 1.0
+    p1 = f(e1)
+    (p0 isa MvNormal && p0.Σ isa Distributions.PDMats.ScalMat) ||
+        throw(ArgumentError("MALA on the device needs proposal(g) = MvNormal(c*g, sigma2*I)"))
+    Lowered(SamplerDesc(SAMPLER_MALA, d, 0, COV_SCALAR, C_NULL, C_NULL, 2.0, 0, p0.Σ.value, mean(p1)[1],
+                        0.234, 0.6, 0.0, Inf, C_NULL), Any[])
+end
+
+function lower(spl::AdvancedMH.RobustAdaptiveMetropolis, d)
+    S0 = spl.S === nothing ? nothing : vec(permutedims(Matrix{Float64}(spl.S)))
+    spl.S === nothing || size(spl.S) == (d, d) || throw(ArgumentError("The provided `S` has the wrong dimensionality."))
+    Lowered(SamplerDesc(SAMPLER_RAM, d, 0, COV_SCALAR, C_NULL, C_NULL, 2.0, 0, 0.0, 0.0, spl.α, spl.γ,
+                        spl.eigenvalue_lower_bound, spl.eigenvalue_upper_bound, S0 === nothing ? C_NULL : pointer(S0)),
+            Any[S0])
+end
+
+# ---------------------------------------------------------------- the ensemble type
+"""
+    MCMCB200(; device = 0)
+
+Run all chains in lock-step on a B200.  `sample(model, sampler, MCMCB200(), N, nchains; kw...)` keeps AbstractMCMC's
+keywords: `initial_params` (one entry per chain), `discard_initial`, `thinning`, `num_warmup`, `chain_type`,
+`param_names`.
+"""
+Base.@kwdef struct MCMCB200 <: AbstractMCMC.AbstractMCMCEnsemble
+    device::Int = 0
+end
+
+function AbstractMCMC.mcmcsample(rng::Random.AbstractRNG, model::AbstractMCMC.AbstractModel,
+                                 sampler::AdvancedMH.MHSampler, par::MCMCB200, N::Integer, nchains::Integer;
+                                 initial_params=nothing, num_warmup::Integer=0,
+                                 discard_initial::Integer=num_warmup, thinning::Integer=1,
+                                 chain_type::Type=Any, kwargs...)
+    target = unwrap(model)
+    d = LogDensityProblems.dimension(target)
+    nw = sampler isa AdvancedMH.Ensemble ? sampler.n_walkers : 1
+    n = nchains * nw
+    seeds = rand(rng, UInt64, nchains)                         # exactly AbstractMCMC's per-chain seeding
+    low = lower(sampler, d)
+    b = blob(target)
+    # device layout: X[dim][chain], chains fastest == Julia Matrix(undef, nchains, dim) (column-major)
+    init = initial_params === nothing ? nothing : permutedims(reduce(hcat, [vec(collect(Float64, p)) for p in initial_params]))
+    out = Array{Float64}(undef, n, d + 1, N)                   # C order [N][d+1][n]
+    acc = Array{UInt8}(undef, n, N)
+    ctx = Ref{Ptr{Cvoid}}(); tg = Ref{Ptr{Cvoid}}(); sp = Ref{Ptr{Cvoid}}(); run = Ref{Ptr{Cvoid}}()
+    GC.@preserve low b seeds init out acc begin
+        check(ccall((:amh_ctx_create, libamh), Int32, (Int32, Ptr{Ptr{Cvoid}}), par.device, ctx))
+        try
+            check(ccall((:amh_target_create, libamh), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Int64, Ptr{Ptr{Cvoid}}),
+                        ctx[], kind(target), d, b, length(b), tg))
+            check(ccall((:amh_sampler_create, libamh), Int32, (Ptr{Cvoid}, Ref{SamplerDesc}, Ptr{Ptr{Cvoid}}), ctx[], low.desc, sp))
+            check(ccall((:amh_run_create, libamh), Int32,
+                        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{UInt64}, Ptr{Float64}, Ptr{Ptr{Cvoid}}),
+                        ctx[], tg[], sp[], n, 0, seeds, init === nothing ? C_NULL : pointer(init), run))
+            check(ccall((:amh_run_sample, libamh), Int32,
+                        (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ptr{Float64}, Ptr{UInt8}, Ptr{Cvoid}),
+                        run[], N, discard_initial, thinning, num_warmup, out, acc, C_NULL))
+        finally
+            run[] == C_NULL || ccall((:amh_run_destroy, libamh), Int32, (Ptr{Cvoid},), run[])
+            sp[] == C_NULL || ccall((:amh_sampler_destroy, libamh), Int32, (Ptr{Cvoid},), sp[])
+            tg[] == C_NULL || ccall((:amh_target_destroy, libamh), Int32, (Ptr{Cvoid},), tg[])
+            ccall((:amh_ctx_destroy, libamh), Int32, (Ptr{Cvoid},), ctx[])
+        end
+    end
+    # hand the arrays to the reference's own bundling: one Vector{Transition} per chain, then bundle_samples +
+    # chainsstack exactly like AbstractMCMC does (src/AdvancedMH.jl:80-123, ext/AdvancedMHMCMCChainsExt.jl)
+    chains = map(1:nchains) do c
+        ts = [AdvancedMH.Transition(out[(c - 1) * nw + 1, 1:d, i], out[(c - 1) * nw + 1, d + 1, i], acc[(c - 1) * nw + 1, i] != 0)
+              for i in 1:N]
+        AbstractMCMC.bundle_samples(ts, model, sampler, nothing, chain_type; discard_initial, thinning, kwargs...)
+    end
+    return AbstractMCMC.chainsstack(AbstractMCMC.tighten_eltype(chains))
+end
+
+# ---------------------------------------------------------------- contract RNG for CPU-side parity runs
+"""
+    PhiloxRNG(seed)
+
+Sequential consumer of the contract stream (include/amh_contract.h): `randn`, `randexp`, `rand` are served from
+Philox4x32-10 blocks with the per-step layout of the kernels, so `sample(rng = PhiloxRNG(seed), ...)` with stock
+AdvancedMH reproduces the device chain seeded `seed`, provided it is re-positioned (`seekstep!`) at every step start.
+The transcendental functions must be the contract's (ccall into the oracle's `amho_probe_*`), not Base's.
+"""
+mutable struct PhiloxRNG <: Random.AbstractRNG
+    seed::UInt64
+    block::UInt64
+    word::Int
+end
+PhiloxRNG(seed::Integer) = PhiloxRNG(UInt64(seed), 0, 0)
+seekstep!(r::PhiloxRNG, k::Integer, d::Integer) = (r.block = UInt64(k) * UInt64(cld(d, 2) + 1); r.word = 0; r)
+
+export MCMCB200, MvNormalTarget, GaussianPrecisionTarget, IIDNormalTarget, RosenbrockTarget, PhiloxRNG, seekstep!
+
+end # module

@@ -1,0 +1,106 @@
+#!/usr/bin/env python3
+"""Throughput of the BASELINE configs C2..C5 through the C ABI on one GPU (parity-test shapes, not bench lines).
+Lengths are shortened; chain-steps/s is per-step and length independent after warm-up.
+Usage: python tools/bench_configs.py [c2 c3 c4 c5 ...]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import amh_b200 as amh   # noqa: E402
+
+PEAK = 6551.7
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def spd(d, seed, lo, hi):
+    rng = np.random.default_rng(seed)
+    Q, _ = np.linalg.qr(rng.normal(size=(d, d)))
+    lam = np.exp(np.linspace(np.log(lo), np.log(hi), d))
+    S = (Q * lam) @ Q.T
+    return (S + S.T) / 2
+
+
+def timed(run, nsteps, warmup=False, spl=0, reps=3, warm=1):
+    for _ in range(warm):
+        run.steps(nsteps, warmup=warmup, steps_per_launch=spl)
+    run.sync()
+    run.kernel_time_ms(reset=True)
+    for _ in range(reps):
+        run.steps(nsteps, warmup=warmup, steps_per_launch=spl)
+    run.sync()
+    ms, nl = run.kernel_time_ms(reset=True)
+    return ms / reps
+
+
+def report(name, nchain_steps, ms, bytes_per, extra=""):
+    v = nchain_steps / (ms * 1e-3)
+    gbs = v * bytes_per / 1e9
+    print(f"{name:34s} {v:10.4g} chain-steps/s   {gbs:8.1f} GB/s algorithmic = {100 * gbs / PEAK:5.1f}% of {PEAK:.0f}  {extra}", flush=True)
+
+
+def main():
+    which = sys.argv[1:] or ["c2", "c3", "c4", "c5"]
+    eng = amh.default_engine(0)
+    seeds = lambda n, s: np.random.default_rng(s).integers(0, 2 ** 64, size=n, dtype=np.uint64)
+    if "c2" in which:
+        for d in (32, 24, 16, 10, 2):
+            n = 65536
+            Sigma = spd(d, 32, 1.0, 100.0)
+            t = amh.MvNormalTarget(None, Sigma)
+            s = amh.RWMH(amh.MvNormal(np.zeros(d), (2.38 ** 2 / d) * Sigma))
+            run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), n, seeds(n, 1))
+            ms = timed(run, 200, spl=100)
+            st = run.state()
+            report(f"C2 RWMH MvNormal d={d} n={n}", n * 200, ms, 2 * (d + 1) * 8, f"accept={st['naccept'].sum() / (n * st['step']):.3f}")
+            run.close()
+    if "c3" in which:
+        d, nw, ne = 10, 4096, 64
+        t = amh.RosenbrockTarget(d)
+        s = amh.Ensemble(nw, amh.StretchProposal(amh.MvNormal(np.zeros(d), amh.I)))
+        run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), nw * ne, seeds(ne, 2))
+        ms = timed(run, 64, spl=16)
+        st = run.state()
+        report(f"C3 stretch Rosenbrock d=10 {ne}x{nw}", nw * ne * 64, ms, 2 * (d + 1) * 8, f"accept={st['naccept'].sum() / (nw * ne * st['step']):.3f}")
+        run.close()
+    if "c4" in which:
+        d, nrows = 128, 10000
+        rng = np.random.default_rng(128)
+        X = rng.normal(size=(nrows, d)) / np.sqrt(d)
+        beta = rng.normal(size=d)
+        y = (rng.random(nrows) < 1 / (1 + np.exp(-X @ beta))).astype(float)
+        t = amh.LogisticRegressionTarget(X, y, tau=10.0)
+        s2 = 2e-3
+        s = amh.MALA(lambda g: amh.MvNormal((s2 / 2) * g, s2 * amh.I))
+        for n in (1024,):
+            run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), n, seeds(n, 3), np.zeros((d, n)))
+            ms = timed(run, 2, spl=1, reps=1, warm=1)
+            st = run.state()
+            report(f"C4 MALA logistic d=128 rows=10k n={n}", n * 2, ms, 2 * (2 * d + 1) * 8,
+                   f"accept={st['naccept'].sum() / (n * st['step']):.3f}  {5.12e6 * n * 2 / (ms * 1e-3) / 1e12:.2f} TFLOP/s fp64")
+            run.close()
+    if "c5" in which:
+        d = 64
+        Sigma = spd(d, 64, 1e-4, 1.0)
+        t = amh.MvNormalTarget(None, Sigma)
+        s = amh.RobustAdaptiveMetropolis()
+        for n in (32768,):
+            run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), n, seeds(n, 4), np.zeros((d, n)))
+            ms = timed(run, 20, warmup=True, spl=1)
+            report(f"C5 RAM warm-up d=64 n={n}", n * 20, ms, 2 * (d + 1) * 8 + d * (d + 1) * 8)
+            ms = timed(run, 20, warmup=False, spl=1)
+            st = run.state()
+            report(f"C5 RAM sampling d=64 n={n}", n * 20, ms, 2 * (d + 1) * 8 + d * (d + 1) // 2 * 8,
+                   f"accept={st['naccept'].sum() / (n * st['step']):.3f}")
+            run.close()
+
+
+if __name__ == "__main__":
+    main()
