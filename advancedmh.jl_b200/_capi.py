@@ -112,7 +112,7 @@ class Engine:
         f("ctx_create").argtypes = [C.c_int32, C.POINTER(C.c_void_p)]
         f("target_create").argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, C.c_int64, C.POINTER(C.c_void_p)]
         f("sampler_create").argtypes = [C.c_void_p, C.POINTER(SamplerDesc), C.POINTER(C.c_void_p)]
-        f("run_create").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, _u64p, _dp,
+        f("run_create").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, _u64p, _dp, C.c_int64,
                                     C.POINTER(C.c_void_p)]
         f("run_steps").argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32]
         f("run_sample").argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _dp, _u8p,
@@ -189,15 +189,21 @@ class Engine:
     def run(self, target: "TargetHandle", sampler: "SamplerHandle", nchains: int, seeds, init=None,
             chain_offset: int = 0) -> "Run":
         seeds = np.ascontiguousarray(seeds, dtype=np.uint64).ravel()
-        init_p = None
+        init_p, init_ld = None, 0
         if init is not None:
-            init = _as_f64(init)
+            init = np.asarray(init)
             if init.shape != (target.dim, nchains):
                 raise AMHArgumentError(AMH_ERR_INVALID, f"init must have shape (dim, nchains) = {(target.dim, nchains)}, got {init.shape}")
-            init_p = init.ctypes.data_as(_dp)
+            # a column block of a larger C-contiguous float64 matrix is passed as is (row stride = init_ld)
+            ok = (init.dtype == np.float64 and init.strides[1] == 8 and init.strides[0] % 8 == 0
+                  and init.strides[0] >= 8 * nchains)
+            if not ok:
+                init = _as_f64(init)
+            init_ld = init.strides[0] // 8
+            init_p = C.cast(init.ctypes.data, _dp)
         h = C.c_void_p()
         self._check(self._f("run_create")(self.ctx, target.h, sampler.h, nchains, chain_offset,
-                                          seeds.ctypes.data_as(_u64p), init_p, C.byref(h)))
+                                          seeds.ctypes.data_as(_u64p), init_p, init_ld, C.byref(h)))
         return Run(self, h, target, sampler, nchains)
 
 

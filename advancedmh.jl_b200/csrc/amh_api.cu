@@ -314,11 +314,13 @@ int32_t amh_sampler_destroy(amh_sampler* s) {
 }
 
 int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, int64_t n, int64_t off,
-                       const uint64_t* seeds, const double* init, amh_run** out) {
+                       const uint64_t* seeds, const double* init, int64_t init_ld, amh_run** out) {
     if (!ctx || !target || !sampler || !out || !seeds) return fail(AMH_ERR_INVALID, "NULL argument");
     if (target->dim != sampler->d.dim) return fail(AMH_ERR_INVALID, "target and sampler dimensions differ");
     if (target->ctx != ctx || sampler->ctx != ctx) return fail(AMH_ERR_INVALID, "target/sampler belong to another ctx");
     if (n < 1) return fail(AMH_ERR_INVALID, "nchains_local must be >= 1");
+    if (init_ld == 0) init_ld = n;
+    if (init && init_ld < n) return fail(AMH_ERR_INVALID, "init_ld must be >= nchains_local");
     const int kind = sampler->d.kind;
     const int d = target->dim;
     if (d > amhd::kGenericCap) return fail(AMH_ERR_UNSUPPORTED, "device samplers support dim <= 128");
@@ -389,7 +391,7 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
     cu(cudaMemcpyAsync(r->seeds, seeds, sizeof(uint64_t) * nseeds, cudaMemcpyHostToDevice, st), "copy seeds");
     int mode;
     if (init) {
-        cu(cudaMemcpy2DAsync(r->X, sizeof(double) * np, init, sizeof(double) * n, sizeof(double) * n, d,
+        cu(cudaMemcpy2DAsync(r->X, sizeof(double) * np, init, sizeof(double) * init_ld, sizeof(double) * n, d,
                              cudaMemcpyHostToDevice, st), "copy init");
         mode = 0;
     } else {

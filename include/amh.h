@@ -131,12 +131,14 @@ int32_t amh_sampler_destroy(amh_sampler* s);
  * (mh-core.jl:76-86, emcee.jl:29-34, MALA.jl:37-40, RAM :175-214):
  *   init == NULL : draw from the proposal (STATIC/RW/STRETCH) or randn (RAM);
  *                  MALA -> AMH_ERR_STATE "please specify initial parameters" (MALA.jl:37)
- *   init != NULL : [dim][nchains_local] float64, chains fastest.
+ *   init != NULL : [dim][nchains_local] float64, chains fastest; row i starts at init + i*init_ld
+ *                  (init_ld = 0 means dense, init_ld = nchains_total lets a rank pass its column block
+ *                  of the global initial_params matrix without repacking).
  * seeds: one uint64 per local chain (MH/MALA/RAM) or per local ENSEMBLE (STRETCH,
  * nchains_local = n_ensembles * n_walkers), i.e. rand(rng, UInt, nchains). */
 int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler,
                        int64_t nchains_local, int64_t chain_offset,
-                       const uint64_t* seeds, const double* init, amh_run** out);
+                       const uint64_t* seeds, const double* init, int64_t init_ld, amh_run** out);
 int32_t amh_run_destroy(amh_run* run);
 
 /* `nsteps` stateful steps for every chain, asynchronously on the ctx stream

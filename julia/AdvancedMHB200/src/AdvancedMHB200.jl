@@ -198,8 +198,8 @@ function AbstractMCMC.mcmcsample(rng::Random.AbstractRNG, model::AbstractMCMC.Ab
                         ctx[], kind(target), d, b, length(b), tg))
             check(ccall((:amh_sampler_create, libamh), Int32, (Ptr{Cvoid}, Ref{SamplerDesc}, Ptr{Ptr{Cvoid}}), ctx[], low.desc, sp))
             check(ccall((:amh_run_create, libamh), Int32,
-                        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{UInt64}, Ptr{Float64}, Ptr{Ptr{Cvoid}}),
-                        ctx[], tg[], sp[], n, 0, seeds, init === nothing ? C_NULL : pointer(init), run))
+                        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{UInt64}, Ptr{Float64}, Int64, Ptr{Ptr{Cvoid}}),
+                        ctx[], tg[], sp[], n, 0, seeds, init === nothing ? C_NULL : pointer(init), 0, run))
             check(ccall((:amh_run_sample, libamh), Int32,
                         (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ptr{Float64}, Ptr{UInt8}, Ptr{Cvoid}),
                         run[], N, discard_initial, thinning, num_warmup, out, acc, C_NULL))

@@ -731,12 +731,14 @@ int32_t amho_sampler_create(amh_ctx*, const amh_sampler_desc* desc, amh_sampler*
 int32_t amho_sampler_destroy(amh_sampler* s) { delete (Sampler*)s; return AMH_OK; }
 
 int32_t amho_run_create(amh_ctx*, amh_target* target, amh_sampler* sampler, int64_t n, int64_t off,
-                        const uint64_t* seeds, const double* init, amh_run** out) {
+                        const uint64_t* seeds, const double* init, int64_t init_ld, amh_run** out) {
     if (!target || !sampler || !out || !seeds) return fail(AMH_ERR_INVALID, "NULL argument");
     Target* t = (Target*)target;
     Sampler* s = (Sampler*)sampler;
     if (t->dim != s->d.dim) return fail(AMH_ERR_INVALID, "target and sampler dimensions differ");
     if (n < 1) return fail(AMH_ERR_INVALID, "nchains_local must be >= 1");
+    if (init_ld == 0) init_ld = n;
+    if (init && init_ld < n) return fail(AMH_ERR_INVALID, "init_ld must be >= nchains_local");
     const int kind = s->d.kind;
     const int d = t->dim;
     int64_t nseeds = n;
@@ -770,7 +772,7 @@ int32_t amho_run_create(amh_ctx*, amh_target* target, amh_sampler* sampler, int6
         std::vector<double> x(d), z(d), g(d);
         for (int64_t ch = a; ch < b; ++ch) {
             if (init) {
-                for (int i = 0; i < d; ++i) x[i] = init[(int64_t)i * n + ch];
+                for (int i = 0; i < d; ++i) x[i] = init[(int64_t)i * init_ld + ch];
             } else if (kind == AMH_SAMPLER_RAM) {
                 normals(r->seeds[ch], 0, 0, d, x.data());            /* randn(rng, T, d)  (:193) */
             } else if (kind == AMH_SAMPLER_STRETCH) {

@@ -2,7 +2,8 @@
  * Python.  Used for ncu captures (no interpreter start-up under the profiler) and as the C example of
  * INTEGRATION.md.  Workload: BASELINE config 2 (RWMH, d-dim full-covariance MvNormal, n chains).
  *
- *   amh_c_driver [d=32] [nchains=65536] [launches=5] [mcmc_steps_per_launch=20] [warmup_launches=3]
+ *   amh_c_driver [d=32] [nchains=65536] [launches=5] [mcmc_steps_per_launch=20] [warmup_launches=3] [events=1]
+ *   events=0 leaves the library's CUDA-event timing off and reports host wall time around the synchronised loop
  *
  * Build: gcc -O2 -o amh_c_driver amh_c_driver.c -I../../include -L../../advancedmh.jl_b200 -lamh_b200 -lm \
  *            -Wl,-rpath,'$ORIGIN/../../advancedmh.jl_b200'
@@ -11,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include "amh.h"
 
 #define CHECK(call) do { int rc_ = (call); if (rc_ != AMH_OK) { fprintf(stderr, "%s failed (%d): %s\n", #call, rc_, amh_last_error()); return 1; } } while (0)
@@ -38,6 +40,7 @@ int main(int argc, char** argv) {
     const int launches = argc > 3 ? atoi(argv[3]) : 5;
     const int spl = argc > 4 ? atoi(argv[4]) : 20;
     const int warm = argc > 5 ? atoi(argv[5]) : 3;
+    const int events = argc > 6 ? atoi(argv[6]) : 1;
     /* Sigma = G G' / d + diag(1..) : some SPD matrix with a spread spectrum */
     double* G = malloc(sizeof(double) * d * d), *S = malloc(sizeof(double) * d * d), *C = malloc(sizeof(double) * d * d);
     double* Ci = malloc(sizeof(double) * d * d), *L = malloc(sizeof(double) * d * d);
@@ -79,14 +82,20 @@ int main(int argc, char** argv) {
     CHECK(amh_sampler_create(ctx, &desc, &sp));
     unsigned long long* seeds = malloc(sizeof(unsigned long long) * n);
     for (long long i = 0; i < n; ++i) { urand(); seeds[i] = s_rng; }
-    CHECK(amh_run_create(ctx, tg, sp, n, 0, (const uint64_t*)seeds, NULL, &run));
+    CHECK(amh_run_create(ctx, tg, sp, n, 0, (const uint64_t*)seeds, NULL, 0, &run));
     for (int i = 0; i < warm; ++i) CHECK(amh_run_steps(run, spl, 0, spl));
     CHECK(amh_run_sync(run));
-    double ms; int64_t nl;
-    CHECK(amh_run_kernel_time_ms(run, 1, &ms, &nl));
+    double ms = 0; int64_t nl = launches;
+    if (events) CHECK(amh_run_kernel_time_ms(run, 1, &ms, &nl));
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int i = 0; i < launches; ++i) CHECK(amh_run_steps(run, spl, 0, spl));
     CHECK(amh_run_sync(run));
-    CHECK(amh_run_kernel_time_ms(run, 1, &ms, &nl));
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const double wall_ms = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+    if (events) CHECK(amh_run_kernel_time_ms(run, 1, &ms, &nl));
+    else { ms = wall_ms; nl = launches; }
+    printf("wall %.3f ms for the synchronised loop (%s)\n", wall_ms, events ? "CUDA-event timing on" : "CUDA-event timing off");
     int64_t* nacc = malloc(sizeof(int64_t) * n); int64_t steps;
     CHECK(amh_run_get_state(run, NULL, NULL, NULL, NULL, NULL, nacc, &steps));
     double acc = 0; for (long long i = 0; i < n; ++i) acc += (double)nacc[i];
