@@ -35,7 +35,7 @@ amhd::ChainState chain_state(amh_run& r) {
 int default_steps_per_launch(const amh_run& r) {
     switch (r.sampler->d.kind) {
     case AMH_SAMPLER_STRETCH: return 16;
-    case AMH_SAMPLER_RAM: return 1;      /* HBM-streaming: nothing to keep resident */
+    case AMH_SAMPLER_RAM: return r.ram_warp ? 16 : 1;   /* K4W keeps the factor in shared memory across fused steps */
     default: return 64;
     }
 }
@@ -114,7 +114,7 @@ static int enqueue_steps(amh_run& r, long long nsteps, bool warmup, int spl, con
         case AMH_SAMPLER_STATIC:
         case AMH_SAMPLER_RW: rc = launch_mh(r, m, sv); break;
         case AMH_SAMPLER_MALA: rc = launch_mala(r, m, sv); break;
-        case AMH_SAMPLER_RAM: rc = launch_ram(r, m, warmup, sv); break;
+        case AMH_SAMPLER_RAM: rc = r.ram_warp ? launch_ram_warp(r, m, warmup, sv) : launch_ram(r, m, warmup, sv); break;
         case AMH_SAMPLER_STRETCH: rc = launch_stretch(r, m, sv); break;
         default: rc = fail(AMH_ERR_INVALID, "unknown sampler kind");
         }
@@ -366,6 +366,13 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
         chk(dev_alloc(ctx, &r->lp2, np));
     }
     if (kind == AMH_SAMPLER_RAM) {
+        r->ram_warp = ram_warp_eligible(*r) && !(std::getenv("AMH_RAM_PATH") && std::strcmp(std::getenv("AMH_RAM_PATH"), "thread") == 0);
+    }
+    if (kind == AMH_SAMPLER_RAM && r->ram_warp) {
+        chk(dev_alloc(ctx, &r->S, ((nt + 1) & ~(size_t)1) * (size_t)n));   /* [chain][column-packed, padded to 16 B], single buffer */
+        chk(dev_alloc(ctx, &r->logalpha, np));
+        chk(dev_alloc(ctx, &r->eta, np));
+    } else if (kind == AMH_SAMPLER_RAM) {
         chk(dev_alloc(ctx, &r->S, nt * np));
         chk(dev_alloc(ctx, &r->logalpha, np));
         chk(dev_alloc(ctx, &r->eta, np));
@@ -397,7 +404,13 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
     } else {
         mode = kind == AMH_SAMPLER_RAM ? 2 : kind == AMH_SAMPLER_STRETCH ? 3 : 1;
     }
-    if (!rc) rc = launch_init(*r, mode);
+    if (!rc && r->ram_warp) {
+        double* Ssave = r->S;
+        r->S = nullptr;                  /* the init kernel writes the thread-kernel layout; K4W has its own */
+        rc = launch_init(*r, mode);
+        r->S = Ssave;
+        if (!rc) rc = ramw_init_S(*r);
+    } else if (!rc) rc = launch_init(*r, mode);
     cu(cudaStreamSynchronize(st), "init sync");       /* host buffers are only read during the call */
     if (rc) { free_run(r); return rc; }
     *out = r;
@@ -535,7 +548,7 @@ int32_t amh_run_get_state(amh_run* run, double* x, double* lp, double* grad, dou
         double* tmp = nullptr;
         int rc = dmalloc(r.ctx, (void**)&tmp, sizeof(double) * nt * np);
         if (rc) return rc;
-        rc = ram_gather_S(r, tmp);
+        rc = r.ram_warp ? ramw_export_S(r, tmp) : ram_gather_S(r, tmp);
         if (!rc) {
             cudaError_t e = cudaStreamSynchronize(r.ctx->stream);
             if (e == cudaSuccess)

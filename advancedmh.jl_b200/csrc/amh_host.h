@@ -67,6 +67,7 @@ struct amh_run {
     long long step = 0;
     long long nsaved = 0;
     long long launches = 0;
+    bool ram_warp = false;         /* RAM: S stored [chain][column-packed] and stepped by K4W */
     int mh_path = 0;               /* 0 = choose (tensor-core K1T when eligible), 1 = force the per-thread DFMA kernel K1 */
     /* kernel timing */
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
@@ -101,6 +102,11 @@ int launch_mala(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_ram(amh_run& r, int nsteps, bool warmup, const amhd::SaveArgs& sv);
 int launch_stretch(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_init(amh_run& r, int mode);
-int ram_gather_S(amh_run& r, double* dst);   /* current factor of every chain -> dst [tri][pitch] */
+int ram_gather_S(amh_run& r, double* dst);
+/* K4W: one warp per chain, factor resident in shared memory (amh_launch_ram_warp.cu) */
+bool ram_warp_eligible(const amh_run& r);
+int launch_ram_warp(amh_run& r, int nsteps, bool warmup, const amhd::SaveArgs& sv);
+int ramw_init_S(amh_run& r);
+int ramw_export_S(amh_run& r, double* dst);   /* current factor of every chain -> dst [tri][pitch] */
 int default_steps_per_launch(const amh_run& r);
 }  // namespace amhh

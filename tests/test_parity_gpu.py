@@ -215,13 +215,13 @@ def test_mala_requires_initial_params_and_gradient(amh, cuda):
 
 
 # ------------------------------------------------------------------------------ RAM (K4)
-@pytest.mark.parametrize("d,bounds", [(2, None), (2, (0.9, 1.1)), (5, None), (16, (0.1, 2.0)), (33, None), (64, None)])
+@pytest.mark.parametrize("d,bounds", [(2, None), (2, (0.9, 1.1)), (5, None), (16, (0.1, 2.0)), (17, (0.5, 1.5)), (33, None), (64, None), (100, None)])
 def test_ram_bit_exact(amh, cuda, oracle, d, bounds):
     Sigma = make_spd(d, seed=60 + d, lo=1e-2, hi=1.0)
     target = amh.MvNormalTarget(None, Sigma)
     kw = {} if bounds is None else dict(eigenvalue_lower_bound=bounds[0], eigenvalue_upper_bound=bounds[1])
     spl = amh.RobustAdaptiveMetropolis(**kw)
-    n = 200 if d < 64 else 96
+    n = 200 if d < 64 else 70
     rg, ro = _pair(amh, cuda, oracle, target, spl, n, _seeds(n, 70 + d))
     _assert_same_state(rg, ro, S=True)                    # x = randn(d), S = I, accepted = true (:175-214)
     assert rg.state()["accepted"].all()
@@ -314,3 +314,25 @@ def test_tensor_core_path_static_symmetric_and_sample(amh, cuda, oracle):
     for k in ("mean", "var", "chain_mean"):
         assert np.array_equal(sg[k], so[k])
     _assert_same_state(rg, ro)
+
+
+def test_ram_warp_kernel_user_S_fused_steps_and_sample(amh, cuda, oracle):
+    """K4W (warp per chain, factor in shared memory): user-supplied S, several fused steps per launch (roll-back and
+    write-through of the factor inside one launch), and the sample schedule with warm-up"""
+    d = 20
+    Sigma = make_spd(d, seed=91, lo=1e-2, hi=1.0)
+    target = amh.MvNormalTarget(np.linspace(-0.2, 0.2, d), Sigma)
+    S0 = np.linalg.cholesky(make_spd(d, 92, 0.05, 0.5))
+    spl = amh.RobustAdaptiveMetropolis(gamma=0.55, S=S0, eigenvalue_lower_bound=0.05, eigenvalue_upper_bound=0.9)
+    n = 50
+    init = np.random.default_rng(4).normal(size=(d, n)) * 0.1
+    rg, ro = _pair(amh, cuda, oracle, target, spl, n, _seeds(n, 93), init)
+    _assert_same_state(rg, ro, S=True)
+    for k, wu, spl_ in [(7, True, 7), (5, False, 2), (24, True, 5)]:
+        rg.steps(k, warmup=wu, steps_per_launch=spl_)
+        ro.steps(k, warmup=wu)
+        _assert_same_state(rg, ro, S=True)
+    og, ag, sg = rg.sample(9, discard_initial=10, thinning=2, num_warmup=50)
+    oo, ao, so = ro.sample(9, discard_initial=10, thinning=2, num_warmup=50)
+    assert np.array_equal(og, oo) and np.array_equal(ag, ao) and np.array_equal(sg["mean"], so["mean"])
+    _assert_same_state(rg, ro, S=True)

@@ -4,6 +4,7 @@
  *
  *   amh_c_driver [d=32] [nchains=65536] [launches=5] [mcmc_steps_per_launch=20] [warmup_launches=3] [events=1]
  *   events=0 leaves the library's CUDA-event timing off and reports host wall time around the synchronised loop
+ *   [sampler=rw|ram|ramwarm]  ram = RobustAdaptiveMetropolis sampling steps, ramwarm = warm-up (adapting) steps
  *
  * Build: gcc -O2 -o amh_c_driver amh_c_driver.c -I../../include -L../../advancedmh.jl_b200 -lamh_b200 -lm \
  *            -Wl,-rpath,'$ORIGIN/../../advancedmh.jl_b200'
@@ -41,6 +42,8 @@ int main(int argc, char** argv) {
     const int spl = argc > 4 ? atoi(argv[4]) : 20;
     const int warm = argc > 5 ? atoi(argv[5]) : 3;
     const int events = argc > 6 ? atoi(argv[6]) : 1;
+    const char* smp = argc > 7 ? argv[7] : "rw";
+    const int is_ram = strncmp(smp, "ram", 3) == 0, ram_warm = strcmp(smp, "ramwarm") == 0;
     /* Sigma = G G' / d + diag(1..) : some SPD matrix with a spread spectrum */
     double* G = malloc(sizeof(double) * d * d), *S = malloc(sizeof(double) * d * d), *C = malloc(sizeof(double) * d * d);
     double* Ci = malloc(sizeof(double) * d * d), *L = malloc(sizeof(double) * d * d);
@@ -79,17 +82,21 @@ int main(int argc, char** argv) {
     CHECK(amh_target_create(ctx, AMH_TARGET_MVNORMAL, d, blob, 1 + d + nt, &tg));
     amh_sampler_desc desc; memset(&desc, 0, sizeof(desc));
     desc.kind = AMH_SAMPLER_RW; desc.dim = d; desc.symmetric = 0; desc.cov_kind = AMH_COV_FULL; desc.scale = scale;
+    if (is_ram) {
+        desc.kind = AMH_SAMPLER_RAM; desc.scale = NULL; desc.ram_alpha = 0.234; desc.ram_gamma = 0.6;
+        desc.ram_eig_lo = 0.0; desc.ram_eig_hi = INFINITY;
+    }
     CHECK(amh_sampler_create(ctx, &desc, &sp));
     unsigned long long* seeds = malloc(sizeof(unsigned long long) * n);
     for (long long i = 0; i < n; ++i) { urand(); seeds[i] = s_rng; }
     CHECK(amh_run_create(ctx, tg, sp, n, 0, (const uint64_t*)seeds, NULL, 0, &run));
-    for (int i = 0; i < warm; ++i) CHECK(amh_run_steps(run, spl, 0, spl));
+    for (int i = 0; i < warm; ++i) CHECK(amh_run_steps(run, spl, ram_warm, spl));
     CHECK(amh_run_sync(run));
     double ms = 0; int64_t nl = launches;
     if (events) CHECK(amh_run_kernel_time_ms(run, 1, &ms, &nl));
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
-    for (int i = 0; i < launches; ++i) CHECK(amh_run_steps(run, spl, 0, spl));
+    for (int i = 0; i < launches; ++i) CHECK(amh_run_steps(run, spl, ram_warm, spl));
     CHECK(amh_run_sync(run));
     clock_gettime(CLOCK_MONOTONIC, &t1);
     const double wall_ms = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
