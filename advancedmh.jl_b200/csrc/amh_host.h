@@ -99,6 +99,9 @@ int launch_mh(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 bool mh_tc_eligible(const amh_run& r);        /* K1T: both mat-vecs on the FP64 tensor cores */
 int launch_mh_tc(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_mala(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
+/* K3L: MALA on the many-row logistic target as two chained DMMA GEMMs (amh_launch_mala_logistic.cu) */
+bool mala_logistic_eligible(const amh_run& r);
+int launch_mala_logistic(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_ram(amh_run& r, int nsteps, bool warmup, const amhd::SaveArgs& sv);
 int launch_stretch(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_init(amh_run& r, int mode);

@@ -9,6 +9,7 @@
  * The many-row logistic-regression configuration (d = 128, 10^4 rows) runs
  * through this kernel's generic instantiation with the scalar per-chain target
  * (TLogistic); its dense tiled variant is the next step of that row. */
+#include <cstdlib>
 #include "amh_params.cuh"
 
 namespace amhh {
@@ -152,6 +153,8 @@ int launch_mala_dim(amh_run& r, int nsteps, const SaveArgs& sv) {
 }
 
 int launch_mala(amh_run& r, int nsteps, const SaveArgs& sv) {
+    static const bool scalar_only = std::getenv("AMH_MALA_PATH") && std::strcmp(std::getenv("AMH_MALA_PATH"), "scalar") == 0;
+    if (!scalar_only && mala_logistic_eligible(r)) return launch_mala_logistic(r, nsteps, sv);
     switch (r.target->kind) {
     case AMH_TARGET_MVNORMAL: return launch_mala_dim<TMvNormal>(r, nsteps, sv);
     case AMH_TARGET_GAUSS_PREC: return launch_mala_dim<TGaussPrec>(r, nsteps, sv);

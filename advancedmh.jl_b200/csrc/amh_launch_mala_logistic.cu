@@ -1,0 +1,369 @@
+/* amh_launch_mala_logistic.cu -- K3L: MALA step (MALA.jl:54-93) on the Bayesian logistic-regression target with
+ * MANY rows (BASELINE config 4: d = 128, 10^4 rows, 16 384 chains): the one place on the hot path where the work
+ * is a real dense contraction, so it runs on the FP64 tensor cores.
+ *
+ * value-and-gradient of the target for 8 chains at a time is two chained GEMMs with a nonlinearity in between
+ * (attention-shaped):
+ *     eta[rows x 8]  = X[rows x d] . C[d x 8]                       GEMM1, K = d
+ *     t = y eta - log1pexp(eta),  r = y - sigmoid(eta)              per (row, chain), contract math
+ *     gg[d x 8]      = X'[d x rows] . r[rows x 8]                   GEMM2, K = rows
+ * A warp owns 8 chains (one DMMA n-tile) for the whole step and streams X in 8-row blocks: per block 32 DMMAs for
+ * GEMM1 (k over d), 2 x (exp, log, 2 divisions) per lane, 32 DMMAs for GEMM2 whose 16 accumulator tiles stay in
+ * registers for all 1250 blocks.  DMMA accumulates k as a sequential IEEE fma chain (tools/ubench/dmma_probe.cu), so
+ * eta and gg are bit-identical to the oracle's row-by-row loops; the log-likelihood is summed as the contract's
+ * 8 interleaved partial sums (one per fragment row) + warp-shuffle tree.
+ *
+ * X blocks (8 KB, contiguous in the row-major design matrix) are pulled into a 4-stage shared-memory ring by the
+ * TMA engine (one cp.async.bulk per padded row, full/empty mbarriers); all warps of the CTA consume the same stage.
+ * Candidate / gradient vectors of the chains live in global memory (L2): a step is ~3 ms of FP64 tensor work, the
+ * 4 KB of per-chain state traffic is noise.
+ */
+#include "amh_params.cuh"
+
+namespace amhh {
+using namespace amhd;
+
+struct MalaLArgs {
+    ChainState st;
+    SaveArgs sv;
+    int nsteps;
+    unsigned long long step0;
+    double sigma, sigma2, drift;
+    const double* Xp;          /* [nblk*8][D] row-major, zero padded */
+    const double* yp;          /* [nblk*8] */
+    long long nrows;
+    int nblk;
+    double inv2tau2, invtau2;
+    double* Xc;                /* [D][pitch] candidate             */
+    double* Gc;                /* [D][pitch] gradient at candidate */
+};
+
+__device__ __forceinline__ unsigned l_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void l_mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(l_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void l_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(l_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void l_mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(l_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void l_mbar_wait(unsigned long long* bar, unsigned phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LWAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LDONE;\n"
+        "bra LWAIT;\n"
+        "LDONE:\n"
+        "}\n" ::"r"(l_smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void l_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(l_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(l_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void l_dmma(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+constexpr int kLStages = 4;
+constexpr int kLPB = 12;       /* row pitch of the per-warp candidate tile  [D][8 chains]: conflict-free B fragments */
+constexpr int kLPR = 12;       /* row pitch of the per-warp residual tile   [8 rows][8 chains]                      */
+
+template <int D>
+__host__ __device__ constexpr int l_stage_doubles() { return 8 * (D + 4) + 8; }          /* 8 padded rows + 8 labels */
+template <int D>
+__host__ __device__ constexpr int l_warp_doubles() { return D * kLPB + 8 * kLPR; }
+template <int D>
+__host__ __device__ constexpr size_t l_smem_bytes(int warps) {
+    return sizeof(double) * ((size_t)kLStages * l_stage_doubles<D>() + (size_t)warps * l_warp_doubles<D>()) + 2 * kLStages * sizeof(unsigned long long);
+}
+
+/* t = y eta - log1pexp(eta) and r = y - sigmoid(eta), sharing exp(-|eta|); same operations as the contract header */
+__device__ __forceinline__ void logistic_terms(double eta, double y, double& t, double& r) {
+    const double ex = amh::exp_(-fabs(eta));             /* in (0,1] */
+    const double w = 1.0 + ex;
+    const double l = (-amh::neglog_normal(w)) + (ex - (w - 1.0)) / w;       /* log_(w) for a normal w in (1,2] */
+    const double l1p = (eta > 0.0 ? eta : 0.0) + l;
+    const double sg0 = 1.0 / (1.0 + ex);
+    const double sg = eta >= 0.0 ? sg0 : ex * sg0;
+    t = y * eta - l1p;
+    r = y - sg;
+}
+
+template <int D>
+__global__ void __launch_bounds__(512)
+mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
+    static_assert(D % 32 == 0 && D <= 128, "D/4 dims per lane part, D/8 noise blocks per part");
+    constexpr int KT1 = D / 4;         /* k-tiles of GEMM1            */
+    constexpr int MT2 = D / 8;         /* m-tiles (features) of GEMM2 */
+    constexpr int XP = D + 4;          /* padded row pitch of a staged X block */
+    constexpr int NPP = D / 8;         /* Philox blocks per lane part (4 parts per chain) */
+    extern __shared__ __align__(16) double lsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    double* stages = lsm;
+    double* Bs = lsm + kLStages * l_stage_doubles<D>() + (size_t)warp * l_warp_doubles<D>();      /* candidate tile [D][8] */
+    double* Rs = Bs + D * kLPB;                                                                     /* residual tile [8][8] */
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(lsm + kLStages * l_stage_doubles<D>() + (size_t)nwarps * l_warp_doubles<D>());
+    unsigned long long* empty = full + kLStages;
+    const long long pitch = a.st.pitch;
+    const int fr = lane >> 2, fc = lane & 3;
+    const int cl = lane & 7, part = lane >> 3;                      /* chain lane / quarter of the dimensions */
+    const long long cbase = ((long long)blockIdx.x * nwarps + warp) * 8;
+    const bool warp_active = cbase < a.st.n;                        /* idle warps still take part in the ring */
+    const long long ch = cbase + cl;
+    const bool active = ch < a.st.n;
+    constexpr unsigned long long B = (unsigned long long)(D / 2 + 1);
+    constexpr unsigned stage_bytes = (unsigned)(8 * D * sizeof(double) + 8 * sizeof(double));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kLStages; ++s) { l_mbar_init(full + s, 1); l_mbar_init(empty + s, nwarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const unsigned long long seed = active ? a.st.seeds[ch] : 0ull;
+    double lp = active ? a.st.lp[ch] : 0.0;
+    unsigned nacc = 0u;
+    unsigned char accepted = active ? a.st.acc[ch] : (unsigned char)0;
+    long long issued = 0, consumed = 0;                             /* X blocks issued / consumed over the whole launch */
+
+    auto issue_block = [&](long long seq) {                         /* thread 0 only */
+        const int blk = (int)(seq % a.nblk), st = (int)(seq % kLStages);
+        double* dst = stages + (size_t)st * l_stage_doubles<D>();
+        l_mbar_expect_tx(full + st, stage_bytes);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) l_bulk_g2s(dst + r * XP, a.Xp + ((size_t)blk * 8 + r) * D, (unsigned)(D * sizeof(double)), full + st);
+        l_bulk_g2s(dst + 8 * XP, a.yp + (size_t)blk * 8, (unsigned)(8 * sizeof(double)), full + st);
+    };
+    const long long total_blocks = (long long)a.nsteps * a.nblk;
+    if (threadIdx.x == 0)
+        for (; issued < kLStages && issued < total_blocks; ++issued) issue_block(issued);
+
+    for (int s = 0; s < a.nsteps; ++s) {
+        const unsigned long long k = a.step0 + (unsigned long long)s + 1ull;
+        /* ---- phase A: candidate = x + (sigma z + drift grad)   (MALA.jl:70 -> proposal.jl:49-56) ---- */
+        double e = 0.0;
+        {
+            double z[2 * NPP];
+            const unsigned long long b0 = k * B + (unsigned long long)(NPP * part);
+            if constexpr (NPP > 8) {
+                noise_group<8, false>(seed, b0, 0ull, z, e);
+                noise_group<NPP - 8, true>(seed, b0 + 8, k * B + (unsigned long long)(D / 2), z + 16, e);
+            } else {
+                noise_group<NPP, true>(seed, b0, k * B + (unsigned long long)(D / 2), z, e);
+            }
+#pragma unroll
+            for (int i = 0; i < 2 * NPP; ++i) {
+                const int j = 2 * NPP * part + i;
+                const long long o = (long long)j * pitch + ch;
+                double c = 0.0;
+                if (active) {
+                    c = a.st.X[o] + (a.sigma * z[i] + a.drift * a.st.G[o]);
+                    a.Xc[o] = c;
+                }
+                Bs[j * kLPB + cl] = c;
+            }
+        }
+        __syncwarp();
+        /* ---- phase B: stream X; eta = X c, residuals, gg = X' r ---- */
+        double gg[MT2][2];
+#pragma unroll
+        for (int m = 0; m < MT2; ++m) { gg[m][0] = 0.0; gg[m][1] = 0.0; }
+        double ll0 = 0.0, ll1 = 0.0;
+        for (int blk = 0; blk < a.nblk; ++blk, ++consumed) {
+            const int st = (int)(consumed % kLStages);
+            const unsigned ph = (unsigned)((consumed / kLStages) & 1);
+            l_mbar_wait(full + st, ph);
+            const double* Xs = stages + (size_t)st * l_stage_doubles<D>();
+            if (warp_active) {
+                double e0 = 0.0, e1 = 0.0;
+#pragma unroll
+                for (int kb = 0; kb < KT1; ++kb) {
+                    const double af = Xs[fr * XP + 4 * kb + fc];
+                    const double bf = Bs[(4 * kb + fc) * kLPB + fr];
+                    l_dmma(e0, e1, af, bf);
+                }
+                const int row = blk * 8 + fr;
+                const double yi = Xs[8 * XP + fr];
+                double t0, r0, t1, r1;
+                logistic_terms(e0, yi, t0, r0);
+                logistic_terms(e1, yi, t1, r1);
+                if (row < a.nrows) { ll0 = ll0 + t0; ll1 = ll1 + t1; }
+                *reinterpret_cast<double2*>(Rs + fr * kLPR + 2 * fc) = make_double2(r0, r1);
+                __syncwarp();
+                const double rb0 = Rs[fc * kLPR + fr];                 /* B fragment: r[k = row fc][n = chain fr]     */
+                const double rb1 = Rs[(4 + fc) * kLPR + fr];           /* second k-tile: rows 4..7                    */
+#pragma unroll
+                for (int m = 0; m < MT2; ++m) {
+                    const double a0 = Xs[fc * XP + 8 * m + fr];        /* A fragment: X'[m = feature 8m+fr][k = row fc] */
+                    const double a1 = Xs[(4 + fc) * XP + 8 * m + fr];
+                    l_dmma(gg[m][0], gg[m][1], a0, rb0);
+                    l_dmma(gg[m][0], gg[m][1], a1, rb1);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) l_mbar_arrive(empty + st);
+            /* refill: the CTA's producer thread re-arms the stage of the PREVIOUS block once every warp released it */
+            if (threadIdx.x == 0 && consumed >= 1 && issued < total_blocks) {
+                const long long prev = consumed - 1;
+                const int pst = (int)(prev % kLStages);
+                l_mbar_wait(empty + pst, (unsigned)((prev / kLStages) & 1));
+                issue_block(issued);
+                ++issued;
+            }
+        }
+        /* log-likelihood: tree over the 8 fragment rows (lane bits 2..4) */
+#pragma unroll
+        for (int m = 4; m <= 16; m <<= 1) {
+            ll0 = ll0 + __shfl_xor_sync(0xffffffffu, ll0, m);
+            ll1 = ll1 + __shfl_xor_sync(0xffffffffu, ll1, m);
+        }
+        /* gradient at the candidate in fragment layout: features 8m+fr, chains cbase + 2fc + {0,1} */
+        if (warp_active) {
+#pragma unroll
+            for (int m = 0; m < MT2; ++m) {
+                const int j = 8 * m + fr;
+                const double2 cc = *reinterpret_cast<const double2*>(Bs + j * kLPB + 2 * fc);
+                const double g0 = gg[m][0] - cc.x * a.invtau2;
+                const double g1 = gg[m][1] - cc.y * a.invtau2;
+                *reinterpret_cast<double2*>(a.Gc + (long long)j * pitch + cbase + 2 * fc) = make_double2(g0, g1);
+            }
+        }
+        __syncwarp();
+        /* ---- phase C: per chain (4 lanes carry the same chain): lp, Hastings terms, accept ---- */
+        const double llsel0 = __shfl_sync(0xffffffffu, ll0, cl >> 1);
+        const double llsel1 = __shfl_sync(0xffffffffu, ll1, cl >> 1);
+        const double ll = (cl & 1) ? llsel1 : llsel0;
+        double q = 0.0, A = 0.0, Bq = 0.0;
+        if (active) {
+            for (int j = 0; j < D; ++j) {
+                const long long o = (long long)j * pitch + ch;
+                const double c = Bs[j * kLPB + cl];
+                const double xi = a.st.X[o], gi = a.st.G[o], gci = __ldcg(a.Gc + o);
+                q = (j == 0) ? c * c : fma(c, c, q);
+                const double da = (xi - c) - a.drift * gci;
+                const double db = (c - xi) - a.drift * gi;
+                A = (j == 0) ? da * da : fma(da, da, A);
+                Bq = (j == 0) ? db * db : fma(db, db, Bq);
+            }
+        }
+        const double lp_c = ll - q * a.inv2tau2;
+        const double logratio = (-0.5 * (A / a.sigma2)) - (-0.5 * (Bq / a.sigma2));
+        const double loga = (lp_c - lp) + logratio;
+        if (active && -e < loga) {                                   /* MALA.jl:86 */
+#pragma unroll 4
+            for (int i = 0; i < 2 * NPP; ++i) {
+                const int j = 2 * NPP * part + i;
+                const long long o = (long long)j * pitch + ch;
+                a.st.X[o] = Bs[j * kLPB + cl];
+                a.st.G[o] = __ldcg(a.Gc + o);
+            }
+            lp = lp_c;
+            accepted = 1;
+            ++nacc;
+        } else {
+            accepted = 0;
+        }
+        __syncwarp();
+    }
+
+    if (!active) return;
+    if (a.sv.out || a.sv.sum) {
+        for (int i = 0; i < 2 * NPP; ++i) {
+            const int j = 2 * NPP * part + i;
+            const long long o = (long long)j * pitch + ch;
+            const double v = a.st.X[o];
+            if (a.sv.out) a.sv.out[(long long)j * a.sv.out_pitch + ch] = v;
+            if (a.sv.sum) {
+                a.sv.sum[o] = a.sv.sum[o] + v;
+                a.sv.sumsq[o] = fma(v, v, a.sv.sumsq[o]);
+            }
+        }
+    }
+    if (part == 0) {
+        a.st.lp[ch] = lp;
+        a.st.nacc[ch] = a.st.nacc[ch] + (unsigned long long)nacc;
+        a.st.acc[ch] = accepted;
+        if (a.sv.out) a.sv.out[(long long)D * a.sv.out_pitch + ch] = lp;
+        if (a.sv.acc_out) a.sv.acc_out[ch] = accepted;
+    }
+}
+
+bool mala_logistic_eligible(const amh_run& r) {
+    const int d = r.dim;
+    return r.sampler->d.kind == AMH_SAMPLER_MALA && r.target->kind == AMH_TARGET_LOGISTIC && (d == 32 || d == 64 || d == 128) &&
+           r.target->ndata >= 64 && r.pitch % 32 == 0;
+}
+
+template <int D>
+static int launch_mala_logistic_t(amh_run& r, int nsteps, const SaveArgs& sv) {
+    const amh_sampler& s = *r.sampler;
+    const amh_target& t = *r.target;
+    const long long n = t.ndata;
+    const int nblk = (int)((n + 7) / 8);
+    const size_t np = (size_t)r.pitch;
+    if (!r.scratch) {
+        /* [Xpad | ypad | Xc | Gc] */
+        const size_t nx = (size_t)nblk * 8 * D, ny = (size_t)nblk * 8;
+        const int rca = dmalloc(r.ctx, &r.scratch, sizeof(double) * (nx + ny + 2 * (size_t)D * np));
+        if (rca) return rca;
+        double* base = (double*)r.scratch;
+        AMH_CUDA_TRY(cudaMemsetAsync(base, 0, sizeof(double) * (nx + ny + 2 * (size_t)D * np), r.ctx->stream));
+        AMH_CUDA_TRY(cudaMemcpyAsync(base, t.dblob + 1, sizeof(double) * (size_t)n * D, cudaMemcpyDeviceToDevice, r.ctx->stream));
+        AMH_CUDA_TRY(cudaMemcpyAsync(base + nx, t.dblob + 1 + (size_t)n * D, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, r.ctx->stream));
+    }
+    MalaLArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.st = chain_state(r);
+    a.sv = sv;
+    a.nsteps = nsteps;
+    a.step0 = (unsigned long long)r.step;
+    a.sigma = s.mala_sigma; a.sigma2 = s.d.mala_sigma2; a.drift = s.d.mala_drift;
+    double* base = (double*)r.scratch;
+    a.Xp = base;
+    a.yp = base + (size_t)nblk * 8 * D;
+    a.Xc = base + (size_t)nblk * 8 * D + (size_t)nblk * 8;
+    a.Gc = a.Xc + (size_t)D * np;
+    a.nrows = n;
+    a.nblk = nblk;
+    a.inv2tau2 = t.inv2tau2; a.invtau2 = t.invtau2;
+    /* warps per CTA: as many 8-chain groups as fit twice per SM beside the X ring; the grid should fill the SMs evenly */
+    const long long groups = (r.n + 7) / 8;
+    int warps = 8;
+    {
+        const int sms = r.ctx->sm_count;
+        int best = 8; double best_eff = 0;
+        for (int w = 4; w <= 8; ++w) {
+            if (2 * (l_smem_bytes<D>(w) + 1024) > 227 * 1024) continue;
+            const long long ctas = (groups + w - 1) / w;
+            const long long waves = (ctas + 2LL * sms - 1) / (2LL * sms);
+            const double eff = (double)groups / ((double)waves * 2.0 * sms * w);
+            if (eff > best_eff + 1e-9) { best_eff = eff; best = w; }
+        }
+        warps = best;
+    }
+    const size_t smem = l_smem_bytes<D>(warps);
+    auto kern = mala_logistic_kernel<D>;
+    AMH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((groups + warps - 1) / warps);
+    kern<<<grid, 32 * warps, smem, r.ctx->stream>>>(a);
+    AMH_CUDA_TRY(cudaGetLastError());
+    r.launches += 1;
+    r.pending_launches += 1;
+    return AMH_OK;
+}
+
+int launch_mala_logistic(amh_run& r, int nsteps, const SaveArgs& sv) {
+    switch (r.dim) {
+    case 32: return launch_mala_logistic_t<32>(r, nsteps, sv);
+    case 64: return launch_mala_logistic_t<64>(r, nsteps, sv);
+    case 128: return launch_mala_logistic_t<128>(r, nsteps, sv);
+    }
+    return fail(AMH_ERR_INVALID, "tiled logistic MALA: unsupported dimension");
+}
+
+}  // namespace amhh

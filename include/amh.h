@@ -52,7 +52,8 @@ extern "C" {
                                     (test/RobustAdaptiveMetropolis.jl:1-9 `Gaussian`)     */
 #define AMH_TARGET_ROSENBROCK  3 /* blob=[a, b, s]; lp = -sum_{i<d-1}[b(x_{i+1}-x_i^2)^2+(a-x_i)^2]/s */
 #define AMH_TARGET_LOGISTIC    4 /* blob=[tau, X[n*d] row-major, y[n]];
-                                    lp = sum_i[y_i eta_i - log1pexp(eta_i)] - |beta|^2/(2 tau^2)  */
+                                    lp = sum_i[y_i eta_i - log1pexp(eta_i)] - |beta|^2/(2 tau^2);
+                                    the row sum runs as 8 interleaved partial sums + a fixed tree (contract)  */
 #define AMH_TARGET_GAUSS_PREC  5 /* blob=A[d*d] row-major symmetric; lp = -x'Ax/2, grad = -Ax
                                     (test/runtests.jl:335-347 `TheNormalLogDensity`)      */
 #define AMH_TARGET_NIG_TOY     6 /* theta=(s,m); blob=[alpha, beta, y_1..y_n]; dim==2;

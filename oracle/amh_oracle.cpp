@@ -222,19 +222,23 @@ struct Target {
             /* blob = [tau, X[n*d], y[n]] */
             const double* X = &blob[1];
             const double* y = &blob[1 + ndata * d];
-            double ll = 0.0;
+            /* log-likelihood: 8 interleaved partial sums (rows i mod 8, each in ascending order) combined by a fixed
+             * tree -- the order of the tiled device kernel (8-row DMMA tiles + warp-shuffle butterfly); the
+             * reference's `sum` over rows has no defined order of its own (pairwise in Julia's Base). */
+            double llp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             std::vector<double> gg;
             if (g) gg.assign(d, 0.0);
             for (int64_t i = 0; i < ndata; ++i) {
                 const double* xi = X + i * d;
                 double eta = xi[0] * x[0];
                 for (int j = 1; j < d; ++j) eta = fma(xi[j], x[j], eta);
-                ll = ll + (y[i] * eta - amh::log1pexp(eta));
+                llp[i & 7] = llp[i & 7] + (y[i] * eta - amh::log1pexp(eta));
                 if (g) {
                     const double r = y[i] - amh::sigmoid(eta);
                     for (int j = 0; j < d; ++j) gg[j] = fma(xi[j], r, gg[j]);
                 }
             }
+            const double ll = ((llp[0] + llp[1]) + (llp[2] + llp[3])) + ((llp[4] + llp[5]) + (llp[6] + llp[7]));
             double q = x[0] * x[0];
             for (int j = 1; j < d; ++j) q = fma(x[j], x[j], q);
             lp = ll - q * inv2tau2;

@@ -79,12 +79,12 @@ def main():
         t = amh.LogisticRegressionTarget(X, y, tau=10.0)
         s2 = 2e-3
         s = amh.MALA(lambda g: amh.MvNormal((s2 / 2) * g, s2 * amh.I))
-        for n in (1024,):
+        for n in (16384,):
             run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), n, seeds(n, 3), np.zeros((d, n)))
-            ms = timed(run, 2, spl=1, reps=1, warm=1)
+            ms = timed(run, 4, spl=2, reps=2, warm=1)
             st = run.state()
-            report(f"C4 MALA logistic d=128 rows=10k n={n}", n * 2, ms, 2 * (2 * d + 1) * 8,
-                   f"accept={st['naccept'].sum() / (n * st['step']):.3f}  {5.12e6 * n * 2 / (ms * 1e-3) / 1e12:.2f} TFLOP/s fp64")
+            report(f"C4 MALA logistic d=128 rows=10k n={n}", n * 4, ms, 2 * (2 * d + 1) * 8,
+                   f"accept={st['naccept'].sum() / (n * st['step']):.3f}  {5.12e6 * n * 4 / (ms * 1e-3) / 1e12:.2f} TFLOP/s fp64")
             run.close()
     if "c5" in which:
         d = 64
