@@ -33,6 +33,7 @@ struct MalaLArgs {
     const double* yp;          /* [nblk*8] */
     long long nrows;
     int nblk;
+    int nst;                   /* stages of the X ring (even) */
     double inv2tau2, invtau2;
     double* Xc;                /* [D][pitch] candidate             */
     double* Gc;                /* [D][pitch] gradient at candidate */
@@ -68,17 +69,16 @@ __device__ __forceinline__ void l_dmma(double& d0, double& d1, double a, double 
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-constexpr int kLStages = 4;
-constexpr int kLPB = 12;       /* row pitch of the per-warp candidate tile  [D][8 chains]: conflict-free B fragments */
-constexpr int kLPR = 12;       /* row pitch of the per-warp residual tile   [8 rows][8 chains]                      */
+constexpr int kLPB = 8;        /* row pitch of the per-warp candidate tile  [D][8 chains] (2-way conflict on B fragments; 12 would be free) */
+constexpr int kLPR = 12;       /* row pitch of the per-warp residual tile   [16 rows][8 chains]                     */
 
 template <int D>
 __host__ __device__ constexpr int l_stage_doubles() { return 8 * (D + 4) + 8; }          /* 8 padded rows + 8 labels */
 template <int D>
-__host__ __device__ constexpr int l_warp_doubles() { return D * kLPB + 8 * kLPR; }
+__host__ __device__ constexpr int l_warp_doubles() { return D * kLPB + 16 * kLPR; }
 template <int D>
-__host__ __device__ constexpr size_t l_smem_bytes(int warps) {
-    return sizeof(double) * ((size_t)kLStages * l_stage_doubles<D>() + (size_t)warps * l_warp_doubles<D>()) + 2 * kLStages * sizeof(unsigned long long);
+__host__ __device__ constexpr size_t l_smem_bytes(int warps, int nst) {
+    return sizeof(double) * ((size_t)nst * l_stage_doubles<D>() + (size_t)warps * l_warp_doubles<D>()) + 2 * (size_t)nst * sizeof(unsigned long long);
 }
 
 /* t = y eta - log1pexp(eta) and r = y - sigmoid(eta), sharing exp(-|eta|); same operations as the contract header */
@@ -103,11 +103,12 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
     constexpr int NPP = D / 8;         /* Philox blocks per lane part (4 parts per chain) */
     extern __shared__ __align__(16) double lsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nwarps = blockDim.x >> 5;
+    const int nwarps = (blockDim.x >> 5) - 1;                       /* consumer warps; the last warp is the TMA producer */
+    const int kLStages = a.nst;
     double* stages = lsm;
-    double* Bs = lsm + kLStages * l_stage_doubles<D>() + (size_t)warp * l_warp_doubles<D>();      /* candidate tile [D][8] */
-    double* Rs = Bs + D * kLPB;                                                                     /* residual tile [8][8] */
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(lsm + kLStages * l_stage_doubles<D>() + (size_t)nwarps * l_warp_doubles<D>());
+    double* Bs = lsm + (size_t)kLStages * l_stage_doubles<D>() + (size_t)(warp < nwarps ? warp : 0) * l_warp_doubles<D>();   /* candidate tile [D][8] */
+    double* Rs = Bs + D * kLPB;                                                                     /* residual tile [16][8] */
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(lsm + (size_t)kLStages * l_stage_doubles<D>() + (size_t)nwarps * l_warp_doubles<D>());
     unsigned long long* empty = full + kLStages;
     const long long pitch = a.st.pitch;
     const int fr = lane >> 2, fc = lane & 3;
@@ -125,23 +126,27 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
     }
     __syncthreads();
 
+    const long long total_blocks = (long long)a.nsteps * a.nblk;
+    if (warp == nwarps) {
+        /* ---- producer warp: keeps the X ring full; one elected lane drives the TMA engine ---- */
+        if (lane == 0) {
+            for (long long seq = 0; seq < total_blocks; ++seq) {
+                const int blk = (int)(seq % a.nblk), st = (int)(seq % kLStages);
+                if (seq >= kLStages) l_mbar_wait(empty + st, (unsigned)(((seq / kLStages) - 1) & 1));
+                double* dst = stages + (size_t)st * l_stage_doubles<D>();
+                l_mbar_expect_tx(full + st, stage_bytes);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) l_bulk_g2s(dst + r * XP, a.Xp + ((size_t)blk * 8 + r) * D, (unsigned)(D * sizeof(double)), full + st);
+                l_bulk_g2s(dst + 8 * XP, a.yp + (size_t)blk * 8, (unsigned)(8 * sizeof(double)), full + st);
+            }
+        }
+        return;
+    }
     const unsigned long long seed = active ? a.st.seeds[ch] : 0ull;
     double lp = active ? a.st.lp[ch] : 0.0;
     unsigned nacc = 0u;
     unsigned char accepted = active ? a.st.acc[ch] : (unsigned char)0;
-    long long issued = 0, consumed = 0;                             /* X blocks issued / consumed over the whole launch */
-
-    auto issue_block = [&](long long seq) {                         /* thread 0 only */
-        const int blk = (int)(seq % a.nblk), st = (int)(seq % kLStages);
-        double* dst = stages + (size_t)st * l_stage_doubles<D>();
-        l_mbar_expect_tx(full + st, stage_bytes);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) l_bulk_g2s(dst + r * XP, a.Xp + ((size_t)blk * 8 + r) * D, (unsigned)(D * sizeof(double)), full + st);
-        l_bulk_g2s(dst + 8 * XP, a.yp + (size_t)blk * 8, (unsigned)(8 * sizeof(double)), full + st);
-    };
-    const long long total_blocks = (long long)a.nsteps * a.nblk;
-    if (threadIdx.x == 0)
-        for (; issued < kLStages && issued < total_blocks; ++issued) issue_block(issued);
+    long long consumed = 0;                                         /* X blocks consumed over the whole launch */
 
     for (int s = 0; s < a.nsteps; ++s) {
         const unsigned long long k = a.step0 + (unsigned long long)s + 1ull;
@@ -174,47 +179,53 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
 #pragma unroll
         for (int m = 0; m < MT2; ++m) { gg[m][0] = 0.0; gg[m][1] = 0.0; }
         double ll0 = 0.0, ll1 = 0.0;
-        for (int blk = 0; blk < a.nblk; ++blk, ++consumed) {
-            const int st = (int)(consumed % kLStages);
-            const unsigned ph = (unsigned)((consumed / kLStages) & 1);
-            l_mbar_wait(full + st, ph);
-            const double* Xs = stages + (size_t)st * l_stage_doubles<D>();
+        for (int blk = 0; blk < a.nblk; blk += 2, consumed += 2) {
+            /* two 8-row blocks per iteration: their GEMM1 chains (32 dependent DMMAs each) interleave */
+            const int st0 = (int)(consumed % kLStages), st1 = (int)((consumed + 1) % kLStages);
+            l_mbar_wait(full + st0, (unsigned)((consumed / kLStages) & 1));
+            l_mbar_wait(full + st1, (unsigned)(((consumed + 1) / kLStages) & 1));
+            const double* Xs0 = stages + (size_t)st0 * l_stage_doubles<D>();
+            const double* Xs1 = stages + (size_t)st1 * l_stage_doubles<D>();
             if (warp_active) {
-                double e0 = 0.0, e1 = 0.0;
+                double e00 = 0.0, e01 = 0.0, e10 = 0.0, e11 = 0.0;
 #pragma unroll
                 for (int kb = 0; kb < KT1; ++kb) {
-                    const double af = Xs[fr * XP + 4 * kb + fc];
                     const double bf = Bs[(4 * kb + fc) * kLPB + fr];
-                    l_dmma(e0, e1, af, bf);
+                    const double af0 = Xs0[fr * XP + 4 * kb + fc];
+                    const double af1 = Xs1[fr * XP + 4 * kb + fc];
+                    l_dmma(e00, e01, af0, bf);
+                    l_dmma(e10, e11, af1, bf);
                 }
-                const int row = blk * 8 + fr;
-                const double yi = Xs[8 * XP + fr];
-                double t0, r0, t1, r1;
-                logistic_terms(e0, yi, t0, r0);
-                logistic_terms(e1, yi, t1, r1);
-                if (row < a.nrows) { ll0 = ll0 + t0; ll1 = ll1 + t1; }
-                *reinterpret_cast<double2*>(Rs + fr * kLPR + 2 * fc) = make_double2(r0, r1);
+                const int row0 = blk * 8 + fr;
+                const double y0 = Xs0[8 * XP + fr], y1 = Xs1[8 * XP + fr];
+                double t00, r00, t01, r01, t10, r10, t11, r11;
+                logistic_terms(e00, y0, t00, r00);
+                logistic_terms(e01, y0, t01, r01);
+                logistic_terms(e10, y1, t10, r10);
+                logistic_terms(e11, y1, t11, r11);
+                if (row0 < a.nrows) { ll0 = ll0 + t00; ll1 = ll1 + t01; }
+                if (row0 + 8 < a.nrows) { ll0 = ll0 + t10; ll1 = ll1 + t11; }
+                *reinterpret_cast<double2*>(Rs + fr * kLPR + 2 * fc) = make_double2(r00, r01);
+                *reinterpret_cast<double2*>(Rs + (8 + fr) * kLPR + 2 * fc) = make_double2(r10, r11);
                 __syncwarp();
-                const double rb0 = Rs[fc * kLPR + fr];                 /* B fragment: r[k = row fc][n = chain fr]     */
-                const double rb1 = Rs[(4 + fc) * kLPR + fr];           /* second k-tile: rows 4..7                    */
+                const double rb0 = Rs[fc * kLPR + fr];                 /* B fragments: r[k = row][n = chain fr], 4 k-tiles */
+                const double rb1 = Rs[(4 + fc) * kLPR + fr];
+                const double rb2 = Rs[(8 + fc) * kLPR + fr];
+                const double rb3 = Rs[(12 + fc) * kLPR + fr];
 #pragma unroll
                 for (int m = 0; m < MT2; ++m) {
-                    const double a0 = Xs[fc * XP + 8 * m + fr];        /* A fragment: X'[m = feature 8m+fr][k = row fc] */
-                    const double a1 = Xs[(4 + fc) * XP + 8 * m + fr];
+                    const double a0 = Xs0[fc * XP + 8 * m + fr];       /* A fragments: X'[m = feature 8m+fr][k = row] */
+                    const double a1 = Xs0[(4 + fc) * XP + 8 * m + fr];
+                    const double a2 = Xs1[fc * XP + 8 * m + fr];
+                    const double a3 = Xs1[(4 + fc) * XP + 8 * m + fr];
                     l_dmma(gg[m][0], gg[m][1], a0, rb0);
                     l_dmma(gg[m][0], gg[m][1], a1, rb1);
+                    l_dmma(gg[m][0], gg[m][1], a2, rb2);
+                    l_dmma(gg[m][0], gg[m][1], a3, rb3);
                 }
             }
             __syncwarp();
-            if (lane == 0) l_mbar_arrive(empty + st);
-            /* refill: the CTA's producer thread re-arms the stage of the PREVIOUS block once every warp released it */
-            if (threadIdx.x == 0 && consumed >= 1 && issued < total_blocks) {
-                const long long prev = consumed - 1;
-                const int pst = (int)(prev % kLStages);
-                l_mbar_wait(empty + pst, (unsigned)((prev / kLStages) & 1));
-                issue_block(issued);
-                ++issued;
-            }
+            if (lane == 0) { l_mbar_arrive(empty + st0); l_mbar_arrive(empty + st1); }
         }
         /* log-likelihood: tree over the 8 fragment rows (lane bits 2..4) */
 #pragma unroll
@@ -304,7 +315,7 @@ static int launch_mala_logistic_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     const amh_sampler& s = *r.sampler;
     const amh_target& t = *r.target;
     const long long n = t.ndata;
-    const int nblk = (int)((n + 7) / 8);
+    const int nblk = (int)((n + 15) / 16) * 2;          /* 8-row blocks, consumed in pairs */
     const size_t np = (size_t)r.pitch;
     if (!r.scratch) {
         /* [Xpad | ypad | Xc | Gc] */
@@ -331,26 +342,29 @@ static int launch_mala_logistic_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     a.nrows = n;
     a.nblk = nblk;
     a.inv2tau2 = t.inv2tau2; a.invtau2 = t.invtau2;
-    /* warps per CTA: as many 8-chain groups as fit twice per SM beside the X ring; the grid should fill the SMs evenly */
+    /* one CTA per SM: W consumer warps (8 chains each) + 1 producer warp; W chosen so that the grid fills the SMs evenly,
+     * the rest of the shared memory becomes X-ring stages (prefetch depth hides the TMA round trip) */
     const long long groups = (r.n + 7) / 8;
-    int warps = 8;
+    const int sms = r.ctx->sm_count;
+    int warps = 14;
     {
-        const int sms = r.ctx->sm_count;
-        int best = 8; double best_eff = 0;
-        for (int w = 4; w <= 8; ++w) {
-            if (2 * (l_smem_bytes<D>(w) + 1024) > 227 * 1024) continue;
+        double best_eff = 0;
+        for (int w = 8; w <= 15; ++w) {
+            if (l_smem_bytes<D>(w, 4) + 1024 > 227 * 1024) continue;
             const long long ctas = (groups + w - 1) / w;
-            const long long waves = (ctas + 2LL * sms - 1) / (2LL * sms);
-            const double eff = (double)groups / ((double)waves * 2.0 * sms * w);
-            if (eff > best_eff + 1e-9) { best_eff = eff; best = w; }
+            const long long waves = (ctas + sms - 1) / sms;
+            const double eff = (double)groups / ((double)waves * sms * w);
+            if (eff > best_eff + 1e-9) { best_eff = eff; warps = w; }
         }
-        warps = best;
     }
-    const size_t smem = l_smem_bytes<D>(warps);
+    int nst = 4;
+    while (nst + 2 <= 16 && l_smem_bytes<D>(warps, nst + 2) + 1024 <= 227 * 1024) nst += 2;
+    a.nst = nst;
+    const size_t smem = l_smem_bytes<D>(warps, nst);
     auto kern = mala_logistic_kernel<D>;
     AMH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((groups + warps - 1) / warps);
-    kern<<<grid, 32 * warps, smem, r.ctx->stream>>>(a);
+    kern<<<grid, 32 * (warps + 1), smem, r.ctx->stream>>>(a);
     AMH_CUDA_TRY(cudaGetLastError());
     r.launches += 1;
     r.pending_launches += 1;
