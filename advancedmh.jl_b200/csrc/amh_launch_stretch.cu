@@ -133,6 +133,112 @@ stretch_sweep_kernel(const __grid_constant__ StretchArgs a, const __grid_constan
     }
 }
 
+/* ---------------------------------------------------------------------------
+ * K2F: same exact sequential semantics, for ensembles of up to WPT * BLOCK walkers.
+ *   - everything that does not depend on the walker positions (partner index, stretch factor z, (d-1) log z, the
+ *     exponential) is computed for the whole sweep in one parallel phase and kept in registers;
+ *   - `done[i]` stores the wavefront in which walker i was finished, so "partner available" is
+ *     done[idx] != 0 && done[idx] < wavefront and ONE barrier per wavefront (the __syncthreads_or that also
+ *     detects completion) orders both the flags and the walker data. */
+template <int DMAX, class T, int BLOCK, int WPT>
+__global__ void __launch_bounds__(BLOCK)
+stretch_sweep_fast_kernel(const __grid_constant__ StretchArgs a, const __grid_constant__ typename T::template Params<DMAX> tp) {
+    using D = Dim<DMAX>;
+    constexpr int CAP = D::cap;
+    constexpr int UNR = D::unr;
+    extern __shared__ __align__(16) double smem_d[];
+    const int nw = (int)a.n_walkers;
+    double* zf = smem_d;                                                     /* [nw] stretch factor z          */
+    double* am = zf + nw;                                                    /* [nw] (d-1) log z               */
+    double* ex = am + nw;                                                    /* [nw] exponential draw          */
+    int* partner = reinterpret_cast<int*>(ex + nw);                          /* [nw]                           */
+    unsigned short* done = reinterpret_cast<unsigned short*>(partner + nw);  /* [nw] wavefront of completion   */
+    const int tid = threadIdx.x;
+    const long long en = blockIdx.x;
+    const long long base = en * nw;
+    const int d = D::fixed ? DMAX : a.d;
+    const int top = D::fixed ? DMAX : d;
+    const long long pitch = a.st.pitch;
+    const unsigned long long seed = a.st.seeds[en];
+    double* Xold = a.st.X;  double* lpold = a.st.lp;
+    double* Xnew = a.X2;    double* lpnew = a.lp2;
+
+    for (int s = 0; s < a.nsteps; ++s) {
+        const unsigned long long k = a.step0 + (unsigned long long)s + 1ull;
+        for (int i = tid; i < nw; i += BLOCK) {
+            const unsigned long long blk = (k * (unsigned long long)nw + (unsigned long long)i) * 2ull;
+            const amh::Block b0 = amh::stream_block(seed, blk, 0u);
+            const amh::Block b1 = amh::stream_block(seed, blk + 1ull, 0u);
+            /* idx = mod1(i + rand(1:(n-1)), n)  (emcee.jl:52) */
+            const long long rr = (long long)amh::bounded(b0.v[0], b0.v[1], (unsigned long long)(nw - 1));
+            partner[i] = (int)((i + rr + 1) % nw);
+            const double u = amh::u01(b0.v[2], b0.v[3]);
+            const double tt = (a.a - 1.0) * u + 1.0;
+            const double z = (tt * tt) / a.a;
+            zf[i] = z;
+            am[i] = (double)(d - 1) * amh::log_(z);
+            ex[i] = amh::exponential(b1.v[0], b1.v[1]);
+            done[i] = 0;
+        }
+        __syncthreads();
+        unsigned wf = 1;
+        int pending;
+        do {
+            pending = 0;
+#pragma unroll 1
+            for (int i = tid; i < nw; i += BLOCK) {
+                if (done[i]) continue;
+                const int idx = partner[i];
+                const unsigned dn = done[idx];
+                const bool ready = (idx > i) || (dn != 0u && dn < wf);
+                if (!ready) { pending = 1; continue; }
+                const double* other = (idx < i) ? Xnew : Xold;          /* emcee.jl:53 */
+                const double z = zf[i];
+                double y[CAP], w[CAP];
+#pragma unroll UNR
+                for (int j = 0; j < top; ++j)
+                    if (j < d) {
+                        const double wj = Xold[(long long)j * pitch + base + i];
+                        const double oj = other[(long long)j * pitch + base + idx];
+                        w[j] = wj;
+                        y[j] = oj + z * (wj - oj);
+                    }
+                const double lpy = T::template logp<DMAX>(y, d, tp);
+                const double lpw = lpold[base + i];
+                const double alpha = (am[i] + lpy) - lpw;
+                const bool acc = (-ex[i] <= alpha);                      /* emcee.jl:93 (non-strict) */
+#pragma unroll UNR
+                for (int j = 0; j < top; ++j)
+                    if (j < d) Xnew[(long long)j * pitch + base + i] = acc ? y[j] : w[j];
+                lpnew[base + i] = acc ? lpy : lpw;
+                a.st.acc[base + i] = acc ? 1 : 0;
+                if (acc) a.st.nacc[base + i] += 1ull;
+                done[i] = (unsigned short)wf;
+            }
+            ++wf;
+            pending = __syncthreads_or(pending);
+        } while (pending);
+        double* tX = Xold; Xold = Xnew; Xnew = tX;
+        double* tl = lpold; lpold = lpnew; lpnew = tl;
+    }
+    if (a.sv.out || a.sv.sum || a.sv.acc_out) {
+        for (int i = tid; i < nw; i += BLOCK) {
+            const long long ch = base + i;
+            for (int j = 0; j < d; ++j) {
+                const double v = Xold[(long long)j * pitch + ch];
+                if (a.sv.out) a.sv.out[(long long)j * a.sv.out_pitch + ch] = v;
+                if (a.sv.sum) {
+                    const long long o = (long long)j * pitch + ch;
+                    a.sv.sum[o] = a.sv.sum[o] + v;
+                    a.sv.sumsq[o] = fma(v, v, a.sv.sumsq[o]);
+                }
+            }
+            if (a.sv.out) a.sv.out[(long long)d * a.sv.out_pitch + ch] = lpold[ch];
+            if (a.sv.acc_out) a.sv.acc_out[ch] = a.st.acc[ch];
+        }
+    }
+}
+
 template <int DMAX, class T>
 int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     constexpr int BLOCK = 1024;
@@ -148,6 +254,21 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     a.n_walkers = s.d.n_walkers;
     a.a = s.d.stretch_a;
     const auto tp = make_tp<T, DMAX>(*r.target);
+    if (a.n_walkers <= 7000) {          /* 30 bytes of shared memory per walker */
+        const size_t smemf = (size_t)a.n_walkers * (3 * sizeof(double) + sizeof(int) + sizeof(unsigned short)) + 16;
+        auto kf = stretch_sweep_fast_kernel<DMAX, T, BLOCK, 4>;
+        if (smemf > 48 * 1024) AMH_CUDA_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemf));
+        const unsigned gridf = (unsigned)(r.n / a.n_walkers);
+        kf<<<gridf, BLOCK, smemf, r.ctx->stream>>>(a, tp);
+        AMH_CUDA_TRY(cudaGetLastError());
+        if (nsteps & 1) {
+            std::swap(r.X, r.X2);
+            std::swap(r.lp, r.lp2);
+        }
+        r.launches += 1;
+        r.pending_launches += 1;
+        return AMH_OK;
+    }
     const size_t smem = (size_t)a.n_walkers * (sizeof(int) + 1) + 16;
     auto kern = stretch_sweep_kernel<DMAX, T, BLOCK>;
     if (smem > 200 * 1024) return fail(AMH_ERR_UNSUPPORTED, "Ensemble on the device supports n_walkers <= 40000");
