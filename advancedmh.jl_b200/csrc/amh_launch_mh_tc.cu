@@ -20,6 +20,7 @@
  *   accept   chain lanes: -randexp < lp_c - lp (strict); accepted lanes copy their column of C to X.
  * Shared memory: 11.6 KB per warp -> 14 warps/SM = the whole 65 536-chain problem in one wave.
  */
+#include <algorithm>
 #include <cstdlib>
 #include "amh_params.cuh"
 
@@ -228,11 +229,13 @@ constexpr int kPW16 = 24;
 template <int D>
 __host__ __device__ constexpr int tc16_smem_doubles_per_warp() { return D * kPZ16 + 8 * kPW16; }
 
-template <int D, int WARPS, bool MU_ZERO, int NG1, bool IS_RW>
+template <int D, int WARPS, bool MU_ZERO, bool IS_RW>
 __global__ void __launch_bounds__(32 * WARPS, 28 / WARPS)
 mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
-    static_assert(D == 32, "the half split assumes 16 noise blocks per chain");
+    static_assert(D % 8 == 0 && D >= 8 && D <= 32, "row blocks of 8; D/4 noise blocks per lane half");
     constexpr int NB = D / 8;
+    constexpr int NPH = D / 4;                 /* Philox blocks per half-chain lane */
+    constexpr int HR = D / 2;                  /* rows of Z / X owned by a half      */
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -257,11 +260,12 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
         const unsigned long long k = a.step0 + (unsigned long long)s + 1ull;
         double e;
         {
-            const unsigned long long b0 = k * B + (unsigned long long)(8 * half);
-            double* zt = ZC + (16 * half) * kPZ16 + cl;            /* Z[16 half + j][cl] */
-            if constexpr (NG1 > 0) noise_group<(NG1 > 0 ? NG1 : 1), false>(seed, b0, 0ull, zt, e, amh::amh_log_tab_dev, kPZ16);
-            noise_group<8 - NG1, true>(seed, b0 + NG1, k * B + (unsigned long long)(D / 2), zt + 2 * NG1 * kPZ16, e,
-                                       amh::amh_log_tab_dev, kPZ16);
+            const unsigned long long b0 = k * B + (unsigned long long)(NPH * half);
+            double* zt = ZC + (HR * half) * kPZ16 + cl;            /* Z[HR half + j][cl] */
+            constexpr int G1 = (NPH >= 6) ? NPH / 2 : 0;           /* two lock-step batches when there are enough blocks */
+            if constexpr (G1 > 0) noise_group<(G1 > 0 ? G1 : 1), false>(seed, b0, 0ull, zt, e, amh::amh_log_tab_dev, kPZ16);
+            noise_group<NPH - G1, true>(seed, b0 + G1, k * B + (unsigned long long)(D / 2), zt + 2 * G1 * kPZ16, e,
+                                        amh::amh_log_tab_dev, kPZ16);
         }
         /* x in accumulator-fragment layout, software-pipelined two row blocks ahead of its use */
         double2 xf[NB][2];
@@ -358,7 +362,7 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
         const double loga = (lp_c - lp) + 0.0;
         if (active && -e < loga) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) X[(long long)(16 * half + i) * pitch + ch] = ZC[(16 * half + i) * kPZ16 + cl];
+            for (int i = 0; i < HR; ++i) X[(long long)(HR * half + i) * pitch + ch] = ZC[(HR * half + i) * kPZ16 + cl];
             lp = lp_c;
             accepted = 1;
             ++nacc;
@@ -371,8 +375,8 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
     if (!active) return;
     if (a.sv.out || a.sv.sum) {
 #pragma unroll 4
-        for (int ii = 0; ii < 16; ++ii) {
-            const int i = 16 * half + ii;
+        for (int ii = 0; ii < HR; ++ii) {
+            const int i = HR * half + ii;
             const long long o = (long long)i * pitch + ch;
             const double v = X[o];
             if (a.sv.out) a.sv.out[(long long)i * a.sv.out_pitch + ch] = v;
@@ -407,7 +411,7 @@ bool mh_tc_eligible(const amh_run& r) {
     const amh_sampler& s = *r.sampler;
     const int d = r.dim;
     if (r.target->kind != AMH_TARGET_MVNORMAL) return false;
-    if (!(d == 16 || d == 24 || d == 32)) return false;
+    if (!(d == 8 || d == 16 || d == 24 || d == 32)) return false;
     if (s.d.cov_kind != AMH_COV_FULL || s.has_mean) return false;
     if (s.d.kind == AMH_SAMPLER_STATIC && !s.d.symmetric) return false;      /* needs logq: generic path */
     if (r.pitch % 32) return false;
@@ -445,38 +449,35 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     a.Uf = a.Lf + (size_t)NT * 32;
     a.mu = a.Uf + (size_t)NT * 32;
     a.c0 = t.blob[0];
-    if constexpr (D == 32) {
-        if (r.mh_path != 2) {
-            constexpr int W16 = 4;
-            const size_t smem16 = (size_t)W16 * tc16_smem_doubles_per_warp<D>() * sizeof(double);
-            const unsigned grid16 = (unsigned)((r.n + 16 * W16 - 1) / (16 * W16));
-            static bool attr16 = false;
-            if (!attr16) {
-                /* 7 CTAs x 27 KB = 189 KB of shared memory; the rest of the 256 KB stays L1 for the L/U fragments */
-                const char* cv = std::getenv("AMH_TC_CARVEOUT");
-                const int carve = cv ? std::atoi(cv) : 84;
+    if (r.mh_path != 2) {
+        /* K1T16: 16 chains per warp, 4 warps per CTA; 28 resident warps per SM */
+        constexpr int W16 = 4;
+        const size_t smem16 = (size_t)W16 * tc16_smem_doubles_per_warp<D>() * sizeof(double);
+        const unsigned grid16 = (unsigned)((r.n + 16 * W16 - 1) / (16 * W16));
+        static bool attr16 = false;
+        if (!attr16) {
+            /* shared memory actually needed by 7 resident CTAs; the rest of the 256 KB stays L1 for the L/U fragments */
+            const char* cv = std::getenv("AMH_TC_CARVEOUT");
+            const int need_kb = (int)((7 * (smem16 + 1024) + 1023) / 1024);
+            const int carve = cv ? std::atoi(cv) : std::min(100, (need_kb * 100 + 227) / 228 + 1);
 #define AMH_TC16_ATTR(...) AMH_CUDA_TRY(cudaFuncSetAttribute(mh_step_tc16_kernel<D, W16, __VA_ARGS__>, cudaFuncAttributePreferredSharedMemoryCarveout, carve))
-                AMH_TC16_ATTR(true, 4, true); AMH_TC16_ATTR(false, 4, true); AMH_TC16_ATTR(true, 4, false); AMH_TC16_ATTR(false, 4, false);
-                AMH_TC16_ATTR(true, 0, true);
+            AMH_TC16_ATTR(true, true); AMH_TC16_ATTR(false, true); AMH_TC16_ATTR(true, false); AMH_TC16_ATTR(false, false);
 #undef AMH_TC16_ATTR
-                attr16 = true;
-            }
-            static const int variant = std::getenv("AMH_TC_VARIANT") ? std::atoi(std::getenv("AMH_TC_VARIANT")) : 0;
-#define AMH_TC16_GO(...) mh_step_tc16_kernel<D, W16, __VA_ARGS__><<<grid16, 32 * W16, smem16, r.ctx->stream>>>(a)
-            if (a.is_rw) {
-                if (!a.mu_zero) AMH_TC16_GO(false, 4, true);
-                else if (variant == 1) AMH_TC16_GO(true, 0, true);
-                else AMH_TC16_GO(true, 4, true);
-            } else {
-                if (!a.mu_zero) AMH_TC16_GO(false, 4, false);
-                else AMH_TC16_GO(true, 4, false);
-            }
-#undef AMH_TC16_GO
-            AMH_CUDA_TRY(cudaGetLastError());
-            r.launches += 1;
-            r.pending_launches += 1;
-            return AMH_OK;
+            attr16 = true;
         }
+#define AMH_TC16_GO(...) mh_step_tc16_kernel<D, W16, __VA_ARGS__><<<grid16, 32 * W16, smem16, r.ctx->stream>>>(a)
+        if (a.is_rw) {
+            if (a.mu_zero) AMH_TC16_GO(true, true);
+            else AMH_TC16_GO(false, true);
+        } else {
+            if (a.mu_zero) AMH_TC16_GO(true, false);
+            else AMH_TC16_GO(false, false);
+        }
+#undef AMH_TC16_GO
+        AMH_CUDA_TRY(cudaGetLastError());
+        r.launches += 1;
+        r.pending_launches += 1;
+        return AMH_OK;
     }
     const size_t smem = (size_t)WARPS * tc_smem_doubles_per_warp<D>() * sizeof(double);
     auto kern = mh_step_tc_kernel<D, WARPS>;
@@ -496,6 +497,7 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
 
 int launch_mh_tc(amh_run& r, int nsteps, const SaveArgs& sv) {
     switch (r.dim) {
+    case 8: return launch_mh_tc_t<8>(r, nsteps, sv);
     case 16: return launch_mh_tc_t<16>(r, nsteps, sv);
     case 24: return launch_mh_tc_t<24>(r, nsteps, sv);
     case 32: return launch_mh_tc_t<32>(r, nsteps, sv);

@@ -30,7 +30,7 @@ def _seeds(n, s=0):
     return np.random.default_rng(s).integers(0, 2 ** 64, size=n, dtype=np.uint64)
 
 
-@pytest.mark.parametrize("d,cov", [(1, "scalar"), (2, "scalar"), (2, "diag"), (3, "full"), (8, "full"), (13, "full"),
+@pytest.mark.parametrize("d,cov", [(1, "scalar"), (2, "scalar"), (2, "diag"), (3, "full"), (8, "full"), (8, "diag"), (13, "full"),
                                    (16, "full"), (24, "full"), (32, "full"), (32, "scalar"), (40, "full")])
 def test_rwmh_mvnormal_bit_exact(amh, cuda, oracle, d, cov):
     Sigma = make_spd(d, seed=d)
