@@ -447,38 +447,62 @@ int32_t amh_run_sample(amh_run* run, int64_t N, int64_t discard_initial, int64_t
     AMH_CUDA_TRY(cudaMemsetAsync(r.sum, 0, sizeof(double) * d * np, st));
     AMH_CUDA_TRY(cudaMemsetAsync(r.sumsq, 0, sizeof(double) * d * np, st));
     r.nsaved = 0;
-    /* device sample ring: `chunk` slabs of [(d+1)][pitch] doubles (+ accepted flags) */
+    /* device sample ring: two buffers of `chunk` slabs of [(d+1)][pitch] doubles (+ accepted flags).  While the
+     * stepping kernels fill one buffer, the copy stream drains the other into the caller's (ideally pinned) array. */
     const size_t slab = (size_t)(d + 1) * np;
     long long chunk = 0;
-    double* dsamp = nullptr;
-    unsigned char* dacc = nullptr;
-    if (out || accepted_out) {
-        chunk = std::max<long long>(1, std::min<long long>(N, (long long)((256ull << 20) / (slab * sizeof(double)))));
-        if (out) { const int rca = dmalloc(r.ctx, (void**)&dsamp, sizeof(double) * slab * chunk); if (rca) return rca; }
-        if (accepted_out) { const int rca = dmalloc(r.ctx, (void**)&dacc, (size_t)np * chunk); if (rca) return rca; }
-    }
+    int nbuf = 0;
+    double* dsamp[2] = {nullptr, nullptr};
+    unsigned char* dacc[2] = {nullptr, nullptr};
+    cudaEvent_t filled[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    cudaStream_t cs = r.ctx->copy_stream;
     int rc = AMH_OK;
-    long long filled = 0, base = 0;
-    auto flush = [&]() -> int {
-        if (filled == 0) return AMH_OK;
+    if (out || accepted_out) {
+        chunk = std::max<long long>(1, std::min<long long>(N, (long long)((128ull << 20) / (slab * sizeof(double)))));
+        if (N >= 2) chunk = std::min<long long>(chunk, (N + 1) / 2);   /* at least two chunks: copies overlap stepping */
+        nbuf = (N > chunk) ? 2 : 1;
+        for (int b = 0; b < nbuf && !rc; ++b) {
+            if (out) rc = dmalloc(r.ctx, (void**)&dsamp[b], sizeof(double) * slab * chunk);
+            if (!rc && accepted_out) rc = dmalloc(r.ctx, (void**)&dacc[b], (size_t)np * chunk);
+            if (!rc && cudaEventCreateWithFlags(&filled[b], cudaEventDisableTiming) != cudaSuccess) rc = fail(AMH_ERR_CUDA, "event");
+            if (!rc && cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming) != cudaSuccess) rc = fail(AMH_ERR_CUDA, "event");
+        }
+    }
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(cs);
+        for (int b = 0; b < 2; ++b) {
+            dfree(r.ctx, dsamp[b]);
+            dfree(r.ctx, dacc[b]);
+            if (filled[b]) cudaEventDestroy(filled[b]);
+            if (copied[b]) cudaEventDestroy(copied[b]);
+        }
+    };
+    auto drain = [&](int b, long long base, long long count) -> int {
+        /* copy stream: wait until the buffer is filled, copy it out, mark it reusable */
+        AMH_CUDA_TRY(cudaEventRecord(filled[b], st));
+        AMH_CUDA_TRY(cudaStreamWaitEvent(cs, filled[b], 0));
         if (out)
-            AMH_CUDA_TRY(cudaMemcpy2DAsync(out + (size_t)base * (d + 1) * n, sizeof(double) * n, dsamp, sizeof(double) * np,
-                                           sizeof(double) * n, (size_t)filled * (d + 1), cudaMemcpyDeviceToHost, st));
+            AMH_CUDA_TRY(cudaMemcpy2DAsync(out + (size_t)base * (d + 1) * n, sizeof(double) * n, dsamp[b], sizeof(double) * np,
+                                           sizeof(double) * n, (size_t)count * (d + 1), cudaMemcpyDeviceToHost, cs));
         if (accepted_out)
-            AMH_CUDA_TRY(cudaMemcpy2DAsync(accepted_out + (size_t)base * n, (size_t)n, dacc, (size_t)np, (size_t)n,
-                                           (size_t)filled, cudaMemcpyDeviceToHost, st));
-        AMH_CUDA_TRY(cudaStreamSynchronize(st));
-        base += filled;
-        filled = 0;
+            AMH_CUDA_TRY(cudaMemcpy2DAsync(accepted_out + (size_t)base * n, (size_t)n, dacc[b], (size_t)np, (size_t)n,
+                                           (size_t)count, cudaMemcpyDeviceToHost, cs));
+        AMH_CUDA_TRY(cudaEventRecord(copied[b], cs));
         return AMH_OK;
     };
     for (long long i = 0; i < N && !rc; ++i) {
         long long k = (i == 0) ? discard_initial : thinning;
+        const int b = chunk ? (int)((i / chunk) % nbuf) : 0;
+        const long long slot = chunk ? i % chunk : 0;
+        if (chunk && slot == 0 && i >= (long long)nbuf * chunk) {
+            cudaError_t e = cudaStreamWaitEvent(st, copied[b], 0);       /* the buffer has been drained */
+            if (e != cudaSuccess) { rc = cuda_fail(e, "wait copied"); break; }
+        }
         amhd::SaveArgs sv;
         std::memset(&sv, 0, sizeof(sv));
-        sv.out = dsamp ? dsamp + (size_t)filled * slab : nullptr;
+        sv.out = dsamp[b] ? dsamp[b] + (size_t)slot * slab : nullptr;
         sv.out_pitch = np;
-        sv.acc_out = dacc ? dacc + (size_t)filled * np : nullptr;
+        sv.acc_out = dacc[b] ? dacc[b] + (size_t)slot * np : nullptr;
         sv.sum = r.sum;
         sv.sumsq = r.sumsq;
         /* stateful step s (1-based, cumulative) is step_warmup iff s <= num_warmup */
@@ -491,14 +515,13 @@ int32_t amh_run_sample(amh_run* run, int64_t N, int64_t discard_initial, int64_t
             done = (k == 0);
         }
         r.nsaved += 1;
-        if (dsamp || dacc) {
-            filled += 1;
-            if (filled == chunk && !rc) rc = flush();
-        }
+        if (chunk && !rc && (slot == chunk - 1 || i == N - 1)) rc = drain(b, i - slot, slot + 1);
     }
-    if (!rc) rc = flush();
-    dfree(r.ctx, dsamp);
-    dfree(r.ctx, dacc);
+    if (!rc) {
+        cudaError_t e = cudaStreamSynchronize(cs);
+        if (e != cudaSuccess) rc = cuda_fail(e, "copy stream sync");
+    }
+    cleanup();
     if (rc) return rc;
     AMH_CUDA_TRY(cudaStreamSynchronize(st));
     if (summary) {

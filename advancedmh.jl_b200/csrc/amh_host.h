@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <set>
 #include <string>
 #include <vector>
 #include "../../include/amh.h"
@@ -12,6 +13,7 @@ struct amh_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     int sm_count = 0;
+    std::set<const void*> configured;     /* kernels whose function attributes were set on this device */
 };
 
 struct amh_target {

@@ -454,8 +454,8 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
         constexpr int W16 = 4;
         const size_t smem16 = (size_t)W16 * tc16_smem_doubles_per_warp<D>() * sizeof(double);
         const unsigned grid16 = (unsigned)((r.n + 16 * W16 - 1) / (16 * W16));
-        static bool attr16 = false;
-        if (!attr16) {
+        const void* key16 = (const void*)mh_step_tc16_kernel<D, W16, true, true>;
+        if (!r.ctx->configured.count(key16)) {
             /* shared memory actually needed by 7 resident CTAs; the rest of the 256 KB stays L1 for the L/U fragments */
             const char* cv = std::getenv("AMH_TC_CARVEOUT");
             const int need_kb = (int)((7 * (smem16 + 1024) + 1023) / 1024);
@@ -463,7 +463,7 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
 #define AMH_TC16_ATTR(...) AMH_CUDA_TRY(cudaFuncSetAttribute(mh_step_tc16_kernel<D, W16, __VA_ARGS__>, cudaFuncAttributePreferredSharedMemoryCarveout, carve))
             AMH_TC16_ATTR(true, true); AMH_TC16_ATTR(false, true); AMH_TC16_ATTR(true, false); AMH_TC16_ATTR(false, false);
 #undef AMH_TC16_ATTR
-            attr16 = true;
+            r.ctx->configured.insert(key16);
         }
 #define AMH_TC16_GO(...) mh_step_tc16_kernel<D, W16, __VA_ARGS__><<<grid16, 32 * W16, smem16, r.ctx->stream>>>(a)
         if (a.is_rw) {
@@ -481,11 +481,10 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     }
     const size_t smem = (size_t)WARPS * tc_smem_doubles_per_warp<D>() * sizeof(double);
     auto kern = mh_step_tc_kernel<D, WARPS>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!r.ctx->configured.count((const void*)kern)) {
         AMH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         AMH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_set = true;
+        r.ctx->configured.insert((const void*)kern);
     }
     const unsigned grid = (unsigned)((r.n + 32 * WARPS - 1) / (32 * WARPS));
     kern<<<grid, 32 * WARPS, smem, r.ctx->stream>>>(a);

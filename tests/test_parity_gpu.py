@@ -362,3 +362,26 @@ def test_mala_logistic_tiled_tensor_core_kernel_bit_exact(amh, cuda, oracle, d, 
     og, ag, sg = rg.sample(5, discard_initial=2, thinning=2)
     oo, ao, so = ro.sample(5, discard_initial=2, thinning=2)
     assert np.array_equal(og, oo) and np.array_equal(ag, ao)
+
+
+def test_sample_pipelined_copy_many_chunks_and_pinned_buffers(amh, cuda, oracle):
+    """amh_run_sample drains the device sample ring through the copy stream in chunks (two buffers): force many
+    chunks (N large, small slabs) and use caller-owned pinned buffers; results must equal the oracle's"""
+    d = 3
+    Sigma = make_spd(d, seed=12, lo=0.5, hi=2.0)
+    target = amh.MvNormalTarget(None, Sigma)
+    spl = amh.RWMH(amh.MvNormal(np.zeros(d), 0.5 * Sigma))
+    n = 40
+    rg, ro = _pair(amh, cuda, oracle, target, spl, n, _seeds(n, 13))
+    N = 257
+    pout = cuda.pinned_empty((N, d + 1, n)); pacc = cuda.pinned_empty((N, n), dtype=np.uint8)
+    og, ag, _ = rg.sample(N, discard_initial=3, thinning=1, out=pout, acc=pacc)
+    oo, ao, _ = ro.sample(N, discard_initial=3, thinning=1)
+    assert og is pout and np.array_equal(og, oo) and np.array_equal(ag, ao)
+    # strided initial parameters (a column block of a larger matrix) go through init_ld without repacking
+    big = np.random.default_rng(5).normal(size=(d, 100))
+    r1 = cuda.run(cuda.target(target.kind, d, target.blob()), spl.lower(cuda, d), n, _seeds(n, 14), big[:, 30:70])
+    r2 = oracle.run(oracle.target(target.kind, d, target.blob()), spl.lower(oracle, d), n, _seeds(n, 14), np.ascontiguousarray(big[:, 30:70]))
+    r1.steps(5); r2.steps(5)
+    _assert_same_state(r1, r2)
+    assert np.array_equal(r1.state()["x"].shape, (d, n))
