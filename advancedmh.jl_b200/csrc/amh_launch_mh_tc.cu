@@ -79,6 +79,29 @@ __host__ __device__ constexpr int tseq_kb(int nb, int t, bool desc) {
     return -1;
 }
 
+/* Interleaved schedule: row blocks are processed in PAIRS (descending (NB-1,NB-2),(NB-3,NB-4).. or ascending
+ * (0,1),(2,3)..), the k-tiles of the two blocks alternating, so that a warp always has 4 independent DMMA
+ * accumulation chains (2 row blocks x 2 n-tiles) in flight instead of 2.  psched(NB, t, desc, what):
+ * what = 0 -> row block of issue slot t, 1 -> k-tile, 2 -> 1 if t is the last slot of its pair. */
+__host__ __device__ constexpr int psched(int nb, int t, bool desc, int what) {
+    for (int p = 0; 2 * p < nb; ++p) {
+        const int A = desc ? nb - 1 - 2 * p : 2 * p;
+        const int Bq = desc ? nb - 2 - 2 * p : 2 * p + 1;
+        const bool hasB = Bq >= 0 && Bq < nb;
+        const int cA = 2 * A + 2, cB = hasB ? 2 * Bq + 2 : 0;
+        if (t < cA + cB) {
+            int c = 0;
+            const int mx = cA > cB ? cA : cB;
+            for (int k = 0; k < mx; ++k) {
+                if (k < cA) { if (c == t) return what == 0 ? A : what == 1 ? k : (t == cA + cB - 1); ++c; }
+                if (k < cB) { if (c == t) return what == 0 ? Bq : what == 1 ? k : (t == cA + cB - 1); ++c; }
+            }
+        }
+        t -= cA + cB;
+    }
+    return -1;
+}
+
 constexpr int kPZ = 36;        /* row pitch (doubles) of the Z/C tile: conflict-free B-fragment loads */
 constexpr int kPW = 40;        /* row pitch of the W staging tile: conflict-free 128-bit stores       */
 
@@ -281,37 +304,47 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
             constexpr int NT = NB * (NB + 1);
             constexpr int P = 4;                       /* A-fragment prefetch distance (tiles) */
             double aq[NT];
-            double acc[2][2];
+            double acc[NB][2][2];
 #pragma unroll
             for (int j = 0; j < P && j < NT; ++j) {
-                constexpr bool DESC = true;
-                const int mbj = tseq_mb(NB, j, DESC), kbj = tseq_kb(NB, j, DESC);
+                const int mbj = psched(NB, j, true, 0), kbj = psched(NB, j, true, 1);
                 aq[j] = ld_a_frag(a.Lf + (mbj * (mbj + 1) + kbj) * 32 + lane);
             }
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
-                const int mb = tseq_mb(NB, t, true), kb = tseq_kb(NB, t, true);
+                const int mb = psched(NB, t, true, 0), kb = psched(NB, t, true, 1);
                 if (t + P < NT) {
-                    const int mbj = tseq_mb(NB, t + P, true), kbj = tseq_kb(NB, t + P, true);
+                    const int mbj = psched(NB, t + P, true, 0), kbj = psched(NB, t + P, true, 1);
                     aq[t + P] = ld_a_frag(a.Lf + (mbj * (mbj + 1) + kbj) * 32 + lane);
                 }
-                if (kb == 0) { acc[0][0] = 0.0; acc[0][1] = 0.0; acc[1][0] = 0.0; acc[1][1] = 0.0; }
+                if (kb == 0) { acc[mb][0][0] = 0.0; acc[mb][0][1] = 0.0; acc[mb][1][0] = 0.0; acc[mb][1][1] = 0.0; }
 #pragma unroll
                 for (int nb = 0; nb < 2; ++nb) {
                     const double bf = ZC[(4 * kb + fc) * kPZ16 + 8 * nb + fr];
-                    dmma(acc[nb][0], acc[nb][1], aq[t], bf);
+                    dmma(acc[mb][nb][0], acc[mb][nb][1], aq[t], bf);
                 }
-                if (kb == 2 * mb + 1) {
+                if (psched(NB, t, true, 2) == 1) {
+                    /* both row blocks of the pair have read Z: their rows of C may now replace it */
 #pragma unroll
-                    for (int nb = 0; nb < 2; ++nb) {
-                        double2 c;
-                        if (IS_RW) { c.x = xf[mb][nb].x + acc[nb][0]; c.y = xf[mb][nb].y + acc[nb][1]; }
-                        else { c.x = acc[nb][0]; c.y = acc[nb][1]; }
-                        *reinterpret_cast<double2*>(ZC + (8 * mb + fr) * kPZ16 + 8 * nb + 2 * fc) = c;
-                    }
-                    if (IS_RW && mb >= 2) {
+                    for (int u = 0; u < 2; ++u) {
+                        const int mw = (u == 0) ? mb : ((mb & 1) == (NB & 1) ? mb + 1 : mb - 1);   /* the pair's other block */
+                        const int pa = (NB - 1 - mb) / 2;                                          /* pair index (descending) */
+                        const int hi = NB - 1 - 2 * pa, lo = NB - 2 - 2 * pa;
+                        const int mq = (u == 0) ? hi : lo;
+                        (void)mw;
+                        if (mq >= 0) {
 #pragma unroll
-                        for (int nb = 0; nb < 2; ++nb) xf[mb - 2][nb] = ld_x_frag(xp + (long long)(8 * (mb - 2)) * pitch + 8 * nb);
+                            for (int nb = 0; nb < 2; ++nb) {
+                                double2 c;
+                                if (IS_RW) { c.x = xf[mq][nb].x + acc[mq][nb][0]; c.y = xf[mq][nb].y + acc[mq][nb][1]; }
+                                else { c.x = acc[mq][nb][0]; c.y = acc[mq][nb][1]; }
+                                *reinterpret_cast<double2*>(ZC + (8 * mq + fr) * kPZ16 + 8 * nb + 2 * fc) = c;
+                            }
+                            if (IS_RW && mq >= 2) {
+#pragma unroll
+                                for (int nb = 0; nb < 2; ++nb) xf[mq - 2][nb] = ld_x_frag(xp + (long long)(8 * (mq - 2)) * pitch + 8 * nb);
+                            }
+                        }
                     }
                 }
             }
@@ -322,39 +355,47 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
             constexpr int NT = NB * (NB + 1);
             constexpr int P = 4;
             double aq[NT];
-            double acc[2][2];
+            double acc[NB][2][2];
 #pragma unroll
             for (int j = 0; j < P && j < NT; ++j) {
-                const int mbj = tseq_mb(NB, j, false), kbj = tseq_kb(NB, j, false);
+                const int mbj = psched(NB, j, false, 0), kbj = psched(NB, j, false, 1);
                 aq[j] = ld_a_frag(a.Uf + (mbj * (mbj + 1) + kbj) * 32 + lane);
             }
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
-                const int mb = tseq_mb(NB, t, false), kb = tseq_kb(NB, t, false);
+                const int mb = psched(NB, t, false, 0), kb = psched(NB, t, false, 1);
                 if (t + P < NT) {
-                    const int mbj = tseq_mb(NB, t + P, false), kbj = tseq_kb(NB, t + P, false);
+                    const int mbj = psched(NB, t + P, false, 0), kbj = psched(NB, t + P, false, 1);
                     aq[t + P] = ld_a_frag(a.Uf + (mbj * (mbj + 1) + kbj) * 32 + lane);
                 }
-                if (kb == 0) { acc[0][0] = 0.0; acc[0][1] = 0.0; acc[1][0] = 0.0; acc[1][1] = 0.0; }
+                if (kb == 0) { acc[mb][0][0] = 0.0; acc[mb][0][1] = 0.0; acc[mb][1][0] = 0.0; acc[mb][1][1] = 0.0; }
                 double muk = 0.0;
                 if (!MU_ZERO) muk = __ldg(a.mu + 4 * kb + fc);
 #pragma unroll
                 for (int nb = 0; nb < 2; ++nb) {
                     double bf = ZC[(4 * kb + fc) * kPZ16 + 8 * nb + fr];
                     if (!MU_ZERO) bf = bf - muk;
-                    dmma(acc[nb][0], acc[nb][1], aq[t], bf);
+                    dmma(acc[mb][nb][0], acc[mb][nb][1], aq[t], bf);
                 }
-                if (kb == 2 * mb + 1) {
+                if (psched(NB, t, false, 2) == 1) {
+                    /* the pair is complete: hand its rows of W to the chain lanes in ascending row order */
+                    const int pa = mb / 2;
 #pragma unroll
-                    for (int nb = 0; nb < 2; ++nb)
-                        *reinterpret_cast<double2*>(WB + fr * kPW16 + 8 * nb + 2 * fc) = make_double2(acc[nb][0], acc[nb][1]);
-                    __syncwarp();
+                    for (int u = 0; u < 2; ++u) {
+                        const int mq = 2 * pa + u;
+                        if (mq < NB) {
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        const double w = WB[r * kPW16 + cl];
-                        q = (mb == 0 && r == 0) ? w * w : fma(w, w, q);
+                            for (int nb = 0; nb < 2; ++nb)
+                                *reinterpret_cast<double2*>(WB + fr * kPW16 + 8 * nb + 2 * fc) = make_double2(acc[mq][nb][0], acc[mq][nb][1]);
+                            __syncwarp();
+#pragma unroll
+                            for (int r = 0; r < 8; ++r) {
+                                const double w = WB[r * kPW16 + cl];
+                                q = (mq == 0 && r == 0) ? w * w : fma(w, w, q);
+                            }
+                            __syncwarp();
+                        }
                     }
-                    __syncwarp();
                 }
             }
         }
