@@ -65,7 +65,8 @@ struct amh_run {
     unsigned long long* seeds = nullptr;
     double* sum = nullptr;
     double* sumsq = nullptr;
-    void* scratch = nullptr;       /* sampler specific (stretch: done flags ...) */
+    void* scratch = nullptr;       /* sampler / kernel specific device buffer */
+    size_t scratch_bytes = 0;
     long long step = 0;
     long long nsaved = 0;
     long long launches = 0;

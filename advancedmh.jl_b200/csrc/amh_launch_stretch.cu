@@ -134,66 +134,132 @@ stretch_sweep_kernel(const __grid_constant__ StretchArgs a, const __grid_constan
 }
 
 /* ---------------------------------------------------------------------------
- * K2F: same exact sequential semantics, for ensembles of up to WPT * BLOCK walkers.
- *   - everything that does not depend on the walker positions (partner index, stretch factor z, (d-1) log z, the
- *     exponential) is computed for the whole sweep in one parallel phase and kept in registers;
- *   - `done[i]` stores the wavefront in which walker i was finished, so "partner available" is
- *     done[idx] != 0 && done[idx] < wavefront and ONE barrier per wavefront (the __syncthreads_or that also
- *     detects completion) orders both the flags and the walker data. */
-template <int DMAX, class T, int BLOCK, int WPT>
+ * K2F: same exact sequential semantics, split in two kernels.
+ *
+ *   stretch_noise_kernel   everything of a launch's sweeps that does not depend on the walker positions -- partner
+ *                          index, stretch factor z, (d-1) log z, the exponential -- for ALL sweeps, ensembles and
+ *                          walkers at once: embarrassingly parallel, runs on all SMs (an ensemble kernel alone only
+ *                          occupies one SM per ensemble).
+ *   stretch_sweep_fast_kernel   one CTA per ensemble; per sweep the dependency forest is executed in wavefronts:
+ *                          `done[i]` holds the wavefront in which walker i was finished, so "partner available" is
+ *                          done[idx] != 0 && done[idx] < wavefront and ONE barrier per wavefront (the
+ *                          __syncthreads_or that also detects completion) orders flags and walker data.  Log-densities,
+ *                          accept flags and counters of the ensemble live in shared memory for the whole launch, so a
+ *                          move costs one round trip to L2 (its 2 x d coordinates + 3 precomputed numbers). */
+struct StretchNoise {
+    int* partner;              /* [nsteps][n] */
+    double* zf;                /* [nsteps][n] */
+    double* am;
+    double* ex;
+};
+
+__global__ void __launch_bounds__(256)
+stretch_noise_kernel(StretchNoise o, const unsigned long long* __restrict__ seeds, long long n, int nw, int d, int nsteps,
+                     unsigned long long step0, double aa) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * nsteps) return;
+    const int s = (int)(t / n);
+    const long long g = t % n;
+    const long long en = g / nw;
+    const int i = (int)(g % nw);
+    const unsigned long long k = step0 + (unsigned long long)s + 1ull;
+    const unsigned long long seed = seeds[en];
+    const unsigned long long blk = (k * (unsigned long long)nw + (unsigned long long)i) * 2ull;
+    const amh::Block b0 = amh::stream_block(seed, blk, 0u);
+    const amh::Block b1 = amh::stream_block(seed, blk + 1ull, 0u);
+    /* idx = mod1(i + rand(1:(n-1)), n)  (emcee.jl:52) */
+    const long long rr = (long long)amh::bounded(b0.v[0], b0.v[1], (unsigned long long)(nw - 1));
+    o.partner[t] = (int)((i + rr + 1) % nw);
+    const double u = amh::u01(b0.v[2], b0.v[3]);
+    const double tt = (aa - 1.0) * u + 1.0;
+    const double z = (tt * tt) / aa;
+    o.zf[t] = z;
+    o.am[t] = (double)(d - 1) * amh::log_(z);
+    o.ex[t] = amh::exponential(b1.v[0], b1.v[1]);
+}
+
+template <int DMAX, class T, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
-stretch_sweep_fast_kernel(const __grid_constant__ StretchArgs a, const __grid_constant__ typename T::template Params<DMAX> tp) {
+stretch_sweep_fast_kernel(const __grid_constant__ StretchArgs a, const __grid_constant__ StretchNoise pre,
+                          const __grid_constant__ typename T::template Params<DMAX> tp) {
     using D = Dim<DMAX>;
     constexpr int CAP = D::cap;
     constexpr int UNR = D::unr;
     extern __shared__ __align__(16) double smem_d[];
     const int nw = (int)a.n_walkers;
-    double* zf = smem_d;                                                     /* [nw] stretch factor z          */
-    double* am = zf + nw;                                                    /* [nw] (d-1) log z               */
-    double* ex = am + nw;                                                    /* [nw] exponential draw          */
-    int* partner = reinterpret_cast<int*>(ex + nw);                          /* [nw]                           */
-    unsigned short* done = reinterpret_cast<unsigned short*>(partner + nw);  /* [nw] wavefront of completion   */
+    double* lpa = smem_d;                                                    /* [nw] log-density, sweep buffer A */
+    double* lpb = lpa + nw;                                                  /* [nw]                    buffer B */
+    int* partner = reinterpret_cast<int*>(lpb + nw);                         /* [nw]                             */
+    int* list_ = partner + nw;                                               /* [nw] work list of a wavefront    */
+    unsigned* naccs = reinterpret_cast<unsigned*>(list_ + nw);               /* [nw] accepted moves this launch  */
+    unsigned short* done = reinterpret_cast<unsigned short*>(naccs + nw);    /* [nw] wavefront of completion     */
+    unsigned char* accs = reinterpret_cast<unsigned char*>(done + nw);       /* [nw] last accept flag            */
+    int* list = list_;
+    __shared__ int cnt[2];
     const int tid = threadIdx.x;
     const long long en = blockIdx.x;
     const long long base = en * nw;
+    const long long n = a.st.n;
     const int d = D::fixed ? DMAX : a.d;
     const int top = D::fixed ? DMAX : d;
     const long long pitch = a.st.pitch;
-    const unsigned long long seed = a.st.seeds[en];
-    double* Xold = a.st.X;  double* lpold = a.st.lp;
-    double* Xnew = a.X2;    double* lpnew = a.lp2;
+    double* Xold = a.st.X;  double* Xnew = a.X2;
+    double* lpo = lpa;      double* lpn = lpb;
+    for (int i = tid; i < nw; i += BLOCK) {
+        lpa[i] = a.st.lp[base + i];
+        naccs[i] = 0u;
+        accs[i] = a.st.acc[base + i];
+    }
 
     for (int s = 0; s < a.nsteps; ++s) {
-        const unsigned long long k = a.step0 + (unsigned long long)s + 1ull;
+        const long long off = (long long)s * n + base;
         for (int i = tid; i < nw; i += BLOCK) {
-            const unsigned long long blk = (k * (unsigned long long)nw + (unsigned long long)i) * 2ull;
-            const amh::Block b0 = amh::stream_block(seed, blk, 0u);
-            const amh::Block b1 = amh::stream_block(seed, blk + 1ull, 0u);
-            /* idx = mod1(i + rand(1:(n-1)), n)  (emcee.jl:52) */
-            const long long rr = (long long)amh::bounded(b0.v[0], b0.v[1], (unsigned long long)(nw - 1));
-            partner[i] = (int)((i + rr + 1) % nw);
-            const double u = amh::u01(b0.v[2], b0.v[3]);
-            const double tt = (a.a - 1.0) * u + 1.0;
-            const double z = (tt * tt) / a.a;
-            zf[i] = z;
-            am[i] = (double)(d - 1) * amh::log_(z);
-            ex[i] = amh::exponential(b1.v[0], b1.v[1]);
+            partner[i] = pre.partner[off + i];
             done[i] = 0;
         }
+        if (tid < 2) cnt[tid] = 0;
         __syncthreads();
         unsigned wf = 1;
         int pending;
+        const int tmax = (nw + BLOCK - 1) / BLOCK;
         do {
             pending = 0;
+            /* (1) compact the walkers whose partner is available into a work list (warp-aggregated append), so that
+             *     the moves below run with full warps instead of a few ready lanes per warp */
+            int* mycnt = cnt + (wf & 1);
 #pragma unroll 1
-            for (int i = tid; i < nw; i += BLOCK) {
-                if (done[i]) continue;
+            for (int t = 0; t < tmax; ++t) {
+                const int i = tid + t * BLOCK;
+                bool cand = false, ready = false;
+                if (i < nw && !done[i]) {
+                    cand = true;
+                    const int idx = partner[i];
+                    const unsigned dn = done[idx];
+                    ready = (idx > i) || (dn != 0u && dn < wf);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, ready);
+                if (m) {
+                    const int lane = tid & 31;
+                    const int leader = __ffs(m) - 1;
+                    int pos = 0;
+                    if (lane == leader) pos = atomicAdd(mycnt, __popc(m));
+                    pos = __shfl_sync(0xffffffffu, pos, leader);
+                    if (ready) list[pos + __popc(m & ((1u << lane) - 1u))] = i;
+                }
+                if (cand && !ready) pending = 1;
+            }
+            __syncthreads();
+            const int nready = *mycnt;
+            if (tid == 0) cnt[(wf + 1) & 1] = 0;                          /* the other counter serves the next wavefront */
+            /* (2) the moves of this wavefront */
+#pragma unroll 1
+            for (int q = tid; q < nready; q += BLOCK) {
+                const int i = list[q];
                 const int idx = partner[i];
-                const unsigned dn = done[idx];
-                const bool ready = (idx > i) || (dn != 0u && dn < wf);
-                if (!ready) { pending = 1; continue; }
                 const double* other = (idx < i) ? Xnew : Xold;          /* emcee.jl:53 */
-                const double z = zf[i];
+                const double z = pre.zf[off + i];
+                const double am = pre.am[off + i];
+                const double ex = pre.ex[off + i];
                 double y[CAP], w[CAP];
 #pragma unroll UNR
                 for (int j = 0; j < top; ++j)
@@ -204,26 +270,32 @@ stretch_sweep_fast_kernel(const __grid_constant__ StretchArgs a, const __grid_co
                         y[j] = oj + z * (wj - oj);
                     }
                 const double lpy = T::template logp<DMAX>(y, d, tp);
-                const double lpw = lpold[base + i];
-                const double alpha = (am[i] + lpy) - lpw;
-                const bool acc = (-ex[i] <= alpha);                      /* emcee.jl:93 (non-strict) */
+                const double lpw = lpo[i];
+                const double alpha = (am + lpy) - lpw;
+                const bool acc = (-ex <= alpha);                         /* emcee.jl:93 (non-strict) */
 #pragma unroll UNR
                 for (int j = 0; j < top; ++j)
                     if (j < d) Xnew[(long long)j * pitch + base + i] = acc ? y[j] : w[j];
-                lpnew[base + i] = acc ? lpy : lpw;
-                a.st.acc[base + i] = acc ? 1 : 0;
-                if (acc) a.st.nacc[base + i] += 1ull;
+                lpn[i] = acc ? lpy : lpw;
+                accs[i] = acc ? 1 : 0;
+                if (acc) naccs[i] += 1u;
                 done[i] = (unsigned short)wf;
             }
             ++wf;
             pending = __syncthreads_or(pending);
         } while (pending);
         double* tX = Xold; Xold = Xnew; Xnew = tX;
-        double* tl = lpold; lpold = lpnew; lpnew = tl;
+        double* tl = lpo; lpo = lpn; lpn = tl;
     }
-    if (a.sv.out || a.sv.sum || a.sv.acc_out) {
-        for (int i = tid; i < nw; i += BLOCK) {
-            const long long ch = base + i;
+    /* write the ensemble's scalars back: the current log-densities go to the buffer that pairs with Xold
+     * (the host swaps its X / lp pointers when the number of sweeps is odd) */
+    double* lpg = (a.nsteps & 1) ? a.lp2 : a.st.lp;
+    for (int i = tid; i < nw; i += BLOCK) {
+        const long long ch = base + i;
+        lpg[ch] = lpo[i];
+        a.st.acc[ch] = accs[i];
+        a.st.nacc[ch] = a.st.nacc[ch] + (unsigned long long)naccs[i];
+        if (a.sv.out || a.sv.sum) {
             for (int j = 0; j < d; ++j) {
                 const double v = Xold[(long long)j * pitch + ch];
                 if (a.sv.out) a.sv.out[(long long)j * a.sv.out_pitch + ch] = v;
@@ -233,9 +305,9 @@ stretch_sweep_fast_kernel(const __grid_constant__ StretchArgs a, const __grid_co
                     a.sv.sumsq[o] = fma(v, v, a.sv.sumsq[o]);
                 }
             }
-            if (a.sv.out) a.sv.out[(long long)d * a.sv.out_pitch + ch] = lpold[ch];
-            if (a.sv.acc_out) a.sv.acc_out[ch] = a.st.acc[ch];
         }
+        if (a.sv.out) a.sv.out[(long long)d * a.sv.out_pitch + ch] = lpo[i];
+        if (a.sv.acc_out) a.sv.acc_out[ch] = accs[i];
     }
 }
 
@@ -254,12 +326,34 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     a.n_walkers = s.d.n_walkers;
     a.a = s.d.stretch_a;
     const auto tp = make_tp<T, DMAX>(*r.target);
-    if (a.n_walkers <= 7000) {          /* 30 bytes of shared memory per walker */
-        const size_t smemf = (size_t)a.n_walkers * (3 * sizeof(double) + sizeof(int) + sizeof(unsigned short)) + 16;
-        auto kf = stretch_sweep_fast_kernel<DMAX, T, BLOCK, 4>;
+    if (a.n_walkers <= 7000) {          /* 31 bytes of shared memory per walker */
+        /* state-independent draws of all `nsteps` sweeps, on all SMs */
+        const size_t per = (size_t)r.n * sizeof(double);
+        const size_t need = (size_t)nsteps * (3 * per + (size_t)r.n * sizeof(int));
+        if (need > r.scratch_bytes) {
+            dfree(r.ctx, r.scratch);
+            r.scratch = nullptr; r.scratch_bytes = 0;
+            const int rca = dmalloc(r.ctx, &r.scratch, need);
+            if (rca) return rca;
+            r.scratch_bytes = need;
+        }
+        StretchNoise pre;
+        pre.zf = (double*)r.scratch;
+        pre.am = pre.zf + (size_t)nsteps * r.n;
+        pre.ex = pre.am + (size_t)nsteps * r.n;
+        pre.partner = (int*)(pre.ex + (size_t)nsteps * r.n);
+        if (nsteps > 0) {
+            const long long total = (long long)nsteps * r.n;
+            stretch_noise_kernel<<<(unsigned)((total + 255) / 256), 256, 0, r.ctx->stream>>>(pre, r.seeds, r.n, (int)a.n_walkers, r.dim,
+                                                                                             nsteps, a.step0, a.a);
+            AMH_CUDA_TRY(cudaGetLastError());
+            r.launches += 1;
+        }
+        const size_t smemf = (size_t)a.n_walkers * (2 * sizeof(double) + 2 * sizeof(int) + sizeof(unsigned) + sizeof(unsigned short) + 1) + 16;
+        auto kf = stretch_sweep_fast_kernel<DMAX, T, BLOCK>;
         if (smemf > 48 * 1024) AMH_CUDA_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemf));
         const unsigned gridf = (unsigned)(r.n / a.n_walkers);
-        kf<<<gridf, BLOCK, smemf, r.ctx->stream>>>(a, tp);
+        kf<<<gridf, BLOCK, smemf, r.ctx->stream>>>(a, pre, tp);
         AMH_CUDA_TRY(cudaGetLastError());
         if (nsteps & 1) {
             std::swap(r.X, r.X2);

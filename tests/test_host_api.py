@@ -166,3 +166,27 @@ def test_shard_bounds_partition(amh):
         assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
         sizes = [b - a for a, b in parts]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_caller_buffers_pinned_alloc_and_strided_init(amh, oracle):
+    """`out=` caller buffers, Engine.pinned_empty (amh_host_alloc; malloc-backed in the oracle) and a column block of
+    a larger initial_params matrix (init_ld) -- the pieces bench.py's e2e path relies on"""
+    target = amh.MvNormalTarget(None, np.array([[2.0, 0.3], [0.3, 1.0]]))
+    spl = amh.RWMH(2)
+    N, n = 6, 5
+    pout = oracle.pinned_empty((N, 3, n)); pacc = oracle.pinned_empty((N, n), dtype=np.uint8)
+    big = np.random.default_rng(0).normal(size=(2, 11))
+    ch = amh.sample(np.random.default_rng(1), target, spl, amh.MCMCSerial(), N, n, chain_type=amh.Chains, engine=oracle,
+                    initial_params=np.ascontiguousarray(big[:, 3:8]), out=(pout, pacc))
+    assert ch.value is pout and ch.accepted is pacc
+    ref = amh.sample(np.random.default_rng(1), target, spl, amh.MCMCSerial(), N, n, chain_type=amh.Chains, engine=oracle,
+                     initial_params=[big[:, 3 + c] for c in range(n)])
+    assert np.array_equal(ch.value, ref.value) and np.array_equal(ch.accepted, ref.accepted)
+    # strided view passed straight to the engine
+    th = oracle.target(target.kind, 2, target.blob()); sh = spl.lower(oracle, 2)
+    seeds = np.arange(n, dtype=np.uint64)
+    r1 = oracle.run(th, sh, n, seeds, big[:, 3:8])
+    r2 = oracle.run(th, sh, n, seeds, np.ascontiguousarray(big[:, 3:8]))
+    assert np.array_equal(r1.state()["x"], r2.state()["x"]) and np.array_equal(r1.state()["lp"], r2.state()["lp"])
+    with pytest.raises(amh.AMHArgumentError):
+        r1.sample(3, out=np.empty((3, 3, n + 1)))
