@@ -21,13 +21,19 @@ AMH_OK, AMH_ERR_INVALID, AMH_ERR_CUDA, AMH_ERR_UNSUPPORTED, AMH_ERR_STATE = 0, 1
 
 TARGET_IID_NORMAL, TARGET_MVNORMAL, TARGET_ROSENBROCK, TARGET_LOGISTIC = 1, 2, 3, 4
 TARGET_GAUSS_PREC, TARGET_NIG_TOY, TARGET_NIG_TOY_LOG = 5, 6, 7
-SAMPLER_STATIC, SAMPLER_RW, SAMPLER_STRETCH, SAMPLER_MALA, SAMPLER_RAM = 1, 2, 3, 4, 5
-COV_SCALAR, COV_DIAG, COV_FULL = 1, 2, 3
+SAMPLER_STATIC, SAMPLER_RW, SAMPLER_STRETCH, SAMPLER_MALA, SAMPLER_RAM, SAMPLER_MIXED = 1, 2, 3, 4, 5, 6
+COV_SCALAR, COV_DIAG, COV_FULL, COV_COMPONENTS = 1, 2, 3, 4
 
 _dp = C.POINTER(C.c_double)
 _u8p = C.POINTER(C.c_uint8)
 _u64p = C.POINTER(C.c_uint64)
 _i64p = C.POINTER(C.c_int64)
+
+
+class Component(C.Structure):
+    """struct amh_component (include/amh.h)"""
+    _fields_ = [("family", C.c_int32), ("rw", C.c_int32), ("symmetric", C.c_int32), ("reserved", C.c_int32),
+                ("p0", C.c_double), ("p1", C.c_double), ("logc", C.c_double)]
 
 
 class SamplerDesc(C.Structure):
@@ -40,6 +46,7 @@ class SamplerDesc(C.Structure):
         ("ram_alpha", C.c_double), ("ram_gamma", C.c_double),
         ("ram_eig_lo", C.c_double), ("ram_eig_hi", C.c_double),
         ("ram_S0", _dp),
+        ("components", C.POINTER(Component)),
     ]
 
 
@@ -70,7 +77,7 @@ ABI_SYMBOLS = [
     "version", "last_error", "contract_version", "ctx_create", "ctx_destroy", "ctx_sync",
     "target_create", "target_destroy", "sampler_create", "sampler_destroy",
     "run_create", "run_destroy", "run_steps", "run_sync", "run_sample",
-    "run_get_state", "run_set_params", "run_dim", "run_nchains", "run_launch_count",
+    "run_get_state", "run_set_params", "run_set_state", "run_get_ram_adapt", "run_dim", "run_nchains", "run_launch_count",
     "run_kernel_time_ms", "host_alloc", "host_free",
 ]
 
@@ -119,6 +126,8 @@ class Engine:
                                     C.POINTER(Summary)]
         f("run_get_state").argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _u8p, _i64p, _i64p]
         f("run_set_params").argtypes = [C.c_void_p, _dp]
+        f("run_set_state").argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _u8p, _i64p, C.c_int64]
+        f("run_get_ram_adapt").argtypes = [C.c_void_p, _dp, _dp]
         f("run_kernel_time_ms").argtypes = [C.c_void_p, C.c_int32, _dp, _i64p]
         f("host_alloc").argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
         f("host_free").argtypes = [C.c_void_p]
@@ -171,7 +180,9 @@ class Engine:
 
     def sampler(self, *, kind, dim, symmetric=False, cov_kind=COV_SCALAR, mean=None, scale=None,
                 stretch_a=2.0, n_walkers=0, mala_sigma2=0.0, mala_drift=0.0,
-                ram_alpha=0.234, ram_gamma=0.6, ram_eig_lo=0.0, ram_eig_hi=float("inf"), ram_S0=None) -> "SamplerHandle":
+                ram_alpha=0.234, ram_gamma=0.6, ram_eig_lo=0.0, ram_eig_hi=float("inf"), ram_S0=None,
+                components=None) -> "SamplerHandle":
+        """components: list of (family, p0, p1, logc[, rw, symmetric]) -- one univariate law per coordinate"""
         keep = []
         def ptr(a):
             if a is None:
@@ -181,7 +192,17 @@ class Engine:
             return a.ctypes.data_as(_dp)
         d = SamplerDesc(kind, dim, int(bool(symmetric)), cov_kind, ptr(mean), ptr(scale), float(stretch_a),
                         int(n_walkers), float(mala_sigma2), float(mala_drift), float(ram_alpha), float(ram_gamma),
-                        float(ram_eig_lo), float(ram_eig_hi), ptr(ram_S0))
+                        float(ram_eig_lo), float(ram_eig_hi), ptr(ram_S0), None)
+        if components is not None:
+            if len(components) != dim:
+                raise AMHArgumentError(AMH_ERR_INVALID, f"need one component per coordinate ({dim}), got {len(components)}")
+            arr = (Component * dim)()
+            for i, c in enumerate(components):
+                fam, p0, p1, logc = c[:4]
+                rw, sym = (c[4], c[5]) if len(c) >= 6 else (0, 0)
+                arr[i] = Component(int(fam), int(bool(rw)), int(bool(sym)), 0, float(p0), float(p1), float(logc))
+            keep.append(arr)
+            d.components = C.cast(arr, C.POINTER(Component))
         h = C.c_void_p()
         self._check(self._f("sampler_create")(self.ctx, C.byref(d), C.byref(h)))
         return SamplerHandle(self, h, kind, dim, int(n_walkers))
@@ -291,10 +312,42 @@ class Run:
             acc.ctypes.data_as(_u8p), nacc.ctypes.data_as(_i64p), C.byref(step)))
         return dict(x=x, lp=lp, grad=g, S=Sm, accepted=acc, naccept=nacc, step=step.value)
 
+    def state_step(self):
+        step = C.c_int64()
+        self.eng._check(self.eng._f("run_get_state")(self.h, None, None, None, None, None, None, C.byref(step)))
+        return step.value
+
     def set_params(self, x):
         x = _as_f64(x)
         assert x.shape == (self.dim, self.n)
         self.eng._check(self.eng._f("run_set_params")(self.h, x.ctypes.data_as(_dp)))
+
+    def set_state(self, state):
+        """resume from a dict returned by `state()` (AbstractMCMC's `initial_state`); missing / None entries keep
+        the run's current values"""
+        d, n = self.dim, self.n
+        keep = []
+        def arr(key, shape, dtype, ptr):
+            a = state.get(key)
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=dtype)
+            if a.shape != shape:
+                raise AMHArgumentError(AMH_ERR_INVALID, f"state[{key!r}] must have shape {shape}, got {a.shape}")
+            keep.append(a)
+            return a.ctypes.data_as(ptr)
+        step = state.get("step")
+        self.eng._check(self.eng._f("run_set_state")(
+            self.h, arr("x", (d, n), np.float64, _dp), arr("lp", (n,), np.float64, _dp),
+            arr("grad", (d, n), np.float64, _dp), arr("S", (d * (d + 1) // 2, n), np.float64, _dp),
+            arr("accepted", (n,), np.uint8, _u8p), arr("naccept", (n,), np.int64, _i64p),
+            C.c_int64(-1 if step is None else int(step))))
+
+    def ram_adapt(self):
+        """(log-alpha, eta) of the last step of every chain -- RobustAdaptiveMetropolisState fields (RAM :107-110)"""
+        la = np.empty(self.n); eta = np.empty(self.n)
+        self.eng._check(self.eng._f("run_get_ram_adapt")(self.h, la.ctypes.data_as(_dp), eta.ctypes.data_as(_dp)))
+        return la, eta
 
     def launch_count(self):
         return int(self.eng._f("run_launch_count")(self.h))

@@ -587,6 +587,53 @@ int32_t amh_run_get_state(amh_run* run, double* x, double* lp, double* grad, dou
     return AMH_OK;
 }
 
+int32_t amh_run_set_state(amh_run* run, const double* x, const double* lp, const double* grad, const double* S,
+                          const uint8_t* accepted, const int64_t* naccept, int64_t step_counter) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    amh_run& r = *run;
+    const long long n = r.n, np = r.pitch;
+    const int d = r.dim;
+    if (grad && !r.G) return fail(AMH_ERR_INVALID, "sampler keeps no gradient");
+    if (S && !r.S) return fail(AMH_ERR_INVALID, "sampler keeps no Cholesky factor");
+    AMH_CUDA_TRY(cudaSetDevice(r.ctx->device));
+    cudaStream_t st = r.ctx->stream;
+    if (x) AMH_CUDA_TRY(cudaMemcpy2DAsync(r.X, sizeof(double) * np, x, sizeof(double) * n, sizeof(double) * n, d, cudaMemcpyHostToDevice, st));
+    if (lp) AMH_CUDA_TRY(cudaMemcpyAsync(r.lp, lp, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    if (grad) AMH_CUDA_TRY(cudaMemcpy2DAsync(r.G, sizeof(double) * np, grad, sizeof(double) * n, sizeof(double) * n, d, cudaMemcpyHostToDevice, st));
+    if (accepted) AMH_CUDA_TRY(cudaMemcpyAsync(r.acc, accepted, (size_t)n, cudaMemcpyHostToDevice, st));
+    if (naccept) AMH_CUDA_TRY(cudaMemcpyAsync(r.nacc, naccept, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
+    int rc = AMH_OK;
+    if (S) {
+        const size_t nt = (size_t)d * (d + 1) / 2;
+        double* tmp = nullptr;
+        rc = dmalloc(r.ctx, (void**)&tmp, sizeof(double) * nt * np);
+        if (rc) return rc;
+        cudaError_t e = cudaMemcpy2DAsync(tmp, sizeof(double) * np, S, sizeof(double) * n, sizeof(double) * n, nt, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "copy S");
+        if (!rc) rc = r.ram_warp ? ramw_import_S(r, tmp) : ram_scatter_S(r, tmp);
+        dfree(r.ctx, tmp);
+        if (rc) return rc;
+    }
+    if (x && r.sampler->d.kind == AMH_SAMPLER_STATIC && !r.sampler->d.symmetric) {
+        rc = launch_relq(r);
+        if (rc) return rc;
+    }
+    if (step_counter >= 0) r.step = step_counter;
+    AMH_CUDA_TRY(cudaStreamSynchronize(st));      /* caller buffers are only read during the call */
+    return AMH_OK;
+}
+
+int32_t amh_run_get_ram_adapt(amh_run* run, double* logalpha, double* eta) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    amh_run& r = *run;
+    if (r.sampler->d.kind != AMH_SAMPLER_RAM) return fail(AMH_ERR_INVALID, "not a RobustAdaptiveMetropolis run");
+    AMH_CUDA_TRY(cudaSetDevice(r.ctx->device));
+    AMH_CUDA_TRY(cudaStreamSynchronize(r.ctx->stream));
+    if (logalpha) AMH_CUDA_TRY(cudaMemcpy(logalpha, r.logalpha, sizeof(double) * r.n, cudaMemcpyDeviceToHost));
+    if (eta) AMH_CUDA_TRY(cudaMemcpy(eta, r.eta, sizeof(double) * r.n, cudaMemcpyDeviceToHost));
+    return AMH_OK;
+}
+
 int32_t amh_run_set_params(amh_run* run, const double* x) {
     if (!run || !x) return fail(AMH_ERR_INVALID, "NULL argument");
     amh_run& r = *run;

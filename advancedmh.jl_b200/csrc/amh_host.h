@@ -109,10 +109,13 @@ int launch_ram(amh_run& r, int nsteps, bool warmup, const amhd::SaveArgs& sv);
 int launch_stretch(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_init(amh_run& r, int mode);
 int ram_gather_S(amh_run& r, double* dst);
+int ram_scatter_S(amh_run& r, const double* src);   /* [tri][pitch] device buffer -> current factor of every chain */
+int launch_relq(amh_run& r);                        /* static MH: recompute the cached logq(state) */
 /* K4W: one warp per chain, factor resident in shared memory (amh_launch_ram_warp.cu) */
 bool ram_warp_eligible(const amh_run& r);
 int launch_ram_warp(amh_run& r, int nsteps, bool warmup, const amhd::SaveArgs& sv);
 int ramw_init_S(amh_run& r);
+int ramw_import_S(amh_run& r, const double* src);
 int ramw_export_S(amh_run& r, double* dst);   /* current factor of every chain -> dst [tri][pitch] */
 int default_steps_per_launch(const amh_run& r);
 }  // namespace amhh

@@ -119,6 +119,24 @@ int launch_init_t(amh_run& r, int mode) {
     return AMH_OK;
 }
 
+/* static MH keeps logq(state) cached (mh-core.jl:119-123 evaluates it per step); amh_run_set_state recomputes it */
+__global__ void __launch_bounds__(64)
+relq_kernel(const __grid_constant__ ChainState st, int d, const __grid_constant__ PropP<0> prop) {
+    const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= st.n) return;
+    double x[Dim<0>::cap];
+    for (int i = 0; i < d; ++i) x[i] = st.X[(long long)i * st.pitch + ch];
+    st.lq[ch] = logq<0>(x, d, prop);
+}
+
+int launch_relq(amh_run& r) {
+    const unsigned grid = (unsigned)((r.n + 63) / 64);
+    relq_kernel<<<grid, 64, 0, r.ctx->stream>>>(chain_state(r), r.dim, make_prop<0>(*r.sampler));
+    AMH_CUDA_TRY(cudaGetLastError());
+    r.launches += 1;
+    return AMH_OK;
+}
+
 int launch_init(amh_run& r, int mode) {
     if (r.dim > kGenericCap) return fail(AMH_ERR_UNSUPPORTED, "device samplers support dim <= 128");
     switch (r.target->kind) {

@@ -238,6 +238,14 @@ int launch_ram(amh_run& r, int nsteps, bool warmup, const SaveArgs& sv) {
     return fail(AMH_ERR_INVALID, "unknown target kind");
 }
 
+/* set_state: `src` ([tri][pitch]) becomes the current factor of every chain (buffer 0) */
+int ram_scatter_S(amh_run& r, const double* src) {
+    const size_t nt = (size_t)r.dim * (r.dim + 1) / 2;
+    AMH_CUDA_TRY(cudaMemcpyAsync(r.S, src, sizeof(double) * nt * r.pitch, cudaMemcpyDeviceToDevice, r.ctx->stream));
+    AMH_CUDA_TRY(cudaMemsetAsync(r.sflag, 0, (size_t)r.pitch, r.ctx->stream));
+    return AMH_OK;
+}
+
 int ram_gather_S(amh_run& r, double* dst) {
     const long long nt = (long long)r.dim * (r.dim + 1) / 2;
     const unsigned grid = (unsigned)((r.n + 127) / 128);

@@ -331,6 +331,13 @@ __global__ void ramw_export_S_kernel(const double* Sw, double* dst, long long n,
     for (int i = 0; i < d; ++i)
         for (int j = 0; j <= i; ++j) dst[(long long)tri(i, j) * pitch + ch] = Sw[(size_t)ch * ntp + colstart(j, d) + (i - j)];
 }
+__global__ void ramw_import_S_kernel(double* Sw, const double* src, long long n, long long pitch, int d) {
+    const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= n) return;
+    const int ntp = (d * (d + 1) / 2 + 1) & ~1;
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j <= i; ++j) Sw[(size_t)ch * ntp + colstart(j, d) + (i - j)] = src[(long long)tri(i, j) * pitch + ch];
+}
 __global__ void ramw_init_S_kernel(double* Sw, const double* S0 /* row-packed or NULL */, long long n, int d) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int nt = d * (d + 1) / 2;
@@ -361,6 +368,14 @@ int ramw_init_S(amh_run& r) {
 int ramw_export_S(amh_run& r, double* dst) {
     const unsigned grid = (unsigned)((r.n + 127) / 128);
     ramw_export_S_kernel<<<grid, 128, 0, r.ctx->stream>>>(r.S, dst, r.n, r.pitch, r.dim);
+    AMH_CUDA_TRY(cudaGetLastError());
+    r.launches += 1;
+    return AMH_OK;
+}
+
+int ramw_import_S(amh_run& r, const double* src) {
+    const unsigned grid = (unsigned)((r.n + 127) / 128);
+    ramw_import_S_kernel<<<grid, 128, 0, r.ctx->stream>>>(r.S, src, r.n, r.pitch, r.dim);
     AMH_CUDA_TRY(cudaGetLastError());
     r.launches += 1;
     return AMH_OK;

@@ -1,9 +1,16 @@
 """The small slice of Distributions.jl the reference's proposal constructors use
-(`Normal`, `MvNormal`; test/runtests.jl:58-60,78-80, README.md:35,104-112): plain
-parameter holders that the sampler layer lowers to an `amh_sampler_desc`."""
+(`Normal`, `MvNormal`; test/runtests.jl:58-60,78-80, README.md:35,104-112; `InverseGamma` in arrays of
+univariate proposals, README.md:106, test/emcee.jl:19): plain parameter holders that the sampler layer lowers to
+an `amh_sampler_desc`.  Univariate laws carry `component()` = (family, p0, p1, logc) in the parametrisation of
+include/amh_contract.h (AMH_FAM_*)."""
 from __future__ import annotations
 
+import math
+
 import numpy as np
+
+FAM_NORMAL, FAM_INVGAMMA, FAM_GAMMA, FAM_UNIFORM, FAM_EXPONENTIAL, FAM_LOGNORMAL = 1, 2, 3, 4, 5, 6
+_HALF_LOG_2PI = 0.5 * math.log(2.0 * math.pi)
 
 
 class _Identity:
@@ -33,6 +40,71 @@ class Normal:
         self.mu, self.sigma = float(mu), float(sigma)
     def __len__(self):
         return 1
+    def component(self):
+        return FAM_NORMAL, self.mu, self.sigma, -math.log(self.sigma) - _HALF_LOG_2PI
+
+
+class LogNormal:
+    """LogNormal(mu, sigma)"""
+    def __init__(self, mu=0.0, sigma=1.0):
+        if not sigma > 0:
+            raise ValueError("LogNormal: sigma must be positive")
+        self.mu, self.sigma = float(mu), float(sigma)
+    def __len__(self):
+        return 1
+    def component(self):
+        return FAM_LOGNORMAL, self.mu, self.sigma, -math.log(self.sigma) - _HALF_LOG_2PI
+
+
+class InverseGamma:
+    """InverseGamma(shape, scale)  (README.md:106 `InverseGamma(2,3)`)"""
+    def __init__(self, shape=1.0, scale=1.0):
+        if not (shape > 0 and scale > 0):
+            raise ValueError("InverseGamma: shape and scale must be positive")
+        self.shape, self.scale = float(shape), float(scale)
+    def __len__(self):
+        return 1
+    def component(self):
+        return FAM_INVGAMMA, self.shape, self.scale, self.shape * math.log(self.scale) - math.lgamma(self.shape)
+
+
+class Gamma:
+    """Gamma(shape, scale)"""
+    def __init__(self, shape=1.0, scale=1.0):
+        if not (shape > 0 and scale > 0):
+            raise ValueError("Gamma: shape and scale must be positive")
+        self.shape, self.scale = float(shape), float(scale)
+    def __len__(self):
+        return 1
+    def component(self):
+        return FAM_GAMMA, self.shape, self.scale, -self.shape * math.log(self.scale) - math.lgamma(self.shape)
+
+
+class Uniform:
+    """Uniform(a, b)"""
+    def __init__(self, a=0.0, b=1.0):
+        if not b > a:
+            raise ValueError("Uniform: need a < b")
+        self.a, self.b = float(a), float(b)
+    def __len__(self):
+        return 1
+    def component(self):
+        return FAM_UNIFORM, self.a, self.b, -math.log(self.b - self.a)
+
+
+class Exponential:
+    """Exponential(scale)"""
+    def __init__(self, scale=1.0):
+        if not scale > 0:
+            raise ValueError("Exponential: scale must be positive")
+        self.scale = float(scale)
+    def __len__(self):
+        return 1
+    def component(self):
+        return FAM_EXPONENTIAL, self.scale, 0.0, -math.log(self.scale)
+
+
+UNIVARIATE = (Normal, LogNormal, InverseGamma, Gamma, Uniform, Exponential)
 
 
 class MvNormal:

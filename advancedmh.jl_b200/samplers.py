@@ -16,7 +16,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _capi as K
-from .distributions import MvNormal, Normal
+from .distributions import MvNormal, Normal, UNIVARIATE
 
 
 # ------------------------------------------------------------------ proposals
@@ -44,6 +44,10 @@ def SymmetricRandomWalkProposal(p):
     return RandomWalkProposal(p, True)
 
 
+def _is_univariate_array(p):
+    return isinstance(p, (list, tuple)) and len(p) > 0 and all(isinstance(q, UNIVARIATE) for q in p)
+
+
 def _lower_gaussian(p):
     """Distribution | list of Normal -> (dim, cov_kind, mean|None, scale)"""
     if isinstance(p, MvNormal):
@@ -65,19 +69,50 @@ class MHSampler:
 
 
 class MetropolisHastings(MHSampler):
-    """MetropolisHastings(proposal)  (mh-core.jl:44-46)"""
+    """MetropolisHastings(proposal)  (mh-core.jl:44-46).  `proposal` is
+
+    * one StaticProposal / RandomWalkProposal over a Normal, an MvNormal, or an ARRAY of univariate distributions
+      (`StaticProposal([Normal(0,1), InverseGamma(2,3)])`, README.md:106; proposal.jl:26-35), or
+    * an ARRAY (or NamedTuple-like dict, in field order) of such proposals over univariate distributions, one per
+      coordinate, each static or random-walk with its own `issymmetric` (README.md:111,125-133; proposal.jl:132-175,
+      199-240).  The device state is a flat vector, so a NamedTuple only contributes its field order and names."""
     def __init__(self, proposal):
+        self.components = None
+        self.names = None
+        if isinstance(proposal, dict):
+            self.names = list(proposal.keys())
+            proposal = list(proposal.values())
+        if isinstance(proposal, (list, tuple)):
+            if not proposal or not all(isinstance(q, (StaticProposal, RandomWalkProposal)) and isinstance(q.proposal, UNIVARIATE)
+                                       for q in proposal):
+                raise ValueError("an array / NamedTuple of proposals must hold Static/RandomWalkProposal objects over "
+                                 "univariate distributions, one per coordinate")
+            self.proposal = list(proposal)
+            self.dim = len(proposal)
+            self.components = [q.proposal.component() + (isinstance(q, RandomWalkProposal), q.issymmetric) for q in proposal]
+            self.kind = K.SAMPLER_MIXED
+            return
         if not isinstance(proposal, (StaticProposal, RandomWalkProposal)):
-            raise ValueError("MetropolisHastings needs a StaticProposal or RandomWalkProposal "
-                             "(NamedTuple / mixed containers are host-only conveniences)")
+            raise ValueError("MetropolisHastings needs a StaticProposal or RandomWalkProposal (or an array of them)")
         self.proposal = proposal
-        self.dim, self.cov_kind, self.mean, self.scale = _lower_gaussian(proposal.proposal)
+        self.kind = K.SAMPLER_RW if isinstance(proposal, RandomWalkProposal) else K.SAMPLER_STATIC
+        p = proposal.proposal
+        if _is_univariate_array(p) and not all(isinstance(q, Normal) for q in p):
+            self.dim = len(p)
+            self.components = [q.component() for q in p]
+        elif isinstance(p, UNIVARIATE) and not isinstance(p, Normal):
+            self.dim = 1
+            self.components = [p.component()]
+        else:
+            self.dim, self.cov_kind, self.mean, self.scale = _lower_gaussian(p)
 
     def lower(self, eng, dim):
         if dim != self.dim:
             raise ValueError(f"proposal dimension {self.dim} != model dimension {dim}")
-        kind = K.SAMPLER_RW if isinstance(self.proposal, RandomWalkProposal) else K.SAMPLER_STATIC
-        return eng.sampler(kind=kind, dim=dim, symmetric=self.proposal.issymmetric, cov_kind=self.cov_kind,
+        if self.components is not None:
+            sym = False if self.kind == K.SAMPLER_MIXED else self.proposal.issymmetric
+            return eng.sampler(kind=self.kind, dim=dim, symmetric=sym, cov_kind=K.COV_COMPONENTS, components=self.components)
+        return eng.sampler(kind=self.kind, dim=dim, symmetric=self.proposal.issymmetric, cov_kind=self.cov_kind,
                            mean=self.mean, scale=self.scale)
 
 
@@ -115,6 +150,13 @@ class Ensemble(MHSampler):
     def lower(self, eng, dim):
         p = self.proposal.proposal
         cov_kind, mean, scale = K.COV_SCALAR, None, None
+        if _is_univariate_array(p) and not all(isinstance(q, Normal) for q in p):
+            # StretchProposal([InverseGamma(2,3), Normal(0,1)]) (test/emcee.jl:19): the law of the initial draw
+            if len(p) != dim:
+                raise ValueError(f"proposal dimension {len(p)} != model dimension {dim}")
+            return eng.sampler(kind=K.SAMPLER_STRETCH, dim=dim, cov_kind=K.COV_COMPONENTS,
+                               components=[q.component() for q in p],
+                               stretch_a=self.proposal.stretch_length, n_walkers=self.n_walkers)
         if p is not None:
             try:
                 pdim, cov_kind, mean, scale = _lower_gaussian(p)

@@ -153,11 +153,14 @@ def _initial_matrix(initial_params, sampler, dim, nchains, multi):
 
 def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None, thinning=1, num_warmup=0,
            chain_type=None, param_names=None, progress=False, callback=None, engine=None, store=True,
-           summary=False, steps_per_launch=0, out=None):
+           summary=False, steps_per_launch=0, out=None, initial_state=None, save_state=False):
     """See module docstring.  Extra device-side keywords (never on the samplers): `engine`
     (a _capi.Engine; default = the CUDA library), `store=False` + `summary=True` for runs whose
     samples cannot be stored (SURVEY.md 7 hard part 7), `out=(values, accepted)` caller-owned (ideally
-    pinned, Engine.pinned_empty) buffers of this rank's shard: (N, dim+1, n_local) float64, (N, n_local) uint8."""
+    pinned, Engine.pinned_empty) buffers of this rank's shard: (N, dim+1, n_local) float64, (N, n_local) uint8.
+    `initial_state=` (AbstractMCMC keyword): a state dict of ALL chains as returned in `info["state"]` by a call with
+    `save_state=True`; the run then continues the old one bit for bit -- its first sample is one `step` from that
+    state, the step counter (hence the noise stream, RAM's `iteration` and the warm-up boundary) carries on."""
     args = list(args)
     if args and isinstance(args[0], np.random.Generator):
         rng = args.pop(0)
@@ -197,13 +200,29 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
     run = None
     try:
         if n_local > 0:
-            run = eng.run(th, sh, n_local, seeds[lo:hi], None if init is None else init[:, lo * nw:hi * nw],
-                          chain_offset=lo * nw)
+            sl = slice(lo * nw, hi * nw)
+            if initial_state is not None:
+                if "seeds" in initial_state:
+                    seeds = np.asarray(initial_state["seeds"], dtype=np.uint64)
+                    if seeds.shape != (nchains,):
+                        raise ValueError("initial_state was saved for a different number of chains")
+                init = np.asarray(initial_state["x"], dtype=np.float64)
+                if init.shape != (dim, nchains * nw):
+                    raise ValueError(f"initial_state['x'] must have shape {(dim, nchains * nw)}")
+            run = eng.run(th, sh, n_local, seeds[lo:hi], None if init is None else init[:, sl], chain_offset=lo * nw)
+            if initial_state is not None:
+                run.set_state({k: (v if k == "step" or v is None else np.asarray(v)[..., sl])
+                               for k, v in initial_state.items() if k != "seeds"})
+                run.steps(1, warmup=run.state_step() < num_warmup)
             out, acc, summ = run.sample(N, discard_initial, thinning, num_warmup, store=store,
                                         store_accepted=store, summary=summary or not store, chain_means=False,
                                         out=None if out is None else out[0], acc=None if out is None else out[1])
             info = dict(summary=summ, launches=run.launch_count(), rank=rank, world=world,
                         chains=(lo * nw, hi * nw))
+            if save_state:
+                stt = run.state(grad=isinstance(sampler, MALA), S=isinstance(sampler, RobustAdaptiveMetropolis))
+                stt["seeds"] = seeds
+                info["state"] = stt
             if callback is not None and store:
                 for i in range(N):
                     callback(rng, model, sampler, out[i], None, i + 1)
@@ -219,6 +238,14 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
 
     if world > 1 and isinstance(parallel, MCMCB200) and parallel.gather and store:
         out, acc = _gather_samples(dist, out, acc, nchains * nw, world, nw)
+    if world > 1 and isinstance(parallel, MCMCB200) and parallel.gather and save_state:
+        # the resumable state of ALL chains on every rank (chains are the last axis of every per-chain array)
+        parts = [None] * world
+        dist.all_gather_object(parts, info.get("state"))
+        parts = [p for p in parts if p is not None]
+        info["state"] = {k: (parts[0][k] if k in ("step", "seeds") else
+                             None if parts[0][k] is None else np.concatenate([p[k] for p in parts], axis=-1))
+                         for k in parts[0]}
 
     if not store:
         return info

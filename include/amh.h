@@ -68,11 +68,27 @@ extern "C" {
 #define AMH_SAMPLER_STRETCH  3  /* Ensemble(n_walkers, StretchProposal(p, a))         emcee.jl:1-102                      */
 #define AMH_SAMPLER_MALA     4  /* MALA(g -> MvNormal(drift*g, sigma2*I))             MALA.jl:1-93                        */
 #define AMH_SAMPLER_RAM      5  /* RobustAdaptiveMetropolis(alpha, gamma, S, lo, hi)  RobustAdaptiveMetropolis.jl:75-278  */
+#define AMH_SAMPLER_MIXED    6  /* MetropolisHastings([StaticProposal(d1), RandomWalkProposal(d2), ...]): an ARRAY OF
+                                   PROPOSALS, one univariate law per coordinate, each static or random-walk and with its
+                                   own `issymmetric` (proposal.jl:132-150, 236-240; README.md:125-133)                  */
 
 /* proposal covariance representation (Distributions' ScalMat / PDiagMat / PDMat) */
 #define AMH_COV_SCALAR 1   /* scale[0]   = sigma                                      */
 #define AMH_COV_DIAG   2   /* scale[dim] = sigma_i  (also: array of Normal(mu_i,sigma_i), proposal.jl:26-35) */
 #define AMH_COV_FULL   3   /* scale[dim(dim+1)/2] = lower Cholesky factor L, packed by rows */
+#define AMH_COV_COMPONENTS 4 /* components[dim]: an array of univariate distributions of any catalogue family
+                                (proposal.jl:26-35), e.g. StaticProposal([Normal(0,1), InverseGamma(2,3)]) README.md:106;
+                                mean / scale are unused */
+
+/* one coordinate of an AMH_COV_COMPONENTS proposal; families and parametrisation: AMH_FAM_* in amh_contract.h */
+typedef struct amh_component {
+    int32_t family;          /* AMH_FAM_NORMAL, _INVGAMMA, _GAMMA, _UNIFORM, _EXPONENTIAL, _LOGNORMAL               */
+    int32_t rw;              /* AMH_SAMPLER_MIXED only: 1 = RandomWalkProposal, 0 = StaticProposal                   */
+    int32_t symmetric;       /* AMH_SAMPLER_MIXED only: the component's `issymmetric` (Hastings term literal 0)      */
+    int32_t reserved;
+    double  p0, p1;          /* distribution parameters                                                              */
+    double  logc;            /* normalising constant of the log-density, computed by the caller                      */
+} amh_component;
 
 typedef struct amh_sampler_desc {
     int32_t kind;            /* AMH_SAMPLER_*                                                   */
@@ -91,6 +107,7 @@ typedef struct amh_sampler_desc {
     double  ram_eig_lo;      /* RAM.eigenvalue_lower_bound = 0   (:84)                          */
     double  ram_eig_hi;      /* RAM.eigenvalue_upper_bound = Inf (:86)                          */
     const double* ram_S0;    /* RAM.S: dense dim x dim row-major (lower triangle used), NULL = I (:82,198-207) */
+    const amh_component* components;  /* [dim], cov_kind == AMH_COV_COMPONENTS or kind == AMH_SAMPLER_MIXED, else NULL */
 } amh_sampler_desc;
 
 /* pooled and per-chain summaries accumulated on the device over SAVED samples */
@@ -169,6 +186,17 @@ int32_t amh_run_get_state(amh_run* run, double* x, double* lp, double* grad, dou
                           uint8_t* accepted, int64_t* naccept, int64_t* step_counter);
 /* setparams!!: replaces x and recomputes lp (and the gradient for MALA) on the device */
 int32_t amh_run_set_params(amh_run* run, const double* x);
+/* resume: installs a state read earlier with amh_run_get_state, so that a new run continues an old one bit for bit
+ * (AbstractMCMC's `initial_state=` keyword; the state structs are Transition src/AdvancedMH.jl:61-65,
+ * GradientTransition MALA.jl:14-19, RobustAdaptiveMetropolisState RAM :99-114 -- RAM's `iteration` is
+ * step_counter + 1 and its eta / log-alpha fields are outputs only).  Same layouts as amh_run_get_state; a NULL
+ * pointer keeps the run's current value, step_counter < 0 keeps the counter.  Nothing is recomputed except static
+ * MH's cached proposal log-density of the state (a pure function of x). */
+int32_t amh_run_set_state(amh_run* run, const double* x, const double* lp, const double* grad, const double* S,
+                          const uint8_t* accepted, const int64_t* naccept, int64_t step_counter);
+/* RAM: the state fields that only report the last step -- log acceptance ratio `log-alpha` and adaptation step size
+ * `eta` (RAM :107-110), [nchains_local] each, either may be NULL (StatesExtractor, test/RobustAdaptiveMetropolis.jl:11-28) */
+int32_t amh_run_get_ram_adapt(amh_run* run, double* logalpha, double* eta);
 
 /* page-locked host memory for initial_params / sample buffers: host<->device copies of pinned buffers run at
  * full PCIe/C2C speed and asynchronously (Julia: unsafe_wrap(Array, Ptr{Float64}(p), dims)) */

@@ -32,7 +32,7 @@
 #define AMH_HD static inline
 #endif
 
-#define AMH_CONTRACT_VERSION 1
+#define AMH_CONTRACT_VERSION 1   /* v1 + univariate families (additive: no v1 stream or result changed) */
 
 namespace amh {
 
@@ -252,6 +252,101 @@ AMH_HD uint64_t bounded(uint32_t wlo, uint32_t whi, uint64_t n) {
 #else
     return (uint64_t)(((unsigned __int128)w * n) >> 64);
 #endif
+}
+
+/* ------------------------------------------- univariate proposal families
+ * Arrays of univariate distributions as proposals (proposal.jl:26-35: `map(rand, p.proposal)` and the
+ * left-to-right sum of `logpdf(p_i, v_i)`; README.md:104-112 `StaticProposal([Normal(0,1), InverseGamma(2,3)])`,
+ * test/emcee.jl:19 `StretchProposal([InverseGamma(2,3), Normal(0,1)])`).  Parametrisations are those of
+ * Distributions.jl; `logc` is the normalising constant, computed once on the host and passed in, so that both
+ * sides use the same bits.
+ *
+ * Stream use: component i of step k (k = 0: the initial draw) of a chain reads
+ *   NORMAL / LOGNORMAL : the chain's regular Box-Muller slot z[i] of that step (stream 0)
+ *   everything else    : blocks (blk = k*d + i, stream = 2, 3, ...) -- a private sub-stream, because the gamma
+ *                        sampler is a rejection loop (attempt t: stream 2+2t -> normal, 3+2t -> uniform;
+ *                        shape < 1 boost: stream 2 + 2*AMH_GAMMA_MAX_TRIES).
+ * For the initial draw of an ensemble walker w the sub-stream block is w*d + i of the ENSEMBLE's key. */
+#define AMH_FAM_NORMAL      1   /* Normal(p0 = mu, p1 = sigma)            logc = -log(sigma) - log(2pi)/2        */
+#define AMH_FAM_INVGAMMA    2   /* InverseGamma(p0 = shape, p1 = scale)   logc = shape*log(scale) - lgamma(shape) */
+#define AMH_FAM_GAMMA       3   /* Gamma(p0 = shape, p1 = scale)          logc = -shape*log(scale) - lgamma(shape) */
+#define AMH_FAM_UNIFORM     4   /* Uniform(p0 = a, p1 = b)                logc = -log(b - a)                      */
+#define AMH_FAM_EXPONENTIAL 5   /* Exponential(p0 = scale)                logc = -log(scale)                      */
+#define AMH_FAM_LOGNORMAL   6   /* LogNormal(p0 = mu, p1 = sigma)         logc = -log(sigma) - log(2pi)/2        */
+#define AMH_GAMMA_MAX_TRIES 32  /* acceptance >= 0.95 per try: the cap is reached with probability < 1e-41       */
+
+AMH_HD bool family_uses_normal_slot(int fam) { return fam == AMH_FAM_NORMAL || fam == AMH_FAM_LOGNORMAL; }
+
+/* Gamma(shape, 1) by Marsaglia & Tsang (2000), "A simple method for generating gamma variables" */
+AMH_HD double gamma_mt(uint64_t seed, uint64_t blk, double shape) {
+    const bool boost = shape < 1.0;
+    const double a = boost ? shape + 1.0 : shape;
+    const double dd = a - 0x1.5555555555555p-2;          /* a - 1/3 */
+    const double c = 1.0 / sqrt(9.0 * dd);
+    double g = dd;
+    for (uint32_t t = 0; t < AMH_GAMMA_MAX_TRIES; ++t) {
+        const Block bn = stream_block(seed, blk, 2u + 2u * t);
+        double x, unused;
+        normal_pair(bn, x, unused);
+        const double v1 = c * x + 1.0;
+        if (!(v1 > 0.0)) continue;
+        const double v = (v1 * v1) * v1;
+        const Block bu = stream_block(seed, blk, 3u + 2u * t);
+        const double u = u01(bu.v[0], bu.v[1]);
+        g = dd * v;
+        const double rhs = ((0.5 * (x * x) + dd) - g) + dd * log_(v);
+        if (-neglog_normal(u) < rhs) break;
+    }
+    if (boost) {
+        const Block bb = stream_block(seed, blk, 2u + 2u * AMH_GAMMA_MAX_TRIES);
+        const double u = u01(bb.v[0], bb.v[1]);
+        g = g * exp_(-neglog_normal(u) / shape);
+    }
+    return g;
+}
+
+/* rand(rng, p_i): `z` is the chain's standard normal of slot i (ignored by the families with a sub-stream) */
+AMH_HD double family_draw(int fam, double p0, double p1, double z, uint64_t seed, uint64_t blk) {
+    switch (fam) {
+    case AMH_FAM_NORMAL:    return p1 * z + p0;
+    case AMH_FAM_LOGNORMAL: return exp_(p1 * z + p0);
+    case AMH_FAM_UNIFORM: {
+        const Block b = stream_block(seed, blk, 2u);
+        return (p1 - p0) * u01(b.v[0], b.v[1]) + p0;
+    }
+    case AMH_FAM_EXPONENTIAL: {
+        const Block b = stream_block(seed, blk, 2u);
+        return p0 * exponential(b.v[0], b.v[1]);
+    }
+    case AMH_FAM_GAMMA:     return p1 * gamma_mt(seed, blk, p0);
+    case AMH_FAM_INVGAMMA:  return p1 / gamma_mt(seed, blk, p0);
+    }
+    return NAN;
+}
+
+/* logpdf(p_i, x), -Inf outside the support (what makes a random walk with a positive-only increment law reject) */
+AMH_HD double family_logpdf(int fam, double p0, double p1, double logc, double x) {
+    switch (fam) {
+    case AMH_FAM_NORMAL: {
+        const double z = (x - p0) / p1;
+        return logc - 0.5 * (z * z);
+    }
+    case AMH_FAM_LOGNORMAL: {
+        if (!(x > 0.0)) return x != x ? x : -INFINITY;
+        const double lx = log_(x);
+        const double z = (lx - p0) / p1;
+        return (logc - lx) - 0.5 * (z * z);
+    }
+    case AMH_FAM_UNIFORM:     return (x >= p0 && x <= p1) ? logc : (x != x ? x : -INFINITY);
+    case AMH_FAM_EXPONENTIAL: return (x >= 0.0) ? logc - x / p0 : (x != x ? x : -INFINITY);
+    case AMH_FAM_GAMMA:
+        if (!(x > 0.0)) return x != x ? x : -INFINITY;
+        return (logc + (p0 - 1.0) * log_(x)) - x / p1;
+    case AMH_FAM_INVGAMMA:
+        if (!(x > 0.0)) return x != x ? x : -INFINITY;
+        return (logc - (p0 + 1.0) * log_(x)) - p1 / x;
+    }
+    return NAN;
 }
 
 /* ----------------------------------------------------- stream word budget

@@ -256,6 +256,23 @@ struct Sampler {
     std::vector<double> mean, scale, S0;
     bool has_mean = false;
     double mala_sigma = 0;
+    std::vector<amh_component> comps;      /* AMH_COV_COMPONENTS / AMH_SAMPLER_MIXED */
+    bool by_components() const { return !comps.empty(); }
+
+    /* v = map(rand, p.proposal) for an array of univariate laws (proposal.jl:26-28); `blk0` = first sub-stream block */
+    void draw_components(const double* z, uint64_t seed, uint64_t blk0, double* v) const {
+        for (int i = 0; i < d.dim; ++i)
+            v[i] = amh::family_draw(comps[i].family, comps[i].p0, comps[i].p1, z[i], seed, blk0 + (uint64_t)i);
+    }
+    /* logpdf(p, a) = mapreduce(logpdf, +, zip(p.proposal, a)): left-to-right sum (proposal.jl:32-35) */
+    double logq_components(const double* a) const {
+        double acc = 0.0;
+        for (int i = 0; i < d.dim; ++i) {
+            const double l = amh::family_logpdf(comps[i].family, comps[i].p0, comps[i].p1, comps[i].logc, a[i]);
+            acc = (i == 0) ? l : acc + l;
+        }
+        return acc;
+    }
 
     /* v = rand(rng, proposal) given the step's standard normals z
      * (proposal.jl:25-28; Distributions: mu + unwhiten(Sigma, z)) */
@@ -399,6 +416,68 @@ void mh_steps(Run& r, int64_t a, int64_t b, int64_t nsteps) {
         }
         for (int i = 0; i < d; ++i) r.X[(int64_t)i * r.n + ch] = x[i];
         r.lp[ch] = lp; r.lq[ch] = lq; r.nacc[ch] = nacc; r.acc[ch] = accepted;
+    }
+}
+
+/* ---- MH step with an array of univariate laws (one Proposal over an array: proposal.jl:26-35,41-85) or an array of
+ * Proposals (AMH_SAMPLER_MIXED: proposal.jl:132-150 propose, :236-240 logratio = left-to-right sum of the per-component
+ * ratios, symmetric components contributing the literal 0 of :195-196) ---- */
+void mh_component_steps(Run& r, int64_t a, int64_t b, int64_t nsteps) {
+    const int d = r.dim;
+    const Sampler& sp = *r.s;
+    const bool mixed = sp.d.kind == AMH_SAMPLER_MIXED;
+    const bool is_rw = sp.d.kind == AMH_SAMPLER_RW;
+    const bool sym = sp.d.symmetric != 0;
+    std::vector<double> x(d), z(d), v(d), c(d), t1(d), t2(d);
+    for (int64_t ch = a; ch < b; ++ch) {
+        const uint64_t seed = r.seeds[ch];
+        for (int i = 0; i < d; ++i) x[i] = r.X[(int64_t)i * r.n + ch];
+        double lp = r.lp[ch];
+        int64_t nacc = r.nacc[ch];
+        uint8_t accepted = r.acc[ch];
+        for (int64_t s = 0; s < nsteps; ++s) {
+            const uint64_t k = (uint64_t)(r.step + s + 1);
+            normals(seed, k, 0, d, z.data());
+            sp.draw_components(z.data(), seed, k * (uint64_t)d, v.data());
+            for (int i = 0; i < d; ++i) {
+                const bool rw_i = mixed ? sp.comps[i].rw != 0 : is_rw;
+                c[i] = rw_i ? x[i] + v[i] : v[i];
+            }
+            const double lp_c = r.t->logp(c.data());
+            double logratio = 0.0;
+            if (mixed) {
+                for (int i = 0; i < d; ++i) {
+                    const amh_component& q = sp.comps[i];
+                    double lr = 0.0;
+                    if (!q.symmetric) {
+                        if (q.rw)
+                            lr = amh::family_logpdf(q.family, q.p0, q.p1, q.logc, x[i] - c[i]) -
+                                 amh::family_logpdf(q.family, q.p0, q.p1, q.logc, c[i] - x[i]);
+                        else
+                            lr = amh::family_logpdf(q.family, q.p0, q.p1, q.logc, x[i]) -
+                                 amh::family_logpdf(q.family, q.p0, q.p1, q.logc, c[i]);
+                    }
+                    logratio = (i == 0) ? lr : logratio + lr;
+                }
+            } else if (!sym) {
+                if (is_rw) {
+                    for (int i = 0; i < d; ++i) { t1[i] = x[i] - c[i]; t2[i] = c[i] - x[i]; }
+                    logratio = sp.logq_components(t1.data()) - sp.logq_components(t2.data());
+                } else {
+                    logratio = sp.logq_components(x.data()) - sp.logq_components(c.data());
+                }
+            }
+            const double loga = (lp_c - lp) + logratio;
+            const double e = step_exponential(seed, k, d);
+            if (-e < loga) {                       /* mh-core.jl:108 (strict; NaN rejects) */
+                for (int i = 0; i < d; ++i) x[i] = c[i];
+                lp = lp_c; accepted = 1; ++nacc;
+            } else {
+                accepted = 0;
+            }
+        }
+        for (int i = 0; i < d; ++i) r.X[(int64_t)i * r.n + ch] = x[i];
+        r.lp[ch] = lp; r.nacc[ch] = nacc; r.acc[ch] = accepted;
     }
 }
 
@@ -598,7 +677,11 @@ int do_steps(Run& r, int64_t nsteps, bool warmup) {
     switch (r.s->d.kind) {
     case AMH_SAMPLER_STATIC:
     case AMH_SAMPLER_RW:
-        parallel_for(r.n, [&](int64_t a, int64_t b) { mh_steps(r, a, b, nsteps); });
+    case AMH_SAMPLER_MIXED:
+        if (r.s->by_components())
+            parallel_for(r.n, [&](int64_t a, int64_t b) { mh_component_steps(r, a, b, nsteps); });
+        else
+            parallel_for(r.n, [&](int64_t a, int64_t b) { mh_steps(r, a, b, nsteps); });
         break;
     case AMH_SAMPLER_MALA:
         parallel_for(r.n, [&](int64_t a, int64_t b) { mala_steps(r, a, b, nsteps); });
@@ -682,6 +765,19 @@ int32_t amho_target_create(amh_ctx*, int32_t kind, int32_t dim, const double* bl
 }
 int32_t amho_target_destroy(amh_target* t) { delete (Target*)t; return AMH_OK; }
 
+/* parameter validation of one univariate law (Distributions.jl constructors throw DomainError) */
+static const char* check_component(const amh_component& q) {
+    switch (q.family) {
+    case AMH_FAM_NORMAL:
+    case AMH_FAM_LOGNORMAL:   return (q.p1 > 0.0) ? nullptr : "Normal / LogNormal need sigma > 0";
+    case AMH_FAM_INVGAMMA:
+    case AMH_FAM_GAMMA:       return (q.p0 > 0.0 && q.p1 > 0.0) ? nullptr : "Gamma / InverseGamma need shape > 0 and scale > 0";
+    case AMH_FAM_UNIFORM:     return (q.p1 > q.p0) ? nullptr : "Uniform needs a < b";
+    case AMH_FAM_EXPONENTIAL: return (q.p0 > 0.0) ? nullptr : "Exponential needs scale > 0";
+    }
+    return "unknown distribution family";
+}
+
 int32_t amho_sampler_create(amh_ctx*, const amh_sampler_desc* desc, amh_sampler** out) {
     if (!desc || !out) return fail(AMH_ERR_INVALID, "desc/out is NULL");
     const int d = desc->dim;
@@ -693,10 +789,20 @@ int32_t amho_sampler_create(amh_ctx*, const amh_sampler_desc* desc, amh_sampler*
     switch (desc->kind) {
     case AMH_SAMPLER_STATIC:
     case AMH_SAMPLER_RW:
+    case AMH_SAMPLER_MIXED:
     case AMH_SAMPLER_STRETCH: {
         if (desc->kind == AMH_SAMPLER_STRETCH) {
             if (desc->n_walkers < 2) return bad("Ensemble needs n_walkers >= 2");
             if (!(desc->stretch_a > 1.0)) return bad("stretch_length must be > 1");
+        }
+        if (desc->kind == AMH_SAMPLER_MIXED || desc->cov_kind == AMH_COV_COMPONENTS) {
+            if (!desc->components) return bad("components is NULL");
+            s->comps.assign(desc->components, desc->components + d);
+            for (const amh_component& q : s->comps) {
+                const char* m = check_component(q);
+                if (m) return bad(m);
+            }
+            break;
         }
         const bool need_cov = desc->kind != AMH_SAMPLER_STRETCH || desc->scale != nullptr;
         if (need_cov) {
@@ -728,7 +834,7 @@ int32_t amho_sampler_create(amh_ctx*, const amh_sampler_desc* desc, amh_sampler*
     default:
         return bad("unknown sampler kind");
     }
-    s->d.mean = nullptr; s->d.scale = nullptr; s->d.ram_S0 = nullptr;
+    s->d.mean = nullptr; s->d.scale = nullptr; s->d.ram_S0 = nullptr; s->d.components = nullptr;
     *out = (amh_sampler*)s;
     return AMH_OK;
 }
@@ -756,7 +862,7 @@ int32_t amho_run_create(amh_ctx*, amh_target* target, amh_sampler* sampler, int6
         if (!t->has_grad()) return fail(AMH_ERR_INVALID,
             "The gradient of the log density function is not defined");   /* MALA.jl:49-51 */
     }
-    if (kind == AMH_SAMPLER_STRETCH && !init && s->scale.empty())
+    if (kind == AMH_SAMPLER_STRETCH && !init && s->scale.empty() && !s->by_components())
         return fail(AMH_ERR_INVALID, "stretch move without init needs an initial-draw proposal");
     Run* r = new Run();
     r->t = t; r->s = s; r->n = n; r->off = off; r->dim = d;
@@ -783,10 +889,12 @@ int32_t amho_run_create(amh_ctx*, amh_target* target, amh_sampler* sampler, int6
                 /* n_walkers draws from the inner proposal (emcee.jl:29-34): stream 1 of the ensemble */
                 const int64_t en = ch / s->d.n_walkers, w = ch % s->d.n_walkers;
                 normals(r->seeds[en], (uint64_t)w, 1, d, z.data());
-                s->draw(z.data(), x.data());
+                if (s->by_components()) s->draw_components(z.data(), r->seeds[en], (uint64_t)w * (uint64_t)d, x.data());
+                else s->draw(z.data(), x.data());
             } else {
                 normals(r->seeds[ch], 0, 0, d, z.data());
-                s->draw(z.data(), x.data());                         /* propose(rng, sampler, model) */
+                if (s->by_components()) s->draw_components(z.data(), r->seeds[ch], 0ull, x.data());   /* proposal.jl:132-140 */
+                else s->draw(z.data(), x.data());                    /* propose(rng, sampler, model) */
             }
             for (int i = 0; i < d; ++i) r->X[(int64_t)i * n + ch] = x[i];
             if (kind == AMH_SAMPLER_MALA) {
@@ -797,7 +905,7 @@ int32_t amho_run_create(amh_ctx*, amh_target* target, amh_sampler* sampler, int6
             } else {
                 r->lp[ch] = t->logp(x.data());
             }
-            if (kind == AMH_SAMPLER_STATIC && !s->d.symmetric) r->lq[ch] = s->logq(x.data());
+            if (kind == AMH_SAMPLER_STATIC && !s->d.symmetric && !s->by_components()) r->lq[ch] = s->logq(x.data());
             if (kind == AMH_SAMPLER_RAM) {
                 for (int i = 0; i < d; ++i)
                     for (int j = 0; j <= i; ++j)
@@ -894,6 +1002,40 @@ int32_t amho_run_get_state(amh_run* run, double* x, double* lp, double* grad, do
     return AMH_OK;
 }
 
+int32_t amho_run_set_state(amh_run* run, const double* x, const double* lp, const double* grad, const double* S,
+                           const uint8_t* accepted, const int64_t* naccept, int64_t step_counter) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    Run& r = *(Run*)run;
+    const int d = r.dim;
+    const int64_t n = r.n;
+    if (grad && r.G.empty()) return fail(AMH_ERR_INVALID, "sampler keeps no gradient");
+    if (S && r.S.empty()) return fail(AMH_ERR_INVALID, "sampler keeps no Cholesky factor");
+    if (x) std::memcpy(r.X.data(), x, sizeof(double) * r.X.size());
+    if (lp) std::memcpy(r.lp.data(), lp, sizeof(double) * r.lp.size());
+    if (grad) std::memcpy(r.G.data(), grad, sizeof(double) * r.G.size());
+    if (S) std::memcpy(r.S.data(), S, sizeof(double) * r.S.size());
+    if (accepted) std::memcpy(r.acc.data(), accepted, r.acc.size());
+    if (naccept) std::memcpy(r.nacc.data(), naccept, sizeof(int64_t) * r.nacc.size());
+    if (step_counter >= 0) r.step = step_counter;
+    if (x && r.s->d.kind == AMH_SAMPLER_STATIC && !r.s->d.symmetric && !r.s->by_components()) {
+        std::vector<double> xx(d);
+        for (int64_t ch = 0; ch < n; ++ch) {
+            for (int i = 0; i < d; ++i) xx[i] = r.X[(int64_t)i * n + ch];
+            r.lq[ch] = r.s->logq(xx.data());
+        }
+    }
+    return AMH_OK;
+}
+
+int32_t amho_run_get_ram_adapt(amh_run* run, double* logalpha, double* eta) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    Run& r = *(Run*)run;
+    if (r.s->d.kind != AMH_SAMPLER_RAM) return fail(AMH_ERR_INVALID, "not a RobustAdaptiveMetropolis run");
+    if (logalpha) std::memcpy(logalpha, r.logalpha.data(), sizeof(double) * r.logalpha.size());
+    if (eta) std::memcpy(eta, r.eta.data(), sizeof(double) * r.eta.size());
+    return AMH_OK;
+}
+
 int32_t amho_run_set_params(amh_run* run, const double* x) {
     if (!run || !x) return fail(AMH_ERR_INVALID, "NULL argument");
     Run& r = *(Run*)run;
@@ -915,7 +1057,7 @@ int32_t amho_run_set_params(amh_run* run, const double* x) {
         } else {
             r.lp[ch] = r.t->logp(xx.data());
         }
-        if (kind == AMH_SAMPLER_STATIC && !r.s->d.symmetric) r.lq[ch] = r.s->logq(xx.data());
+        if (kind == AMH_SAMPLER_STATIC && !r.s->d.symmetric && !r.s->by_components()) r.lq[ch] = r.s->logq(xx.data());
     }
     return AMH_OK;
 }

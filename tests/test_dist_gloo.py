@@ -35,6 +35,13 @@ out["st_chains"] = np.array(ch.info["chains"])
 ch = amh.sample(np.random.default_rng(3), target, amh.RWMH(2), amh.MCMCB200(gather=False), 25, 7, chain_type=amh.Chains,
                 engine=orc, discard_initial=5, thinning=2)
 out["mh_local"] = ch.value
+# resume across ranks: the gathered state of all chains continues the run on a sharded call
+a = amh.sample(np.random.default_rng(3), target, amh.RWMH(2), amh.MCMCB200(), 10, 7, chain_type=amh.Chains, engine=orc,
+               save_state=True)
+b = amh.sample(np.random.default_rng(5), target, amh.RWMH(2), amh.MCMCB200(), 8, 7, chain_type=amh.Chains, engine=orc,
+               initial_state=a.info["state"])
+out["resume"] = np.concatenate([a.value, b.value])
+out["state_x"] = a.info["state"]["x"]
 np.savez(os.path.join({tmp!r}, f"rank{{rank}}.npz"), **out)
 dist.destroy_process_group()
 """
@@ -58,6 +65,9 @@ def test_world_size_2_gloo_sharding_and_gather(tmp_path, amh, oracle):
         assert np.array_equal(r["mh"], ref.value) and np.array_equal(r["mh_acc"], ref.accepted)
     assert list(r0["mh_chains"]) == [0, 4] and list(r1["mh_chains"]) == [4, 7]
     assert np.array_equal(r0["mh_local"], ref.value[:, :, :4]) and np.array_equal(r1["mh_local"], ref.value[:, :, 4:])
+    ref = amh.sample(np.random.default_rng(3), target, amh.RWMH(2), amh.MCMCSerial(), 18, 7, chain_type=amh.Chains, engine=oracle)
+    for r in (r0, r1):
+        assert np.array_equal(r["resume"], ref.value) and r["state_x"].shape == (2, 7)
     spl = amh.Ensemble(8, amh.StretchProposal(amh.MvNormal(np.zeros(2), amh.I)))
     ref = amh.sample(np.random.default_rng(4), target, spl, amh.MCMCSerial(), 10, 3, chain_type=amh.Chains, engine=oracle)
     assert np.array_equal(r0["st"], ref.value) and np.array_equal(r1["st"], ref.value)

@@ -190,3 +190,33 @@ def test_caller_buffers_pinned_alloc_and_strided_init(amh, oracle):
     assert np.array_equal(r1.state()["x"], r2.state()["x"]) and np.array_equal(r1.state()["lp"], r2.state()["lp"])
     with pytest.raises(amh.AMHArgumentError):
         r1.sample(3, out=np.empty((3, 3, n + 1)))
+
+
+@pytest.mark.parametrize("kind", ["rwmh", "static", "mala", "ram", "stretch"])
+def test_initial_state_resume_continues_bit_for_bit(amh, oracle, kind):
+    """`initial_state=` / `save_state=`: two calls == one long call, for every sampler's state layout (host logic + oracle)"""
+    S = np.array([[2.0, 0.3, 0.0], [0.3, 1.0, 0.2], [0.0, 0.2, 0.7]])
+    target = amh.MvNormalTarget(None, S)
+    kw, nch, wu = {}, 6, 0
+    if kind == "rwmh":
+        spl = amh.RWMH(amh.MvNormal(np.zeros(3), 0.5 * S))
+    elif kind == "static":
+        spl = amh.MetropolisHastings(amh.StaticProposal(amh.MvNormal(np.full(3, 0.1), 1.5 * S)))
+    elif kind == "mala":
+        target = amh.GaussianPrecisionTarget(np.linalg.inv(S))
+        spl = amh.MALA(lambda g: amh.MvNormal(0.1 * g, 0.2 * amh.I))
+        kw = dict(initial_params=[np.ones(3)] * nch)
+    elif kind == "ram":
+        spl, wu = amh.RobustAdaptiveMetropolis(), 14
+    else:
+        spl, nch = amh.Ensemble(9, amh.StretchProposal(amh.MvNormal(np.zeros(3), amh.I))), 2
+    common = dict(chain_type=amh.Chains, engine=oracle, num_warmup=wu, discard_initial=0)
+    full = amh.sample(np.random.default_rng(9), target, spl, amh.MCMCThreads(), 30, nch, **common, **kw)
+    a = amh.sample(np.random.default_rng(9), target, spl, amh.MCMCThreads(), 10, nch, save_state=True, **common, **kw)
+    st = a.info["state"]
+    assert st["step"] == 9 and st["x"].shape[0] == 3
+    b = amh.sample(np.random.default_rng(77), target, spl, amh.MCMCThreads(), 20, nch, initial_state=st, **common)
+    assert np.array_equal(np.concatenate([a.value, b.value]), full.value)
+    assert np.array_equal(np.concatenate([a.accepted, b.accepted]), full.accepted)
+    with pytest.raises(ValueError):
+        amh.sample(target, spl, amh.MCMCThreads(), 5, nch + 1, initial_state=st, **common)

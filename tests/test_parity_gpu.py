@@ -385,3 +385,75 @@ def test_sample_pipelined_copy_many_chunks_and_pinned_buffers(amh, cuda, oracle)
     r1.steps(5); r2.steps(5)
     _assert_same_state(r1, r2)
     assert np.array_equal(r1.state()["x"].shape, (d, n))
+
+
+def _resume_cases(amh):
+    """(name, target, sampler, n, nseeds, init) -- one case per state layout amh_run_set_state must restore"""
+    rng = np.random.default_rng(5)
+    S5 = make_spd(5, 2, 0.5, 4.0)
+    S32 = make_spd(32, 32)
+    S20 = make_spd(20, 6, 0.01, 1.0)
+    cases = [
+        ("rw_k1", amh.MvNormalTarget(None, S5), amh.RWMH(amh.MvNormal(np.zeros(5), 0.5 * S5)), 130, 130, None),
+        ("rw_k1t16", amh.MvNormalTarget(None, S32), amh.RWMH(amh.MvNormal(np.zeros(32), (2.38 ** 2 / 32) * S32)), 200, 200, None),
+        ("static_lq", amh.MvNormalTarget(None, S5), amh.MetropolisHastings(amh.StaticProposal(amh.MvNormal(np.full(5, 0.1), 1.5 * S5))), 130, 130, None),
+        ("mala", amh.GaussianPrecisionTarget(np.linalg.inv(S5)), amh.MALA(lambda g: amh.MvNormal(0.1 * g, 0.2 * amh.I)), 100, 100,
+         rng.normal(size=(5, 100))),
+        ("ram_k4", amh.MvNormalTarget(None, S5), amh.RobustAdaptiveMetropolis(), 90, 90, None),
+        ("ram_k4w", amh.MvNormalTarget(None, S20), amh.RobustAdaptiveMetropolis(eigenvalue_lower_bound=0.05, eigenvalue_upper_bound=3.0), 70, 70, None),
+        ("stretch", amh.RosenbrockTarget(4), amh.Ensemble(50, amh.StretchProposal(amh.MvNormal(np.zeros(4), amh.I))), 150, 3, None),
+    ]
+    return cases
+
+
+@pytest.mark.parametrize("case", range(7))
+def test_set_state_resume_bit_exact(amh, cuda, oracle, case):
+    """amh_run_set_state: a fresh run that is handed the state of another one continues it bit for bit
+    (initial_state resume; state structs src/AdvancedMH.jl:61-65, MALA.jl:14-19, RAM :99-114), on the GPU and in the oracle"""
+    name, target, spl, n, ns, init = _resume_cases(amh)[case]
+    seeds = _seeds(ns, 40 + case)
+    is_ram = isinstance(spl, amh.RobustAdaptiveMetropolis)
+    kw = dict(grad=isinstance(spl, amh.MALA), S=is_ram)
+    rg, ro = _pair(amh, cuda, oracle, target, spl, n, seeds, init)
+    for r in (rg, ro):
+        r.steps(13, warmup=is_ram)              # odd number of sweeps: the stretch double buffer is swapped
+    _assert_same_state(rg, ro, **kw)
+    saved = rg.state(**kw)
+    # fresh handles started somewhere else entirely
+    other = np.random.default_rng(1).normal(size=(target.dim, n))
+    rg2, ro2 = _pair(amh, cuda, oracle, target, spl, n, seeds, other)
+    for r in (rg2, ro2):
+        r.set_state(saved)
+        assert r.state()["step"] == 13
+    _assert_same_state(rg2, rg, **kw)
+    for r in (rg, ro, rg2, ro2):
+        r.steps(6, warmup=is_ram)
+        r.steps(5, warmup=False)
+    _assert_same_state(rg2, rg, **kw)
+    _assert_same_state(rg2, ro2, **kw)
+    _assert_same_state(rg, ro, **kw)
+    if is_ram:
+        for a, b in zip(rg2.ram_adapt(), ro.ram_adapt()):
+            assert np.array_equal(a, b)
+    with pytest.raises(ValueError):
+        rg.set_state(dict(x=np.zeros((target.dim, n + 1))))
+    if not is_ram:
+        with pytest.raises(ValueError):
+            rg.ram_adapt()
+        with pytest.raises(ValueError):
+            rg.set_state(dict(S=np.zeros((target.dim * (target.dim + 1) // 2, n))))
+
+
+def test_sample_initial_state_continues_run(amh, cuda):
+    """sample(...; initial_state=) after sample(...; save_state=true) == one long sample call"""
+    S = make_spd(6, 8, 0.5, 3.0)
+    target = amh.MvNormalTarget(None, S)
+    for spl, wu in ((amh.RWMH(amh.MvNormal(np.zeros(6), 0.4 * S)), 0), (amh.RobustAdaptiveMetropolis(), 17)):
+        full = amh.sample(np.random.default_rng(9), target, spl, amh.MCMCThreads(), 30, 40, chain_type=amh.Chains, engine=cuda,
+                          num_warmup=wu, discard_initial=0)
+        a = amh.sample(np.random.default_rng(9), target, spl, amh.MCMCThreads(), 10, 40, chain_type=amh.Chains, engine=cuda,
+                       num_warmup=wu, discard_initial=0, save_state=True)
+        b = amh.sample(np.random.default_rng(123), target, spl, amh.MCMCThreads(), 20, 40, chain_type=amh.Chains, engine=cuda,
+                       num_warmup=wu, discard_initial=0, initial_state=a.info["state"])
+        assert np.array_equal(np.concatenate([a.value, b.value]), full.value)
+        assert np.array_equal(np.concatenate([a.accepted, b.accepted]), full.accepted)
