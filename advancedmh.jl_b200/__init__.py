@@ -5,7 +5,7 @@ Importable as `advancedmh_jl_b200` through the loader `amh_b200.py` at the
 repository root (the directory name contains a dot)."""
 from . import _capi
 from ._capi import AMHArgumentError, AMHError, AMHStateError, Engine
-from .distributions import I, MvNormal, Normal, Zeros
+from .distributions import (Exponential, Gamma, I, InverseGamma, LogNormal, MvNormal, Normal, Uniform, Zeros)
 from .models import (DensityModel, DeviceTarget, GaussianPrecisionTarget, IIDNormalTarget,
                      LogisticRegressionTarget, MvNormalTarget, NormalInverseGammaToy, RosenbrockTarget)
 from .samplers import (MALA, RWMH, Ensemble, MetropolisHastings, RandomWalkProposal,

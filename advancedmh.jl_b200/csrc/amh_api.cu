@@ -112,7 +112,8 @@ static int enqueue_steps(amh_run& r, long long nsteps, bool warmup, int spl, con
         const amhd::SaveArgs& sv = (last && sv_last) ? *sv_last : none;
         switch (r.sampler->d.kind) {
         case AMH_SAMPLER_STATIC:
-        case AMH_SAMPLER_RW: rc = launch_mh(r, m, sv); break;
+        case AMH_SAMPLER_RW:
+        case AMH_SAMPLER_MIXED: rc = r.sampler->by_components() ? launch_mh_comp(r, m, sv) : launch_mh(r, m, sv); break;
         case AMH_SAMPLER_MALA: rc = launch_mala(r, m, sv); break;
         case AMH_SAMPLER_RAM: rc = r.ram_warp ? launch_ram_warp(r, m, warmup, sv) : launch_ram(r, m, warmup, sv); break;
         case AMH_SAMPLER_STRETCH: rc = launch_stretch(r, m, sv); break;
@@ -247,6 +248,19 @@ int32_t amh_target_destroy(amh_target* t) {
     return AMH_OK;
 }
 
+/* parameter validation of one univariate law (Distributions.jl constructors throw DomainError) */
+static const char* check_component(const amh_component& q) {
+    switch (q.family) {
+    case AMH_FAM_NORMAL:
+    case AMH_FAM_LOGNORMAL:   return (q.p1 > 0.0) ? nullptr : "Normal / LogNormal need sigma > 0";
+    case AMH_FAM_INVGAMMA:
+    case AMH_FAM_GAMMA:       return (q.p0 > 0.0 && q.p1 > 0.0) ? nullptr : "Gamma / InverseGamma need shape > 0 and scale > 0";
+    case AMH_FAM_UNIFORM:     return (q.p1 > q.p0) ? nullptr : "Uniform needs a < b";
+    case AMH_FAM_EXPONENTIAL: return (q.p0 > 0.0) ? nullptr : "Exponential needs scale > 0";
+    }
+    return "unknown distribution family";
+}
+
 int32_t amh_sampler_create(amh_ctx* ctx, const amh_sampler_desc* desc, amh_sampler** out) {
     if (!ctx || !desc || !out) return fail(AMH_ERR_INVALID, "ctx/desc/out is NULL");
     const int d = desc->dim;
@@ -259,10 +273,21 @@ int32_t amh_sampler_create(amh_ctx* ctx, const amh_sampler_desc* desc, amh_sampl
     switch (desc->kind) {
     case AMH_SAMPLER_STATIC:
     case AMH_SAMPLER_RW:
+    case AMH_SAMPLER_MIXED:
     case AMH_SAMPLER_STRETCH: {
         if (desc->kind == AMH_SAMPLER_STRETCH) {
             if (desc->n_walkers < 2) return bad("Ensemble needs n_walkers >= 2");
             if (!(desc->stretch_a > 1.0)) return bad("stretch_length must be > 1");
+        }
+        if (desc->kind == AMH_SAMPLER_MIXED || desc->cov_kind == AMH_COV_COMPONENTS) {
+            if (!desc->components) return bad("components is NULL");
+            if (d > amhd::kGenericCap) return bad("component proposals support dim <= 128");
+            s->comps.assign(desc->components, desc->components + d);
+            for (const amh_component& q : s->comps) {
+                const char* m = check_component(q);
+                if (m) return bad(m);
+            }
+            break;
         }
         const bool need_cov = desc->kind != AMH_SAMPLER_STRETCH || desc->scale != nullptr;
         if (need_cov) {
@@ -294,9 +319,18 @@ int32_t amh_sampler_create(amh_ctx* ctx, const amh_sampler_desc* desc, amh_sampl
     default:
         return bad("unknown sampler kind");
     }
-    s->d.mean = nullptr; s->d.scale = nullptr; s->d.ram_S0 = nullptr;
+    s->d.mean = nullptr; s->d.scale = nullptr; s->d.ram_S0 = nullptr; s->d.components = nullptr;
     cudaSetDevice(ctx->device);
     int rc = upload(ctx, &s->dmean, s->mean);
+    if (!rc && !s->comps.empty()) {
+        rc = dmalloc(ctx, (void**)&s->dcomps, s->comps.size() * sizeof(amh_component));
+        if (!rc) {
+            cudaError_t e = cudaMemcpyAsync(s->dcomps, s->comps.data(), s->comps.size() * sizeof(amh_component),
+                                            cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) rc = cuda_fail(e, "copy components");
+        }
+    }
     if (!rc) rc = upload(ctx, &s->dscale, s->scale);
     if (!rc) rc = upload(ctx, &s->dS0, s->S0);
     if (rc) { amh_sampler_destroy(s); return rc; }
@@ -309,6 +343,7 @@ int32_t amh_sampler_destroy(amh_sampler* s) {
     dfree(s->ctx, s->dmean);
     dfree(s->ctx, s->dscale);
     dfree(s->ctx, s->dS0);
+    dfree(s->ctx, s->dcomps);
     delete s;
     return AMH_OK;
 }
@@ -335,7 +370,7 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
         /* check_capabilities (MALA.jl:42-52) */
         if (!target->has_grad()) return fail(AMH_ERR_INVALID, "The gradient of the log density function is not defined");
     }
-    if (kind == AMH_SAMPLER_STRETCH && !init && sampler->scale.empty())
+    if (kind == AMH_SAMPLER_STRETCH && !init && sampler->scale.empty() && !sampler->by_components())
         return fail(AMH_ERR_INVALID, "stretch move without init needs an initial-draw proposal");
     AMH_CUDA_TRY(cudaSetDevice(ctx->device));
     amh_run* r = new amh_run();
@@ -614,7 +649,7 @@ int32_t amh_run_set_state(amh_run* run, const double* x, const double* lp, const
         dfree(r.ctx, tmp);
         if (rc) return rc;
     }
-    if (x && r.sampler->d.kind == AMH_SAMPLER_STATIC && !r.sampler->d.symmetric) {
+    if (x && r.sampler->d.kind == AMH_SAMPLER_STATIC && !r.sampler->d.symmetric && !r.sampler->by_components()) {
         rc = launch_relq(r);
         if (rc) return rc;
     }

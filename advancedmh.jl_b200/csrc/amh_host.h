@@ -38,6 +38,9 @@ struct amh_sampler {
     double* dmean = nullptr;
     double* dscale = nullptr;
     double* dS0 = nullptr;
+    std::vector<amh_component> comps;      /* AMH_COV_COMPONENTS / AMH_SAMPLER_MIXED: one univariate law per coordinate */
+    amh_component* dcomps = nullptr;
+    bool by_components() const { return !comps.empty(); }
 };
 
 struct amh_run {
@@ -99,6 +102,8 @@ void dfree(amh_ctx* ctx, void* p);
 
 /* per-sampler launchers; each enqueues kernels on r.ctx->stream and bumps r.launches */
 int launch_mh(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
+/* K1C: arrays of univariate proposal laws / arrays of proposals (amh_launch_mh_comp.cu) */
+int launch_mh_comp(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 bool mh_tc_eligible(const amh_run& r);        /* K1T: both mat-vecs on the FP64 tensor cores */
 int launch_mh_tc(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_mala(amh_run& r, int nsteps, const amhd::SaveArgs& sv);

@@ -143,6 +143,7 @@ struct InitArgs {
     /* RAM */
     double* S;         /* [tri][pitch] or NULL */
     const double* S0;  /* packed lower or NULL = identity */
+    const amh_component* comps;   /* array of univariate laws (proposal.jl:26-28, 132-140) or NULL */
 };
 
 template <class T>
@@ -166,10 +167,14 @@ init_kernel(const __grid_constant__ InitArgs a, const __grid_constant__ typename
             x[2 * j] = z0;
             if (2 * j + 1 < CAP) x[2 * j + 1] = z1;
         }
-        draw_inplace<0>(x, d, a.prop);
+        if (a.comps) draw_components(x, d, a.comps, seed, (unsigned long long)w * (unsigned long long)d);
+        else draw_inplace<0>(x, d, a.prop);
     } else {
         step_normals<0>(a.st.seeds[ch], 0ull, d, x);
-        if (a.mode == 1) draw_inplace<0>(x, d, a.prop);
+        if (a.mode == 1) {
+            if (a.comps) draw_components(x, d, a.comps, a.st.seeds[ch], 0ull);
+            else draw_inplace<0>(x, d, a.prop);
+        }
     }
     if (a.mode != 0)
         for (int i = 0; i < d; ++i) a.st.X[(long long)i * a.st.pitch + ch] = x[i];

@@ -111,6 +111,8 @@ int launch_init_t(amh_run& r, int mode) {
     a.prop = make_prop<0>(s);
     a.S = r.S;
     a.S0 = s.dS0;
+    a.comps = s.dcomps;
+    if (s.by_components()) a.want_lq = 0;        /* component proposals recompute logq(state) every step */
     const auto tp = make_tp<T, 0>(*r.target);
     const unsigned grid = (unsigned)((r.n + 63) / 64);
     init_kernel<T><<<grid, 64, 0, r.ctx->stream>>>(a, tp);

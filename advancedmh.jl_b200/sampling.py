@@ -249,6 +249,8 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
 
     if not store:
         return info
+    if param_names is None and getattr(sampler, "names", None):
+        param_names = sampler.names          # NamedTuple of proposals: the field names (src/AdvancedMH.jl:80-104)
     names = list(param_names) if param_names is not None else [f"param_{i + 1}" for i in range(dim)]
     if len(names) != dim:
         raise ValueError("param_names must have one entry per parameter")

@@ -20,8 +20,14 @@ const libamh = get(ENV, "AMH_B200_LIB", "libamh_b200")
 # ---------------------------------------------------------------- ABI constants (include/amh.h)
 const AMH_OK = Int32(0)
 const TARGET_IID_NORMAL, TARGET_MVNORMAL, TARGET_ROSENBROCK, TARGET_LOGISTIC, TARGET_GAUSS_PREC = Int32.(1:5)
-const SAMPLER_STATIC, SAMPLER_RW, SAMPLER_STRETCH, SAMPLER_MALA, SAMPLER_RAM = Int32.(1:5)
-const COV_SCALAR, COV_DIAG, COV_FULL = Int32.(1:3)
+const SAMPLER_STATIC, SAMPLER_RW, SAMPLER_STRETCH, SAMPLER_MALA, SAMPLER_RAM, SAMPLER_MIXED = Int32.(1:6)
+const COV_SCALAR, COV_DIAG, COV_FULL, COV_COMPONENTS = Int32.(1:4)
+const FAM_NORMAL, FAM_INVGAMMA, FAM_GAMMA, FAM_UNIFORM, FAM_EXPONENTIAL, FAM_LOGNORMAL = Int32.(1:6)
+
+struct Component              # struct amh_component: one univariate law of an array proposal (proposal.jl:26-35)
+    family::Int32; rw::Int32; symmetric::Int32; reserved::Int32
+    p0::Float64; p1::Float64; logc::Float64
+end
 
 struct SamplerDesc            # struct amh_sampler_desc, field for field
     kind::Int32; dim::Int32; symmetric::Int32; cov_kind::Int32
@@ -30,6 +36,7 @@ struct SamplerDesc            # struct amh_sampler_desc, field for field
     mala_sigma2::Float64; mala_drift::Float64
     ram_alpha::Float64; ram_gamma::Float64; ram_eig_lo::Float64; ram_eig_hi::Float64
     ram_S0::Ptr{Float64}
+    components::Ptr{Component}
 end
 
 function check(rc::Int32)
@@ -123,24 +130,56 @@ struct Lowered
     keep::Vector{Any}       # arrays the desc points into
 end
 
+# one univariate law -> (family, p0, p1, logc) in the parametrisation of include/amh_contract.h
+component(q::Normal) = (FAM_NORMAL, q.μ, q.σ, -log(q.σ) - log(2π) / 2)
+component(q::LogNormal) = (FAM_LOGNORMAL, q.μ, q.σ, -log(q.σ) - log(2π) / 2)
+component(q::InverseGamma) = (FAM_INVGAMMA, shape(q), scale(q), shape(q) * log(scale(q)) - first(logabsgamma(shape(q))))
+component(q::Gamma) = (FAM_GAMMA, shape(q), scale(q), -shape(q) * log(scale(q)) - first(logabsgamma(shape(q))))
+component(q::Uniform) = (FAM_UNIFORM, q.a, q.b, -log(q.b - q.a))
+component(q::Exponential) = (FAM_EXPONENTIAL, scale(q), 0.0, -log(scale(q)))
+component(q) = throw(ArgumentError("unsupported univariate proposal law on the device path: $(typeof(q))"))
+logabsgamma(x) = Distributions.SpecialFunctions.logabsgamma(x)
+
+function components_desc(kind, d, sym, comps::Vector{Component}, stretch_a=2.0, n_walkers=0)
+    length(comps) == d || throw(ArgumentError("proposal dimension $(length(comps)) != model dimension $d"))
+    Lowered(SamplerDesc(kind, d, sym, COV_COMPONENTS, C_NULL, C_NULL, stretch_a, n_walkers, 0.0, 0.0,
+                        0.234, 0.6, 0.0, Inf, C_NULL, pointer(comps)), Any[comps])
+end
+
 function lower(spl::AdvancedMH.MetropolisHastings, d)
     p = spl.proposal
+    if p isa Union{AbstractVector{<:AdvancedMH.Proposal},NamedTuple}
+        # array / NamedTuple of proposals, one univariate law per coordinate (proposal.jl:132-175, 199-240)
+        comps = [Component(component(q.proposal)[1], q isa AdvancedMH.RandomWalkProposal, issym(q), 0,
+                           component(q.proposal)[2:4]...) for q in values(p)]
+        return components_desc(SAMPLER_MIXED, d, 0, comps)
+    end
     p isa Union{AdvancedMH.StaticProposal,AdvancedMH.RandomWalkProposal} ||
-        throw(ArgumentError("container / function-valued proposals are host-only"))
-    ck, mu, sc = gaussian(p.proposal)
+        throw(ArgumentError("function-valued proposals are host-only"))
     k = p isa AdvancedMH.RandomWalkProposal ? SAMPLER_RW : SAMPLER_STATIC
+    if p.proposal isa AbstractVector{<:UnivariateDistribution} && !(p.proposal isa AbstractVector{<:Normal})
+        # StaticProposal([Normal(0,1), InverseGamma(2,3)]) (README.md:106; proposal.jl:26-35)
+        comps = [Component(component(q)[1], 0, 0, 0, component(q)[2:4]...) for q in p.proposal]
+        return components_desc(k, d, issym(p), comps)
+    end
+    ck, mu, sc = gaussian(p.proposal)
     keep = Any[mu, sc]
     Lowered(SamplerDesc(k, d, issym(p), ck, mu === nothing ? C_NULL : pointer(mu), pointer(sc), 2.0, 0, 0.0, 0.0,
-                        0.234, 0.6, 0.0, Inf, C_NULL), keep)
+                        0.234, 0.6, 0.0, Inf, C_NULL, C_NULL), keep)
 end
 
 function lower(spl::AdvancedMH.Ensemble, d)
     sp = spl.proposal::AdvancedMH.StretchProposal
+    if sp.proposal isa AbstractVector{<:UnivariateDistribution} && !(sp.proposal isa AbstractVector{<:Normal})
+        # StretchProposal([InverseGamma(2,3), Normal(0,1)]) (test/emcee.jl:19): the law of the initial draw
+        comps = [Component(component(q)[1], 0, 0, 0, component(q)[2:4]...) for q in sp.proposal]
+        return components_desc(SAMPLER_STRETCH, d, 0, comps, sp.stretch_length, spl.n_walkers)
+    end
     ck, mu, sc = try gaussian(sp.proposal) catch; (COV_SCALAR, nothing, nothing) end
     keep = Any[mu, sc]
     Lowered(SamplerDesc(SAMPLER_STRETCH, d, 0, ck, mu === nothing ? C_NULL : pointer(mu),
                         sc === nothing ? C_NULL : pointer(sc), sp.stretch_length, spl.n_walkers, 0.0, 0.0,
-                        0.234, 0.6, 0.0, Inf, C_NULL), keep)
+                        0.234, 0.6, 0.0, Inf, C_NULL, C_NULL), keep)
 end
 
 function lower(spl::AdvancedMH.MALA, d)
@@ -151,14 +190,14 @@ function lower(spl::AdvancedMH.MALA, d)
     (p0 isa MvNormal && p0.Σ isa Distributions.PDMats.ScalMat) ||
         throw(ArgumentError("MALA on the device needs proposal(g) = MvNormal(c*g, sigma2*I)"))
     Lowered(SamplerDesc(SAMPLER_MALA, d, 0, COV_SCALAR, C_NULL, C_NULL, 2.0, 0, p0.Σ.value, mean(p1)[1],
-                        0.234, 0.6, 0.0, Inf, C_NULL), Any[])
+                        0.234, 0.6, 0.0, Inf, C_NULL, C_NULL), Any[])
 end
 
 function lower(spl::AdvancedMH.RobustAdaptiveMetropolis, d)
     S0 = spl.S === nothing ? nothing : vec(permutedims(Matrix{Float64}(spl.S)))
     spl.S === nothing || size(spl.S) == (d, d) || throw(ArgumentError("The provided `S` has the wrong dimensionality."))
     Lowered(SamplerDesc(SAMPLER_RAM, d, 0, COV_SCALAR, C_NULL, C_NULL, 2.0, 0, 0.0, 0.0, spl.α, spl.γ,
-                        spl.eigenvalue_lower_bound, spl.eigenvalue_upper_bound, S0 === nothing ? C_NULL : pointer(S0)),
+                        spl.eigenvalue_lower_bound, spl.eigenvalue_upper_bound, S0 === nothing ? C_NULL : pointer(S0), C_NULL),
             Any[S0])
 end
 

@@ -1088,6 +1088,9 @@ void amho_probe_log(const double* x, double* y, int64_t n) { for (int64_t i = 0;
 void amho_probe_exp(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = amh::exp_(x[i]); }
 void amho_probe_log1pexp(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = amh::log1pexp(x[i]); }
 void amho_probe_sigmoid(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = amh::sigmoid(x[i]); }
+void amho_probe_family_logpdf(int32_t fam, double p0, double p1, double logc, const double* x, double* y, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) y[i] = amh::family_logpdf(fam, p0, p1, logc, x[i]);
+}
 void amho_probe_u01(const uint64_t* w, double* y, int64_t n) {
     for (int64_t i = 0; i < n; ++i) y[i] = amh::u01((uint32_t)w[i], (uint32_t)(w[i] >> 32));
 }

@@ -220,3 +220,33 @@ def test_initial_state_resume_continues_bit_for_bit(amh, oracle, kind):
     assert np.array_equal(np.concatenate([a.accepted, b.accepted]), full.accepted)
     with pytest.raises(ValueError):
         amh.sample(target, spl, amh.MCMCThreads(), 5, nch + 1, initial_state=st, **common)
+
+
+def test_component_proposal_lowering_and_errors(amh, oracle):
+    """arrays of univariate laws / arrays of proposals (README.md:104-133): lowering, dimension and parameter checks"""
+    K = amh.package._capi
+    s = amh.MetropolisHastings(amh.StaticProposal([amh.Normal(0, 1), amh.InverseGamma(2, 3)]))
+    assert s.dim == 2 and s.kind == K.SAMPLER_STATIC and [c[0] for c in s.components] == [1, 2]
+    # an all-Normal array keeps the diagonal-Gaussian path
+    assert amh.MetropolisHastings(amh.StaticProposal([amh.Normal(0, 1), amh.Normal(0, 2)])).components is None
+    m = amh.MetropolisHastings([amh.StaticProposal(amh.Normal(0, 1)), amh.SymmetricRandomWalkProposal(amh.Uniform(-1, 1))])
+    assert m.kind == K.SAMPLER_MIXED and m.components[1][4:] == (True, True) and m.components[0][4:] == (False, False)
+    nt = amh.MetropolisHastings(dict(a=amh.StaticProposal(amh.Normal(0, 1)), b=amh.StaticProposal(amh.InverseGamma(2, 3))))
+    assert nt.names == ["a", "b"]
+    h = m.lower(oracle, 2); h.close()
+    with pytest.raises(ValueError):
+        m.lower(oracle, 3)
+    with pytest.raises(ValueError):
+        amh.MetropolisHastings([amh.StaticProposal(amh.MvNormal(np.zeros(2), amh.I))])       # not univariate
+    with pytest.raises(ValueError):
+        amh.InverseGamma(-1, 3)
+    with pytest.raises(ValueError):
+        oracle.sampler(kind=K.SAMPLER_STATIC, dim=1, cov_kind=K.COV_COMPONENTS, components=[(2, -1.0, 3.0, 0.0)])
+    with pytest.raises(ValueError):
+        oracle.sampler(kind=K.SAMPLER_STATIC, dim=1, cov_kind=K.COV_COMPONENTS, components=[(99, 1.0, 3.0, 0.0)])
+    with pytest.raises(ValueError):
+        oracle.sampler(kind=K.SAMPLER_MIXED, dim=2, components=[(1, 0.0, 1.0, 0.0)])
+    # README c2: sample(m2, MetropolisHastings(p2), 100; chain_type=Vector{NamedTuple})
+    c2 = amh.sample(amh.DensityModel(amh.IIDNormalTarget(np.array([1.0]))), s, 100, chain_type="namedtuples", engine=oracle,
+                    param_names=["mu", "sigma"])
+    assert len(c2) == 100 and set(c2[0]) == {"mu", "sigma", "lp"} and all(r["sigma"] > 0 for r in c2)

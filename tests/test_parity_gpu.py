@@ -457,3 +457,76 @@ def test_sample_initial_state_continues_run(amh, cuda):
                        num_warmup=wu, discard_initial=0, initial_state=a.info["state"])
         assert np.array_equal(np.concatenate([a.value, b.value]), full.value)
         assert np.array_equal(np.concatenate([a.accepted, b.accepted]), full.accepted)
+
+
+def _all_families(amh, d):
+    fams = [amh.Normal(0.1, 0.7), amh.InverseGamma(2, 3), amh.Gamma(0.6, 1.5), amh.Gamma(4, 0.5), amh.Uniform(-2, 2),
+            amh.Exponential(0.8), amh.LogNormal(-0.2, 0.4)]
+    return [fams[i % len(fams)] for i in range(d)]
+
+
+@pytest.mark.parametrize("form", ["static_array", "static_array_symmetric", "rw_array", "rw_array_symmetric", "mixed",
+                                  "mixed_d40", "univariate_invgamma"])
+def test_component_proposals_bit_exact(amh, cuda, oracle, form):
+    """K1C: arrays of univariate laws / arrays of proposals (proposal.jl:26-35, 132-150, 236-240; README.md:104-133) --
+    initial draw, candidate, Hastings term (incl. -Inf / NaN outside a law's support), accept/reject: bit-exact"""
+    init = None
+    n = 700
+    if form.startswith("static_array"):
+        target = amh.NormalInverseGammaToy()
+        P = amh.SymmetricStaticProposal if form.endswith("symmetric") else amh.StaticProposal
+        spl = amh.MetropolisHastings(P([amh.InverseGamma(2, 3), amh.Normal(0, 1)]))
+    elif form.startswith("rw_array"):
+        # positive-only increment laws: x - c is outside the support -> logpdf = -Inf -> NaN / -Inf log-ratios
+        target = amh.MvNormalTarget(None, make_spd(7, 3, 0.5, 4.0))
+        P = amh.SymmetricRandomWalkProposal if form.endswith("symmetric") else amh.RandomWalkProposal
+        laws = _all_families(amh, 7)
+        if not form.endswith("symmetric"):
+            laws = [amh.Normal(0.05, 0.3), amh.Uniform(-0.5, 0.4), amh.Normal(-0.02, 0.2), amh.Uniform(-0.3, 0.3),
+                    amh.Normal(0, 0.3), amh.Uniform(-0.2, 0.25), amh.Normal(0.0, 0.25)]
+        spl = amh.MetropolisHastings(P(laws))
+    elif form == "mixed":
+        target = amh.NormalInverseGammaToy()
+        spl = amh.MetropolisHastings([amh.StaticProposal(amh.InverseGamma(2, 3)), amh.RandomWalkProposal(amh.Normal(0.01, 0.8))])
+    elif form == "mixed_d40":
+        d = 40
+        target = amh.MvNormalTarget(np.linspace(0.5, 1.5, d), make_spd(d, 4, 0.2, 2.0))
+        laws = _all_families(amh, d)
+        props = []
+        for i, law in enumerate(laws):
+            if i % 3 == 0:
+                props.append(amh.StaticProposal(law))
+            elif i % 3 == 1:
+                props.append(amh.RandomWalkProposal(amh.Normal(0.0, 0.05 + 0.01 * i)))
+            else:
+                props.append(amh.SymmetricRandomWalkProposal(amh.Uniform(-0.1, 0.1)))
+        spl = amh.MetropolisHastings(props)
+    else:
+        target = amh.IIDNormalTarget(np.array([1.0]))       # README m2 shape: logpdf(Normal(x[1], x[2]), 1.0)
+        spl = amh.MetropolisHastings(amh.StaticProposal([amh.Normal(0, 1), amh.InverseGamma(2, 3)]))
+    rg, ro = _pair(amh, cuda, oracle, target, spl, n, _seeds(n, 60), init)
+    _assert_same_state(rg, ro)
+    x0 = rg.state()["x"]
+    assert np.all(np.isfinite(x0))
+    for k, spl_ in [(1, 1), (9, 4), (40, 0)]:
+        rg.steps(k, steps_per_launch=spl_)
+        ro.steps(k)
+        _assert_same_state(rg, ro)
+    acc = rg.state()["naccept"].sum() / (n * 50)
+    assert 0.0 < acc < 1.0
+
+
+def test_component_proposals_sample_and_stretch_init_bit_exact(amh, cuda, oracle):
+    """`sample` over an array of proposals (schedule + save epilogue of K1C), and the ensemble's initial draw from
+    `StretchProposal([InverseGamma(2,3), Normal(0,1)])` (test/emcee.jl:19)"""
+    target = amh.NormalInverseGammaToy()
+    spl = amh.MetropolisHastings(dict(s=amh.StaticProposal(amh.InverseGamma(2, 3)), m=amh.RandomWalkProposal(amh.Normal(0, 0.8))))
+    chains = [amh.sample(np.random.default_rng(3), target, spl, amh.MCMCThreads(), 40, 300, chain_type=amh.Chains, engine=e,
+                         discard_initial=7, thinning=3) for e in (cuda, oracle)]
+    assert np.array_equal(chains[0].value, chains[1].value) and np.array_equal(chains[0].accepted, chains[1].accepted)
+    ens = amh.Ensemble(100, amh.StretchProposal([amh.InverseGamma(2, 3), amh.Normal(0, 1)]))
+    rg, ro = _pair(amh, cuda, oracle, target, ens, 300, _seeds(3, 8))
+    _assert_same_state(rg, ro)
+    assert np.all(rg.state()["x"][0] > 0)
+    rg.steps(15); ro.steps(15)
+    _assert_same_state(rg, ro)
