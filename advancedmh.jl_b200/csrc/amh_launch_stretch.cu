@@ -134,180 +134,269 @@ stretch_sweep_kernel(const __grid_constant__ StretchArgs a, const __grid_constan
 }
 
 /* ---------------------------------------------------------------------------
- * K2F: same exact sequential semantics, split in two kernels.
+ * K2F: same exact sequential semantics, scheduled ahead of time and executed as a dataflow graph.
  *
- *   stretch_noise_kernel   everything of a launch's sweeps that does not depend on the walker positions -- partner
- *                          index, stretch factor z, (d-1) log z, the exponential -- for ALL sweeps, ensembles and
- *                          walkers at once: embarrassingly parallel, runs on all SMs (an ensemble kernel alone only
- *                          occupies one SM per ensemble).
- *   stretch_sweep_fast_kernel   one CTA per ensemble; per sweep the dependency forest is executed in wavefronts:
- *                          `done[i]` holds the wavefront in which walker i was finished, so "partner available" is
- *                          done[idx] != 0 && done[idx] < wavefront and ONE barrier per wavefront (the
- *                          __syncthreads_or that also detects completion) orders flags and walker data.  Log-densities,
- *                          accept flags and counters of the ensemble live in shared memory for the whole launch, so a
- *                          move costs one round trip to L2 (its 2 x d coordinates + 3 precomputed numbers). */
-struct StretchNoise {
-    int* partner;              /* [nsteps][n] */
-    double* zf;                /* [nsteps][n] */
+ * Everything of a sweep that does not depend on the walker positions is known before the sweep runs: the partner
+ * index, the stretch factor z, (d-1) log z, the exponential -- and therefore also the whole DEPENDENCY FOREST
+ * ("walker i needs the new value of partner idx_i < i").  Two kernels per launch:
+ *
+ *   stretch_plan_kernel   one CTA per (sweep, ensemble), on all SMs: draws the partners, computes every walker's
+ *                         LEVEL in the forest (0 if idx > i, else level(idx) + 1; a pointer chase through shared
+ *                         memory, expected length e - 1), counting-sorts the walkers by level -- every level padded
+ *                         to whole warps with sentinel slots -- and stores, in slot order, (self, partner) packed
+ *                         in 32 bits, z, (d-1) log z and the exponential.
+ *   stretch_sweep_flow_kernel   one CTA per ensemble.  Warps take 32-slot chunks in slot order; a lane whose partner
+ *                         is a NEW value spins on that walker's version flag in shared memory (`ver[j]` = last sweep
+ *                         walker j finished), executes its move, fences and publishes its own flag.  A chunk never
+ *                         mixes levels, so every dependency points to a lower slot owned by a warp that reaches it
+ *                         first: the lowest unfinished chunk can always run -- no deadlock, no barrier per level,
+ *                         one __syncthreads per sweep (it protects the old buffer from the next sweep's writes).
+ *                         Walker data stays in L2 (ld/st .cg); plan entries are prefetched one chunk ahead.
+ *
+ * Levels >= lcap - 1 (lcap = kStretchLevels; never reached in practice: a chain of length L has probability ~ 1/L!)
+ * share the last bucket, which one thread executes in increasing walker order -- the sequential sweep itself. */
+constexpr int kStretchLevels = 32;
+constexpr unsigned kStretchSentinel = 0xffffffffu;
+
+struct StretchPlan {
+    unsigned* pair;            /* [nsteps][n_ensembles][nwp] slot order: self | partner << 16, or the sentinel */
+    double* zf;                /* same indexing */
     double* am;
     double* ex;
+    int* meta;                 /* [nsteps][n_ensembles][4]: padded slots of the parallel levels, overflow lo, hi, - */
+    long long nwp;             /* slots per (sweep, ensemble) = roundup(nw, 32) + 32 * kStretchLevels */
 };
 
-__global__ void __launch_bounds__(256)
-stretch_noise_kernel(StretchNoise o, const unsigned long long* __restrict__ seeds, long long n, int nw, int d, int nsteps,
-                     unsigned long long step0, double aa) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * nsteps) return;
-    const int s = (int)(t / n);
-    const long long g = t % n;
-    const long long en = g / nw;
-    const int i = (int)(g % nw);
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+stretch_plan_kernel(StretchPlan o, const unsigned long long* __restrict__ seeds, long long n, int nw, int d,
+                    unsigned long long step0, double aa, int lcap) {
+    extern __shared__ int smem_pl[];
+    int* partner = smem_pl;                    /* [nw] */
+    int* slotinfo = partner + nw;              /* [nw] bucket << 16 | rank within the bucket */
+    __shared__ int hist[kStretchLevels];
+    __shared__ int start[kStretchLevels + 1];
+    const int tid = threadIdx.x;
+    const long long nens = n / nw;
+    const int s = (int)(blockIdx.x / nens);
+    const long long en = blockIdx.x % nens;
     const unsigned long long k = step0 + (unsigned long long)s + 1ull;
     const unsigned long long seed = seeds[en];
-    const unsigned long long blk = (k * (unsigned long long)nw + (unsigned long long)i) * 2ull;
-    const amh::Block b0 = amh::stream_block(seed, blk, 0u);
-    const amh::Block b1 = amh::stream_block(seed, blk + 1ull, 0u);
-    /* idx = mod1(i + rand(1:(n-1)), n)  (emcee.jl:52) */
-    const long long rr = (long long)amh::bounded(b0.v[0], b0.v[1], (unsigned long long)(nw - 1));
-    o.partner[t] = (int)((i + rr + 1) % nw);
-    const double u = amh::u01(b0.v[2], b0.v[3]);
-    const double tt = (aa - 1.0) * u + 1.0;
-    const double z = (tt * tt) / aa;
-    o.zf[t] = z;
-    o.am[t] = (double)(d - 1) * amh::log_(z);
-    o.ex[t] = amh::exponential(b1.v[0], b1.v[1]);
+    if (tid < kStretchLevels) hist[tid] = 0;
+    for (int i = tid; i < nw; i += BLOCK) {
+        const unsigned long long blk = (k * (unsigned long long)nw + (unsigned long long)i) * 2ull;
+        const amh::Block b0 = amh::stream_block(seed, blk, 0u);
+        /* idx = mod1(i + rand(1:(n-1)), n)  (emcee.jl:52) */
+        const long long rr = (long long)amh::bounded(b0.v[0], b0.v[1], (unsigned long long)(nw - 1));
+        partner[i] = (int)((i + rr + 1) % nw);
+    }
+    __syncthreads();
+    for (int i = tid; i < nw; i += BLOCK) {
+        int lvl = 0, cur = i, j = partner[i];
+        while (j < cur && lvl < lcap - 1) { ++lvl; cur = j; j = partner[cur]; }
+        slotinfo[i] = (lvl << 16) | atomicAdd(&hist[lvl], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int l = 0; l < kStretchLevels; ++l) { start[l] = acc; acc += (hist[l] + 31) & ~31; }
+        start[kStretchLevels] = acc;
+    }
+    __syncthreads();
+    const size_t off = ((size_t)s * nens + en) * (size_t)o.nwp;
+    if (tid == 0) {
+        int* m = o.meta + ((size_t)s * nens + en) * 4;
+        m[0] = start[lcap - 1];                               /* padded slots of the parallel levels */
+        m[1] = start[lcap - 1];                               /* overflow bucket [lo, hi) */
+        m[2] = start[lcap - 1] + hist[lcap - 1];
+        m[3] = 0;
+    }
+    /* sentinels in the padding of every level */
+    for (int l = tid >> 5; l < kStretchLevels; l += BLOCK >> 5) {
+        const int q = start[l] + hist[l] + (tid & 31);
+        if (q < start[l + 1]) o.pair[off + q] = kStretchSentinel;
+    }
+    for (int i = tid; i < nw; i += BLOCK) {
+        const unsigned long long blk = (k * (unsigned long long)nw + (unsigned long long)i) * 2ull;
+        const amh::Block b0 = amh::stream_block(seed, blk, 0u);
+        const amh::Block b1 = amh::stream_block(seed, blk + 1ull, 0u);
+        const int si = slotinfo[i];
+        const size_t slot = off + start[si >> 16] + (si & 0xffff);
+        const double u = amh::u01(b0.v[2], b0.v[3]);
+        const double tt = (aa - 1.0) * u + 1.0;
+        const double z = (tt * tt) / aa;
+        o.pair[slot] = (unsigned)i | ((unsigned)partner[i] << 16);
+        o.zf[slot] = z;
+        o.am[slot] = (double)(d - 1) * amh::log_(z);
+        o.ex[slot] = amh::exponential(b1.v[0], b1.v[1]);
+    }
+}
+
+/* 256-bit global accesses through L2 (sm_100: LDG/STG.E.ENL2.256) */
+__device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st256(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.cg.v4.f64 [%4], {%0,%1,%2,%3};" :: "d"(a), "d"(b), "d"(c), "d"(d), "l"(p) : "memory");
+}
+
+/* Inside a launch the walkers of an ensemble live as RECORDS [x_0 .. x_{d-1}, lp, pad] of RS = roundup(d + 1, 4)
+ * doubles (32-byte multiples), double-buffered (old sweep / new sweep): a move touches 3 records with 256-bit
+ * accesses -- RS/4 128-byte-line requests per lane and record instead of one per coordinate in the [dim][chain]
+ * layout, and it is the L1 line-request rate of the ensemble's SM that bounds the sweep (random partners). */
+template <int DMAX>
+struct Rec {
+    static constexpr int cap = Dim<DMAX>::fixed ? ((DMAX + 1 + 3) & ~3) : ((kGenericCap + 1 + 3) & ~3);
+    __host__ __device__ static int size(int d) { return (d + 1 + 3) & ~3; }
+};
+
+/* one stretch move (emcee.jl:70-102) of walker `i` with partner `idx` */
+template <int DMAX, class T>
+__device__ __forceinline__ void stretch_move(const StretchArgs& a, const typename T::template Params<DMAX>& tp, int d,
+                                             long long base, int i, int idx, double z, double am, double ex,
+                                             const double* __restrict__ Rold, double* __restrict__ Rnew) {
+    using D = Dim<DMAX>;
+    constexpr int CAP = D::cap;
+    constexpr int RC = Rec<DMAX>::cap;
+    const int rs = D::fixed ? RC : Rec<DMAX>::size(d);
+    const double* other = (idx < i) ? Rnew : Rold;          /* emcee.jl:53 */
+    double w[RC], o[RC], y[CAP];
+    const double* pw = Rold + (size_t)(base + i) * rs;
+    const double* po = other + (size_t)(base + idx) * rs;
+    if constexpr (D::fixed) {
+#pragma unroll
+        for (int j = 0; j < RC; j += 4) ld256(pw + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
+#pragma unroll
+        for (int j = 0; j < ((DMAX + 3) & ~3); j += 4) ld256(po + j, o[j], o[j + 1], o[j + 2], o[j + 3]);
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j) y[j] = o[j] + z * (w[j] - o[j]);
+    } else {
+        for (int j = 0; j < rs; j += 4) ld256(pw + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
+        for (int j = 0; j < d; j += 4) ld256(po + j, o[j], o[j + 1], o[j + 2], o[j + 3]);
+        for (int j = 0; j < d; ++j) y[j] = o[j] + z * (w[j] - o[j]);
+    }
+    const double lpw = w[d];
+    const double lpy = T::template logp<DMAX>(y, d, tp);
+    const double alpha = (am + lpy) - lpw;
+    const bool acc = (-ex <= alpha);                         /* emcee.jl:93 (non-strict) */
+    double* pn = Rnew + (size_t)(base + i) * rs;
+    if constexpr (D::fixed) {
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j) w[j] = acc ? y[j] : w[j];
+        w[DMAX] = acc ? lpy : lpw;
+#pragma unroll
+        for (int j = 0; j < RC; j += 4) st256(pn + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
+    } else {
+        for (int j = 0; j < d; ++j) w[j] = acc ? y[j] : w[j];
+        w[d] = acc ? lpy : lpw;
+        for (int j = 0; j < rs; j += 4) st256(pn + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
+    }
+    a.st.acc[base + i] = acc ? 1 : 0;
+    if (acc) a.st.nacc[base + i] += 1ull;                   /* only ever touched by the thread that moves walker i */
 }
 
 template <int DMAX, class T, int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
-stretch_sweep_fast_kernel(const __grid_constant__ StretchArgs a, const __grid_constant__ StretchNoise pre,
-                          const __grid_constant__ typename T::template Params<DMAX> tp) {
+__global__ void __launch_bounds__(BLOCK, 1)
+stretch_sweep_flow_kernel(const __grid_constant__ StretchArgs a, const __grid_constant__ StretchPlan plan,
+                          const __grid_constant__ typename T::template Params<DMAX> tp, double* RA, double* RB) {
     using D = Dim<DMAX>;
-    constexpr int CAP = D::cap;
-    constexpr int UNR = D::unr;
-    extern __shared__ __align__(16) double smem_d[];
+    extern __shared__ unsigned short smem_ver[];
+    volatile unsigned short* ver = smem_ver;                /* [nw] last sweep (1-based, this launch) walker finished */
     const int nw = (int)a.n_walkers;
-    double* lpa = smem_d;                                                    /* [nw] log-density, sweep buffer A */
-    double* lpb = lpa + nw;                                                  /* [nw]                    buffer B */
-    int* partner = reinterpret_cast<int*>(lpb + nw);                         /* [nw]                             */
-    int* list_ = partner + nw;                                               /* [nw] work list of a wavefront    */
-    unsigned* naccs = reinterpret_cast<unsigned*>(list_ + nw);               /* [nw] accepted moves this launch  */
-    unsigned short* done = reinterpret_cast<unsigned short*>(naccs + nw);    /* [nw] wavefront of completion     */
-    unsigned char* accs = reinterpret_cast<unsigned char*>(done + nw);       /* [nw] last accept flag            */
-    int* list = list_;
-    __shared__ int cnt[2];
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARP = BLOCK / 32;
     const long long en = blockIdx.x;
+    const long long nens = a.st.n / nw;
     const long long base = en * nw;
-    const long long n = a.st.n;
     const int d = D::fixed ? DMAX : a.d;
-    const int top = D::fixed ? DMAX : d;
-    const long long pitch = a.st.pitch;
-    double* Xold = a.st.X;  double* Xnew = a.X2;
-    double* lpo = lpa;      double* lpn = lpb;
+    const int rs = D::fixed ? Rec<DMAX>::cap : Rec<DMAX>::size(d);
+    double* Rold = RA;  double* Rnew = RB;
+    /* prologue: [dim][chain] state -> records */
     for (int i = tid; i < nw; i += BLOCK) {
-        lpa[i] = a.st.lp[base + i];
-        naccs[i] = 0u;
-        accs[i] = a.st.acc[base + i];
+        smem_ver[i] = 0;
+        double* rec = RA + (size_t)(base + i) * rs;
+        for (int j = 0; j < d; ++j) rec[j] = a.st.X[(long long)j * a.st.pitch + base + i];
+        rec[d] = a.st.lp[base + i];
+        for (int j = d + 1; j < rs; ++j) rec[j] = 0.0;
     }
+    __syncthreads();
 
     for (int s = 0; s < a.nsteps; ++s) {
-        const long long off = (long long)s * n + base;
-        for (int i = tid; i < nw; i += BLOCK) {
-            partner[i] = pre.partner[off + i];
-            done[i] = 0;
+        const size_t off = ((size_t)s * nens + en) * (size_t)plan.nwp;
+        const int* __restrict__ meta = plan.meta + ((size_t)s * nens + en) * 4;
+        const int npar = meta[0];
+        const unsigned short want = (unsigned short)(s + 1);
+        /* plan entries one chunk ahead: they do not depend on the walkers */
+        int q = warp * 32 + lane;
+        unsigned pr = kStretchSentinel;
+        double z = 0.0, am = 0.0, ex = 0.0;
+        if (q < npar) {
+            pr = __ldg(plan.pair + off + q); z = __ldg(plan.zf + off + q);
+            am = __ldg(plan.am + off + q);   ex = __ldg(plan.ex + off + q);
         }
-        if (tid < 2) cnt[tid] = 0;
-        __syncthreads();
-        unsigned wf = 1;
-        int pending;
-        const int tmax = (nw + BLOCK - 1) / BLOCK;
-        do {
-            pending = 0;
-            /* (1) compact the walkers whose partner is available into a work list (warp-aggregated append), so that
-             *     the moves below run with full warps instead of a few ready lanes per warp */
-            int* mycnt = cnt + (wf & 1);
 #pragma unroll 1
-            for (int t = 0; t < tmax; ++t) {
-                const int i = tid + t * BLOCK;
-                bool cand = false, ready = false;
-                if (i < nw && !done[i]) {
-                    cand = true;
-                    const int idx = partner[i];
-                    const unsigned dn = done[idx];
-                    ready = (idx > i) || (dn != 0u && dn < wf);
+        for (; q - lane < npar; q += NWARP * 32) {
+            const unsigned pr_c = pr;
+            const double z_c = z, am_c = am, ex_c = ex;
+            const int qn = q + NWARP * 32;
+            if (qn < npar) {
+                pr = __ldg(plan.pair + off + qn); z = __ldg(plan.zf + off + qn);
+                am = __ldg(plan.am + off + qn);   ex = __ldg(plan.ex + off + qn);
+            } else {
+                pr = kStretchSentinel;
+            }
+            if (pr_c != kStretchSentinel) {
+                const int i = (int)(pr_c & 0xffffu), idx = (int)(pr_c >> 16);
+                if (idx < i) {
+                    while (ver[idx] != want) { }             /* the partner's new value (emcee.jl:53) */
+                    __threadfence_block();
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, ready);
-                if (m) {
-                    const int lane = tid & 31;
-                    const int leader = __ffs(m) - 1;
-                    int pos = 0;
-                    if (lane == leader) pos = atomicAdd(mycnt, __popc(m));
-                    pos = __shfl_sync(0xffffffffu, pos, leader);
-                    if (ready) list[pos + __popc(m & ((1u << lane) - 1u))] = i;
+                stretch_move<DMAX, T>(a, tp, d, base, i, idx, z_c, am_c, ex_c, Rold, Rnew);
+                __threadfence_block();
+                ver[i] = want;
+            }
+        }
+        __syncthreads();
+        /* overflow bucket: in increasing walker order by one thread = the reference's own loop */
+        const int olo = meta[1], ohi = meta[2];
+        if (ohi > olo) {
+            if (tid == 0) {
+                int last = -1;
+                for (int c = olo; c < ohi; ++c) {
+                    int best = 0x7fffffff, bq = olo;
+                    for (int qq = olo; qq < ohi; ++qq) {
+                        const int self = (int)(plan.pair[off + qq] & 0xffffu);
+                        if (self > last && self < best) { best = self; bq = qq; }
+                    }
+                    const unsigned po = plan.pair[off + bq];
+                    stretch_move<DMAX, T>(a, tp, d, base, (int)(po & 0xffffu), (int)(po >> 16), plan.zf[off + bq],
+                                          plan.am[off + bq], plan.ex[off + bq], Rold, Rnew);
+                    last = best;
                 }
-                if (cand && !ready) pending = 1;
             }
             __syncthreads();
-            const int nready = *mycnt;
-            if (tid == 0) cnt[(wf + 1) & 1] = 0;                          /* the other counter serves the next wavefront */
-            /* (2) the moves of this wavefront */
-#pragma unroll 1
-            for (int q = tid; q < nready; q += BLOCK) {
-                const int i = list[q];
-                const int idx = partner[i];
-                const double* other = (idx < i) ? Xnew : Xold;          /* emcee.jl:53 */
-                const double z = pre.zf[off + i];
-                const double am = pre.am[off + i];
-                const double ex = pre.ex[off + i];
-                double y[CAP], w[CAP];
-#pragma unroll UNR
-                for (int j = 0; j < top; ++j)
-                    if (j < d) {
-                        const double wj = Xold[(long long)j * pitch + base + i];
-                        const double oj = other[(long long)j * pitch + base + idx];
-                        w[j] = wj;
-                        y[j] = oj + z * (wj - oj);
-                    }
-                const double lpy = T::template logp<DMAX>(y, d, tp);
-                const double lpw = lpo[i];
-                const double alpha = (am + lpy) - lpw;
-                const bool acc = (-ex <= alpha);                         /* emcee.jl:93 (non-strict) */
-#pragma unroll UNR
-                for (int j = 0; j < top; ++j)
-                    if (j < d) Xnew[(long long)j * pitch + base + i] = acc ? y[j] : w[j];
-                lpn[i] = acc ? lpy : lpw;
-                accs[i] = acc ? 1 : 0;
-                if (acc) naccs[i] += 1u;
-                done[i] = (unsigned short)wf;
-            }
-            ++wf;
-            pending = __syncthreads_or(pending);
-        } while (pending);
-        double* tX = Xold; Xold = Xnew; Xnew = tX;
-        double* tl = lpo; lpo = lpn; lpn = tl;
+        }
+        double* tR = Rold; Rold = Rnew; Rnew = tR;
     }
-    /* write the ensemble's scalars back: the current log-densities go to the buffer that pairs with Xold
-     * (the host swaps its X / lp pointers when the number of sweeps is odd) */
-    double* lpg = (a.nsteps & 1) ? a.lp2 : a.st.lp;
+    /* epilogue: records -> [dim][chain] state (always the run's primary buffers), save point outputs */
     for (int i = tid; i < nw; i += BLOCK) {
         const long long ch = base + i;
-        lpg[ch] = lpo[i];
-        a.st.acc[ch] = accs[i];
-        a.st.nacc[ch] = a.st.nacc[ch] + (unsigned long long)naccs[i];
-        if (a.sv.out || a.sv.sum) {
-            for (int j = 0; j < d; ++j) {
-                const double v = Xold[(long long)j * pitch + ch];
-                if (a.sv.out) a.sv.out[(long long)j * a.sv.out_pitch + ch] = v;
-                if (a.sv.sum) {
-                    const long long o = (long long)j * pitch + ch;
-                    a.sv.sum[o] = a.sv.sum[o] + v;
-                    a.sv.sumsq[o] = fma(v, v, a.sv.sumsq[o]);
-                }
+        const double* rec = Rold + (size_t)ch * rs;
+        for (int j = 0; j < d; ++j) {
+            const double v = __ldcg(rec + j);
+            const long long o = (long long)j * a.st.pitch + ch;
+            a.st.X[o] = v;
+            if (a.sv.out) a.sv.out[(long long)j * a.sv.out_pitch + ch] = v;
+            if (a.sv.sum) {
+                a.sv.sum[o] = a.sv.sum[o] + v;
+                a.sv.sumsq[o] = fma(v, v, a.sv.sumsq[o]);
             }
         }
-        if (a.sv.out) a.sv.out[(long long)d * a.sv.out_pitch + ch] = lpo[i];
-        if (a.sv.acc_out) a.sv.acc_out[ch] = accs[i];
+        const double lpv = __ldcg(rec + d);
+        a.st.lp[ch] = lpv;
+        if (a.sv.out) a.sv.out[(long long)d * a.sv.out_pitch + ch] = lpv;
+        if (a.sv.acc_out) a.sv.acc_out[ch] = a.st.acc[ch];
     }
 }
 
@@ -326,10 +415,14 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     a.n_walkers = s.d.n_walkers;
     a.a = s.d.stretch_a;
     const auto tp = make_tp<T, DMAX>(*r.target);
-    if (a.n_walkers <= 7000) {          /* 31 bytes of shared memory per walker */
-        /* state-independent draws of all `nsteps` sweeps, on all SMs */
-        const size_t per = (size_t)r.n * sizeof(double);
-        const size_t need = (size_t)nsteps * (3 * per + (size_t)r.n * sizeof(int));
+    if (a.n_walkers <= 16384 && nsteps < 65535) {   /* 16-bit walker indices / sweep versions, 8 B of shared memory per walker */
+        const long long nens = r.n / a.n_walkers;
+        StretchPlan plan;
+        plan.nwp = ((a.n_walkers + 31) & ~31ll) + 32 * kStretchLevels;
+        const size_t slots = (size_t)nsteps * nens * plan.nwp;
+        const size_t recs = (size_t)r.n * (size_t)Rec<DMAX>::size(r.dim);          /* doubles per record buffer */
+        const size_t need = slots * (3 * sizeof(double) + sizeof(unsigned)) + (size_t)nsteps * nens * 4 * sizeof(int) +
+                            2 * recs * sizeof(double) + 64;
         if (need > r.scratch_bytes) {
             dfree(r.ctx, r.scratch);
             r.scratch = nullptr; r.scratch_bytes = 0;
@@ -337,28 +430,37 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
             if (rca) return rca;
             r.scratch_bytes = need;
         }
-        StretchNoise pre;
-        pre.zf = (double*)r.scratch;
-        pre.am = pre.zf + (size_t)nsteps * r.n;
-        pre.ex = pre.am + (size_t)nsteps * r.n;
-        pre.partner = (int*)(pre.ex + (size_t)nsteps * r.n);
+        double* RA = (double*)r.scratch;                 /* record buffers first: 256-byte aligned pool memory */
+        double* RB = RA + recs;
+        plan.zf = RB + recs;
+        plan.am = plan.zf + slots;
+        plan.ex = plan.am + slots;
+        plan.pair = (unsigned*)(plan.ex + slots);
+        plan.meta = (int*)(plan.pair + slots);
+        int lcap = kStretchLevels;
+        if (const char* ev = std::getenv("AMH_STRETCH_LEVELS")) {      /* test switch: forces the overflow bucket */
+            const int v = std::atoi(ev);
+            if (v >= 2 && v <= kStretchLevels) lcap = v;
+        }
+        int blk = 512;                                                  /* threads of the ensemble's CTA: 512 leaves 128 registers per thread (no spills) */
+        if (const char* ev = std::getenv("AMH_STRETCH_BLOCK")) {
+            const int v = std::atoi(ev);
+            if (v == 768 || v == 1024) blk = v;
+        }
         if (nsteps > 0) {
-            const long long total = (long long)nsteps * r.n;
-            stretch_noise_kernel<<<(unsigned)((total + 255) / 256), 256, 0, r.ctx->stream>>>(pre, r.seeds, r.n, (int)a.n_walkers, r.dim,
-                                                                                             nsteps, a.step0, a.a);
+            constexpr int PB = 1024;
+            const size_t smemp = (size_t)a.n_walkers * 2 * sizeof(int);
+            auto kp = stretch_plan_kernel<PB>;
+            if (smemp > 48 * 1024) AMH_CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp));
+            kp<<<(unsigned)(nsteps * nens), PB, smemp, r.ctx->stream>>>(plan, r.seeds, r.n, (int)a.n_walkers, r.dim, a.step0, a.a, lcap);
             AMH_CUDA_TRY(cudaGetLastError());
             r.launches += 1;
         }
-        const size_t smemf = (size_t)a.n_walkers * (2 * sizeof(double) + 2 * sizeof(int) + sizeof(unsigned) + sizeof(unsigned short) + 1) + 16;
-        auto kf = stretch_sweep_fast_kernel<DMAX, T, BLOCK>;
-        if (smemf > 48 * 1024) AMH_CUDA_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemf));
-        const unsigned gridf = (unsigned)(r.n / a.n_walkers);
-        kf<<<gridf, BLOCK, smemf, r.ctx->stream>>>(a, pre, tp);
+        const size_t smemv = (size_t)a.n_walkers * sizeof(unsigned short);
+        if (blk == 512) stretch_sweep_flow_kernel<DMAX, T, 512><<<(unsigned)nens, 512, smemv, r.ctx->stream>>>(a, plan, tp, RA, RB);
+        else if (blk == 768) stretch_sweep_flow_kernel<DMAX, T, 768><<<(unsigned)nens, 768, smemv, r.ctx->stream>>>(a, plan, tp, RA, RB);
+        else stretch_sweep_flow_kernel<DMAX, T, 1024><<<(unsigned)nens, 1024, smemv, r.ctx->stream>>>(a, plan, tp, RA, RB);
         AMH_CUDA_TRY(cudaGetLastError());
-        if (nsteps & 1) {
-            std::swap(r.X, r.X2);
-            std::swap(r.lp, r.lp2);
-        }
         r.launches += 1;
         r.pending_launches += 1;
         return AMH_OK;

@@ -530,3 +530,24 @@ def test_component_proposals_sample_and_stretch_init_bit_exact(amh, cuda, oracle
     assert np.all(rg.state()["x"][0] > 0)
     rg.steps(15); ro.steps(15)
     _assert_same_state(rg, ro)
+
+
+@pytest.mark.parametrize("cfg", ["512", "768", "1024"])
+@pytest.mark.parametrize("levels", [None, 3])
+def test_stretch_level_schedule_configs_and_overflow_bucket(amh, cuda, oracle, monkeypatch, cfg, levels):
+    """K2F: every CTA size of the dataflow sweep, and the ordered overflow bucket (forced by capping the number of
+    parallel levels at 3), reproduce the sequential sweep of emcee.jl:39-58 bit for bit"""
+    monkeypatch.setenv("AMH_STRETCH_BLOCK", cfg)
+    if levels is not None:
+        monkeypatch.setenv("AMH_STRETCH_LEVELS", str(levels))
+    target = amh.RosenbrockTarget(10)
+    nw, ne = 333, 3
+    spl = amh.Ensemble(nw, amh.StretchProposal(amh.MvNormal(np.zeros(10), amh.I)))
+    rg, ro = _pair(amh, cuda, oracle, target, spl, nw * ne, _seeds(ne, 90))
+    for k, spl_ in [(1, 1), (6, 4), (21, 0)]:
+        rg.steps(k, steps_per_launch=spl_)
+        ro.steps(k)
+        _assert_same_state(rg, ro)
+    out_g, acc_g, _ = rg.sample(5, 2, 3)
+    out_o, acc_o, _ = ro.sample(5, 2, 3)
+    assert np.array_equal(out_g, out_o) and np.array_equal(acc_g, acc_o)
