@@ -151,7 +151,10 @@ stretch_sweep_kernel(const __grid_constant__ StretchArgs a, const __grid_constan
  *                         mixes levels, so every dependency points to a lower slot owned by a warp that reaches it
  *                         first: the lowest unfinished chunk can always run -- no deadlock, no barrier per level,
  *                         one __syncthreads per sweep (it protects the old buffer from the next sweep's writes).
- *                         Walker data stays in L2 (ld/st .cg); plan entries are prefetched one chunk ahead.
+ *                         Walker data stays in L2 (ld/st .cg); plan entries are prefetched one chunk ahead.  NEW values
+ *                         that a later walker of the same sweep reads (e^-1 of the walkers; the plan knows which)
+ *                         are also FORWARDED through shared memory, so a level of the dependency chain costs the
+ *                         move itself plus a shared-memory hop instead of a store->load round trip through L2.
  *
  * Levels >= lcap - 1 (lcap = kStretchLevels; never reached in practice: a chain of length L has probability ~ 1/L!)
  * share the last bucket, which one thread executes in increasing walker order -- the sequential sweep itself. */
@@ -160,6 +163,7 @@ constexpr unsigned kStretchSentinel = 0xffffffffu;
 
 struct StretchPlan {
     unsigned* pair;            /* [nsteps][n_ensembles][nwp] slot order: self | partner << 16, or the sentinel */
+    unsigned* fwd;             /* same indexing: forwarding slot of self | of the partner << 16 (0xffff = none) */
     double* zf;                /* same indexing */
     double* am;
     double* ex;
@@ -170,12 +174,14 @@ struct StretchPlan {
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 stretch_plan_kernel(StretchPlan o, const unsigned long long* __restrict__ seeds, long long n, int nw, int d,
-                    unsigned long long step0, double aa, int lcap) {
+                    unsigned long long step0, double aa, int lcap, int fcap) {
     extern __shared__ int smem_pl[];
     int* partner = smem_pl;                    /* [nw] */
     int* slotinfo = partner + nw;              /* [nw] bucket << 16 | rank within the bucket */
+    int* fslot = slotinfo + nw;                /* [nw] 1 = some later walker reads this walker's new value -> slot */
     __shared__ int hist[kStretchLevels];
     __shared__ int start[kStretchLevels + 1];
+    __shared__ int wsum[BLOCK / 32];
     const int tid = threadIdx.x;
     const long long nens = n / nw;
     const int s = (int)(blockIdx.x / nens);
@@ -189,10 +195,12 @@ stretch_plan_kernel(StretchPlan o, const unsigned long long* __restrict__ seeds,
         /* idx = mod1(i + rand(1:(n-1)), n)  (emcee.jl:52) */
         const long long rr = (long long)amh::bounded(b0.v[0], b0.v[1], (unsigned long long)(nw - 1));
         partner[i] = (int)((i + rr + 1) % nw);
+        fslot[i] = 0;
     }
     __syncthreads();
     for (int i = tid; i < nw; i += BLOCK) {
         int lvl = 0, cur = i, j = partner[i];
+        if (j < i) fslot[j] = 1;               /* benign race: everybody writes 1 */
         while (j < cur && lvl < lcap - 1) { ++lvl; cur = j; j = partner[cur]; }
         slotinfo[i] = (lvl << 16) | atomicAdd(&hist[lvl], 1);
     }
@@ -201,6 +209,35 @@ stretch_plan_kernel(StretchPlan o, const unsigned long long* __restrict__ seeds,
         int acc = 0;
         for (int l = 0; l < kStretchLevels; ++l) { start[l] = acc; acc += (hist[l] + 31) & ~31; }
         start[kStretchLevels] = acc;
+    }
+    /* forwarding slots: exclusive scan of the flags (thread t owns the contiguous walkers [t*per, (t+1)*per)) */
+    {
+        const int per = (nw + BLOCK - 1) / BLOCK;
+        const int lo = tid * per, hi = min(nw, lo + per);
+        int cnt = 0;
+        for (int i = lo; i < hi; ++i) cnt += fslot[i];
+        int inc = cnt;
+        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o2);
+            if ((tid & 31) >= o2) inc += v;
+        }
+        if ((tid & 31) == 31) wsum[tid >> 5] = inc;
+        __syncthreads();
+        if (tid < 32) {
+            int v = (tid < BLOCK / 32) ? wsum[tid] : 0;
+            for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, v, o2);
+                if (tid >= o2) v += u;
+            }
+            if (tid < BLOCK / 32) wsum[tid] = v;           /* inclusive over warps */
+        }
+        __syncthreads();
+        int run = inc - cnt + ((tid >> 5) ? wsum[(tid >> 5) - 1] : 0);
+        for (int i = lo; i < hi; ++i) {
+            const int f = fslot[i];
+            fslot[i] = (f && run < fcap) ? run : 0xffff;
+            run += f;
+        }
     }
     __syncthreads();
     const size_t off = ((size_t)s * nens + en) * (size_t)o.nwp;
@@ -214,7 +251,7 @@ stretch_plan_kernel(StretchPlan o, const unsigned long long* __restrict__ seeds,
     /* sentinels in the padding of every level */
     for (int l = tid >> 5; l < kStretchLevels; l += BLOCK >> 5) {
         const int q = start[l] + hist[l] + (tid & 31);
-        if (q < start[l + 1]) o.pair[off + q] = kStretchSentinel;
+        if (q < start[l + 1]) { o.pair[off + q] = kStretchSentinel; o.fwd[off + q] = 0xffffffffu; }
     }
     for (int i = tid; i < nw; i += BLOCK) {
         const unsigned long long blk = (k * (unsigned long long)nw + (unsigned long long)i) * 2ull;
@@ -225,7 +262,9 @@ stretch_plan_kernel(StretchPlan o, const unsigned long long* __restrict__ seeds,
         const double u = amh::u01(b0.v[2], b0.v[3]);
         const double tt = (aa - 1.0) * u + 1.0;
         const double z = (tt * tt) / aa;
-        o.pair[slot] = (unsigned)i | ((unsigned)partner[i] << 16);
+        const int pj = partner[i];
+        o.pair[slot] = (unsigned)i | ((unsigned)pj << 16);
+        o.fwd[slot] = (unsigned)fslot[i] | ((pj < i ? (unsigned)fslot[pj] : 0xffffu) << 16);
         o.zf[slot] = z;
         o.am[slot] = (double)(d - 1) * amh::log_(z);
         o.ex[slot] = amh::exponential(b1.v[0], b1.v[1]);
@@ -250,29 +289,48 @@ struct Rec {
     __host__ __device__ static int size(int d) { return (d + 1 + 3) & ~3; }
 };
 
-/* one stretch move (emcee.jl:70-102) of walker `i` with partner `idx` */
+/* shared memory of the sweep kernel */
+struct StretchSmem {
+    double* fwd;                          /* [fcap][d] forwarded new positions */
+    unsigned* naccs;                      /* [nw] accepted moves of this launch */
+    volatile unsigned short* ver;         /* [nw] last sweep (1-based, this launch) the walker finished */
+    unsigned char* accs;                  /* [nw] last accept flag */
+};
+
+/* one stretch move (emcee.jl:70-102) of walker `i` with partner `idx`.  `w` = the walker's own record (already loaded);
+ * the partner comes from the forwarding slot `pslot` (shared memory) if it has one, else from its record in L2;
+ * the result goes to the walker's new record and, if somebody reads it later in this sweep, to slot `sslot`. */
 template <int DMAX, class T>
-__device__ __forceinline__ void stretch_move(const StretchArgs& a, const typename T::template Params<DMAX>& tp, int d,
-                                             long long base, int i, int idx, double z, double am, double ex,
-                                             const double* __restrict__ Rold, double* __restrict__ Rnew) {
+__device__ __forceinline__ void stretch_move(const typename T::template Params<DMAX>& tp, int d, long long base, int i,
+                                             int idx, unsigned sslot, unsigned pslot, double z, double am, double ex,
+                                             double (&w)[Rec<DMAX>::cap], const double* __restrict__ Rold,
+                                             double* __restrict__ Rnew, const StretchSmem& sm) {
     using D = Dim<DMAX>;
     constexpr int CAP = D::cap;
     constexpr int RC = Rec<DMAX>::cap;
     const int rs = D::fixed ? RC : Rec<DMAX>::size(d);
-    const double* other = (idx < i) ? Rnew : Rold;          /* emcee.jl:53 */
-    double w[RC], o[RC], y[CAP];
-    const double* pw = Rold + (size_t)(base + i) * rs;
-    const double* po = other + (size_t)(base + idx) * rs;
+    double o[RC], y[CAP];
+    if (pslot != 0xffffu) {
+        const double* ps = sm.fwd + (size_t)pslot * d;
+        if constexpr (D::fixed) {
+#pragma unroll
+            for (int j = 0; j < DMAX; ++j) o[j] = ps[j];
+        } else {
+            for (int j = 0; j < d; ++j) o[j] = ps[j];
+        }
+    } else {
+        const double* po = ((idx < i) ? Rnew : Rold) + (size_t)(base + idx) * rs;      /* emcee.jl:53 */
+        if constexpr (D::fixed) {
+#pragma unroll
+            for (int j = 0; j < ((DMAX + 3) & ~3); j += 4) ld256(po + j, o[j], o[j + 1], o[j + 2], o[j + 3]);
+        } else {
+            for (int j = 0; j < d; j += 4) ld256(po + j, o[j], o[j + 1], o[j + 2], o[j + 3]);
+        }
+    }
     if constexpr (D::fixed) {
-#pragma unroll
-        for (int j = 0; j < RC; j += 4) ld256(pw + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
-#pragma unroll
-        for (int j = 0; j < ((DMAX + 3) & ~3); j += 4) ld256(po + j, o[j], o[j + 1], o[j + 2], o[j + 3]);
 #pragma unroll
         for (int j = 0; j < DMAX; ++j) y[j] = o[j] + z * (w[j] - o[j]);
     } else {
-        for (int j = 0; j < rs; j += 4) ld256(pw + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
-        for (int j = 0; j < d; j += 4) ld256(po + j, o[j], o[j + 1], o[j + 2], o[j + 3]);
         for (int j = 0; j < d; ++j) y[j] = o[j] + z * (w[j] - o[j]);
     }
     const double lpw = w[d];
@@ -284,82 +342,120 @@ __device__ __forceinline__ void stretch_move(const StretchArgs& a, const typenam
 #pragma unroll
         for (int j = 0; j < DMAX; ++j) w[j] = acc ? y[j] : w[j];
         w[DMAX] = acc ? lpy : lpw;
+        if (sslot != 0xffffu) {
+            double* ps = sm.fwd + (size_t)sslot * d;
+#pragma unroll
+            for (int j = 0; j < DMAX; ++j) ps[j] = w[j];
+        }
 #pragma unroll
         for (int j = 0; j < RC; j += 4) st256(pn + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
     } else {
         for (int j = 0; j < d; ++j) w[j] = acc ? y[j] : w[j];
         w[d] = acc ? lpy : lpw;
+        if (sslot != 0xffffu) {
+            double* ps = sm.fwd + (size_t)sslot * d;
+            for (int j = 0; j < d; ++j) ps[j] = w[j];
+        }
         for (int j = 0; j < rs; j += 4) st256(pn + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
     }
-    a.st.acc[base + i] = acc ? 1 : 0;
-    if (acc) a.st.nacc[base + i] += 1ull;                   /* only ever touched by the thread that moves walker i */
+    sm.accs[i] = acc ? 1 : 0;
+    if (acc) sm.naccs[i] += 1u;                              /* only ever touched by the thread that moves walker i */
+}
+
+template <int DMAX>
+__device__ __forceinline__ void stretch_load_own(double (&w)[Rec<DMAX>::cap], const double* __restrict__ Rold, long long base,
+                                                 int i, int d) {
+    constexpr int RC = Rec<DMAX>::cap;
+    if constexpr (Dim<DMAX>::fixed) {
+        const double* pw = Rold + (size_t)(base + i) * RC;
+#pragma unroll
+        for (int j = 0; j < RC; j += 4) ld256(pw + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
+    } else {
+        const int rs = Rec<DMAX>::size(d);
+        const double* pw = Rold + (size_t)(base + i) * rs;
+        for (int j = 0; j < rs; j += 4) ld256(pw + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
+    }
 }
 
 template <int DMAX, class T, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 1)
 stretch_sweep_flow_kernel(const __grid_constant__ StretchArgs a, const __grid_constant__ StretchPlan plan,
-                          const __grid_constant__ typename T::template Params<DMAX> tp, double* RA, double* RB) {
+                          const __grid_constant__ typename T::template Params<DMAX> tp, double* RA, double* RB, int fcap) {
     using D = Dim<DMAX>;
-    extern __shared__ unsigned short smem_ver[];
-    volatile unsigned short* ver = smem_ver;                /* [nw] last sweep (1-based, this launch) walker finished */
+    extern __shared__ __align__(16) double smem_fl[];
     const int nw = (int)a.n_walkers;
+    const int d = D::fixed ? DMAX : a.d;
+    StretchSmem sm;
+    sm.fwd = smem_fl;
+    sm.naccs = reinterpret_cast<unsigned*>(sm.fwd + (size_t)fcap * d);
+    unsigned short* ver_nv = reinterpret_cast<unsigned short*>(sm.naccs + nw);
+    sm.ver = ver_nv;
+    sm.accs = reinterpret_cast<unsigned char*>(ver_nv + nw);
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int NWARP = BLOCK / 32;
     const long long en = blockIdx.x;
     const long long nens = a.st.n / nw;
     const long long base = en * nw;
-    const int d = D::fixed ? DMAX : a.d;
     const int rs = D::fixed ? Rec<DMAX>::cap : Rec<DMAX>::size(d);
     double* Rold = RA;  double* Rnew = RB;
     /* prologue: [dim][chain] state -> records */
     for (int i = tid; i < nw; i += BLOCK) {
-        smem_ver[i] = 0;
+        ver_nv[i] = 0;
+        sm.naccs[i] = 0u;
+        sm.accs[i] = a.st.acc[base + i];
         double* rec = RA + (size_t)(base + i) * rs;
         for (int j = 0; j < d; ++j) rec[j] = a.st.X[(long long)j * a.st.pitch + base + i];
         rec[d] = a.st.lp[base + i];
         for (int j = d + 1; j < rs; ++j) rec[j] = 0.0;
     }
+    const int* __restrict__ meta0 = plan.meta + (size_t)en * 4;
+    int npar = a.nsteps > 0 ? meta0[0] : 0, olo = a.nsteps > 0 ? meta0[1] : 0, ohi = a.nsteps > 0 ? meta0[2] : 0;
     __syncthreads();
 
     for (int s = 0; s < a.nsteps; ++s) {
         const size_t off = ((size_t)s * nens + en) * (size_t)plan.nwp;
-        const int* __restrict__ meta = plan.meta + ((size_t)s * nens + en) * 4;
-        const int npar = meta[0];
         const unsigned short want = (unsigned short)(s + 1);
+        /* the next sweep's meta data, long before it is needed */
+        int npar_n = 0, olo_n = 0, ohi_n = 0;
+        if (s + 1 < a.nsteps) {
+            const int* __restrict__ mn = plan.meta + ((size_t)(s + 1) * nens + en) * 4;
+            npar_n = mn[0]; olo_n = mn[1]; ohi_n = mn[2];
+        }
         /* plan entries one chunk ahead: they do not depend on the walkers */
         int q = warp * 32 + lane;
-        unsigned pr = kStretchSentinel;
+        unsigned pr = kStretchSentinel, fw = 0xffffffffu;
         double z = 0.0, am = 0.0, ex = 0.0;
         if (q < npar) {
-            pr = __ldg(plan.pair + off + q); z = __ldg(plan.zf + off + q);
+            pr = __ldg(plan.pair + off + q); fw = __ldg(plan.fwd + off + q); z = __ldg(plan.zf + off + q);
             am = __ldg(plan.am + off + q);   ex = __ldg(plan.ex + off + q);
         }
 #pragma unroll 1
         for (; q - lane < npar; q += NWARP * 32) {
-            const unsigned pr_c = pr;
+            const unsigned pr_c = pr, fw_c = fw;
             const double z_c = z, am_c = am, ex_c = ex;
             const int qn = q + NWARP * 32;
             if (qn < npar) {
-                pr = __ldg(plan.pair + off + qn); z = __ldg(plan.zf + off + qn);
+                pr = __ldg(plan.pair + off + qn); fw = __ldg(plan.fwd + off + qn); z = __ldg(plan.zf + off + qn);
                 am = __ldg(plan.am + off + qn);   ex = __ldg(plan.ex + off + qn);
             } else {
                 pr = kStretchSentinel;
             }
             if (pr_c != kStretchSentinel) {
                 const int i = (int)(pr_c & 0xffffu), idx = (int)(pr_c >> 16);
+                double w[Rec<DMAX>::cap];
+                stretch_load_own<DMAX>(w, Rold, base, i, d);             /* in flight while the lane waits */
                 if (idx < i) {
-                    while (ver[idx] != want) { }             /* the partner's new value (emcee.jl:53) */
+                    while (sm.ver[idx] != want) { }                      /* the partner's new value (emcee.jl:53) */
                     __threadfence_block();
                 }
-                stretch_move<DMAX, T>(a, tp, d, base, i, idx, z_c, am_c, ex_c, Rold, Rnew);
+                stretch_move<DMAX, T>(tp, d, base, i, idx, fw_c & 0xffffu, fw_c >> 16, z_c, am_c, ex_c, w, Rold, Rnew, sm);
                 __threadfence_block();
-                ver[i] = want;
+                sm.ver[i] = want;
             }
         }
         __syncthreads();
         /* overflow bucket: in increasing walker order by one thread = the reference's own loop */
-        const int olo = meta[1], ohi = meta[2];
         if (ohi > olo) {
             if (tid == 0) {
                 int last = -1;
@@ -369,17 +465,21 @@ stretch_sweep_flow_kernel(const __grid_constant__ StretchArgs a, const __grid_co
                         const int self = (int)(plan.pair[off + qq] & 0xffffu);
                         if (self > last && self < best) { best = self; bq = qq; }
                     }
-                    const unsigned po = plan.pair[off + bq];
-                    stretch_move<DMAX, T>(a, tp, d, base, (int)(po & 0xffffu), (int)(po >> 16), plan.zf[off + bq],
-                                          plan.am[off + bq], plan.ex[off + bq], Rold, Rnew);
+                    const unsigned po = plan.pair[off + bq], fo = plan.fwd[off + bq];
+                    double w[Rec<DMAX>::cap];
+                    stretch_load_own<DMAX>(w, Rold, base, (int)(po & 0xffffu), d);
+                    stretch_move<DMAX, T>(tp, d, base, (int)(po & 0xffffu), (int)(po >> 16), fo & 0xffffu, fo >> 16,
+                                          plan.zf[off + bq], plan.am[off + bq], plan.ex[off + bq], w, Rold, Rnew, sm);
+                    __threadfence_block();
                     last = best;
                 }
             }
             __syncthreads();
         }
         double* tR = Rold; Rold = Rnew; Rnew = tR;
+        npar = npar_n; olo = olo_n; ohi = ohi_n;
     }
-    /* epilogue: records -> [dim][chain] state (always the run's primary buffers), save point outputs */
+    /* epilogue: records -> [dim][chain] state (always the run's primary buffers), counters, save point outputs */
     for (int i = tid; i < nw; i += BLOCK) {
         const long long ch = base + i;
         const double* rec = Rold + (size_t)ch * rs;
@@ -395,8 +495,10 @@ stretch_sweep_flow_kernel(const __grid_constant__ StretchArgs a, const __grid_co
         }
         const double lpv = __ldcg(rec + d);
         a.st.lp[ch] = lpv;
+        a.st.acc[ch] = sm.accs[i];
+        a.st.nacc[ch] = a.st.nacc[ch] + (unsigned long long)sm.naccs[i];
         if (a.sv.out) a.sv.out[(long long)d * a.sv.out_pitch + ch] = lpv;
-        if (a.sv.acc_out) a.sv.acc_out[ch] = a.st.acc[ch];
+        if (a.sv.acc_out) a.sv.acc_out[ch] = sm.accs[i];
     }
 }
 
@@ -421,7 +523,7 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
         plan.nwp = ((a.n_walkers + 31) & ~31ll) + 32 * kStretchLevels;
         const size_t slots = (size_t)nsteps * nens * plan.nwp;
         const size_t recs = (size_t)r.n * (size_t)Rec<DMAX>::size(r.dim);          /* doubles per record buffer */
-        const size_t need = slots * (3 * sizeof(double) + sizeof(unsigned)) + (size_t)nsteps * nens * 4 * sizeof(int) +
+        const size_t need = slots * (3 * sizeof(double) + 2 * sizeof(unsigned)) + (size_t)nsteps * nens * 4 * sizeof(int) +
                             2 * recs * sizeof(double) + 64;
         if (need > r.scratch_bytes) {
             dfree(r.ctx, r.scratch);
@@ -436,7 +538,8 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
         plan.am = plan.zf + slots;
         plan.ex = plan.am + slots;
         plan.pair = (unsigned*)(plan.ex + slots);
-        plan.meta = (int*)(plan.pair + slots);
+        plan.fwd = plan.pair + slots;
+        plan.meta = (int*)(plan.fwd + slots);
         int lcap = kStretchLevels;
         if (const char* ev = std::getenv("AMH_STRETCH_LEVELS")) {      /* test switch: forces the overflow bucket */
             const int v = std::atoi(ev);
@@ -447,19 +550,32 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
             const int v = std::atoi(ev);
             if (v == 768 || v == 1024) blk = v;
         }
+        /* forwarding slots: what is left of 200 KB of shared memory beside the per-walker flags and counters */
+        const size_t fixed_sm = (size_t)a.n_walkers * (sizeof(unsigned) + sizeof(unsigned short) + 1) + 32;
+        long long fcap = ((long long)(200 * 1024) - (long long)fixed_sm) / (long long)(sizeof(double) * r.dim);
+        fcap = std::max<long long>(0, std::min<long long>(fcap, 65534));
+        if (const char* ev = std::getenv("AMH_STRETCH_FWD")) fcap = std::min<long long>(fcap, std::atoll(ev));   /* test switch */
         if (nsteps > 0) {
             constexpr int PB = 1024;
-            const size_t smemp = (size_t)a.n_walkers * 2 * sizeof(int);
+            const size_t smemp = (size_t)a.n_walkers * 3 * sizeof(int);
             auto kp = stretch_plan_kernel<PB>;
-            if (smemp > 48 * 1024) AMH_CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp));
-            kp<<<(unsigned)(nsteps * nens), PB, smemp, r.ctx->stream>>>(plan, r.seeds, r.n, (int)a.n_walkers, r.dim, a.step0, a.a, lcap);
+            if (smemp > 40 * 1024) AMH_CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp));
+            kp<<<(unsigned)(nsteps * nens), PB, smemp, r.ctx->stream>>>(plan, r.seeds, r.n, (int)a.n_walkers, r.dim, a.step0, a.a, lcap, (int)fcap);
             AMH_CUDA_TRY(cudaGetLastError());
             r.launches += 1;
         }
-        const size_t smemv = (size_t)a.n_walkers * sizeof(unsigned short);
-        if (blk == 512) stretch_sweep_flow_kernel<DMAX, T, 512><<<(unsigned)nens, 512, smemv, r.ctx->stream>>>(a, plan, tp, RA, RB);
-        else if (blk == 768) stretch_sweep_flow_kernel<DMAX, T, 768><<<(unsigned)nens, 768, smemv, r.ctx->stream>>>(a, plan, tp, RA, RB);
-        else stretch_sweep_flow_kernel<DMAX, T, 1024><<<(unsigned)nens, 1024, smemv, r.ctx->stream>>>(a, plan, tp, RA, RB);
+        const size_t smemv = (size_t)fcap * r.dim * sizeof(double) + fixed_sm;
+#define AMH_STRETCH_LAUNCH(BL)                                                                                             \
+        do {                                                                                                               \
+            auto kf = stretch_sweep_flow_kernel<DMAX, T, BL>;                                                              \
+            if (smemv > 48 * 1024)                                                                                         \
+                AMH_CUDA_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv));           \
+            kf<<<(unsigned)nens, BL, smemv, r.ctx->stream>>>(a, plan, tp, RA, RB, (int)fcap);                              \
+        } while (0)
+        if (blk == 512) AMH_STRETCH_LAUNCH(512);
+        else if (blk == 768) AMH_STRETCH_LAUNCH(768);
+        else AMH_STRETCH_LAUNCH(1024);
+#undef AMH_STRETCH_LAUNCH
         AMH_CUDA_TRY(cudaGetLastError());
         r.launches += 1;
         r.pending_launches += 1;

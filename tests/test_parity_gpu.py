@@ -532,12 +532,15 @@ def test_component_proposals_sample_and_stretch_init_bit_exact(amh, cuda, oracle
     _assert_same_state(rg, ro)
 
 
-@pytest.mark.parametrize("cfg", ["512", "768", "1024"])
+@pytest.mark.parametrize("cfg,fwd", [("512", None), ("768", None), ("1024", None), ("512", "0"), ("512", "40")])
 @pytest.mark.parametrize("levels", [None, 3])
-def test_stretch_level_schedule_configs_and_overflow_bucket(amh, cuda, oracle, monkeypatch, cfg, levels):
-    """K2F: every CTA size of the dataflow sweep, and the ordered overflow bucket (forced by capping the number of
-    parallel levels at 3), reproduce the sequential sweep of emcee.jl:39-58 bit for bit"""
+def test_stretch_level_schedule_configs_and_overflow_bucket(amh, cuda, oracle, monkeypatch, cfg, fwd, levels):
+    """K2F: every CTA size of the dataflow sweep, no / too few shared-memory forwarding slots, and the ordered overflow
+    bucket (forced by capping the number of parallel levels at 3) reproduce the sequential sweep of emcee.jl:39-58
+    bit for bit"""
     monkeypatch.setenv("AMH_STRETCH_BLOCK", cfg)
+    if fwd is not None:
+        monkeypatch.setenv("AMH_STRETCH_FWD", fwd)
     if levels is not None:
         monkeypatch.setenv("AMH_STRETCH_LEVELS", str(levels))
     target = amh.RosenbrockTarget(10)
