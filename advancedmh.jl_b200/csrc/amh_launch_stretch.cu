@@ -163,7 +163,8 @@ constexpr unsigned kStretchSentinel = 0xffffffffu;
 
 struct StretchPlan {
     unsigned* pair;            /* [nsteps][n_ensembles][nwp] slot order: self | partner << 16, or the sentinel */
-    unsigned* fwd;             /* same indexing: forwarding slot of self | of the partner << 16 (0xffff = none) */
+    unsigned* fwd;             /* same indexing: forwarding slot of self (0xffff: nobody reads the new value in this
+                                  sweep, 0xfffe: somebody does, through L2) | of the partner << 16 (0xffff = L2) */
     double* zf;                /* same indexing */
     double* am;
     double* ex;
@@ -235,7 +236,7 @@ stretch_plan_kernel(StretchPlan o, const unsigned long long* __restrict__ seeds,
         int run = inc - cnt + ((tid >> 5) ? wsum[(tid >> 5) - 1] : 0);
         for (int i = lo; i < hi; ++i) {
             const int f = fslot[i];
-            fslot[i] = (f && run < fcap) ? run : 0xffff;
+            fslot[i] = f ? (run < fcap ? run : 0xfffe) : 0xffff;     /* 0xfffe: read later in this sweep, through L2 */
             run += f;
         }
     }
@@ -264,7 +265,7 @@ stretch_plan_kernel(StretchPlan o, const unsigned long long* __restrict__ seeds,
         const double z = (tt * tt) / aa;
         const int pj = partner[i];
         o.pair[slot] = (unsigned)i | ((unsigned)pj << 16);
-        o.fwd[slot] = (unsigned)fslot[i] | ((pj < i ? (unsigned)fslot[pj] : 0xffffu) << 16);
+        o.fwd[slot] = (unsigned)fslot[i] | (((pj < i && fslot[pj] < 0xfffe) ? (unsigned)fslot[pj] : 0xffffu) << 16);
         o.zf[slot] = z;
         o.am[slot] = (double)(d - 1) * amh::log_(z);
         o.ex[slot] = amh::exponential(b1.v[0], b1.v[1]);
@@ -304,7 +305,7 @@ template <int DMAX, class T>
 __device__ __forceinline__ void stretch_move(const typename T::template Params<DMAX>& tp, int d, long long base, int i,
                                              int idx, unsigned sslot, unsigned pslot, double z, double am, double ex,
                                              double (&w)[Rec<DMAX>::cap], const double* __restrict__ Rold,
-                                             double* __restrict__ Rnew, const StretchSmem& sm) {
+                                             double* __restrict__ Rnew, const StretchSmem& sm, unsigned short want) {
     using D = Dim<DMAX>;
     constexpr int CAP = D::cap;
     constexpr int RC = Rec<DMAX>::cap;
@@ -342,21 +343,32 @@ __device__ __forceinline__ void stretch_move(const typename T::template Params<D
 #pragma unroll
         for (int j = 0; j < DMAX; ++j) w[j] = acc ? y[j] : w[j];
         w[DMAX] = acc ? lpy : lpw;
-        if (sslot != 0xffffu) {
-            double* ps = sm.fwd + (size_t)sslot * d;
-#pragma unroll
-            for (int j = 0; j < DMAX; ++j) ps[j] = w[j];
-        }
-#pragma unroll
-        for (int j = 0; j < RC; j += 4) st256(pn + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
     } else {
         for (int j = 0; j < d; ++j) w[j] = acc ? y[j] : w[j];
         w[d] = acc ? lpy : lpw;
-        if (sslot != 0xffffu) {
-            double* ps = sm.fwd + (size_t)sslot * d;
+    }
+    /* publish: a forwarded value only has to be ordered against the shared-memory copy, so the flag goes up before
+     * the record's round trip to L2 (which the next sweep needs, and the sweep's closing barrier orders) */
+    if (sslot < 0xfffeu) {
+        double* ps = sm.fwd + (size_t)sslot * d;
+        if constexpr (D::fixed) {
+#pragma unroll
+            for (int j = 0; j < DMAX; ++j) ps[j] = w[j];
+        } else {
             for (int j = 0; j < d; ++j) ps[j] = w[j];
         }
+        __threadfence_block();
+        sm.ver[i] = want;
+    }
+    if constexpr (D::fixed) {
+#pragma unroll
+        for (int j = 0; j < RC; j += 4) st256(pn + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
+    } else {
         for (int j = 0; j < rs; j += 4) st256(pn + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
+    }
+    if (sslot == 0xfffeu) {                                  /* read through L2 later in this sweep */
+        __threadfence_block();
+        sm.ver[i] = want;
     }
     sm.accs[i] = acc ? 1 : 0;
     if (acc) sm.naccs[i] += 1u;                              /* only ever touched by the thread that moves walker i */
@@ -449,9 +461,7 @@ stretch_sweep_flow_kernel(const __grid_constant__ StretchArgs a, const __grid_co
                     while (sm.ver[idx] != want) { }                      /* the partner's new value (emcee.jl:53) */
                     __threadfence_block();
                 }
-                stretch_move<DMAX, T>(tp, d, base, i, idx, fw_c & 0xffffu, fw_c >> 16, z_c, am_c, ex_c, w, Rold, Rnew, sm);
-                __threadfence_block();
-                sm.ver[i] = want;
+                stretch_move<DMAX, T>(tp, d, base, i, idx, fw_c & 0xffffu, fw_c >> 16, z_c, am_c, ex_c, w, Rold, Rnew, sm, want);
             }
         }
         __syncthreads();
@@ -469,7 +479,7 @@ stretch_sweep_flow_kernel(const __grid_constant__ StretchArgs a, const __grid_co
                     double w[Rec<DMAX>::cap];
                     stretch_load_own<DMAX>(w, Rold, base, (int)(po & 0xffffu), d);
                     stretch_move<DMAX, T>(tp, d, base, (int)(po & 0xffffu), (int)(po >> 16), fo & 0xffffu, fo >> 16,
-                                          plan.zf[off + bq], plan.am[off + bq], plan.ex[off + bq], w, Rold, Rnew, sm);
+                                          plan.zf[off + bq], plan.am[off + bq], plan.ex[off + bq], w, Rold, Rnew, sm, want);
                     __threadfence_block();
                     last = best;
                 }
