@@ -7,7 +7,7 @@ from . import _capi
 from ._capi import AMHArgumentError, AMHError, AMHStateError, Engine
 from .distributions import (Exponential, Gamma, I, InverseGamma, LogNormal, MvNormal, Normal, Uniform, Zeros)
 from .models import (DensityModel, DeviceTarget, GaussianPrecisionTarget, IIDNormalTarget,
-                     LogisticRegressionTarget, MvNormalTarget, NormalInverseGammaToy, RosenbrockTarget)
+                     LogisticRegressionTarget, MvNormalTarget, NormalInverseGammaToy, RosenbrockTarget, SourceTarget)
 from .samplers import (MALA, RWMH, Ensemble, MetropolisHastings, RandomWalkProposal,
                        RobustAdaptiveMetropolis, StaticMH, StaticProposal, StretchProposal,
                        SymmetricRandomWalkProposal, SymmetricStaticProposal)

@@ -21,6 +21,7 @@ AMH_OK, AMH_ERR_INVALID, AMH_ERR_CUDA, AMH_ERR_UNSUPPORTED, AMH_ERR_STATE = 0, 1
 
 TARGET_IID_NORMAL, TARGET_MVNORMAL, TARGET_ROSENBROCK, TARGET_LOGISTIC = 1, 2, 3, 4
 TARGET_GAUSS_PREC, TARGET_NIG_TOY, TARGET_NIG_TOY_LOG = 5, 6, 7
+TARGET_USER = 100
 SAMPLER_STATIC, SAMPLER_RW, SAMPLER_STRETCH, SAMPLER_MALA, SAMPLER_RAM, SAMPLER_MIXED = 1, 2, 3, 4, 5, 6
 COV_SCALAR, COV_DIAG, COV_FULL, COV_COMPONENTS = 1, 2, 3, 4
 
@@ -75,7 +76,7 @@ class AMHStateError(AMHError):
 # every symbol include/amh.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
     "version", "last_error", "contract_version", "ctx_create", "ctx_destroy", "ctx_sync",
-    "target_create", "target_destroy", "sampler_create", "sampler_destroy",
+    "target_create", "target_create_source", "target_destroy", "sampler_create", "sampler_destroy",
     "run_create", "run_destroy", "run_steps", "run_sync", "run_sample",
     "run_get_state", "run_set_params", "run_set_state", "run_get_ram_adapt", "run_dim", "run_nchains", "run_launch_count",
     "run_kernel_time_ms", "host_alloc", "host_free",
@@ -118,6 +119,8 @@ class Engine:
             f(n).argtypes = [C.c_void_p]
         f("ctx_create").argtypes = [C.c_int32, C.POINTER(C.c_void_p)]
         f("target_create").argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, C.c_int64, C.POINTER(C.c_void_p)]
+        f("target_create_source").argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, _dp, C.c_int64,
+                                              C.POINTER(C.c_void_p)]
         f("sampler_create").argtypes = [C.c_void_p, C.POINTER(SamplerDesc), C.POINTER(C.c_void_p)]
         f("run_create").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, _u64p, _dp, C.c_int64,
                                     C.POINTER(C.c_void_p)]
@@ -177,6 +180,20 @@ class Engine:
         h = C.c_void_p()
         self._check(self._f("target_create")(self.ctx, kind, dim, blob.ctypes.data_as(_dp), blob.size, C.byref(h)))
         return TargetHandle(self, h, kind, dim)
+
+    def target_source(self, dim: int, source: str, data=None, has_gradient: bool = False) -> "TargetHandle":
+        """amh_target_create_source: a log-density given as source text (DensityModel(f), src/AdvancedMH.jl:52-54)"""
+        data = np.zeros(0) if data is None else _as_f64(data).ravel()
+        h = C.c_void_p()
+        self._check(self._f("target_create_source")(self.ctx, dim, source.encode(), int(bool(has_gradient)),
+                                                    data.ctypes.data_as(_dp) if data.size else None, data.size, C.byref(h)))
+        return TargetHandle(self, h, TARGET_USER, dim)
+
+    def target_of(self, t) -> "TargetHandle":
+        """handle for a host-side target description (models.py): catalogue entry or source text"""
+        if getattr(t, "kind", None) == TARGET_USER:
+            return self.target_source(t.dim, t.source, t.data, t.has_gradient)
+        return self.target(t.kind, t.dim, t.blob())
 
     def sampler(self, *, kind, dim, symmetric=False, cov_kind=COV_SCALAR, mean=None, scale=None,
                 stretch_a=2.0, n_walkers=0, mala_sigma2=0.0, mala_drift=0.0,

@@ -240,9 +240,32 @@ int32_t amh_target_create(amh_ctx* ctx, int32_t kind, int32_t dim, const double*
     *out = t;
     return AMH_OK;
 }
+int32_t amh_target_create_source(amh_ctx* ctx, int32_t dim, const char* source, int32_t has_gradient,
+                                 const double* data, int64_t ndata, amh_target** out) {
+    if (!ctx || !out) return fail(AMH_ERR_INVALID, "ctx/out is NULL");
+    if (!source || !*source) return fail(AMH_ERR_INVALID, "source is NULL or empty");
+    if (dim < 1) return fail(AMH_ERR_INVALID, "dim must be >= 1");
+    if (dim > amhd::kGenericCap) return fail(AMH_ERR_UNSUPPORTED, "user-supplied targets support dim <= 128");
+    if (ndata < 0 || (ndata > 0 && !data)) return fail(AMH_ERR_INVALID, "data is NULL");
+    AMH_CUDA_TRY(cudaSetDevice(ctx->device));
+    amh_target* t = new amh_target();
+    t->ctx = ctx; t->kind = AMH_TARGET_USER; t->dim = dim; t->ndata = ndata;
+    t->user_grad = has_gradient != 0;
+    if (ndata > 0) t->blob.assign(data, data + ndata);
+    else t->blob.assign(1, 0.0);                      /* the kernels always get a valid pointer */
+    int rc = upload(ctx, &t->dblob, t->blob);
+    if (!rc) rc = rtc_build(*t, source, t->user_grad);
+    if (rc) { amh_target_destroy(t); return rc; }
+    *out = t;
+    return AMH_OK;
+}
 int32_t amh_target_destroy(amh_target* t) {
     if (!t) return AMH_OK;
     cudaSetDevice(t->ctx->device);
+    if (t->rtc) {
+        cudaStreamSynchronize(t->ctx->stream);        /* no kernel of the module may still be running */
+        rtc_destroy(*t);
+    }
     dfree(t->ctx, t->dblob);
     delete t;
     return AMH_OK;

@@ -16,6 +16,8 @@ struct amh_ctx {
     std::set<const void*> configured;     /* kernels whose function attributes were set on this device */
 };
 
+namespace amhh { struct RtcState; }
+
 struct amh_target {
     amh_ctx* ctx = nullptr;
     int kind = 0, dim = 0;
@@ -23,7 +25,12 @@ struct amh_target {
     double* dblob = nullptr;       /* device copy of the whole blob */
     long long ndata = 0;
     double inv2tau2 = 0, invtau2 = 0;
+    /* AMH_TARGET_USER: run-time compiled kernels (amh_rtc.cu) */
+    amhh::RtcState* rtc = nullptr;
+    bool user_grad = false;
+    std::string build_log;
     bool has_grad() const {
+        if (kind == AMH_TARGET_USER) return user_grad;
         return kind == AMH_TARGET_MVNORMAL || kind == AMH_TARGET_GAUSS_PREC || kind == AMH_TARGET_IID_NORMAL ||
                kind == AMH_TARGET_LOGISTIC || kind == AMH_TARGET_ROSENBROCK;
     }
@@ -123,4 +130,10 @@ int ramw_init_S(amh_run& r);
 int ramw_import_S(amh_run& r, const double* src);
 int ramw_export_S(amh_run& r, double* dst);   /* current factor of every chain -> dst [tri][pitch] */
 int default_steps_per_launch(const amh_run& r);
+/* user-supplied targets: kernels compiled at run time by NVRTC (amh_rtc.cu) */
+enum RtcKernel { RK_INIT = 0, RK_MH, RK_COMP, RK_MALA, RK_RAM128, RK_RAM64, RK_RAM32, RK_STRETCH, RK_FLOW512, RK_FLOW768,
+                 RK_FLOW1024, RK_COUNT };
+int rtc_build(amh_target& t, const char* source, bool has_grad);
+void rtc_destroy(amh_target& t);
+int rtc_launch(amh_run& r, int which, unsigned grid, unsigned block, size_t smem, void** params);
 }  // namespace amhh

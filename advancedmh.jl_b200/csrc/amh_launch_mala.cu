@@ -15,6 +15,7 @@
 namespace amhh {
 using namespace amhd;
 
+/* @rtc-begin: the device code from here to @rtc-end is also compiled by NVRTC for user-supplied targets (amh_rtc.cu) */
 struct MalaArgs {
     ChainState st;
     SaveArgs sv;
@@ -114,6 +115,7 @@ mala_step_kernel(const __grid_constant__ MalaArgs a, const __grid_constant__ typ
     if (a.sv.acc_out) a.sv.acc_out[ch] = accepted;
 }
 
+/* @rtc-end */
 template <int DMAX, class T>
 int launch_mala_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     constexpr int BLOCK = (DMAX == 0) ? 32 : 128;
@@ -128,11 +130,18 @@ int launch_mala_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     a.sigma = s.mala_sigma; a.sigma2 = s.d.mala_sigma2; a.drift = s.d.mala_drift;
     const auto tp = make_tp<T, DMAX>(*r.target);
     const size_t smem = 2 * (size_t)r.dim * BLOCK * sizeof(double);
-    auto kern = mala_step_kernel<DMAX, T, BLOCK>;
-    if (smem > 48 * 1024) AMH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((r.n + BLOCK - 1) / BLOCK);
-    kern<<<grid, BLOCK, smem, r.ctx->stream>>>(a, tp);
-    AMH_CUDA_TRY(cudaGetLastError());
+    if constexpr (T::kind == AMH_TARGET_USER) {
+        static_assert(DMAX == 0 && BLOCK == 32, "RK_MALA names mala_step_kernel<0, TUser, 32>");
+        void* params[] = {(void*)&a, (void*)&tp};
+        const int rc = rtc_launch(r, RK_MALA, grid, BLOCK, smem, params);
+        if (rc) return rc;
+    } else {
+        auto kern = mala_step_kernel<DMAX, T, BLOCK>;
+        if (smem > 48 * 1024) AMH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, BLOCK, smem, r.ctx->stream>>>(a, tp);
+        AMH_CUDA_TRY(cudaGetLastError());
+    }
     r.launches += 1;
     r.pending_launches += 1;
     return AMH_OK;
@@ -161,6 +170,9 @@ int launch_mala(amh_run& r, int nsteps, const SaveArgs& sv) {
     case AMH_TARGET_ROSENBROCK: return launch_mala_dim<TRosenbrock>(r, nsteps, sv);
     case AMH_TARGET_IID_NORMAL: return launch_mala_t<2, TIidNormal>(r, nsteps, sv);
     case AMH_TARGET_LOGISTIC: return launch_mala_t<0, TLogistic>(r, nsteps, sv);
+    case AMH_TARGET_USER:
+        if (r.target->has_grad()) return launch_mala_t<0, TUser>(r, nsteps, sv);
+        break;
     }
     return fail(AMH_ERR_INVALID, "The gradient of the log density function is not defined");
 }

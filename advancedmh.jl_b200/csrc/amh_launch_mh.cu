@@ -36,11 +36,18 @@ int launch_mh_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     a.prop = make_prop<DMAX>(s);
     const auto tp = make_tp<T, DMAX>(*r.target);
     const size_t smem = (size_t)r.dim * BLOCK * sizeof(double);
-    auto kern = mh_step_kernel<DMAX, T, BLOCK, MINB>;
-    if (smem > 48 * 1024) AMH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((r.n + BLOCK - 1) / BLOCK);
-    kern<<<grid, BLOCK, smem, r.ctx->stream>>>(a, tp);
-    AMH_CUDA_TRY(cudaGetLastError());
+    if constexpr (T::kind == AMH_TARGET_USER) {
+        static_assert(DMAX == 0 && BLOCK == 64 && MINB == 4, "RK_MH names mh_step_kernel<0, TUser, 64, 4>");
+        void* params[] = {(void*)&a, (void*)&tp};
+        const int rc = rtc_launch(r, RK_MH, grid, BLOCK, smem, params);
+        if (rc) return rc;
+    } else {
+        auto kern = mh_step_kernel<DMAX, T, BLOCK, MINB>;
+        if (smem > 48 * 1024) AMH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, BLOCK, smem, r.ctx->stream>>>(a, tp);
+        AMH_CUDA_TRY(cudaGetLastError());
+    }
     r.launches += 1;
     r.pending_launches += 1;
     return AMH_OK;
@@ -91,6 +98,7 @@ int launch_mh(amh_run& r, int nsteps, const SaveArgs& sv) {
     case AMH_TARGET_NIG_TOY:
     case AMH_TARGET_NIG_TOY_LOG: return launch_mh_d2<TNig>(r, nsteps, sv);
     case AMH_TARGET_LOGISTIC: return launch_mh_t<0, TLogistic>(r, nsteps, sv);
+    case AMH_TARGET_USER: return launch_mh_t<0, TUser>(r, nsteps, sv);
     }
     return fail(AMH_ERR_INVALID, "unknown target kind");
 }
@@ -115,8 +123,14 @@ int launch_init_t(amh_run& r, int mode) {
     if (s.by_components()) a.want_lq = 0;        /* component proposals recompute logq(state) every step */
     const auto tp = make_tp<T, 0>(*r.target);
     const unsigned grid = (unsigned)((r.n + 63) / 64);
-    init_kernel<T><<<grid, 64, 0, r.ctx->stream>>>(a, tp);
-    AMH_CUDA_TRY(cudaGetLastError());
+    if constexpr (T::kind == AMH_TARGET_USER) {
+        void* params[] = {(void*)&a, (void*)&tp};
+        const int rc = rtc_launch(r, RK_INIT, grid, 64, 0, params);
+        if (rc) return rc;
+    } else {
+        init_kernel<T><<<grid, 64, 0, r.ctx->stream>>>(a, tp);
+        AMH_CUDA_TRY(cudaGetLastError());
+    }
     r.launches += 1;
     return AMH_OK;
 }
@@ -149,6 +163,7 @@ int launch_init(amh_run& r, int mode) {
     case AMH_TARGET_NIG_TOY:
     case AMH_TARGET_NIG_TOY_LOG: return launch_init_t<TNig>(r, mode);
     case AMH_TARGET_LOGISTIC: return launch_init_t<TLogistic>(r, mode);
+    case AMH_TARGET_USER: return launch_init_t<TUser>(r, mode);
     }
     return fail(AMH_ERR_INVALID, "unknown target kind");
 }

@@ -14,6 +14,7 @@
 namespace amhh {
 using namespace amhd;
 
+/* @rtc-begin: the device code from here to @rtc-end is also compiled by NVRTC for user-supplied targets (amh_rtc.cu) */
 struct MhCompArgs {
     ChainState st;
     SaveArgs sv;
@@ -114,6 +115,7 @@ mh_comp_kernel(const __grid_constant__ MhCompArgs a, const __grid_constant__ typ
     if (a.sv.acc_out) a.sv.acc_out[ch] = accepted;
 }
 
+/* @rtc-end */
 template <class T>
 static int launch_mh_comp_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     constexpr int BLOCK = 64;
@@ -131,11 +133,18 @@ static int launch_mh_comp_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     a.comps = s.dcomps;
     const auto tp = make_tp<T, 0>(*r.target);
     const size_t smem = (size_t)r.dim * BLOCK * sizeof(double);
-    auto kern = mh_comp_kernel<T, BLOCK>;
-    if (smem > 48 * 1024) AMH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((r.n + BLOCK - 1) / BLOCK);
-    kern<<<grid, BLOCK, smem, r.ctx->stream>>>(a, tp);
-    AMH_CUDA_TRY(cudaGetLastError());
+    if constexpr (T::kind == AMH_TARGET_USER) {
+        static_assert(BLOCK == 64, "RK_COMP names mh_comp_kernel<TUser, 64>");
+        void* params[] = {(void*)&a, (void*)&tp};
+        const int rc = rtc_launch(r, RK_COMP, grid, BLOCK, smem, params);
+        if (rc) return rc;
+    } else {
+        auto kern = mh_comp_kernel<T, BLOCK>;
+        if (smem > 48 * 1024) AMH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, BLOCK, smem, r.ctx->stream>>>(a, tp);
+        AMH_CUDA_TRY(cudaGetLastError());
+    }
     r.launches += 1;
     r.pending_launches += 1;
     return AMH_OK;
@@ -151,6 +160,7 @@ int launch_mh_comp(amh_run& r, int nsteps, const SaveArgs& sv) {
     case AMH_TARGET_NIG_TOY:
     case AMH_TARGET_NIG_TOY_LOG: return launch_mh_comp_t<TNig>(r, nsteps, sv);
     case AMH_TARGET_LOGISTIC: return launch_mh_comp_t<TLogistic>(r, nsteps, sv);
+    case AMH_TARGET_USER: return launch_mh_comp_t<TUser>(r, nsteps, sv);
     }
     return fail(AMH_ERR_INVALID, "unknown target kind");
 }

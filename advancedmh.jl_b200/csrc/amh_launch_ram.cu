@@ -21,6 +21,7 @@
 namespace amhh {
 using namespace amhd;
 
+/* @rtc-begin: the device code from here to @rtc-end is also compiled by NVRTC for user-supplied targets (amh_rtc.cu) */
 struct RamArgs {
     ChainState st;
     SaveArgs sv;
@@ -176,6 +177,7 @@ ram_step_kernel(const __grid_constant__ RamArgs a, const __grid_constant__ typen
     if (a.sv.acc_out) a.sv.acc_out[ch] = accepted;
 }
 
+/* @rtc-end */
 /* gathers the current buffer of every chain into `dst` ([tri][pitch]) for get_state */
 __global__ void ram_gather_S_kernel(const double* S, const double* S2, const unsigned char* sflag, double* dst,
                                     long long n, long long pitch, long long nt) {
@@ -208,6 +210,11 @@ int launch_ram_t(amh_run& r, int nsteps, bool warmup, const SaveArgs& sv) {
     const auto tp = make_tp<T, 0>(*r.target);
     const size_t smem = per_thread * block;
     const unsigned grid = (unsigned)((r.n + block - 1) / block);
+    if constexpr (T::kind == AMH_TARGET_USER) {
+        void* params[] = {(void*)&a, (void*)&tp};
+        const int rc = rtc_launch(r, block == 128 ? RK_RAM128 : block == 64 ? RK_RAM64 : RK_RAM32, grid, (unsigned)block, smem, params);
+        if (rc) return rc;
+    } else {
 #define AMH_RAM_LAUNCH(BL)                                                                                             \
     do {                                                                                                               \
         auto kern = ram_step_kernel<T, BL>;                                                                            \
@@ -215,11 +222,12 @@ int launch_ram_t(amh_run& r, int nsteps, bool warmup, const SaveArgs& sv) {
             AMH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
         kern<<<grid, BL, smem, r.ctx->stream>>>(a, tp);                                                                \
     } while (0)
-    if (block == 128) AMH_RAM_LAUNCH(128);
-    else if (block == 64) AMH_RAM_LAUNCH(64);
-    else AMH_RAM_LAUNCH(32);
+        if (block == 128) AMH_RAM_LAUNCH(128);
+        else if (block == 64) AMH_RAM_LAUNCH(64);
+        else AMH_RAM_LAUNCH(32);
 #undef AMH_RAM_LAUNCH
-    AMH_CUDA_TRY(cudaGetLastError());
+        AMH_CUDA_TRY(cudaGetLastError());
+    }
     r.launches += 1;
     r.pending_launches += 1;
     return AMH_OK;
@@ -234,6 +242,7 @@ int launch_ram(amh_run& r, int nsteps, bool warmup, const SaveArgs& sv) {
     case AMH_TARGET_NIG_TOY:
     case AMH_TARGET_NIG_TOY_LOG: return launch_ram_t<TNig>(r, nsteps, warmup, sv);
     case AMH_TARGET_LOGISTIC: return launch_ram_t<TLogistic>(r, nsteps, warmup, sv);
+    case AMH_TARGET_USER: return launch_ram_t<TUser>(r, nsteps, warmup, sv);
     }
     return fail(AMH_ERR_INVALID, "unknown target kind");
 }

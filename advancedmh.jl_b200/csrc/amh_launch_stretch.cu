@@ -20,6 +20,7 @@
 namespace amhh {
 using namespace amhd;
 
+/* @rtc-begin: the device code from here to @rtc-end is also compiled by NVRTC for user-supplied targets (amh_rtc.cu) */
 struct StretchArgs {
     ChainState st;              /* X/lp = buffer A */
     SaveArgs sv;
@@ -512,6 +513,7 @@ stretch_sweep_flow_kernel(const __grid_constant__ StretchArgs a, const __grid_co
     }
 }
 
+/* @rtc-end */
 template <int DMAX, class T>
 int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     constexpr int BLOCK = 1024;
@@ -575,6 +577,14 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
             r.launches += 1;
         }
         const size_t smemv = (size_t)fcap * r.dim * sizeof(double) + fixed_sm;
+        if constexpr (T::kind == AMH_TARGET_USER) {
+            static_assert(DMAX == 0, "RK_FLOW* name stretch_sweep_flow_kernel<0, TUser, BL>");
+            int fcap_i = (int)fcap;
+            void* params[] = {(void*)&a, (void*)&plan, (void*)&tp, (void*)&RA, (void*)&RB, (void*)&fcap_i};
+            const int rc = rtc_launch(r, blk == 512 ? RK_FLOW512 : blk == 768 ? RK_FLOW768 : RK_FLOW1024, (unsigned)nens,
+                                      (unsigned)blk, smemv, params);
+            if (rc) return rc;
+        } else {
 #define AMH_STRETCH_LAUNCH(BL)                                                                                             \
         do {                                                                                                               \
             auto kf = stretch_sweep_flow_kernel<DMAX, T, BL>;                                                              \
@@ -582,22 +592,30 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
                 AMH_CUDA_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv));           \
             kf<<<(unsigned)nens, BL, smemv, r.ctx->stream>>>(a, plan, tp, RA, RB, (int)fcap);                              \
         } while (0)
-        if (blk == 512) AMH_STRETCH_LAUNCH(512);
-        else if (blk == 768) AMH_STRETCH_LAUNCH(768);
-        else AMH_STRETCH_LAUNCH(1024);
+            if (blk == 512) AMH_STRETCH_LAUNCH(512);
+            else if (blk == 768) AMH_STRETCH_LAUNCH(768);
+            else AMH_STRETCH_LAUNCH(1024);
 #undef AMH_STRETCH_LAUNCH
-        AMH_CUDA_TRY(cudaGetLastError());
+            AMH_CUDA_TRY(cudaGetLastError());
+        }
         r.launches += 1;
         r.pending_launches += 1;
         return AMH_OK;
     }
     const size_t smem = (size_t)a.n_walkers * (sizeof(int) + 1) + 16;
-    auto kern = stretch_sweep_kernel<DMAX, T, BLOCK>;
     if (smem > 200 * 1024) return fail(AMH_ERR_UNSUPPORTED, "Ensemble on the device supports n_walkers <= 40000");
-    if (smem > 48 * 1024) AMH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)(r.n / a.n_walkers);
-    kern<<<grid, BLOCK, smem, r.ctx->stream>>>(a, tp);
-    AMH_CUDA_TRY(cudaGetLastError());
+    if constexpr (T::kind == AMH_TARGET_USER) {
+        static_assert(DMAX == 0 && BLOCK == 1024, "RK_STRETCH names stretch_sweep_kernel<0, TUser, 1024>");
+        void* params[] = {(void*)&a, (void*)&tp};
+        const int rc = rtc_launch(r, RK_STRETCH, grid, BLOCK, smem, params);
+        if (rc) return rc;
+    } else {
+        auto kern = stretch_sweep_kernel<DMAX, T, BLOCK>;
+        if (smem > 48 * 1024) AMH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, BLOCK, smem, r.ctx->stream>>>(a, tp);
+        AMH_CUDA_TRY(cudaGetLastError());
+    }
     if (nsteps & 1) {          /* the current state now lives in the other buffer */
         std::swap(r.X, r.X2);
         std::swap(r.lp, r.lp2);
@@ -630,6 +648,7 @@ int launch_stretch(amh_run& r, int nsteps, const SaveArgs& sv) {
     case AMH_TARGET_NIG_TOY:
     case AMH_TARGET_NIG_TOY_LOG: return launch_stretch_t<2, TNig>(r, nsteps, sv);
     case AMH_TARGET_LOGISTIC: return launch_stretch_t<0, TLogistic>(r, nsteps, sv);
+    case AMH_TARGET_USER: return launch_stretch_t<0, TUser>(r, nsteps, sv);
     }
     return fail(AMH_ERR_INVALID, "unknown target kind");
 }

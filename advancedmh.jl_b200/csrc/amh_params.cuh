@@ -58,6 +58,8 @@ typename T::template Params<DMAX> make_tp(const amh_target& t) {
         p.y = t.dblob + 1 + t.ndata * d;
         p.n = t.ndata;
         p.inv2tau2 = t.inv2tau2; p.invtau2 = t.invtau2;
+    } else if constexpr (T::kind == AMH_TARGET_USER) {
+        p.data = t.dblob; p.n = t.ndata;
     }
     return p;
 }

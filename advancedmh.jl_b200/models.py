@@ -97,15 +97,37 @@ class NormalInverseGammaToy(DeviceTarget):
         return np.concatenate([[self.alpha, self.beta, cig], self.obs])
 
 
+class SourceTarget(DeviceTarget):
+    """A log-density stated as C++ source text (include/amh_user_target.h), compiled for the device by NVRTC
+    (amh_target_create_source): the route from the catalogue to `DensityModel(f)` for an arbitrary `f`
+    (src/AdvancedMH.jl:52-54) and, with `gradient=True`, to a LogDensityProblems object with
+    `logdensity_and_gradient` (MALA.jl:100-105).  The source defines
+
+        AMH_TARGET double amh_user_logdensity(const double* x, int dim, const double* data, long long ndata);
+        AMH_TARGET void   amh_user_logdensity_and_gradient(const double* x, int dim, const double* data,
+                                                           long long ndata, double* lp, double* grad);  // gradient=True
+
+    `data` (optional float64 array) is copied to the device and passed to every call."""
+    kind = K.TARGET_USER
+    def __init__(self, dim, source, data=None, gradient=False):
+        self.dim = int(dim)
+        self.source = str(source)
+        self.data = np.zeros(0) if data is None else np.ascontiguousarray(data, dtype=np.float64).ravel()
+        self.has_gradient = bool(gradient)
+    def blob(self):
+        return self.data
+
+
 class DensityModel:
-    """DensityModel(target): same name and role as src/AdvancedMH.jl:52-54, restricted to the
-    device catalogue."""
+    """DensityModel(target): same name and role as src/AdvancedMH.jl:52-54.  `target` is a catalogue entry or a
+    `SourceTarget` (the closure stated as source text); a Python callable cannot run on the device."""
     def __init__(self, logdensity):
         if not isinstance(logdensity, DeviceTarget):
             raise ValueError(
                 "DensityModel on the B200 path needs a catalogue target (IIDNormalTarget, MvNormalTarget, "
-                "GaussianPrecisionTarget, RosenbrockTarget, LogisticRegressionTarget, NormalInverseGammaToy); "
-                "arbitrary closures cannot run on the device and there is no CPU fallback")
+                "GaussianPrecisionTarget, RosenbrockTarget, LogisticRegressionTarget, NormalInverseGammaToy) or a "
+                "SourceTarget (the log-density as source text); host closures cannot run on the device and there "
+                "is no CPU fallback")
         self.logdensity = logdensity
 
 

@@ -194,7 +194,7 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
     lo, hi = shard_bounds(nchains, rank, world)
     eng = engine or default_engine(parallel.device if isinstance(parallel, MCMCB200) else None)
 
-    th = eng.target(target.kind, dim, target.blob())
+    th = eng.target_of(target)
     sh = sampler.lower(eng, dim)
     n_local = (hi - lo) * nw
     run = None

@@ -165,6 +165,10 @@ def main():
         run_reference(args)
         return
 
+    # stdout carries exactly ONE JSON line: everything else a library prints there (NCCL's version banner ...) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import amh_b200 as amh
     rank = int(os.environ.get("RANK", "0"))
@@ -302,7 +306,8 @@ def main():
             "clocks": clk.result(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "wall_s_timed_region": t_wall,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     run.close()
     if dist is not None:
         dist.destroy_process_group()

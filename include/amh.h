@@ -61,6 +61,7 @@ extern "C" {
                                           + sum_i logpdf(Normal(m,sqrt s),y_i) : -Inf
                                     (test/emcee.jl:5-15)                                   */
 #define AMH_TARGET_NIG_TOY_LOG 7 /* same in (log s, m) with the Jacobian term (test/emcee.jl:46-56) */
+#define AMH_TARGET_USER      100 /* log-density given as source text: amh_target_create_source below        */
 
 /* ---- sampler kinds: the reference constructors they stand for ---- */
 #define AMH_SAMPLER_STATIC   1  /* MetropolisHastings(StaticProposal(..)), StaticMH   mh-core.jl:44-49, proposal.jl:70-85 */
@@ -125,6 +126,7 @@ typedef struct amh_target  amh_target;
 typedef struct amh_sampler amh_sampler;
 typedef struct amh_run     amh_run;
 
+#ifndef AMH_RTC   /* (the NVRTC translation unit of user-supplied targets needs the constants and structs only) */
 /* handshake, diagnostics */
 int32_t     amh_version(int32_t* major, int32_t* minor);
 const char* amh_last_error(void);
@@ -139,6 +141,23 @@ int32_t amh_ctx_sync(amh_ctx* ctx);
 int32_t amh_target_create(amh_ctx* ctx, int32_t kind, int32_t dim,
                           const double* blob, int64_t nblob, amh_target** out);
 int32_t amh_target_destroy(amh_target* t);
+
+/* model given as SOURCE TEXT: the route from the catalogue to DensityModel(f)
+ * (src/AdvancedMH.jl:52-54: an arbitrary log-density closure) and to LogDensityProblems objects with
+ * `logdensity` / `logdensity_and_gradient` (src/AdvancedMH.jl:76, MALA.jl:100-105).  A Julia closure cannot cross a
+ * C ABI into a kernel, so the caller states the function in the C++ subset described in include/amh_user_target.h:
+ *
+ *   AMH_TARGET double amh_user_logdensity(const double* x, int dim, const double* data, long long ndata);
+ *   AMH_TARGET void   amh_user_logdensity_and_gradient(const double* x, int dim, const double* data, long long ndata,
+ *                                                      double* lp, double* grad);      // iff has_gradient != 0
+ *
+ * The library compiles it with NVRTC for sm_100a (-fmad=false, as the numerical contract requires) together with
+ * its own generic kernels; every sampler then runs on it: StaticMH / RWMH incl. arrays of proposals, Ensemble, RAM,
+ * and MALA when has_gradient != 0 (otherwise MALA fails like the reference: "The gradient of the log density
+ * function is not defined", MALA.jl:44-50).  `data` ([ndata] float64, may be NULL) is copied to the device and handed
+ * to every call.  dim <= 128.  A compile error returns AMH_ERR_INVALID with the compiler log in amh_last_error(). */
+int32_t amh_target_create_source(amh_ctx* ctx, int32_t dim, const char* source, int32_t has_gradient,
+                                 const double* data, int64_t ndata, amh_target** out);
 
 /* sampler: POD image of the unchanged AdvancedMH constructor */
 int32_t amh_sampler_create(amh_ctx* ctx, const amh_sampler_desc* desc, amh_sampler** out);
@@ -212,6 +231,7 @@ int64_t amh_run_launch_count(amh_run* run);
  * The first call switches event recording on for this run (off by default: two
  * event records per amh_run_steps call are not free at one launch per step). */
 int32_t amh_run_kernel_time_ms(amh_run* run, int32_t reset, double* ms, int64_t* launches);
+#endif /* AMH_RTC */
 
 #ifdef __cplusplus
 }

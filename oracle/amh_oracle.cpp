@@ -27,7 +27,10 @@
  *
  * Build: see oracle/Makefile  (g++ -O2 -ffp-contract=off, never -ffast-math).
  */
+#include <dlfcn.h>
+#include <unistd.h>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
@@ -55,6 +58,17 @@ struct Target {
     std::vector<double> blob;
     int64_t ndata = 0;       /* IID_NORMAL / NIG / LOGISTIC rows */
     double inv2tau2 = 0, invtau2 = 0;
+    /* AMH_TARGET_USER: the user's source text compiled by g++ with the contract flags (amho_target_create_source) */
+    typedef double (*user_lp_fn)(const double*, int, const double*, long long);
+    typedef void (*user_lpg_fn)(const double*, int, const double*, long long, double*, double*);
+    void* user_lib = nullptr;
+    user_lp_fn user_lp = nullptr;
+    user_lpg_fn user_lpg = nullptr;
+    std::string user_so;
+    ~Target() {
+        if (user_lib) dlclose(user_lib);
+        if (!user_so.empty()) std::remove(user_so.c_str());
+    }
 
     /* Normal(mu, sigma) log-density of y: Distributions' normlogpdf
      * -(z^2 + log 2pi)/2 - log sigma  (SURVEY.md A.2). */
@@ -67,6 +81,7 @@ struct Target {
     double logp(const double* x) const {
         const int d = dim;
         switch (kind) {
+        case AMH_TARGET_USER: return user_lp(x, d, blob.data(), (long long)ndata);
         case AMH_TARGET_IID_NORMAL: {
             /* density(theta) = insupport(theta) ? sum(logpdf.(Normal(theta1,theta2), data)) : -Inf
              * test/runtests.jl:26-28, README.md:29-31 */
@@ -141,6 +156,7 @@ struct Target {
     }
 
     bool has_grad() const {
+        if (kind == AMH_TARGET_USER) return user_lpg != nullptr;
         return kind == AMH_TARGET_MVNORMAL || kind == AMH_TARGET_GAUSS_PREC ||
                kind == AMH_TARGET_IID_NORMAL || kind == AMH_TARGET_LOGISTIC ||
                kind == AMH_TARGET_ROSENBROCK;
@@ -150,6 +166,7 @@ struct Target {
     void logp_grad(const double* x, double& lp, double* g) const {
         const int d = dim;
         switch (kind) {
+        case AMH_TARGET_USER: user_lpg(x, d, blob.data(), (long long)ndata, &lp, g); return;
         case AMH_TARGET_GAUSS_PREC: {
             /* (-x'Ax/2, -A x)  test/runtests.jl:343-345 */
             lp = logp(x);
@@ -760,6 +777,63 @@ int32_t amho_target_create(amh_ctx*, int32_t kind, int32_t dim, const double* bl
     default: ok = false;
     }
     if (!ok) { delete t; return fail(AMH_ERR_INVALID, "target kind/dim/blob size mismatch"); }
+    *out = (amh_target*)t;
+    return AMH_OK;
+}
+/* The oracle's side of amh_target_create_source: the SAME source text, compiled for the host with the contract flags
+ * (g++ -O2 -ffp-contract=off, include/amh_user_target.h in front) into a scratch shared object and dlopen'ed. */
+int32_t amho_target_create_source(amh_ctx*, int32_t dim, const char* source, int32_t has_gradient,
+                                  const double* data, int64_t ndata, amh_target** out) {
+    if (!out) return fail(AMH_ERR_INVALID, "out is NULL");
+    if (!source || !*source) return fail(AMH_ERR_INVALID, "source is NULL or empty");
+    if (dim < 1) return fail(AMH_ERR_INVALID, "dim must be >= 1");
+    if (dim > 128) return fail(AMH_ERR_UNSUPPORTED, "user-supplied targets support dim <= 128");
+    if (ndata < 0 || (ndata > 0 && !data)) return fail(AMH_ERR_INVALID, "data is NULL");
+    Dl_info info;
+    std::string incdir = "../include";
+    if (dladdr((void*)&amho_target_create_source, &info) && info.dli_fname) {
+        std::string p(info.dli_fname);
+        const size_t k = p.rfind('/');
+        incdir = (k == std::string::npos ? std::string(".") : p.substr(0, k)) + "/../include";
+    }
+    char tmpl[] = "/tmp/amho_user_XXXXXX";
+    const int fd = mkstemp(tmpl);
+    if (fd < 0) return fail(AMH_ERR_STATE, "mkstemp failed");
+    close(fd);
+    const std::string base(tmpl), cpp = base + ".cpp", so = base + ".so", log = base + ".log";
+    {
+        FILE* f = fopen(cpp.c_str(), "w");
+        if (!f) return fail(AMH_ERR_STATE, "cannot write the scratch source file");
+        fputs("#include \"amh_user_target.h\"\n#line 1 \"amh_user_target.cu\"\n", f);
+        fputs(source, f);
+        fputs("\n", f);
+        fclose(f);
+    }
+    const char* cxx = getenv("AMHO_CXX");
+    const std::string cmd = std::string(cxx ? cxx : "g++") + " -O2 -std=c++17 -fPIC -shared -ffp-contract=off -fno-fast-math -mfma -I'" +
+                            incdir + "' -o '" + so + "' '" + cpp + "' > '" + log + "' 2>&1";
+    const int rc = system(cmd.c_str());
+    std::string logtxt;
+    if (FILE* f = fopen(log.c_str(), "r")) {
+        char buf[4096];
+        size_t n;
+        while ((n = fread(buf, 1, sizeof(buf), f)) > 0) logtxt.append(buf, n);
+        fclose(f);
+    }
+    std::remove(cpp.c_str()); std::remove(log.c_str()); std::remove(base.c_str());
+    if (rc != 0) { std::remove(so.c_str()); return fail(AMH_ERR_INVALID, "the target source does not compile:\n" + logtxt); }
+    Target* t = new Target();
+    t->kind = AMH_TARGET_USER; t->dim = dim; t->ndata = ndata; t->user_so = so;
+    if (ndata > 0) t->blob.assign(data, data + ndata);
+    else t->blob.assign(1, 0.0);
+    t->user_lib = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!t->user_lib) { const std::string e = dlerror(); delete t; return fail(AMH_ERR_INVALID, "dlopen of the compiled target failed: " + e); }
+    t->user_lp = (Target::user_lp_fn)dlsym(t->user_lib, "amh_user_logdensity");
+    if (!t->user_lp) { delete t; return fail(AMH_ERR_INVALID, "the target source does not define amh_user_logdensity"); }
+    if (has_gradient) {
+        t->user_lpg = (Target::user_lpg_fn)dlsym(t->user_lib, "amh_user_logdensity_and_gradient");
+        if (!t->user_lpg) { delete t; return fail(AMH_ERR_INVALID, "the target source does not define amh_user_logdensity_and_gradient"); }
+    }
     *out = (amh_target*)t;
     return AMH_OK;
 }

@@ -51,15 +51,15 @@ def main():
     eng = amh.default_engine(0)
     seeds = lambda n, s: np.random.default_rng(s).integers(0, 2 ** 64, size=n, dtype=np.uint64)
     if "c2" in which:
-        for d in (32, 24, 16, 10, 2):
+        for d in [int(v) for v in os.environ.get("AMH_BENCH_DIMS", "32,24,16,10,2").split(",")]:
             n = 65536
             Sigma = spd(d, 32, 1.0, 100.0)
             t = amh.MvNormalTarget(None, Sigma)
             s = amh.RWMH(amh.MvNormal(np.zeros(d), (2.38 ** 2 / d) * Sigma))
             run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), n, seeds(n, 1))
-            ms = timed(run, 200, spl=100)
+            ms = timed(run, 500, spl=500) if os.environ.get("AMH_BENCH_LONG") else timed(run, 200, spl=100)
             st = run.state()
-            report(f"C2 RWMH MvNormal d={d} n={n}", n * 200, ms, 2 * (d + 1) * 8, f"accept={st['naccept'].sum() / (n * st['step']):.3f}")
+            report(f"C2 RWMH MvNormal d={d} n={n}", n * (500 if os.environ.get("AMH_BENCH_LONG") else 200), ms, 2 * (d + 1) * 8, f"accept={st['naccept'].sum() / (n * st['step']):.3f}")
             run.close()
     if "c3" in which:
         d, nw, ne = 10, 4096, 64
