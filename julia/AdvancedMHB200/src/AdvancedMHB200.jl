@@ -20,6 +20,7 @@ const libamh = get(ENV, "AMH_B200_LIB", "libamh_b200")
 # ---------------------------------------------------------------- ABI constants (include/amh.h)
 const AMH_OK = Int32(0)
 const TARGET_IID_NORMAL, TARGET_MVNORMAL, TARGET_ROSENBROCK, TARGET_LOGISTIC, TARGET_GAUSS_PREC = Int32.(1:5)
+const TARGET_USER = Int32(100)
 const SAMPLER_STATIC, SAMPLER_RW, SAMPLER_STRETCH, SAMPLER_MALA, SAMPLER_RAM, SAMPLER_MIXED = Int32.(1:6)
 const COV_SCALAR, COV_DIAG, COV_FULL, COV_COMPONENTS = Int32.(1:4)
 const FAM_NORMAL, FAM_INVGAMMA, FAM_GAMMA, FAM_UNIFORM, FAM_EXPONENTIAL, FAM_LOGNORMAL = Int32.(1:6)
@@ -98,6 +99,43 @@ LogDensityProblems.logdensity(t::RosenbrockTarget, x) =
     -sum(t.b * (x[i + 1] - x[i]^2)^2 + (t.a - x[i])^2 for i in 1:(t.dim - 1)) / t.s
 LogDensityProblems.dimension(t::RosenbrockTarget) = t.dim
 LogDensityProblems.capabilities(::Type{RosenbrockTarget}) = LogDensityProblems.LogDensityOrder{0}()
+
+"""
+    SourceTarget(dim, source; data = Float64[], gradient = false, logdensity = nothing)
+
+A log-density stated as C++ source text (include/amh_user_target.h), compiled for the device by NVRTC inside the
+library (`amh_target_create_source`): the route from the catalogue to `DensityModel(f)` for an arbitrary `f`
+(AdvancedMH.jl src/AdvancedMH.jl:52-54).  `logdensity` may carry the Julia closure the text restates, so that the same
+object also runs through stock `MCMCThreads()`.
+"""
+struct SourceTarget{F} <: DeviceTarget
+    dim::Int
+    source::String
+    data::Vector{Float64}
+    gradient::Bool
+    logdensity::F
+end
+SourceTarget(dim, source; data=Float64[], gradient=false, logdensity=nothing) =
+    SourceTarget(Int(dim), String(source), collect(Float64, data), gradient, logdensity)
+kind(::SourceTarget) = TARGET_USER
+blob(t::SourceTarget) = t.data
+LogDensityProblems.logdensity(t::SourceTarget, x) =
+    t.logdensity === nothing ? throw(ArgumentError("this SourceTarget carries no Julia closure")) : t.logdensity(x)
+LogDensityProblems.dimension(t::SourceTarget) = t.dim
+LogDensityProblems.capabilities(::Type{<:SourceTarget}) = LogDensityProblems.LogDensityOrder{0}()
+
+# handle creation: catalogue entry (kind, blob) or source text
+function create_target(ctx, target::DeviceTarget, d, tg)
+    b = blob(target)
+    GC.@preserve b check(ccall((:amh_target_create, libamh), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Int64, Ptr{Ptr{Cvoid}}),
+                               ctx, kind(target), d, b, length(b), tg))
+end
+function create_target(ctx, target::SourceTarget, d, tg)
+    b = target.data
+    GC.@preserve b check(ccall((:amh_target_create_source, libamh), Int32,
+                               (Ptr{Cvoid}, Int32, Cstring, Int32, Ptr{Float64}, Int64, Ptr{Ptr{Cvoid}}),
+                               ctx, d, target.source, target.gradient, isempty(b) ? C_NULL : pointer(b), length(b), tg))
+end
 
 # a DensityModel / LogDensityModel must wrap a catalogue target; anything else cannot run on the device
 unwrap(m::AdvancedMH.DensityModel) = unwrap(m.logdensity)
@@ -233,8 +271,7 @@ function AbstractMCMC.mcmcsample(rng::Random.AbstractRNG, model::AbstractMCMC.Ab
     GC.@preserve low b seeds init out acc begin
         check(ccall((:amh_ctx_create, libamh), Int32, (Int32, Ptr{Ptr{Cvoid}}), par.device, ctx))
         try
-            check(ccall((:amh_target_create, libamh), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Int64, Ptr{Ptr{Cvoid}}),
-                        ctx[], kind(target), d, b, length(b), tg))
+            create_target(ctx[], target, d, tg)
             check(ccall((:amh_sampler_create, libamh), Int32, (Ptr{Cvoid}, Ref{SamplerDesc}, Ptr{Ptr{Cvoid}}), ctx[], low.desc, sp))
             check(ccall((:amh_run_create, libamh), Int32,
                         (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{UInt64}, Ptr{Float64}, Int64, Ptr{Ptr{Cvoid}}),
