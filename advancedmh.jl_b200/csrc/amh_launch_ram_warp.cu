@@ -18,7 +18,9 @@
  * All arithmetic is the oracle's, operation for operation (row dot products accumulate over columns in ascending
  * order, which is exactly the order of the column sweep).
  */
+#include <cstdlib>
 #include "amh_params.cuh"
+#include "amh_fastmath.cuh"
 
 namespace amhh {
 using namespace amhd;
@@ -83,13 +85,164 @@ __host__ __device__ constexpr int ramw_doubles_per_warp(int d) {
     return ((d * (d + 1) / 2 + 1) & ~1) + 2 * 32 * RPL + 2;
 }
 
+/* out-of-line IEEE operators for the operands the branch-free sequences of amh_fastmath.cuh do not cover */
+__device__ __noinline__ double div_slow(double a, double b) { return a / b; }
+
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Rank-1 Cholesky up/down-date of the warp's tile (LinearAlgebra lowrankupdate / lowrankdowndate).
+ * Tile layout: column i holds rows i..d-1 contiguously; lanes = rows (row j = lane + 32 r), v[r] in registers.
+ *
+ * The sweep is ONE serial recurrence over the columns (g_i = v_i after i rotations), ~20 dependent fp64 operations
+ * per column, and only ~12 chains fit in an SM's shared memory: every instruction of the loop body is on the
+ * critical path of its warp.  The fast variants are therefore
+ *   - branch free: sqrt and the divisions are the correctly rounded straight-line sequences of amh_fastmath.cuh
+ *     (the two quotients of a rotation share one reciprocal, a downdate column shares 1/c); operands outside their
+ *     exponent range only clear the returned flag and the caller redoes the sweep with givens_sweep_slow;
+ *   - split by row block (the compile-time `rb` loop), so that v[] is never indexed dynamically (it stays in
+ *     registers) and rows above the diagonal block cost no predicate.
+ * Results are bit-identical to the operators (tools/ubench/fdiv_probe.cu; RAM parity tests). */
 template <int RPL>
+__device__ __forceinline__ bool givens_update_fast(double* __restrict__ Sb, int d, int lane, double (&v)[RPL], bool check,
+                                                   double lo, double hi, bool& out_of_bounds) {
+    bool ok = true;
+    double* col = Sb;                                   /* col[j] = S[j][i] */
+#pragma unroll
+    for (int rb = 0; rb < RPL; ++rb) {
+        const int iend = (32 * (rb + 1) < d) ? 32 * (rb + 1) : d;
+#pragma unroll 2
+        for (int i = 32 * rb; i < iend; ++i) {
+            const double f = col[i];
+            const double g = __shfl_sync(0xffffffffu, v[rb], i & 31);
+            const double t = fma(f, f, g * g);
+            ok = ok && (f > 1e-60) && (fabs(g) > 1e-100) && (t < 1e100);
+            const double rr = sqrt_fast(t);
+            double c, sn;
+            div2_same_den(f, g, rr, c, sn);
+            if (check && !(lo <= rr && rr <= hi)) out_of_bounds = true;
+            __syncwarp();
+            if (lane == (i & 31)) col[i] = rr;
+#pragma unroll
+            for (int r = rb; r < RPL; ++r) {
+                const int j = lane + 32 * r;
+                if ((r > rb || j > i) && j < d) {
+                    const double Aji = col[j];
+                    const double vj = v[r];
+                    col[j] = c * Aji + sn * vj;
+                    v[r] = c * vj - sn * Aji;
+                }
+            }
+            col += d - i - 1;
+        }
+    }
+    return ok;
+}
+
+template <int RPL>
+__device__ __forceinline__ bool givens_downdate_fast(double* __restrict__ Sb, int d, int lane, double (&v)[RPL], bool check,
+                                                     double lo, double hi, bool& posdef_fail, bool& out_of_bounds) {
+    bool ok = true;
+    double* col = Sb;
+    double Aii = col[0];
+    double ra = rcp_refined(Aii);                      /* 1/A_ii does not depend on the recurrence: one column ahead */
+#pragma unroll
+    for (int rb = 0; rb < RPL; ++rb) {
+        const int iend = (32 * (rb + 1) < d) ? 32 * (rb + 1) : d;
+#pragma unroll 2
+        for (int i = 32 * rb; i < iend; ++i) {
+            const double g = __shfl_sync(0xffffffffu, v[rb], i & 31);
+            double* coln = col + (d - i - 1);
+            const double Ann = (i + 1 < d) ? coln[i + 1] : 1.0;
+            const double sn = div_with_rcp(g, Aii, ra);
+            ok = ok && (Aii > 1e-100) && (Aii < 1e100) && (fabs(g) > 1e-100) && (fabs(g) < 1e100);
+            const double s2 = sn * sn;
+            if (s2 > 1.0) posdef_fail = true;          /* the reference throws here; the tile is rolled back */
+            const double om = 1.0 - s2;
+            ok = ok && (posdef_fail || om > 1e-100);
+            const double c = sqrt_fast(om);
+            const double rc = rcp_refined(c);
+            const double dg = c * Aii;
+            if (check && !posdef_fail && !(lo <= dg && dg <= hi)) out_of_bounds = true;
+            __syncwarp();
+            if (lane == (i & 31)) col[i] = dg;
+#pragma unroll
+            for (int r = rb; r < RPL; ++r) {
+                const int j = lane + 32 * r;
+                if ((r > rb || j > i) && j < d) {
+                    const double num = col[j] - sn * v[r];
+                    ok = ok && (posdef_fail || (fabs(num) > 1e-100 && fabs(num) < 1e100));
+                    const double Aji = div_with_rcp(num, c, rc);
+                    col[j] = Aji;
+                    v[r] = -sn * Aji + c * v[r];
+                }
+            }
+            Aii = Ann;
+            ra = rcp_refined(Ann);
+            col = coln;
+        }
+    }
+    return ok;
+}
+
+/* the same sweeps with the IEEE operators (any operands); out of line: it is the redo path */
+template <int RPL>
+__device__ __noinline__ void givens_sweep_slow(double* __restrict__ Sb, int d, int lane, double (&v)[RPL], bool update, bool check,
+                                               double lo, double hi, bool& posdef_fail, bool& out_of_bounds) {
+    for (int i = 0; i < d; ++i) {
+        double* col = Sb + colstart(i, d) - i;
+        const double f = col[i];
+        double g = 0.0;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r)
+            if ((i >> 5) == r) g = __shfl_sync(0xffffffffu, v[r], i & 31);
+        if (update) {
+            const double rr = sqrt(fma(f, f, g * g));
+            const double c = f / rr, sn = g / rr;
+            if (check && !(lo <= rr && rr <= hi)) out_of_bounds = true;
+            __syncwarp();
+            if (lane == (i & 31)) col[i] = rr;
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                const int j = lane + 32 * r;
+                if (j > i && j < d) {
+                    const double Aji = col[j];
+                    const double vj = v[r];
+                    col[j] = c * Aji + sn * vj;
+                    v[r] = c * vj - sn * Aji;
+                }
+            }
+        } else {
+            const double sn = g / f;
+            const double s2 = sn * sn;
+            if (s2 > 1.0) { posdef_fail = true; break; }
+            const double c = sqrt(1.0 - s2);
+            const double dg = c * f;
+            if (check && !(lo <= dg && dg <= hi)) out_of_bounds = true;
+            __syncwarp();
+            if (lane == (i & 31)) col[i] = dg;
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                const int j = lane + 32 * r;
+                if (j > i && j < d) {
+                    const double Aji = (col[j] - sn * v[r]) / c;
+                    col[j] = Aji;
+                    v[r] = -sn * Aji + c * v[r];
+                }
+            }
+        }
+    }
+}
+
+/* DF = the dimension as a compile-time constant (0: runtime).  With DF the column loops unroll completely: column
+ * offsets and row predicates of the two mat-vecs and the two sums become immediates. */
+template <int RPL, int DF>
 __global__ void __launch_bounds__(512)
 ram_warp_kernel(const __grid_constant__ RamWArgs a) {
+    constexpr int UNRC = DF ? DF : 4;          /* matvec / sum loops */
     extern __shared__ __align__(16) double smem_w[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int WARPS = blockDim.x >> 5;
-    const int d = a.d;
+    const int d = DF ? DF : a.d;
     const int nt = d * (d + 1) / 2;
     const int ntp = (nt + 1) & ~1;
     /* the target factor (column-packed) is shared by the CTA's warps */
@@ -147,7 +300,7 @@ ram_warp_kernel(const __grid_constant__ RamWArgs a) {
             double y[RPL], xn[RPL];
 #pragma unroll
             for (int r = 0; r < RPL; ++r) y[r] = 0.0;
-#pragma unroll 4
+#pragma unroll UNRC
             for (int i = 0; i < d; ++i) {
                 const double ui = Us[i];
                 const double* col = Sb + colstart(i, d) - i;
@@ -168,7 +321,7 @@ ram_warp_kernel(const __grid_constant__ RamWArgs a) {
             double w[RPL];
 #pragma unroll
             for (int r = 0; r < RPL; ++r) w[r] = 0.0;
-#pragma unroll 4
+#pragma unroll UNRC
             for (int i = 0; i < d; ++i) {
                 const double vi = Vs[i];
                 const double* col = Ut + colstart(i, d) - i;
@@ -186,7 +339,7 @@ ram_warp_kernel(const __grid_constant__ RamWArgs a) {
             }
             __syncwarp();
             double q = Vs[0] * Vs[0];
-#pragma unroll 8
+#pragma unroll UNRC
             for (int j = 1; j < d; ++j) q = fma(Vs[j], Vs[j], q);
             const double lp_new = fma(-0.5, q, a.c0);
             const double dl = lp_new - lp;
@@ -199,70 +352,43 @@ ram_warp_kernel(const __grid_constant__ RamWArgs a) {
                 if (dalpha == dalpha) {
                     const double cc = sqrt(eta * fabs(dalpha));
                     double nu = Us[0] * Us[0];
-#pragma unroll 8
+#pragma unroll UNRC
                     for (int i = 1; i < d; ++i) nu = fma(Us[i], Us[i], nu);
                     nu = sqrt(nu);
                     double v[RPL];
+                    const bool nfast = nu > 1e-100 && nu < 1e100;
+                    const double rnu = rcp_refined(nu);
 #pragma unroll
-                    for (int r = 0; r < RPL; ++r) v[r] = (cc * y[r]) / nu;
+                    for (int r = 0; r < RPL; ++r) {
+                        const double num = cc * y[r];
+                        v[r] = div_with_rcp(num, nu, rnu);
+                        if (!(nfast && fabs(num) > 1e-100 && fabs(num) < 1e100)) v[r] = div_slow(num, nu);
+                    }
                     if (lane == 0) bulk_wait_read();  /* the previous write-back has finished reading the tile */
                     __syncwarp();
                     bool posdef_fail = false, out_of_bounds = false;
-                    if (dalpha > 0.0) {
-                        /* lowrankupdate: Givens sweep over columns */
-#pragma unroll 2
-                        for (int i = 0; i < d; ++i) {
-                            double* col = Sb + colstart(i, d) - i;
-                            const double f = col[i];
-                            double g = 0.0;
-#pragma unroll
-                            for (int r = 0; r < RPL; ++r)
-                                if ((i >> 5) == r) g = __shfl_sync(0xffffffffu, v[r], i & 31);
-                            const double rr = sqrt(fma(f, f, g * g));
-                            const double c = f / rr, sn = g / rr;
-                            if (a.check && !(a.lo <= rr && rr <= a.hi)) out_of_bounds = true;
-                            __syncwarp();
-                            if (lane == (i & 31)) col[i] = rr;
-#pragma unroll
-                            for (int r = 0; r < RPL; ++r) {
-                                const int j = lane + 32 * r;
-                                if (j > i && j < d) {
-                                    const double Aji = col[j];
-                                    const double vj = v[r];
-                                    col[j] = c * Aji + sn * vj;
-                                    v[r] = c * vj - sn * Aji;
-                                }
-                            }
+                    /* speculative branch-free sweep; `ok` is false when some operand left the exponent range the
+                     * straight-line sqrt / division sequences cover (never, in practice) */
+                    bool ok = (dalpha > 0.0) ? givens_update_fast<RPL>(Sb, d, lane, v, a.check != 0, a.lo, a.hi, out_of_bounds)
+                                             : givens_downdate_fast<RPL>(Sb, d, lane, v, a.check != 0, a.lo, a.hi, posdef_fail, out_of_bounds);
+                    ok = __all_sync(0xffffffffu, ok);
+                    if (!ok) {
+                        /* redo with the IEEE operators from the last good factor (global memory holds it) */
+                        if (lane == 0) {
+                            fence_async_smem();
+                            bulk_wait_all();
+                            mbar_expect_tx(bar, sbytes);
+                            bulk_g2s(Sb, Sg, sbytes, bar);
                         }
-                    } else {
-                        /* lowrankdowndate; s^2 > 1 is the reference's PosDefException */
-                        for (int i = 0; i < d; ++i) {
-                            double* col = Sb + colstart(i, d) - i;
-                            const double Aii = col[i];
-                            double g = 0.0;
+                        mbar_wait(bar, phase);
+                        phase ^= 1u;
 #pragma unroll
-                            for (int r = 0; r < RPL; ++r)
-                                if ((i >> 5) == r) g = __shfl_sync(0xffffffffu, v[r], i & 31);
-                            const double sn = g / Aii;
-                            const double s2 = sn * sn;
-                            if (s2 > 1.0) { posdef_fail = true; break; }
-                            const double c = sqrt(1.0 - s2);
-                            const double dg = c * Aii;
-                            if (a.check && !(a.lo <= dg && dg <= a.hi)) out_of_bounds = true;
-                            __syncwarp();
-                            if (lane == (i & 31)) col[i] = dg;
-#pragma unroll
-                            for (int r = 0; r < RPL; ++r) {
-                                const int j = lane + 32 * r;
-                                if (j > i && j < d) {
-                                    const double Aji = (col[j] - sn * v[r]) / c;
-                                    col[j] = Aji;
-                                    v[r] = -sn * Aji + c * v[r];
-                                }
-                            }
-                        }
-                        if (posdef_fail) failed = 1;
+                        for (int r = 0; r < RPL; ++r) v[r] = div_slow(cc * y[r], nu);
+                        posdef_fail = false;
+                        out_of_bounds = false;
+                        givens_sweep_slow<RPL>(Sb, d, lane, v, dalpha > 0.0, a.check != 0, a.lo, a.hi, posdef_fail, out_of_bounds);
                     }
+                    if (posdef_fail) failed = 1;
                     __syncwarp();
                     if (posdef_fail || out_of_bounds) {
                         /* S is kept (:259-264): roll the tile back to the last good factor */
@@ -381,7 +507,7 @@ int ramw_import_S(amh_run& r, const double* src) {
     return AMH_OK;
 }
 
-template <int RPL>
+template <int RPL, int DF>
 static int launch_ram_warp_t(amh_run& r, int nsteps, bool warmup, const SaveArgs& sv) {
     const amh_sampler& s = *r.sampler;
     const amh_target& t = *r.target;
@@ -422,7 +548,7 @@ static int launch_ram_warp_t(amh_run& r, int nsteps, bool warmup, const SaveArgs
     if (warps > 16) warps = 16;
     if (warps < 1) return fail(AMH_ERR_UNSUPPORTED, "RAM warp kernel: factor does not fit in shared memory");
     const size_t smem = fixed + (size_t)warps * per_warp;
-    auto kern = ram_warp_kernel<RPL>;
+    auto kern = ram_warp_kernel<RPL, DF>;
     AMH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     AMH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * warps, smem));
@@ -438,12 +564,17 @@ static int launch_ram_warp_t(amh_run& r, int nsteps, bool warmup, const SaveArgs
 }
 
 int launch_ram_warp(amh_run& r, int nsteps, bool warmup, const SaveArgs& sv) {
+    static const bool generic_only = std::getenv("AMH_RAMW_GENERIC") != nullptr;     /* A/B switch, tests */
+    if (!generic_only) {
+        if (r.dim == 64) return launch_ram_warp_t<2, 64>(r, nsteps, warmup, sv);       /* BASELINE config 5 */
+        if (r.dim == 32) return launch_ram_warp_t<1, 32>(r, nsteps, warmup, sv);
+    }
     const int rpl = (r.dim + 31) / 32;
     switch (rpl) {
-    case 1: return launch_ram_warp_t<1>(r, nsteps, warmup, sv);
-    case 2: return launch_ram_warp_t<2>(r, nsteps, warmup, sv);
-    case 3: return launch_ram_warp_t<3>(r, nsteps, warmup, sv);
-    case 4: return launch_ram_warp_t<4>(r, nsteps, warmup, sv);
+    case 1: return launch_ram_warp_t<1, 0>(r, nsteps, warmup, sv);
+    case 2: return launch_ram_warp_t<2, 0>(r, nsteps, warmup, sv);
+    case 3: return launch_ram_warp_t<3, 0>(r, nsteps, warmup, sv);
+    case 4: return launch_ram_warp_t<4, 0>(r, nsteps, warmup, sv);
     }
     return fail(AMH_ERR_UNSUPPORTED, "RAM warp kernel supports dim <= 128");
 }
