@@ -102,10 +102,18 @@ __device__ __noinline__ double div_slow(double a, double b) { return a / b; }
  *   - split by row block (the compile-time `rb` loop), so that v[] is never indexed dynamically (it stays in
  *     registers) and rows above the diagonal block cost no predicate.
  * Results are bit-identical to the operators (tools/ubench/fdiv_probe.cu; RAM parity tests). */
-template <int RPL>
-__device__ __forceinline__ bool givens_update_fast(double* __restrict__ Sb, int d, int lane, double (&v)[RPL], bool check,
+/* range bookkeeping of the speculative sweeps: instead of testing every operand against the exponent range of the
+ * straight-line sequences, the loops keep a running minimum / maximum of the operands' HIGH WORDS (for doubles of one
+ * sign the integer order of the high words is the order of the values; a negative value gives a negative word, NaN and
+ * Inf large positive ones) -- two integer min/max per operand, off the fp64 pipe and off the critical path */
+constexpr int kHiLo = 0x2B800000;          /* high word of 2^-327 ~ 3.7e-99  */
+constexpr int kHiHi = 0x54B00000;          /* high word of 2^332  ~ 8.7e99   */
+__device__ __forceinline__ int hi_abs(double x) { return __double2hiint(x) & 0x7fffffff; }
+
+template <int RPL, bool CHECK>
+__device__ __forceinline__ bool givens_update_fast(double* __restrict__ Sb, int d, int lane, double (&v)[RPL],
                                                    double lo, double hi, bool& out_of_bounds) {
-    bool ok = true;
+    int hmin = 0x7fffffff, hmax = 0;
     double* col = Sb;                                   /* col[j] = S[j][i] */
 #pragma unroll
     for (int rb = 0; rb < RPL; ++rb) {
@@ -115,11 +123,12 @@ __device__ __forceinline__ bool givens_update_fast(double* __restrict__ Sb, int 
             const double f = col[i];
             const double g = __shfl_sync(0xffffffffu, v[rb], i & 31);
             const double t = fma(f, f, g * g);
-            ok = ok && (f > 1e-60) && (fabs(g) > 1e-100) && (t < 1e100);
+            hmin = min(hmin, min(__double2hiint(f), hi_abs(g)));     /* f > 0 and |g| not tiny: t >= f^2 is in range */
+            hmax = max(hmax, __double2hiint(t));
             const double rr = sqrt_fast(t);
             double c, sn;
             div2_same_den(f, g, rr, c, sn);
-            if (check && !(lo <= rr && rr <= hi)) out_of_bounds = true;
+            if (CHECK && !(lo <= rr && rr <= hi)) out_of_bounds = true;
             __syncwarp();
             if (lane == (i & 31)) col[i] = rr;
 #pragma unroll
@@ -135,13 +144,14 @@ __device__ __forceinline__ bool givens_update_fast(double* __restrict__ Sb, int 
             col += d - i - 1;
         }
     }
-    return ok;
+    /* f, |g| in [2^-163, ..): f^2 + g^2 >= 2^-326; t <= 2^332: rr, c, sn and every intermediate stay normal */
+    return hmin >= 0x35C00000 && hmax < kHiHi;
 }
 
-template <int RPL>
-__device__ __forceinline__ bool givens_downdate_fast(double* __restrict__ Sb, int d, int lane, double (&v)[RPL], bool check,
+template <int RPL, bool CHECK>
+__device__ __forceinline__ bool givens_downdate_fast(double* __restrict__ Sb, int d, int lane, double (&v)[RPL],
                                                      double lo, double hi, bool& posdef_fail, bool& out_of_bounds) {
-    bool ok = true;
+    int hmin = 0x7fffffff, hmax = 0;
     double* col = Sb;
     double Aii = col[0];
     double ra = rcp_refined(Aii);                      /* 1/A_ii does not depend on the recurrence: one column ahead */
@@ -154,15 +164,17 @@ __device__ __forceinline__ bool givens_downdate_fast(double* __restrict__ Sb, in
             double* coln = col + (d - i - 1);
             const double Ann = (i + 1 < d) ? coln[i + 1] : 1.0;
             const double sn = div_with_rcp(g, Aii, ra);
-            ok = ok && (Aii > 1e-100) && (Aii < 1e100) && (fabs(g) > 1e-100) && (fabs(g) < 1e100);
             const double s2 = sn * sn;
             if (s2 > 1.0) posdef_fail = true;          /* the reference throws here; the tile is rolled back */
             const double om = 1.0 - s2;
-            ok = ok && (posdef_fail || om > 1e-100);
+            if (!posdef_fail) {                        /* (after a failure nothing of the sweep is kept) */
+                hmin = min(hmin, min(min(__double2hiint(Aii), hi_abs(g)), __double2hiint(om)));
+                hmax = max(hmax, max(__double2hiint(Aii), hi_abs(g)));
+            }
             const double c = sqrt_fast(om);
             const double rc = rcp_refined(c);
             const double dg = c * Aii;
-            if (check && !posdef_fail && !(lo <= dg && dg <= hi)) out_of_bounds = true;
+            if (CHECK && !posdef_fail && !(lo <= dg && dg <= hi)) out_of_bounds = true;
             __syncwarp();
             if (lane == (i & 31)) col[i] = dg;
 #pragma unroll
@@ -170,7 +182,10 @@ __device__ __forceinline__ bool givens_downdate_fast(double* __restrict__ Sb, in
                 const int j = lane + 32 * r;
                 if ((r > rb || j > i) && j < d) {
                     const double num = col[j] - sn * v[r];
-                    ok = ok && (posdef_fail || (fabs(num) > 1e-100 && fabs(num) < 1e100));
+                    if (!posdef_fail) {
+                        hmin = min(hmin, hi_abs(num));
+                        hmax = max(hmax, hi_abs(num));
+                    }
                     const double Aji = div_with_rcp(num, c, rc);
                     col[j] = Aji;
                     v[r] = -sn * Aji + c * v[r];
@@ -181,7 +196,7 @@ __device__ __forceinline__ bool givens_downdate_fast(double* __restrict__ Sb, in
             col = coln;
         }
     }
-    return ok;
+    return hmin >= kHiLo && hmax < kHiHi;
 }
 
 /* the same sweeps with the IEEE operators (any operands); out of line: it is the redo path */
@@ -369,8 +384,13 @@ ram_warp_kernel(const __grid_constant__ RamWArgs a) {
                     bool posdef_fail = false, out_of_bounds = false;
                     /* speculative branch-free sweep; `ok` is false when some operand left the exponent range the
                      * straight-line sqrt / division sequences cover (never, in practice) */
-                    bool ok = (dalpha > 0.0) ? givens_update_fast<RPL>(Sb, d, lane, v, a.check != 0, a.lo, a.hi, out_of_bounds)
-                                             : givens_downdate_fast<RPL>(Sb, d, lane, v, a.check != 0, a.lo, a.hi, posdef_fail, out_of_bounds);
+                    bool ok;
+                    if (a.check)
+                        ok = (dalpha > 0.0) ? givens_update_fast<RPL, true>(Sb, d, lane, v, a.lo, a.hi, out_of_bounds)
+                                            : givens_downdate_fast<RPL, true>(Sb, d, lane, v, a.lo, a.hi, posdef_fail, out_of_bounds);
+                    else
+                        ok = (dalpha > 0.0) ? givens_update_fast<RPL, false>(Sb, d, lane, v, a.lo, a.hi, out_of_bounds)
+                                            : givens_downdate_fast<RPL, false>(Sb, d, lane, v, a.lo, a.hi, posdef_fail, out_of_bounds);
                     ok = __all_sync(0xffffffffu, ok);
                     if (!ok) {
                         /* redo with the IEEE operators from the last good factor (global memory holds it) */

@@ -93,12 +93,14 @@ def main():
         s = amh.RobustAdaptiveMetropolis()
         for n in (32768,):
             run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), n, seeds(n, 4), np.zeros((d, n)))
-            ms = timed(run, 20, warmup=True, spl=1)
-            report(f"C5 RAM warm-up d=64 n={n}", n * 20, ms, 2 * (d + 1) * 8 + d * (d + 1) * 8)
-            ms = timed(run, 20, warmup=False, spl=1)
-            st = run.state()
-            report(f"C5 RAM sampling d=64 n={n}", n * 20, ms, 2 * (d + 1) * 8 + d * (d + 1) // 2 * 8,
-                   f"accept={st['naccept'].sum() / (n * st['step']):.3f}")
+            for spl, tag in ((1, "1 step/launch"), (16, "16 steps/launch")):
+                ms = timed(run, 32, warmup=True, spl=spl)
+                report(f"C5 RAM warm-up d=64 n={n}", n * 32, ms, 2 * (d + 1) * 8 + d * (d + 1) * 8, tag)
+            for spl, tag in ((1, "1 step/launch"), (16, "16 steps/launch")):
+                ms = timed(run, 32, warmup=False, spl=spl)
+                st = run.state()
+                report(f"C5 RAM sampling d=64 n={n}", n * 32, ms, 2 * (d + 1) * 8 + d * (d + 1) // 2 * 8,
+                       f"{tag} accept={st['naccept'].sum() / (n * st['step']):.3f}")
             run.close()
 
 
