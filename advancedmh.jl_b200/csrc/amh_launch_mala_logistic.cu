@@ -19,6 +19,7 @@
  * 4 KB of per-chain state traffic is noise.
  */
 #include "amh_params.cuh"
+#include "amh_fastmath.cuh"
 
 namespace amhh {
 using namespace amhd;
@@ -83,11 +84,15 @@ __host__ __device__ constexpr size_t l_smem_bytes(int warps, int nst) {
 
 /* t = y eta - log1pexp(eta) and r = y - sigmoid(eta), sharing exp(-|eta|); same operations as the contract header */
 __device__ __forceinline__ void logistic_terms(double eta, double y, double& t, double& r) {
-    const double ex = amh::exp_(-fabs(eta));             /* in (0,1] */
+    const double ex = amh::exp_(-fabs(eta));             /* in [0,1] */
     const double w = 1.0 + ex;
-    const double l = (-amh::neglog_normal(w)) + (ex - (w - 1.0)) / w;       /* log_(w) for a normal w in (1,2] */
+    /* both quotients have the denominator w in [1,2]: one shared reciprocal refinement + Markstein corrections
+     * (amh_fastmath.cuh) = the correctly rounded IEEE quotients, without a slow-path branch.  The first numerator is
+     * the rounding error of w: +0 or at least 2^-105 in magnitude (exact when w == 1), so nothing is subnormal. */
+    double qc, sg0;
+    div2_same_den(ex - (w - 1.0), 1.0, w, qc, sg0);
+    const double l = (-amh::neglog_normal(w)) + qc;                          /* log_(w) for a normal w in [1,2] */
     const double l1p = (eta > 0.0 ? eta : 0.0) + l;
-    const double sg0 = 1.0 / (1.0 + ex);
     const double sg = eta >= 0.0 ? sg0 : ex * sg0;
     t = y * eta - l1p;
     r = y - sg;
