@@ -141,6 +141,14 @@ static void free_run(amh_run* r) {
     if (!r) return;
     cudaSetDevice(r->ctx->device);
     cudaStreamSynchronize(r->ctx->stream);
+    if (r->aux_stream) {
+        cudaStreamSynchronize(r->aux_stream);
+        cudaStreamDestroy(r->aux_stream);
+        for (int b = 0; b < 2; ++b) {
+            if (r->ev_plan[b]) cudaEventDestroy(r->ev_plan[b]);
+            if (r->ev_sweep[b]) cudaEventDestroy(r->ev_sweep[b]);
+        }
+    }
     void* ptrs[] = {r->X, r->X2, r->lp, r->lp2, r->lq, r->G, r->S, r->S2, r->logalpha, r->eta, r->acc, r->failed,
                     r->sflag, r->nacc, r->seeds, r->sum, r->sumsq, r->scratch};
     for (void* p : ptrs) dfree(r->ctx, p);

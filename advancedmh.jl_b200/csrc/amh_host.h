@@ -80,6 +80,14 @@ struct amh_run {
     long long step = 0;
     long long nsaved = 0;
     long long launches = 0;
+    /* stretch move (K2F): the sweep plans are state independent, so the plan of the NEXT launch is computed on a second
+     * stream while the current sweeps run (the sweep kernel occupies one SM per ensemble, the rest of the GPU is idle) */
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_plan[2] = {nullptr, nullptr};     /* plan in buffer b complete (recorded on the stream that made it) */
+    cudaEvent_t ev_sweep[2] = {nullptr, nullptr};    /* last sweep kernel that read buffer b complete                   */
+    long long plan_step0[2] = {-1, -1};              /* what buffer b holds: first step and number of sweeps            */
+    int plan_nsteps[2] = {0, 0};
+    int plan_layout_nsteps = -1;                     /* launch length the two plan buffers are laid out for            */
     bool ram_warp = false;         /* RAM: S stored [chain][column-packed] and stepped by K4W */
     int mh_path = 0;               /* 0 = choose (tensor-core K1T when eligible), 1 = force the per-thread DFMA kernel K1 */
     /* kernel timing */

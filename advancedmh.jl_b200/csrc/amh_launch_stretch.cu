@@ -535,9 +535,26 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
         plan.nwp = ((a.n_walkers + 31) & ~31ll) + 32 * kStretchLevels;
         const size_t slots = (size_t)nsteps * nens * plan.nwp;
         const size_t recs = (size_t)r.n * (size_t)Rec<DMAX>::size(r.dim);          /* doubles per record buffer */
-        const size_t need = slots * (3 * sizeof(double) + 2 * sizeof(unsigned)) + (size_t)nsteps * nens * 4 * sizeof(int) +
-                            2 * recs * sizeof(double) + 64;
+        /* one plan buffer: zf, am, ex (doubles), pair, fwd (unsigned), meta (4 ints per sweep and ensemble), 256-byte aligned */
+        const size_t pbytes = (slots * (3 * sizeof(double) + 2 * sizeof(unsigned)) + (size_t)nsteps * nens * 4 * sizeof(int) + 255) & ~(size_t)255;
+        const size_t need = 2 * recs * sizeof(double) + 256 + 2 * pbytes;
+        if (!r.aux_stream) {
+            AMH_CUDA_TRY(cudaStreamCreateWithFlags(&r.aux_stream, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; ++b) {
+                AMH_CUDA_TRY(cudaEventCreateWithFlags(&r.ev_plan[b], cudaEventDisableTiming));
+                AMH_CUDA_TRY(cudaEventCreateWithFlags(&r.ev_sweep[b], cudaEventDisableTiming));
+            }
+        }
+        if (r.plan_layout_nsteps != nsteps) {
+            /* the two plan buffers are laid out for one launch length: on a change nothing in flight may touch them */
+            AMH_CUDA_TRY(cudaStreamSynchronize(r.ctx->stream));
+            AMH_CUDA_TRY(cudaStreamSynchronize(r.aux_stream));
+            r.plan_step0[0] = r.plan_step0[1] = -1;
+            r.plan_layout_nsteps = nsteps;
+        }
         if (need > r.scratch_bytes) {
+            AMH_CUDA_TRY(cudaStreamSynchronize(r.aux_stream));      /* a plan made ahead may still be running */
+            r.plan_step0[0] = r.plan_step0[1] = -1;
             dfree(r.ctx, r.scratch);
             r.scratch = nullptr; r.scratch_bytes = 0;
             const int rca = dmalloc(r.ctx, &r.scratch, need);
@@ -546,12 +563,18 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
         }
         double* RA = (double*)r.scratch;                 /* record buffers first: 256-byte aligned pool memory */
         double* RB = RA + recs;
-        plan.zf = RB + recs;
-        plan.am = plan.zf + slots;
-        plan.ex = plan.am + slots;
-        plan.pair = (unsigned*)(plan.ex + slots);
-        plan.fwd = plan.pair + slots;
-        plan.meta = (int*)(plan.fwd + slots);
+        char* pbase = (char*)(((uintptr_t)(RB + recs) + 255) & ~(uintptr_t)255);
+        auto plan_at = [&](int b) {
+            StretchPlan q = plan;
+            char* p0 = pbase + (size_t)b * pbytes;
+            q.zf = (double*)p0;
+            q.am = q.zf + slots;
+            q.ex = q.am + slots;
+            q.pair = (unsigned*)(q.ex + slots);
+            q.fwd = q.pair + slots;
+            q.meta = (int*)(q.fwd + slots);
+            return q;
+        };
         int lcap = kStretchLevels;
         if (const char* ev = std::getenv("AMH_STRETCH_LEVELS")) {      /* test switch: forces the overflow bucket */
             const int v = std::atoi(ev);
@@ -567,14 +590,37 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
         long long fcap = ((long long)(200 * 1024) - (long long)fixed_sm) / (long long)(sizeof(double) * r.dim);
         fcap = std::max<long long>(0, std::min<long long>(fcap, 65534));
         if (const char* ev = std::getenv("AMH_STRETCH_FWD")) fcap = std::min<long long>(fcap, std::atoll(ev));   /* test switch */
-        if (nsteps > 0) {
-            constexpr int PB = 1024;
-            const size_t smemp = (size_t)a.n_walkers * 3 * sizeof(int);
-            auto kp = stretch_plan_kernel<PB>;
-            if (smemp > 40 * 1024) AMH_CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp));
-            kp<<<(unsigned)(nsteps * nens), PB, smemp, r.ctx->stream>>>(plan, r.seeds, r.n, (int)a.n_walkers, r.dim, a.step0, a.a, lcap, (int)fcap);
+        static const bool no_ahead = std::getenv("AMH_STRETCH_NO_AHEAD") != nullptr;                              /* A/B switch */
+        constexpr int PB = 1024;
+        const size_t smemp = (size_t)a.n_walkers * 3 * sizeof(int);
+        auto kp = stretch_plan_kernel<PB>;
+        if (smemp > 40 * 1024) AMH_CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp));
+        auto enqueue_plan = [&](cudaStream_t st, int b, unsigned long long step0) -> int {
+            kp<<<(unsigned)(nsteps * nens), PB, smemp, st>>>(plan_at(b), r.seeds, r.n, (int)a.n_walkers, r.dim, step0, a.a, lcap, (int)fcap);
             AMH_CUDA_TRY(cudaGetLastError());
+            AMH_CUDA_TRY(cudaEventRecord(r.ev_plan[b], st));
+            r.plan_step0[b] = (long long)step0;
+            r.plan_nsteps[b] = nsteps;
             r.launches += 1;
+            return AMH_OK;
+        };
+        int cur = -1;
+        if (nsteps > 0) {
+            for (int b = 0; b < 2; ++b)
+                if (r.plan_step0[b] == (long long)a.step0 && r.plan_nsteps[b] == nsteps) cur = b;
+            if (cur >= 0) {
+                AMH_CUDA_TRY(cudaStreamWaitEvent(r.ctx->stream, r.ev_plan[cur], 0));      /* made ahead on the aux stream */
+            } else {
+                /* nothing usable was made ahead (first launch, different length, state was reset): plan now.  Buffer 0
+                 * may hold a stale plan still being written by the aux stream: order behind it. */
+                cur = 0;
+                if (r.plan_step0[0] >= 0) AMH_CUDA_TRY(cudaStreamWaitEvent(r.ctx->stream, r.ev_plan[0], 0));
+                const int rcp = enqueue_plan(r.ctx->stream, 0, a.step0);
+                if (rcp) return rcp;
+            }
+            plan = plan_at(cur);
+        } else {
+            plan = plan_at(0);
         }
         const size_t smemv = (size_t)fcap * r.dim * sizeof(double) + fixed_sm;
         if constexpr (T::kind == AMH_TARGET_USER) {
@@ -600,6 +646,17 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
         }
         r.launches += 1;
         r.pending_launches += 1;
+        if (cur >= 0) {
+            AMH_CUDA_TRY(cudaEventRecord(r.ev_sweep[cur], r.ctx->stream));
+            if (!no_ahead) {
+                /* the next launch will most likely continue with the same number of sweeps: make its plan now, on the
+                 * aux stream, behind the last sweep that read the other buffer */
+                const int o = cur ^ 1;
+                AMH_CUDA_TRY(cudaStreamWaitEvent(r.aux_stream, r.ev_sweep[o], 0));
+                const int rcp = enqueue_plan(r.aux_stream, o, a.step0 + (unsigned long long)nsteps);
+                if (rcp) return rcp;
+            }
+        }
         return AMH_OK;
     }
     const size_t smem = (size_t)a.n_walkers * (sizeof(int) + 1) + 16;
