@@ -297,12 +297,40 @@ struct StretchSmem {
     unsigned* naccs;                      /* [nw] accepted moves of this launch */
     volatile unsigned short* ver;         /* [nw] last sweep (1-based, this launch) the walker finished */
     unsigned char* accs;                  /* [nw] last accept flag */
+    /* 2-CTA cluster variant (one ensemble on two SMs): every CTA keeps its own copy of `fwd` and `ver`, the mover of a
+     * walker writes both (the peer's through distributed shared memory); naccs / accs live in rank 0 only */
+    double* fwd_peer;
+    volatile unsigned short* ver_peer;
 };
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+/* acquire side of a flag that a thread of the peer CTA raised after a cluster-scope release fence: unlike a fence it
+ * does not wait for this thread's own outstanding stores */
+__device__ __forceinline__ unsigned short ld_acquire_cluster_u16(const volatile unsigned short* p) {
+    unsigned short v;
+    asm volatile("ld.acquire.cluster.shared::cta.u16 %0, [%1];" : "=h"(v) : "r"((unsigned)__cvta_generic_to_shared((const void*)p)) : "memory");
+    return v;
+}
+/* generic address of the same shared-memory location in CTA `rank` of the cluster */
+template <class P>
+__device__ __forceinline__ P* map_cta(P* p, unsigned rank) {
+    unsigned long long in = (unsigned long long)p, out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"(in), "r"(rank));
+    return (P*)out;
+}
 
 /* one stretch move (emcee.jl:70-102) of walker `i` with partner `idx`.  `w` = the walker's own record (already loaded);
  * the partner comes from the forwarding slot `pslot` (shared memory) if it has one, else from its record in L2;
  * the result goes to the walker's new record and, if somebody reads it later in this sweep, to slot `sslot`. */
-template <int DMAX, class T>
+template <int DMAX, class T, int CL = 1>
 __device__ __forceinline__ void stretch_move(const typename T::template Params<DMAX>& tp, int d, long long base, int i,
                                              int idx, unsigned sslot, unsigned pslot, double z, double am, double ex,
                                              double (&w)[Rec<DMAX>::cap], const double* __restrict__ Rold,
@@ -358,8 +386,21 @@ __device__ __forceinline__ void stretch_move(const typename T::template Params<D
         } else {
             for (int j = 0; j < d; ++j) ps[j] = w[j];
         }
-        __threadfence_block();
-        sm.ver[i] = want;
+        if constexpr (CL == 2) {
+            double* pp = sm.fwd_peer + (size_t)sslot * d;
+            if constexpr (D::fixed) {
+#pragma unroll
+                for (int j = 0; j < DMAX; ++j) pp[j] = w[j];
+            } else {
+                for (int j = 0; j < d; ++j) pp[j] = w[j];
+            }
+            fence_cluster();
+            sm.ver[i] = want;
+            sm.ver_peer[i] = want;
+        } else {
+            __threadfence_block();
+            sm.ver[i] = want;
+        }
     }
     if constexpr (D::fixed) {
 #pragma unroll
@@ -368,11 +409,21 @@ __device__ __forceinline__ void stretch_move(const typename T::template Params<D
         for (int j = 0; j < rs; j += 4) st256(pn + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
     }
     if (sslot == 0xfffeu) {                                  /* read through L2 later in this sweep */
-        __threadfence_block();
-        sm.ver[i] = want;
+        if constexpr (CL == 2) {
+            fence_cluster();
+            sm.ver[i] = want;
+            sm.ver_peer[i] = want;
+        } else {
+            __threadfence_block();
+            sm.ver[i] = want;
+        }
     }
     sm.accs[i] = acc ? 1 : 0;
-    if (acc) sm.naccs[i] += 1u;                              /* only ever touched by the thread that moves walker i */
+    if constexpr (CL == 2) {
+        if (acc) atomicAdd(sm.naccs + i, 1u);                /* rank 0's counter, possibly remote: fire and forget */
+    } else {
+        if (acc) sm.naccs[i] += 1u;                          /* only ever touched by the thread that moves walker i */
+    }
 }
 
 template <int DMAX>
@@ -390,10 +441,9 @@ __device__ __forceinline__ void stretch_load_own(double (&w)[Rec<DMAX>::cap], co
     }
 }
 
-template <int DMAX, class T, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 1)
-stretch_sweep_flow_kernel(const __grid_constant__ StretchArgs a, const __grid_constant__ StretchPlan plan,
-                          const __grid_constant__ typename T::template Params<DMAX> tp, double* RA, double* RB, int fcap) {
+template <int DMAX, class T, int BLOCK, int CL>
+__device__ __forceinline__ void stretch_flow_body(const StretchArgs& a, const StretchPlan& plan,
+                                                  const typename T::template Params<DMAX>& tp, double* RA, double* RB, int fcap) {
     using D = Dim<DMAX>;
     extern __shared__ __align__(16) double smem_fl[];
     const int nw = (int)a.n_walkers;
@@ -404,16 +454,29 @@ stretch_sweep_flow_kernel(const __grid_constant__ StretchArgs a, const __grid_co
     unsigned short* ver_nv = reinterpret_cast<unsigned short*>(sm.naccs + nw);
     sm.ver = ver_nv;
     sm.accs = reinterpret_cast<unsigned char*>(ver_nv + nw);
+    sm.fwd_peer = nullptr;
+    sm.ver_peer = nullptr;
+    const unsigned rank = (CL == 2) ? cluster_ctarank() : 0u;
+    if constexpr (CL == 2) {
+        sm.fwd_peer = map_cta(sm.fwd, rank ^ 1u);
+        sm.ver_peer = map_cta(ver_nv, rank ^ 1u);
+        if (rank != 0u) {
+            sm.naccs = map_cta(sm.naccs, 0u);
+            sm.accs = map_cta(sm.accs, 0u);
+        }
+    }
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int NWARP = BLOCK / 32;
-    const long long en = blockIdx.x;
+    const long long en = blockIdx.x / CL;
     const long long nens = a.st.n / nw;
     const long long base = en * nw;
     const int rs = D::fixed ? Rec<DMAX>::cap : Rec<DMAX>::size(d);
     double* Rold = RA;  double* Rnew = RB;
     /* prologue: [dim][chain] state -> records */
-    for (int i = tid; i < nw; i += BLOCK) {
+    if constexpr (CL == 2)
+        for (int i = tid; i < nw; i += BLOCK) ver_nv[i] = 0;              /* every CTA clears its own copy */
+    for (int i = tid + (int)rank * BLOCK; i < nw; i += CL * BLOCK) {
         ver_nv[i] = 0;
         sm.naccs[i] = 0u;
         sm.accs[i] = a.st.acc[base + i];
@@ -424,7 +487,7 @@ stretch_sweep_flow_kernel(const __grid_constant__ StretchArgs a, const __grid_co
     }
     const int* __restrict__ meta0 = plan.meta + (size_t)en * 4;
     int npar = a.nsteps > 0 ? meta0[0] : 0, olo = a.nsteps > 0 ? meta0[1] : 0, ohi = a.nsteps > 0 ? meta0[2] : 0;
-    __syncthreads();
+    if constexpr (CL == 2) { __threadfence(); cluster_sync_all(); } else __syncthreads();
 
     for (int s = 0; s < a.nsteps; ++s) {
         const size_t off = ((size_t)s * nens + en) * (size_t)plan.nwp;
@@ -436,7 +499,7 @@ stretch_sweep_flow_kernel(const __grid_constant__ StretchArgs a, const __grid_co
             npar_n = mn[0]; olo_n = mn[1]; ohi_n = mn[2];
         }
         /* plan entries one chunk ahead: they do not depend on the walkers */
-        int q = warp * 32 + lane;
+        int q = ((int)rank * NWARP + warp) * 32 + lane;
         unsigned pr = kStretchSentinel, fw = 0xffffffffu;
         double z = 0.0, am = 0.0, ex = 0.0;
         if (q < npar) {
@@ -444,10 +507,10 @@ stretch_sweep_flow_kernel(const __grid_constant__ StretchArgs a, const __grid_co
             am = __ldg(plan.am + off + q);   ex = __ldg(plan.ex + off + q);
         }
 #pragma unroll 1
-        for (; q - lane < npar; q += NWARP * 32) {
+        for (; q - lane < npar; q += CL * NWARP * 32) {
             const unsigned pr_c = pr, fw_c = fw;
             const double z_c = z, am_c = am, ex_c = ex;
-            const int qn = q + NWARP * 32;
+            const int qn = q + CL * NWARP * 32;
             if (qn < npar) {
                 pr = __ldg(plan.pair + off + qn); fw = __ldg(plan.fwd + off + qn); z = __ldg(plan.zf + off + qn);
                 am = __ldg(plan.am + off + qn);   ex = __ldg(plan.ex + off + qn);
@@ -460,15 +523,15 @@ stretch_sweep_flow_kernel(const __grid_constant__ StretchArgs a, const __grid_co
                 stretch_load_own<DMAX>(w, Rold, base, i, d);             /* in flight while the lane waits */
                 if (idx < i) {
                     while (sm.ver[idx] != want) { }                      /* the partner's new value (emcee.jl:53) */
-                    __threadfence_block();
+                    if constexpr (CL == 2) (void)ld_acquire_cluster_u16(sm.ver + idx); else __threadfence_block();
                 }
-                stretch_move<DMAX, T>(tp, d, base, i, idx, fw_c & 0xffffu, fw_c >> 16, z_c, am_c, ex_c, w, Rold, Rnew, sm, want);
+                stretch_move<DMAX, T, CL>(tp, d, base, i, idx, fw_c & 0xffffu, fw_c >> 16, z_c, am_c, ex_c, w, Rold, Rnew, sm, want);
             }
         }
-        __syncthreads();
+        if constexpr (CL == 2) { __threadfence(); cluster_sync_all(); } else __syncthreads();
         /* overflow bucket: in increasing walker order by one thread = the reference's own loop */
         if (ohi > olo) {
-            if (tid == 0) {
+            if (tid == 0 && rank == 0u) {
                 int last = -1;
                 for (int c = olo; c < ohi; ++c) {
                     int best = 0x7fffffff, bq = olo;
@@ -479,19 +542,19 @@ stretch_sweep_flow_kernel(const __grid_constant__ StretchArgs a, const __grid_co
                     const unsigned po = plan.pair[off + bq], fo = plan.fwd[off + bq];
                     double w[Rec<DMAX>::cap];
                     stretch_load_own<DMAX>(w, Rold, base, (int)(po & 0xffffu), d);
-                    stretch_move<DMAX, T>(tp, d, base, (int)(po & 0xffffu), (int)(po >> 16), fo & 0xffffu, fo >> 16,
-                                          plan.zf[off + bq], plan.am[off + bq], plan.ex[off + bq], w, Rold, Rnew, sm, want);
+                    stretch_move<DMAX, T, CL>(tp, d, base, (int)(po & 0xffffu), (int)(po >> 16), fo & 0xffffu, fo >> 16,
+                                              plan.zf[off + bq], plan.am[off + bq], plan.ex[off + bq], w, Rold, Rnew, sm, want);
                     __threadfence_block();
                     last = best;
                 }
             }
-            __syncthreads();
+            if constexpr (CL == 2) { __threadfence(); cluster_sync_all(); } else __syncthreads();
         }
         double* tR = Rold; Rold = Rnew; Rnew = tR;
         npar = npar_n; olo = olo_n; ohi = ohi_n;
     }
     /* epilogue: records -> [dim][chain] state (always the run's primary buffers), counters, save point outputs */
-    for (int i = tid; i < nw; i += BLOCK) {
+    for (int i = tid + (int)rank * BLOCK; i < nw; i += CL * BLOCK) {
         const long long ch = base + i;
         const double* rec = Rold + (size_t)ch * rs;
         for (int j = 0; j < d; ++j) {
@@ -511,6 +574,25 @@ stretch_sweep_flow_kernel(const __grid_constant__ StretchArgs a, const __grid_co
         if (a.sv.out) a.sv.out[(long long)d * a.sv.out_pitch + ch] = lpv;
         if (a.sv.acc_out) a.sv.acc_out[ch] = sm.accs[i];
     }
+    if constexpr (CL == 2) cluster_sync_all();             /* rank 0's shared memory must outlive the peer's reads */
+}
+
+template <int DMAX, class T, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1)
+stretch_sweep_flow_kernel(const __grid_constant__ StretchArgs a, const __grid_constant__ StretchPlan plan,
+                          const __grid_constant__ typename T::template Params<DMAX> tp, double* RA, double* RB, int fcap) {
+    stretch_flow_body<DMAX, T, BLOCK, 1>(a, plan, tp, RA, RB, fcap);
+}
+
+/* the same sweep with one ensemble on a CLUSTER OF TWO CTAs (two SMs, two L1s): chunks alternate between the 2 x NWARP
+ * warps of the cluster in slot order, so every dependency still points to a chunk that a resident warp owns; flags and
+ * forwarded values are mirrored into the peer's shared memory (DSMEM), sweeps end in a cluster barrier.  Used when two
+ * CTAs per ensemble still fit the GPU in one wave (BASELINE config 3: 64 ensembles -> 128 of 148 SMs). */
+template <int DMAX, class T, int BLOCK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BLOCK, 1)
+stretch_sweep_flow2_kernel(const __grid_constant__ StretchArgs a, const __grid_constant__ StretchPlan plan,
+                           const __grid_constant__ typename T::template Params<DMAX> tp, double* RA, double* RB, int fcap) {
+    stretch_flow_body<DMAX, T, BLOCK, 2>(a, plan, tp, RA, RB, fcap);
 }
 
 /* @rtc-end */
@@ -631,6 +713,14 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
                                       (unsigned)blk, smemv, params);
             if (rc) return rc;
         } else {
+            static const char* cl_env = std::getenv("AMH_STRETCH_CLUSTER");                                 /* A/B switch: 0 / 1 */
+            const bool use_cluster = cl_env ? std::atoi(cl_env) != 0 : (2 * nens <= r.ctx->sm_count && a.n_walkers >= 1024);
+            if (use_cluster && blk == 512) {
+                auto kf2 = stretch_sweep_flow2_kernel<DMAX, T, 512>;
+                if (smemv > 48 * 1024)
+                    AMH_CUDA_TRY(cudaFuncSetAttribute(kf2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv));
+                kf2<<<(unsigned)(2 * nens), 512, smemv, r.ctx->stream>>>(a, plan, tp, RA, RB, (int)fcap);
+            } else
 #define AMH_STRETCH_LAUNCH(BL)                                                                                             \
         do {                                                                                                               \
             auto kf = stretch_sweep_flow_kernel<DMAX, T, BL>;                                                              \
