@@ -77,7 +77,7 @@ class AMHStateError(AMHError):
 ABI_SYMBOLS = [
     "version", "last_error", "contract_version", "ctx_create", "ctx_destroy", "ctx_sync",
     "target_create", "target_create_source", "target_destroy", "sampler_create", "sampler_destroy",
-    "run_create", "run_destroy", "run_steps", "run_sync", "run_sample",
+    "run_create", "run_destroy", "run_steps", "run_sync", "run_sample", "run_sample_ld",
     "run_get_state", "run_set_params", "run_set_state", "run_get_ram_adapt", "run_dim", "run_nchains", "run_launch_count",
     "run_kernel_time_ms", "host_alloc", "host_free",
 ]
@@ -127,6 +127,8 @@ class Engine:
         f("run_steps").argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32]
         f("run_sample").argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _dp, _u8p,
                                     C.POINTER(Summary)]
+        f("run_sample_ld").argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _dp, C.c_int64, _u8p, C.c_int64,
+                                       C.POINTER(Summary)]
         f("run_get_state").argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _u8p, _i64p, _i64p]
         f("run_set_params").argtypes = [C.c_void_p, _dp]
         f("run_set_state").argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _u8p, _i64p, C.c_int64]
@@ -288,14 +290,21 @@ class Run:
         """`out` / `acc`: optional caller buffers ((N, d+1, n) float64 / (N, n) uint8, C-contiguous), e.g. pinned
         ones from Engine.pinned_empty; otherwise pageable numpy arrays are allocated."""
         d, n = self.dim, self.n
+        out_ld = acc_ld = n
         if out is not None:
-            if out.shape != (N, d + 1, n) or out.dtype != np.float64 or not out.flags.c_contiguous:
-                raise AMHArgumentError(AMH_ERR_INVALID, f"out must be a C-contiguous float64 array of shape {(N, d + 1, n)}")
+            # C-contiguous, or a block of chains out[:, :, a:b] of a C-contiguous (N, d+1, n_total) array
+            ok = (out.shape == (N, d + 1, n) and out.dtype == np.float64 and out.strides[2] == 8 and
+                  out.strides[1] % 8 == 0 and out.strides[1] >= 8 * n and out.strides[0] == (d + 1) * out.strides[1])
+            if not ok:
+                raise AMHArgumentError(AMH_ERR_INVALID, f"out must be a float64 array of shape {(N, d + 1, n)}, C-contiguous or a block of chains of one")
+            out_ld = out.strides[1] // 8
         elif store:
             out = np.empty((N, d + 1, n), dtype=np.float64)
         if acc is not None:
-            if acc.shape != (N, n) or acc.dtype != np.uint8 or not acc.flags.c_contiguous:
-                raise AMHArgumentError(AMH_ERR_INVALID, f"acc must be a C-contiguous uint8 array of shape {(N, n)}")
+            ok = acc.shape == (N, n) and acc.dtype == np.uint8 and acc.strides[1] == 1 and acc.strides[0] >= n
+            if not ok:
+                raise AMHArgumentError(AMH_ERR_INVALID, f"acc must be a uint8 array of shape {(N, n)}, C-contiguous or a block of chains of one")
+            acc_ld = acc.strides[0]
         elif store_accepted:
             acc = np.empty((N, n), dtype=np.uint8)
         summ = None
@@ -305,10 +314,10 @@ class Run:
             cm = np.zeros((d, n)) if chain_means else None
             s = Summary(0, 0, 0.0, mean.ctypes.data_as(_dp), var.ctypes.data_as(_dp),
                         cm.ctypes.data_as(_dp) if cm is not None else None)
-        self.eng._check(self.eng._f("run_sample")(
+        self.eng._check(self.eng._f("run_sample_ld")(
             self.h, N, discard_initial, thinning, num_warmup,
-            out.ctypes.data_as(_dp) if out is not None else None,
-            acc.ctypes.data_as(_u8p) if acc is not None else None,
+            C.cast(out.ctypes.data, _dp) if out is not None else None, out_ld,
+            C.cast(acc.ctypes.data, _u8p) if acc is not None else None, acc_ld,
             C.byref(s) if s is not None else None))
         if s is not None:
             summ = dict(n_saved=s.n_saved, n_steps=s.n_steps, accept_rate=s.accept_rate, mean=mean, var=var,

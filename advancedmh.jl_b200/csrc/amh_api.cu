@@ -43,7 +43,8 @@ int default_steps_per_launch(const amh_run& r) {
 int dmalloc(amh_ctx* ctx, void** p, size_t bytes) {
     *p = nullptr;
     if (bytes == 0) return AMH_OK;
-    AMH_CUDA_TRY(cudaMallocAsync(p, bytes, ctx->stream));
+    if (ctx->pool) AMH_CUDA_TRY(cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream));
+    else AMH_CUDA_TRY(cudaMallocAsync(p, bytes, ctx->stream));
     return AMH_OK;
 }
 void dfree(amh_ctx* ctx, void* p) {
@@ -185,11 +186,19 @@ int32_t amh_ctx_create(int32_t device, amh_ctx** out) {
     AMH_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     AMH_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     AMH_CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
-    {   /* keep freed blocks cached in the stream-ordered pool instead of returning them to the driver */
-        cudaMemPool_t pool;
-        AMH_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    {   /* a stream-ordered pool PER CONTEXT: freed blocks stay cached (run handles are created and destroyed per
+         * `sample` call), and a block is only ever reused on the stream that freed it -- with the device's default
+         * pool the driver orders a context's stream behind another context's to recycle its memory, which serialises
+         * contexts that are meant to run concurrently (MCMCB200(streams=k)) */
+        cudaMemPoolProps props;
+        std::memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        AMH_CUDA_TRY(cudaMemPoolCreate(&c->pool, &props));
         unsigned long long keep = ~0ull;
-        AMH_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        AMH_CUDA_TRY(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
     *out = c;
     return AMH_OK;
@@ -200,6 +209,7 @@ int32_t amh_ctx_destroy(amh_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
+    if (c->pool) cudaMemPoolDestroy(c->pool);
     delete c;
     return AMH_OK;
 }
@@ -408,6 +418,7 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
     r->ctx = ctx; r->target = target; r->sampler = sampler;
     r->n = n; r->off = off; r->dim = d; r->nseeds = nseeds;
     r->pitch = (n + 31) / 32 * 32;          /* rows start 256-byte aligned; a warp's 32 chains never straddle a row end */
+    if (const char* ev = std::getenv("AMH_PITCH_PAD")) r->pitch += 32ll * std::atoll(ev);      /* experiment switch */
     {
         const char* ev = std::getenv("AMH_MH_PATH");     /* developer switch for A/B measurements: "dfma" forces K1 */
         if (ev && std::strcmp(ev, "dfma") == 0) r->mh_path = 1;
@@ -503,8 +514,16 @@ int32_t amh_run_sync(amh_run* run) {
 int32_t amh_run_sample(amh_run* run, int64_t N, int64_t discard_initial, int64_t thinning, int64_t num_warmup,
                        double* out, uint8_t* accepted_out, amh_summary* summary) {
     if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    return amh_run_sample_ld(run, N, discard_initial, thinning, num_warmup, out, run->n, accepted_out, run->n, summary);
+}
+
+int32_t amh_run_sample_ld(amh_run* run, int64_t N, int64_t discard_initial, int64_t thinning, int64_t num_warmup,
+                          double* out, int64_t out_ld, uint8_t* accepted_out, int64_t acc_ld, amh_summary* summary) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
     if (N < 1 || thinning < 1 || discard_initial < 0 || num_warmup < 0)
         return fail(AMH_ERR_INVALID, "need N >= 1, thinning >= 1, discard_initial >= 0, num_warmup >= 0");
+    if ((out && out_ld < run->n) || (accepted_out && acc_ld < run->n))
+        return fail(AMH_ERR_INVALID, "out_ld / acc_ld must be >= nchains_local");
     amh_run& r = *run;
     const long long n = r.n, np = r.pitch;
     const int d = r.dim;
@@ -548,10 +567,10 @@ int32_t amh_run_sample(amh_run* run, int64_t N, int64_t discard_initial, int64_t
         AMH_CUDA_TRY(cudaEventRecord(filled[b], st));
         AMH_CUDA_TRY(cudaStreamWaitEvent(cs, filled[b], 0));
         if (out)
-            AMH_CUDA_TRY(cudaMemcpy2DAsync(out + (size_t)base * (d + 1) * n, sizeof(double) * n, dsamp[b], sizeof(double) * np,
+            AMH_CUDA_TRY(cudaMemcpy2DAsync(out + (size_t)base * (d + 1) * out_ld, sizeof(double) * out_ld, dsamp[b], sizeof(double) * np,
                                            sizeof(double) * n, (size_t)count * (d + 1), cudaMemcpyDeviceToHost, cs));
         if (accepted_out)
-            AMH_CUDA_TRY(cudaMemcpy2DAsync(accepted_out + (size_t)base * n, (size_t)n, dacc[b], (size_t)np, (size_t)n,
+            AMH_CUDA_TRY(cudaMemcpy2DAsync(accepted_out + (size_t)base * acc_ld, (size_t)acc_ld, dacc[b], (size_t)np, (size_t)n,
                                            (size_t)count, cudaMemcpyDeviceToHost, cs));
         AMH_CUDA_TRY(cudaEventRecord(copied[b], cs));
         return AMH_OK;

@@ -12,6 +12,7 @@ struct amh_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaMemPool_t pool = nullptr;         /* this context's stream-ordered memory pool */
     int sm_count = 0;
     std::set<const void*> configured;     /* kernels whose function attributes were set on this device */
 };

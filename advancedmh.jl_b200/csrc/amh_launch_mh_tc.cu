@@ -21,6 +21,7 @@
  * Shared memory: 11.6 KB per warp -> 14 warps/SM = the whole 65 536-chain problem in one wave.
  */
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include "amh_params.cuh"
 
@@ -252,9 +253,18 @@ constexpr int kPW16 = 24;
 template <int D>
 __host__ __device__ constexpr int tc16_smem_doubles_per_warp() { return D * kPZ16 + 8 * kPW16; }
 
+/* WARPS == 28 (one CTA per SM) adds a PROGRESS BOUND: the warp schedulers favour some warp slots (B200: highest slot
+ * first), so over a 500-step launch the favoured warps finish long before the others and the launch ends with a tail
+ * of a few warps per scheduler that cannot fill the FP64 pipe -- 8 % of the launch (tools/concurrency_probe.py: the
+ * loss vanishes when the next launch may start under the tail).  Here no warp may run more than kLead steps ahead of
+ * the slowest warp of its SM: the favoured warps idle now and then (the pipe stays saturated by the other ~24 warps)
+ * and all warps finish within kLead steps of each other. */
+constexpr int kLead = 6;
 template <int D, int WARPS, bool MU_ZERO, bool IS_RW>
 __global__ void __launch_bounds__(32 * WARPS, 28 / WARPS)
 mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
+    constexpr bool BOUND = WARPS == 28;
+    __shared__ volatile int prog[32];
     static_assert(D % 8 == 0 && D >= 8 && D <= 32, "row blocks of 8; D/4 noise blocks per lane half");
     constexpr int NB = D / 8;
     constexpr int NPH = D / 4;                 /* Philox blocks per half-chain lane */
@@ -265,6 +275,11 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
     double* __restrict__ ZC = smem + warp * tc16_smem_doubles_per_warp<D>();
     double* __restrict__ WB = ZC + D * kPZ16;
     const long long cbase = ((long long)blockIdx.x * WARPS + warp) * 16;
+    if (BOUND) {
+        if (lane == 0) prog[warp] = (cbase >= a.st.n) ? 0x7fffffff : 0;
+        if (warp == 0 && lane >= WARPS) prog[lane] = 0x7fffffff;
+        __syncthreads();
+    }
     if (cbase >= a.st.n) return;
     const int cl = lane & 15, half = lane >> 4;
     const long long ch = cbase + cl;
@@ -281,6 +296,18 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
 
     for (int s = 0; s < a.nsteps; ++s) {
         const unsigned long long k = a.step0 + (unsigned long long)s + 1ull;
+        if (BOUND) {
+            if (lane == 0) prog[warp] = s;
+            if ((s & 1) == 0) {
+                for (;;) {
+                    int m = prog[lane];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+                    if (s - m <= kLead) break;
+                    __nanosleep(256);
+                }
+            }
+        }
         double e;
         {
             const unsigned long long b0 = k * B + (unsigned long long)(NPH * half);
@@ -413,6 +440,10 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
         __syncwarp();
     }
 
+    if (BOUND) {
+        __syncwarp();
+        if (lane == 0) prog[warp] = 0x7fffffff;            /* done: no longer holds anybody back */
+    }
     if (!active) return;
     if (a.sv.out || a.sv.sum) {
 #pragma unroll 4
@@ -491,7 +522,34 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     a.mu = a.Uf + (size_t)NT * 32;
     a.c0 = t.blob[0];
     if (r.mh_path != 2) {
-        /* K1T16: 16 chains per warp, 4 warps per CTA; 28 resident warps per SM */
+        /* K1T16: 16 chains per warp, 28 resident warps per SM: as ONE CTA per SM with the progress bound (default), or as
+         * 7 CTAs of 4 warps (AMH_TC_WARPS=4) */
+        static const int w16_env = std::getenv("AMH_TC_WARPS") ? std::atoi(std::getenv("AMH_TC_WARPS")) : 28;
+        if (w16_env == 28) {
+            constexpr int W28 = 28;
+            const size_t smem28 = (size_t)W28 * tc16_smem_doubles_per_warp<D>() * sizeof(double);
+            const unsigned grid28 = (unsigned)((r.n + 16 * W28 - 1) / (16 * W28));
+            const void* key28 = (const void*)mh_step_tc16_kernel<D, W28, true, true>;
+            if (!r.ctx->configured.count(key28)) {
+#define AMH_TC28_ATTR(...) AMH_CUDA_TRY(cudaFuncSetAttribute(mh_step_tc16_kernel<D, W28, __VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem28))
+                AMH_TC28_ATTR(true, true); AMH_TC28_ATTR(false, true); AMH_TC28_ATTR(true, false); AMH_TC28_ATTR(false, false);
+#undef AMH_TC28_ATTR
+                r.ctx->configured.insert(key28);
+            }
+#define AMH_TC28_GO(...) mh_step_tc16_kernel<D, W28, __VA_ARGS__><<<grid28, 32 * W28, smem28, r.ctx->stream>>>(a)
+            if (a.is_rw) {
+                if (a.mu_zero) AMH_TC28_GO(true, true);
+                else AMH_TC28_GO(false, true);
+            } else {
+                if (a.mu_zero) AMH_TC28_GO(true, false);
+                else AMH_TC28_GO(false, false);
+            }
+#undef AMH_TC28_GO
+            AMH_CUDA_TRY(cudaGetLastError());
+            r.launches += 1;
+            r.pending_launches += 1;
+            return AMH_OK;
+        }
         constexpr int W16 = 4;
         const size_t smem16 = (size_t)W16 * tc16_smem_doubles_per_warp<D>() * sizeof(double);
         const unsigned grid16 = (unsigned)((r.n + 16 * W16 - 1) / (16 * W16));
@@ -505,6 +563,14 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
             AMH_TC16_ATTR(true, true); AMH_TC16_ATTR(false, true); AMH_TC16_ATTR(true, false); AMH_TC16_ATTR(false, false);
 #undef AMH_TC16_ATTR
             r.ctx->configured.insert(key16);
+            if (std::getenv("AMH_TC_DEBUG")) {
+                int per_sm = -1;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mh_step_tc16_kernel<D, W16, true, true>, 32 * W16, smem16);
+                cudaFuncAttributes fa;
+                cudaFuncGetAttributes(&fa, mh_step_tc16_kernel<D, W16, true, true>);
+                std::fprintf(stderr, "[amh] K1T16 D=%d: smem/CTA %zu B, carveout %d%%, regs %d, occupancy API: %d CTAs/SM, grid %u\n", D, smem16,
+                             carve, fa.numRegs, per_sm, grid16);
+            }
         }
 #define AMH_TC16_GO(...) mh_step_tc16_kernel<D, W16, __VA_ARGS__><<<grid16, 32 * W16, smem16, r.ctx->stream>>>(a)
         if (a.is_rw) {

@@ -39,6 +39,10 @@ class MCMCB200:
     across ranks; there is no per-step collective."""
     device: int | None = None
     gather: bool = True
+    # this rank's chains as `streams` contiguous shards, each with its own context (stream, copy stream) on the same
+    # GPU and driven by its own host thread: the host->device copy of one shard's initial parameters and the
+    # device->host copy of its samples overlap the stepping kernels of the others.  Same results (global chain identity).
+    streams: int = 1
 
 
 # ---------------------------------------------------------------- chain types
@@ -105,6 +109,35 @@ def default_engine(device: int | None = None) -> K.Engine:
     if device not in _ENGINES:
         _ENGINES[device] = K.Engine(device=device)
     return _ENGINES[device]
+
+
+_STREAM_ENGINES: dict = {}
+_POOL = None
+
+
+def _stream_engines(eng: K.Engine, k: int):
+    """`k` engines (contexts) on eng's device and library; eng itself is the first"""
+    key = (eng.path, eng.prefix, eng.device)
+    lst = _STREAM_ENGINES.setdefault(key, [eng])
+    while len(lst) < k:
+        lst.append(K.Engine(lib_path=eng.path, prefix=eng.prefix, device=eng.device))
+    return lst[:k]
+
+
+def _sample_block(eng, target, sampler, dim, n_blk, seeds, init, offset, N, discard_initial, thinning, num_warmup, out, acc):
+    th = eng.target_of(target)
+    sh = sampler.lower(eng, dim)
+    run = None
+    try:
+        run = eng.run(th, sh, n_blk, seeds, init, chain_offset=offset)
+        run.sample(N, discard_initial, thinning, num_warmup, store=True, store_accepted=True, summary=False,
+                   chain_means=False, out=out, acc=acc)
+        return run.launch_count()
+    finally:
+        if run is not None:
+            run.close()
+        sh.close()
+        th.close()
 
 
 def _dist_info():
@@ -194,12 +227,37 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
     lo, hi = shard_bounds(nchains, rank, world)
     eng = engine or default_engine(parallel.device if isinstance(parallel, MCMCB200) else None)
 
-    th = eng.target_of(target)
-    sh = sampler.lower(eng, dim)
     n_local = (hi - lo) * nw
+    nstreams = parallel.streams if isinstance(parallel, MCMCB200) else 1
+    if (nstreams > 1 and hi - lo >= nstreams and store and not summary and initial_state is None and not save_state
+            and callback is None and getattr(target, "kind", None) != K.TARGET_USER):
+        # shards of this rank's chains on separate streams of the GPU, one host thread each
+        global _POOL
+        from concurrent.futures import ThreadPoolExecutor
+        if _POOL is None:
+            _POOL = ThreadPoolExecutor(max_workers=16)
+        engs = _stream_engines(eng, nstreams)
+        if out is None:
+            out = (np.empty((N, dim + 1, n_local)), np.empty((N, n_local), dtype=np.uint8))
+        vals, accs = out
+        futs = []
+        for k, e in enumerate(engs):
+            a, b = shard_bounds(hi - lo, k, nstreams)
+            ca, cb = (lo + a) * nw, (lo + b) * nw                      # global chain (walker) range of the shard
+            futs.append(_POOL.submit(_sample_block, e, target, sampler, dim, cb - ca, seeds[lo + a:lo + b],
+                                     None if init is None else init[:, ca:cb], ca, N, discard_initial, thinning, num_warmup,
+                                     vals[:, :, ca - lo * nw:cb - lo * nw], accs[:, ca - lo * nw:cb - lo * nw]))
+        launches = sum(f.result() for f in futs)
+        out, acc = vals, accs
+        info = dict(summary=None, launches=launches, rank=rank, world=world, chains=(lo * nw, hi * nw), streams=nstreams)
+        n_local = -1                                                   # done: skip the single-stream path below
+    th = eng.target_of(target) if n_local >= 0 else None
+    sh = sampler.lower(eng, dim) if n_local >= 0 else None
     run = None
     try:
-        if n_local > 0:
+        if n_local < 0:
+            pass
+        elif n_local > 0:
             sl = slice(lo * nw, hi * nw)
             if initial_state is not None:
                 if "seeds" in initial_state:
@@ -233,8 +291,10 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
     finally:
         if run is not None:
             run.close()
-        sh.close()
-        th.close()
+        if sh is not None:
+            sh.close()
+        if th is not None:
+            th.close()
 
     if world > 1 and isinstance(parallel, MCMCB200) and parallel.gather and store:
         out, acc = _gather_samples(dist, out, acc, nchains * nw, world, nw)

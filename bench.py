@@ -158,6 +158,9 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-streams", type=int, default=4,
+                    help="MCMCB200(streams=...) of the e2e call: shards of a rank's chains on separate streams, so that "
+                         "host<->device copies overlap the stepping kernels")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -247,12 +250,12 @@ def main():
         pout = eng.pinned_empty((2, d + 1, n))          # this rank's shard of the two saved samples
         pacc = eng.pinned_empty((2, n), dtype=np.uint8)
         model = amh.DensityModel(target)
-        amh.sample(model, sampler, amh.MCMCB200(device=local, gather=False), 2, n * world, initial_params=hinit,
+        amh.sample(model, sampler, amh.MCMCB200(device=local, gather=False, streams=args.e2e_streams), 2, n * world, initial_params=hinit,
                    thinning=spl, chain_type=amh.Chains, seed=99, out=(pout, pacc))          # warm-up call
         barrier()
         t0 = time.perf_counter()
         for i in range(args.e2e_steps):
-            ch = amh.sample(model, sampler, amh.MCMCB200(device=local, gather=False), 2, n * world,
+            ch = amh.sample(model, sampler, amh.MCMCB200(device=local, gather=False, streams=args.e2e_streams), 2, n * world,
                             initial_params=hinit, thinning=spl, chain_type=amh.Chains, seed=i, out=(pout, pacc))
         barrier()
         dt = time.perf_counter() - t0
@@ -263,7 +266,7 @@ def main():
         h2d = 8 * d * n + 8 * n + target.blob().nbytes + 8 * (d * (d + 1) // 2)       # per rank: init, seeds, target, L
         d2h = 2 * (d + 1) * n * 8 + 2 * n                                             # per rank: 2 samples + accepted flags
         e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "call": "sample(model, RWMH(MvNormal), MCMCB200(), N=2, nchains; thinning=spl, out=pinned) incl. handle "
+               "call": f"sample(model, RWMH(MvNormal), MCMCB200(streams={args.e2e_streams}), N=2, nchains; thinning=spl, out=pinned) incl. handle "
                        "creation, H2D of initial_params/seeds/target from pinned host memory, D2H of 2 samples into pinned memory"}
         del hinit, ch, pout, pacc
 

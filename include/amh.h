@@ -197,6 +197,13 @@ int32_t amh_run_sample(amh_run* run, int64_t N, int64_t discard_initial, int64_t
                        int64_t num_warmup, double* out, uint8_t* accepted_out,
                        amh_summary* summary);
 
+/* the same with caller buffers that are COLUMN BLOCKS of larger arrays: row stride out_ld >= nchains_local doubles
+ * ([N][dim+1][out_ld]) and acc_ld >= nchains_local bytes.  Lets several runs -- shards of one job on several streams of
+ * a GPU, or on several GPUs of a process -- fill one [N][dim+1][nchains] array in place. */
+int32_t amh_run_sample_ld(amh_run* run, int64_t N, int64_t discard_initial, int64_t thinning,
+                          int64_t num_warmup, double* out, int64_t out_ld, uint8_t* accepted_out, int64_t acc_ld,
+                          amh_summary* summary);
+
 /* state introspection / resume (getparams/setparams!!: src/AdvancedMH.jl:146-157,
  * MALA.jl:23-35, RAM :116-121; StatesExtractor: test/RobustAdaptiveMetropolis.jl:11-28).
  * Any pointer may be NULL.  x:[dim][n] lp:[n] grad:[dim][n] (MALA)

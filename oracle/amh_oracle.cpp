@@ -1000,11 +1000,22 @@ int32_t amho_run_steps(amh_run* run, int64_t nsteps, int32_t warmup, int32_t) {
 }
 int32_t amho_run_sync(amh_run*) { return AMH_OK; }
 
+int32_t amho_run_sample_ld(amh_run* run, int64_t N, int64_t discard_initial, int64_t thinning,
+                           int64_t num_warmup, double* out, int64_t out_ld, uint8_t* accepted_out, int64_t acc_ld,
+                           amh_summary* summary);
 int32_t amho_run_sample(amh_run* run, int64_t N, int64_t discard_initial, int64_t thinning,
                         int64_t num_warmup, double* out, uint8_t* accepted_out, amh_summary* summary) {
     if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    return amho_run_sample_ld(run, N, discard_initial, thinning, num_warmup, out, ((Run*)run)->n, accepted_out, ((Run*)run)->n, summary);
+}
+int32_t amho_run_sample_ld(amh_run* run, int64_t N, int64_t discard_initial, int64_t thinning,
+                           int64_t num_warmup, double* out, int64_t out_ld, uint8_t* accepted_out, int64_t acc_ld,
+                           amh_summary* summary) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
     if (N < 1 || thinning < 1 || discard_initial < 0 || num_warmup < 0)
         return fail(AMH_ERR_INVALID, "need N >= 1, thinning >= 1, discard_initial >= 0, num_warmup >= 0");
+    if ((out && out_ld < ((Run*)run)->n) || (accepted_out && acc_ld < ((Run*)run)->n))
+        return fail(AMH_ERR_INVALID, "out_ld / acc_ld must be >= nchains_local");
     Run& r = *(Run*)run;
     const int64_t n = r.n;
     const int d = r.dim;
@@ -1027,11 +1038,11 @@ int32_t amho_run_sample(amh_run* run, int64_t N, int64_t discard_initial, int64_
         const int rc = advance(i == 0 ? discard_initial : thinning);
         if (rc) return rc;
         if (out) {
-            double* o = out + (size_t)i * (d + 1) * n;
-            std::memcpy(o, r.X.data(), sizeof(double) * (size_t)d * n);
-            std::memcpy(o + (size_t)d * n, r.lp.data(), sizeof(double) * n);
+            double* o = out + (size_t)i * (d + 1) * out_ld;
+            for (int j = 0; j < d; ++j) std::memcpy(o + (size_t)j * out_ld, r.X.data() + (size_t)j * n, sizeof(double) * n);
+            std::memcpy(o + (size_t)d * out_ld, r.lp.data(), sizeof(double) * n);
         }
-        if (accepted_out) std::memcpy(accepted_out + (size_t)i * n, r.acc.data(), n);
+        if (accepted_out) std::memcpy(accepted_out + (size_t)i * acc_ld, r.acc.data(), n);
         accumulate(r);
     }
     if (summary) {

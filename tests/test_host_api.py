@@ -250,3 +250,21 @@ def test_component_proposal_lowering_and_errors(amh, oracle):
     c2 = amh.sample(amh.DensityModel(amh.IIDNormalTarget(np.array([1.0]))), s, 100, chain_type="namedtuples", engine=oracle,
                     param_names=["mu", "sigma"])
     assert len(c2) == 100 and set(c2[0]) == {"mu", "sigma", "lp"} and all(r["sigma"] > 0 for r in c2)
+
+
+def test_stream_shards_reproduce_the_single_stream_run(amh, oracle):
+    """MCMCB200(streams=k): contiguous shards of a rank's chains, one context + host thread each, filling column blocks
+    of one output array (amh_run_sample_ld) -- identical to the unsharded run (global chain identity)."""
+    d = 3
+    model = amh.DensityModel(amh.MvNormalTarget(None, np.eye(d) * 0.5 + 0.5))
+    spl = amh.RWMH(amh.MvNormal(np.zeros(d), 0.3 * amh.I))
+    init = np.random.default_rng(0).normal(size=(d, 53))
+    kw = dict(seed=3, thinning=3, discard_initial=5, initial_params=init, chain_type=amh.Chains, engine=oracle)
+    a = amh.sample(model, spl, amh.MCMCB200(streams=1), 12, 53, **kw)
+    b = amh.sample(model, spl, amh.MCMCB200(streams=4), 12, 53, **kw)
+    assert b.info["streams"] == 4
+    assert np.array_equal(a.value, b.value) and np.array_equal(a.accepted, b.accepted)
+    ens = amh.Ensemble(8, amh.StretchProposal(amh.MvNormal(np.zeros(d), amh.I)))      # an ensemble is indivisible
+    a = amh.sample(model, ens, amh.MCMCB200(streams=1), 6, 5, seed=1, chain_type=amh.Chains, engine=oracle)
+    b = amh.sample(model, ens, amh.MCMCB200(streams=2), 6, 5, seed=1, chain_type=amh.Chains, engine=oracle)
+    assert np.array_equal(a.value, b.value)

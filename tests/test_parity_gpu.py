@@ -554,3 +554,19 @@ def test_stretch_level_schedule_configs_and_overflow_bucket(amh, cuda, oracle, m
     out_g, acc_g, _ = rg.sample(5, 2, 3)
     out_o, acc_o, _ = ro.sample(5, 2, 3)
     assert np.array_equal(out_g, out_o) and np.array_equal(acc_g, acc_o)
+
+
+def test_sample_on_four_streams_equals_one_stream_and_the_oracle(amh, cuda, oracle):
+    d, n = 8, 4096 + 37
+    Sigma = make_spd(d, seed=2)
+    model = amh.DensityModel(amh.MvNormalTarget(None, Sigma))
+    spl = amh.RWMH(amh.MvNormal(np.zeros(d), (2.38 ** 2 / d) * Sigma))
+    init = np.random.default_rng(5).normal(size=(d, n))
+    kw = dict(seed=11, thinning=7, initial_params=init, chain_type=amh.Chains)
+    one = amh.sample(model, spl, amh.MCMCB200(device=0), 5, n, **kw)
+    pout, pacc = cuda.pinned_empty((5, d + 1, n)), cuda.pinned_empty((5, n), dtype=np.uint8)
+    four = amh.sample(model, spl, amh.MCMCB200(device=0, streams=4), 5, n, out=(pout, pacc), **kw)
+    ref = amh.sample(model, spl, amh.MCMCB200(device=0), 5, n, engine=oracle, **kw)
+    assert four.info["streams"] == 4
+    assert np.array_equal(one.value, four.value) and np.array_equal(one.accepted, four.accepted)
+    assert np.array_equal(four.value, ref.value)

@@ -52,7 +52,7 @@ def main():
     seeds = lambda n, s: np.random.default_rng(s).integers(0, 2 ** 64, size=n, dtype=np.uint64)
     if "c2" in which:
         for d in [int(v) for v in os.environ.get("AMH_BENCH_DIMS", "32,24,16,10,2").split(",")]:
-            n = 65536
+            n = int(os.environ.get("AMH_BENCH_N", "65536"))
             Sigma = spd(d, 32, 1.0, 100.0)
             t = amh.MvNormalTarget(None, Sigma)
             s = amh.RWMH(amh.MvNormal(np.zeros(d), (2.38 ** 2 / d) * Sigma))
