@@ -253,18 +253,17 @@ constexpr int kPW16 = 24;
 template <int D>
 __host__ __device__ constexpr int tc16_smem_doubles_per_warp() { return D * kPZ16 + 8 * kPW16; }
 
-/* WARPS == 28 (one CTA per SM) adds a PROGRESS BOUND: the warp schedulers favour some warp slots (B200: highest slot
- * first), so over a 500-step launch the favoured warps finish long before the others and the launch ends with a tail
- * of a few warps per scheduler that cannot fill the FP64 pipe -- 8 % of the launch (tools/concurrency_probe.py: the
- * loss vanishes when the next launch may start under the tail).  Here no warp may run more than kLead steps ahead of
- * the slowest warp of its SM: the favoured warps idle now and then (the pipe stays saturated by the other ~24 warps)
- * and all warps finish within kLead steps of each other. */
-constexpr int kLead = 6;
+/* WARPS: 28 = ONE CTA per SM (default), 4 = seven CTAs per SM.  Same code per warp, same 28 resident warps -- but the
+ * warp schedulers arbitrate by warp slot (B200: highest slot first, round-robin among equals): the warps of seven
+ * small CTAs get equal treatment and stay in lock-step, all in the noise phase (issue-slot and DFMA bound) or all in the
+ * DMMA phase (FP64-pipe bound, few issue slots) at the same time; the 28 warps of one CTA have distinct priorities,
+ * drift apart and overlap the two phases.  Measured on C2: 4.93e9 -> 5.53e9 chain-steps/s (tools/bench_configs.py with
+ * AMH_TC_WARPS=4 / 28).  A bound on the drift (no warp more than k steps ahead of the slowest) was tried to cut the
+ * end-of-launch tail and LOSES throughput for every k (5.28e9 at k <= 16). */
 template <int D, int WARPS, bool MU_ZERO, bool IS_RW>
 __global__ void __launch_bounds__(32 * WARPS, 28 / WARPS)
 mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
-    constexpr bool BOUND = WARPS == 28;
-    __shared__ volatile int prog[32];
+
     static_assert(D % 8 == 0 && D >= 8 && D <= 32, "row blocks of 8; D/4 noise blocks per lane half");
     constexpr int NB = D / 8;
     constexpr int NPH = D / 4;                 /* Philox blocks per half-chain lane */
@@ -275,11 +274,6 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
     double* __restrict__ ZC = smem + warp * tc16_smem_doubles_per_warp<D>();
     double* __restrict__ WB = ZC + D * kPZ16;
     const long long cbase = ((long long)blockIdx.x * WARPS + warp) * 16;
-    if (BOUND) {
-        if (lane == 0) prog[warp] = (cbase >= a.st.n) ? 0x7fffffff : 0;
-        if (warp == 0 && lane >= WARPS) prog[lane] = 0x7fffffff;
-        __syncthreads();
-    }
     if (cbase >= a.st.n) return;
     const int cl = lane & 15, half = lane >> 4;
     const long long ch = cbase + cl;
@@ -296,18 +290,6 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
 
     for (int s = 0; s < a.nsteps; ++s) {
         const unsigned long long k = a.step0 + (unsigned long long)s + 1ull;
-        if (BOUND) {
-            if (lane == 0) prog[warp] = s;
-            if ((s & 1) == 0) {
-                for (;;) {
-                    int m = prog[lane];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
-                    if (s - m <= kLead) break;
-                    __nanosleep(256);
-                }
-            }
-        }
         double e;
         {
             const unsigned long long b0 = k * B + (unsigned long long)(NPH * half);
@@ -440,10 +422,6 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
         __syncwarp();
     }
 
-    if (BOUND) {
-        __syncwarp();
-        if (lane == 0) prog[warp] = 0x7fffffff;            /* done: no longer holds anybody back */
-    }
     if (!active) return;
     if (a.sv.out || a.sv.sum) {
 #pragma unroll 4
@@ -522,8 +500,8 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     a.mu = a.Uf + (size_t)NT * 32;
     a.c0 = t.blob[0];
     if (r.mh_path != 2) {
-        /* K1T16: 16 chains per warp, 28 resident warps per SM: as ONE CTA per SM with the progress bound (default), or as
-         * 7 CTAs of 4 warps (AMH_TC_WARPS=4) */
+        /* K1T16: 16 chains per warp, 28 resident warps per SM: as ONE CTA per SM (default), or as 7 CTAs of 4 warps
+         * (AMH_TC_WARPS=4, kept for A/B measurements) */
         static const int w16_env = std::getenv("AMH_TC_WARPS") ? std::atoi(std::getenv("AMH_TC_WARPS")) : 28;
         if (w16_env == 28) {
             constexpr int W28 = 28;
@@ -531,7 +509,12 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
             const unsigned grid28 = (unsigned)((r.n + 16 * W28 - 1) / (16 * W28));
             const void* key28 = (const void*)mh_step_tc16_kernel<D, W28, true, true>;
             if (!r.ctx->configured.count(key28)) {
-#define AMH_TC28_ATTR(...) AMH_CUDA_TRY(cudaFuncSetAttribute(mh_step_tc16_kernel<D, W28, __VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem28))
+                const char* cv = std::getenv("AMH_TC_CARVEOUT");
+#define AMH_TC28_ATTR(...)                                                                                                                     \
+                do {                                                                                                                               \
+                    AMH_CUDA_TRY(cudaFuncSetAttribute(mh_step_tc16_kernel<D, W28, __VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem28)); \
+                    if (cv) AMH_CUDA_TRY(cudaFuncSetAttribute(mh_step_tc16_kernel<D, W28, __VA_ARGS__>, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(cv))); \
+                } while (0)
                 AMH_TC28_ATTR(true, true); AMH_TC28_ATTR(false, true); AMH_TC28_ATTR(true, false); AMH_TC28_ATTR(false, false);
 #undef AMH_TC28_ATTR
                 r.ctx->configured.insert(key28);

@@ -275,10 +275,20 @@ stretch_plan_kernel(StretchPlan o, const unsigned long long* __restrict__ seeds,
 
 /* 256-bit global accesses through L2 (sm_100: LDG/STG.E.ENL2.256) */
 __device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
+#if defined(AMH_NO_V4_F64)      /* run-time compilation with an NVRTC older than CUDA 12.9 (amh_rtc.cu) */
+    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(p) : "memory");
+    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(c), "=d"(d) : "l"(p + 2) : "memory");
+#else
     asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
+#endif
 }
 __device__ __forceinline__ void st256(double* p, double a, double b, double c, double d) {
+#if defined(AMH_NO_V4_F64)
+    asm volatile("st.global.cg.v2.f64 [%2], {%0,%1};" :: "d"(a), "d"(b), "l"(p) : "memory");
+    asm volatile("st.global.cg.v2.f64 [%2], {%0,%1};" :: "d"(c), "d"(d), "l"(p + 2) : "memory");
+#else
     asm volatile("st.global.cg.v4.f64 [%4], {%0,%1,%2,%3};" :: "d"(a), "d"(b), "d"(c), "d"(d), "l"(p) : "memory");
+#endif
 }
 
 /* Inside a launch the walkers of an ensemble live as RECORDS [x_0 .. x_{d-1}, lp, pad] of RS = roundup(d + 1, 4)

@@ -39,7 +39,10 @@ struct Nvrtc {
     decltype(&nvrtcAddNameExpression) AddNameExpression = nullptr;
     decltype(&nvrtcGetLoweredName) GetLoweredName = nullptr;
     decltype(&nvrtcGetErrorString) GetErrorString = nullptr;
+    decltype(&nvrtcVersion) Version = nullptr;
+    int major = 0, minor = 0;
     std::string why;
+    bool has_v4_f64() const { return major > 12 || (major == 12 && minor >= 9); }   /* 256-bit ld/st.global in PTX */
 };
 
 struct Driver {
@@ -56,14 +59,29 @@ Nvrtc& nvrtc() {
     static Nvrtc n;
     static std::once_flag once;
     std::call_once(once, [] {
-        const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
-                               "/usr/local/cuda/targets/x86_64-linux/lib/libnvrtc.so.12"};
+        /* the toolkit's own library first, by absolute path: another component of the process (PyTorch) may already
+         * have loaded an OLDER libnvrtc.so.12 under the same soname, and a bare name would return that one */
+        const char* names[] = {"/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/targets/x86_64-linux/lib/libnvrtc.so.12",
+                               "libnvrtc.so.12", "libnvrtc.so"};
         std::string tried;
-        if (const char* ev = std::getenv("AMH_NVRTC_LIB")) n.h = dlopen(ev, RTLD_NOW | RTLD_LOCAL);
-        for (size_t i = 0; !n.h && i < sizeof(names) / sizeof(names[0]); ++i) {
-            n.h = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
-            if (!n.h) tried += std::string(" ") + names[i];
-        }
+        void* best = nullptr;
+        int bmaj = 0, bmin = 0;
+        auto consider = [&](const char* name) {
+            void* h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (!h) { tried += std::string(" ") + name; return; }
+            auto ver = (decltype(&nvrtcVersion))dlsym(h, "nvrtcVersion");
+            int mj = 0, mn = 0;
+            if (ver) ver(&mj, &mn);
+            if (!best || mj > bmaj || (mj == bmaj && mn > bmin)) {
+                if (best) dlclose(best);
+                best = h; bmaj = mj; bmin = mn;
+            } else {
+                dlclose(h);
+            }
+        };
+        if (const char* ev = std::getenv("AMH_NVRTC_LIB")) consider(ev);
+        for (size_t i = 0; i < sizeof(names) / sizeof(names[0]) && !(bmaj > 12 || (bmaj == 12 && bmin >= 9)); ++i) consider(names[i]);
+        n.h = best; n.major = bmaj; n.minor = bmin;
         if (!n.h) { n.why = "libnvrtc not found (tried" + tried + "; set AMH_NVRTC_LIB)"; return; }
 #define AMH_NVRTC_SYM(name)                                                             \
         n.name = (decltype(n.name))dlsym(n.h, "nvrtc" #name);                          \
@@ -189,6 +207,8 @@ int rtc_build(amh_target& t, const char* source, bool has_grad) {
     t.rtc->tu.reserve(total + std::strlen(source) + 64);
     /* without a gradient the kernels never reference amh_user_logdensity_and_gradient (amh_device.cuh, TUser) */
     if (!has_grad) t.rtc->tu += "#define AMH_RTC_NO_GRADIENT 1\n";
+    /* ld/st.global.v4.f64 (256-bit) needs the ptxas of CUDA 12.9; an older NVRTC gets two 128-bit accesses instead */
+    if (nvrtc().h && !nvrtc().has_v4_f64()) t.rtc->tu += "#define AMH_NO_V4_F64 1\n";
     for (int i = 0; i < kRtcSourceChunkCount; ++i) t.rtc->tu += kRtcSourceChunks[i];
     t.rtc->tu += source;
     t.rtc->tu += "\n";

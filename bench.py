@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--e2e-streams", type=int, default=4,
+    ap.add_argument("--e2e-streams", type=int, default=1,
                     help="MCMCB200(streams=...) of the e2e call: shards of a rank's chains on separate streams, so that "
                          "host<->device copies overlap the stepping kernels")
     args = ap.parse_args()

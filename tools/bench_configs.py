@@ -48,7 +48,7 @@ def report(name, nchain_steps, ms, bytes_per, extra=""):
 
 def main():
     which = sys.argv[1:] or ["c2", "c3", "c4", "c5"]
-    eng = amh.default_engine(0)
+    eng = amh.Engine(lib_path=os.environ["AMH_LIB"]) if os.environ.get("AMH_LIB") else amh.default_engine(0)
     seeds = lambda n, s: np.random.default_rng(s).integers(0, 2 ** 64, size=n, dtype=np.uint64)
     if "c2" in which:
         for d in [int(v) for v in os.environ.get("AMH_BENCH_DIMS", "32,24,16,10,2").split(",")]:
