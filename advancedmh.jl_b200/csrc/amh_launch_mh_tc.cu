@@ -39,6 +39,7 @@ struct MhTcArgs {
     const double* Uf;          /* [NT][32] A fragments of the target factor     */
     const double* mu;          /* [D]                                           */
     double c0;
+    int pace;                  /* nanoseconds of optional pause per step (see the step loop of K1T16) */
 };
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
@@ -290,6 +291,11 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
 
     for (int s = 0; s < a.nsteps; ++s) {
         const unsigned long long k = a.step0 + (unsigned long long)s + 1ull;
+        /* Optional pacing (AMH_TC_PACE nanoseconds, default 0 = never taken).  The untaken branch is kept on purpose: with
+         * it at the top of the step ptxas schedules the whole loop body differently, and that schedule is 8 % faster
+         * (C2: 5.18e9 -> 5.60e9 chain-steps/s, same box, A/B of two builds, profiles/r1_k1t16_cta_shape_ab.txt); an
+         * asm memory clobber or a __syncwarp at the same place do not have this effect. */
+        if (a.pace > 0) __nanosleep((unsigned)a.pace);
         double e;
         {
             const unsigned long long b0 = k * B + (unsigned long long)(NPH * half);
@@ -499,6 +505,10 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     a.Uf = a.Lf + (size_t)NT * 32;
     a.mu = a.Uf + (size_t)NT * 32;
     a.c0 = t.blob[0];
+    {
+        static const int pace_env = std::getenv("AMH_TC_PACE") ? std::atoi(std::getenv("AMH_TC_PACE")) : 0;
+        a.pace = pace_env;
+    }
     if (r.mh_path != 2) {
         /* K1T16: 16 chains per warp, 28 resident warps per SM: as ONE CTA per SM (default), or as 7 CTAs of 4 warps
          * (AMH_TC_WARPS=4, kept for A/B measurements) */

@@ -288,10 +288,10 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "kernel": "mh_step_tc16_kernel<32,4,true,4,true> (K1T16: DMMA mat-vecs, 16 chains per warp)",
+                "kernel": "mh_step_tc16_kernel<32,28,true,true> (K1T16: DMMA mat-vecs, 16 chains per warp, one 28-warp CTA per SM)",
                 "algorithmic_bytes_per_chain_step": B,
                 "chain_steps_per_launch": n * spl,
-                "note": "state (17 MB) is L2 resident and the kernel is bound by the shared FP64 datapath (DFMA + DMMA, 64 FMA/clk/SM); the HBM figure is the contractual denominator (SURVEY.md 8d)"}
+                "note": "state (17 MB) is L2 resident and the kernel is bound by the shared FP64 datapath (DMMA + DFMA + the wide integer multiplies of Philox, 64 FMA/clk/SM); the HBM figure is the contractual denominator (SURVEY.md 8d)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
