@@ -7,6 +7,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <limits>
 #include "amh_host.h"
@@ -528,6 +530,12 @@ int32_t amh_run_sample_ld(amh_run* run, int64_t N, int64_t discard_initial, int6
     const long long n = r.n, np = r.pitch;
     const int d = r.dim;
     cudaStream_t st = r.ctx->stream;
+    static const bool trace = std::getenv("AMH_TRACE") != nullptr;
+    const auto tr0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (trace) std::fprintf(stderr, "[amh] run_sample %-22s %8.3f ms\n", what,
+                                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count());
+    };
     AMH_CUDA_TRY(cudaSetDevice(r.ctx->device));
     AMH_CUDA_TRY(cudaMemsetAsync(r.sum, 0, sizeof(double) * d * np, st));
     AMH_CUDA_TRY(cudaMemsetAsync(r.sumsq, 0, sizeof(double) * d * np, st));
@@ -575,6 +583,7 @@ int32_t amh_run_sample_ld(amh_run* run, int64_t N, int64_t discard_initial, int6
         AMH_CUDA_TRY(cudaEventRecord(copied[b], cs));
         return AMH_OK;
     };
+    lap("setup done");
     for (long long i = 0; i < N && !rc; ++i) {
         long long k = (i == 0) ? discard_initial : thinning;
         const int b = chunk ? (int)((i / chunk) % nbuf) : 0;
@@ -602,11 +611,15 @@ int32_t amh_run_sample_ld(amh_run* run, int64_t N, int64_t discard_initial, int6
         r.nsaved += 1;
         if (chunk && !rc && (slot == chunk - 1 || i == N - 1)) rc = drain(b, i - slot, slot + 1);
     }
+    lap("all enqueued");
+    if (trace) { cudaStreamSynchronize(st); lap("step stream idle"); }
     if (!rc) {
         cudaError_t e = cudaStreamSynchronize(cs);
         if (e != cudaSuccess) rc = cuda_fail(e, "copy stream sync");
     }
+    lap("copies done");
     cleanup();
+    lap("cleanup done");
     if (rc) return rc;
     AMH_CUDA_TRY(cudaStreamSynchronize(st));
     if (summary) {
