@@ -268,3 +268,14 @@ def test_stream_shards_reproduce_the_single_stream_run(amh, oracle):
     a = amh.sample(model, ens, amh.MCMCB200(streams=1), 6, 5, seed=1, chain_type=amh.Chains, engine=oracle)
     b = amh.sample(model, ens, amh.MCMCB200(streams=2), 6, 5, seed=1, chain_type=amh.Chains, engine=oracle)
     assert np.array_equal(a.value, b.value)
+
+
+def test_run_sample_ld_rejects_a_leading_dimension_smaller_than_the_shard(amh, oracle):
+    d, n = 2, 9
+    t = amh.MvNormalTarget(None, np.eye(d))
+    run = oracle.run(oracle.target(t.kind, d, t.blob()), amh.RWMH(d).lower(oracle, d), n, np.arange(n, dtype=np.uint64))
+    big = np.zeros((3, d + 1, 2 * n))
+    out, acc, _ = run.sample(3, out=big[:, :, n:], acc=None, summary=False)          # a block of chains of a larger array
+    assert np.all(big[:, :, :n] == 0) and np.any(big[:, :, n:] != 0)
+    with pytest.raises(amh.AMHArgumentError):
+        run.sample(3, out=np.zeros((3, d + 1, n))[:, :, ::2], summary=False)        # not unit stride along chains

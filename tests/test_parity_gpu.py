@@ -570,3 +570,23 @@ def test_sample_on_four_streams_equals_one_stream_and_the_oracle(amh, cuda, orac
     assert four.info["streams"] == 4
     assert np.array_equal(one.value, four.value) and np.array_equal(one.accepted, four.accepted)
     assert np.array_equal(four.value, ref.value)
+
+
+def test_stretch_plans_made_ahead_and_mispredictions(amh, cuda, oracle):
+    """K2F computes the plan of the NEXT launch on a second stream while the sweeps of the current one run; equal
+    consecutive launches use it, a different length or a state reset must discard it (amh_launch_stretch.cu)."""
+    d, nw, ne = 6, 1536, 3
+    target = amh.RosenbrockTarget(d)
+    spl = amh.Ensemble(nw, amh.StretchProposal(amh.MvNormal(np.zeros(d), amh.I)))
+    rg, ro = _pair(amh, cuda, oracle, target, spl, nw * ne, _seeds(ne, 21))
+    for k in (8, 8, 8, 3, 8, 8):                       # predicted, predicted, mispredicted (3), mispredicted (8), predicted
+        rg.steps(k, steps_per_launch=k)
+        ro.steps(k)
+    _assert_same_state(rg, ro)
+    st = ro.state()                                    # resume from an earlier point: the step counter jumps back
+    rg.steps(5, steps_per_launch=5); ro.steps(5)
+    for r in (rg, ro):
+        r.set_state(st)
+    rg.steps(5, steps_per_launch=5); ro.steps(5)
+    rg.steps(5, steps_per_launch=5); ro.steps(5)
+    _assert_same_state(rg, ro)
