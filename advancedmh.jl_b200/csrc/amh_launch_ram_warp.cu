@@ -39,6 +39,7 @@ struct RamWArgs {
     double alpha, gamma, lo, hi;
     int check;
     const double* Utc;         /* target factor, column-packed [nt] */
+    int force_redo;            /* test switch: treat every speculative sweep as out of range (exercises the redo path) */
     const double* mu;          /* [d] */
     double c0;
 };
@@ -391,7 +392,7 @@ ram_warp_kernel(const __grid_constant__ RamWArgs a) {
                     else
                         ok = (dalpha > 0.0) ? givens_update_fast<RPL, false>(Sb, d, lane, v, a.lo, a.hi, out_of_bounds)
                                             : givens_downdate_fast<RPL, false>(Sb, d, lane, v, a.lo, a.hi, posdef_fail, out_of_bounds);
-                    ok = __all_sync(0xffffffffu, ok);
+                    ok = __all_sync(0xffffffffu, ok) && !a.force_redo;
                     if (!ok) {
                         /* redo with the IEEE operators from the last good factor (global memory holds it) */
                         if (lane == 0) {
@@ -558,6 +559,7 @@ static int launch_ram_warp_t(amh_run& r, int nsteps, bool warmup, const SaveArgs
     a.alpha = s.d.ram_alpha; a.gamma = s.d.ram_gamma; a.lo = s.d.ram_eig_lo; a.hi = s.d.ram_eig_hi;
     a.check = !(a.lo == 0.0 && a.hi == INFINITY);
     a.Utc = (const double*)r.scratch;
+    a.force_redo = std::getenv("AMH_RAMW_FORCE_REDO") != nullptr;      /* test switch, read per launch */
     a.mu = a.Utc + nt;
     a.c0 = t.blob[0];
     /* one CTA per SM holding as many chain tiles as fit beside the shared target factor */

@@ -590,3 +590,20 @@ def test_stretch_plans_made_ahead_and_mispredictions(amh, cuda, oracle):
     rg.steps(5, steps_per_launch=5); ro.steps(5)
     rg.steps(5, steps_per_launch=5); ro.steps(5)
     _assert_same_state(rg, ro)
+
+
+def test_ram_warp_redo_path_with_ieee_operators_is_bit_exact(amh, cuda, oracle, monkeypatch):
+    """K4W runs its Givens sweeps speculatively with branch-free sqrt / division sequences and redoes a sweep with the
+    IEEE operators from the last good factor if an operand left their exponent range.  That never happens with sane
+    inputs, so the switch forces it on every step: reload, recomputed v, slow sweep -- same bits as the oracle."""
+    monkeypatch.setenv("AMH_RAMW_FORCE_REDO", "1")
+    for d in (20, 64):
+        Sigma = make_spd(d, seed=d, lo=0.01, hi=1.0)
+        target = amh.MvNormalTarget(None, Sigma)
+        spl = amh.RobustAdaptiveMetropolis(eigenvalue_lower_bound=0.05, eigenvalue_upper_bound=2.0) if d == 20 else amh.RobustAdaptiveMetropolis()
+        n = 300
+        rg, ro = _pair(amh, cuda, oracle, target, spl, n, _seeds(n, d), np.zeros((d, n)))
+        for k in (1, 12):
+            rg.steps(k, warmup=True, steps_per_launch=k)
+            ro.steps(k, warmup=True)
+        _assert_same_state(rg, ro, S=True)
