@@ -288,6 +288,7 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
     unsigned nacc = 0u;                         /* accepted moves of this launch */
     unsigned char accepted = active ? a.st.acc[ch] : (unsigned char)0;
     constexpr unsigned long long B = (unsigned long long)((D + 1) / 2 + 1);
+    double e_next = 0.0;
 
     for (int s = 0; s < a.nsteps; ++s) {
         const unsigned long long k = a.step0 + (unsigned long long)s + 1ull;
@@ -302,8 +303,19 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
             double* zt = ZC + (HR * half) * kPZ16 + cl;            /* Z[HR half + j][cl] */
             constexpr int G1 = (NPH >= 6) ? NPH / 2 : 0;           /* two lock-step batches when there are enough blocks */
             if constexpr (G1 > 0) noise_group<(G1 > 0 ? G1 : 1), false>(seed, b0, 0ull, zt, e, amh::amh_log_tab_dev, kPZ16);
-            noise_group<NPH - G1, true>(seed, b0 + G1, k * B + (unsigned long long)(D / 2), zt + 2 * G1 * kPZ16, e,
-                                        amh::amh_log_tab_dev, kPZ16);
+            /* the exponential: both lanes of a chain run the same instructions, so on even steps of the launch lane half
+             * h draws the exponential of step k + h, and odd steps draw none */
+            if ((s & 1) == 0) {
+                double eh;
+                noise_group<NPH - G1, true>(seed, b0 + G1, (k + (unsigned long long)half) * B + (unsigned long long)(D / 2),
+                                            zt + 2 * G1 * kPZ16, eh, amh::amh_log_tab_dev, kPZ16);
+                e = __shfl_sync(0xffffffffu, eh, cl);
+                e_next = __shfl_sync(0xffffffffu, eh, cl + 16);
+            } else {
+                double dummy;
+                noise_group<NPH - G1, false>(seed, b0 + G1, 0ull, zt + 2 * G1 * kPZ16, dummy, amh::amh_log_tab_dev, kPZ16);
+                e = e_next;
+            }
         }
         /* x in accumulator-fragment layout, software-pipelined two row blocks ahead of its use */
         double2 xf[NB][2];
