@@ -77,14 +77,17 @@ def main():
         beta = rng.normal(size=d)
         y = (rng.random(nrows) < 1 / (1 + np.exp(-X @ beta))).astype(float)
         t = amh.LogisticRegressionTarget(X, y, tau=10.0)
-        s2 = 2e-3
+        s2 = float(os.environ.get("AMH_C4_S2", "3.3e-2"))       # step size near the MALA optimum for this posterior (sd ~ 0.2 per coordinate)
         s = amh.MALA(lambda g: amh.MvNormal((s2 / 2) * g, s2 * amh.I))
         for n in (16384,):
             run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), n, seeds(n, 3), np.zeros((d, n)))
+            run.steps(60, steps_per_launch=4)                  # from zeros to the posterior mode region
+            st0 = run.state()
             ms = timed(run, 4, spl=2, reps=2, warm=1)
             st = run.state()
+            acc = (st['naccept'].sum() - st0['naccept'].sum()) / (n * (st['step'] - st0['step']))
             report(f"C4 MALA logistic d=128 rows=10k n={n}", n * 4, ms, 2 * (2 * d + 1) * 8,
-                   f"accept={st['naccept'].sum() / (n * st['step']):.3f}  {5.12e6 * n * 4 / (ms * 1e-3) / 1e12:.2f} TFLOP/s fp64")
+                   f"accept(recent)={acc:.3f}  {5.12e6 * n * 4 / (ms * 1e-3) / 1e12:.2f} TFLOP/s fp64")
             run.close()
     if "c5" in which:
         d = 64
