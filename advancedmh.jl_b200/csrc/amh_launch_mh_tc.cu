@@ -39,6 +39,7 @@ struct MhTcArgs {
     const double* Uf;          /* [NT][32] A fragments of the target factor     */
     const double* mu;          /* [D]                                           */
     double c0;
+    const double* dscale;      /* [D] standard deviations of a diagonal / isotropic proposal (COVD variants) */
     int pace;                  /* nanoseconds of optional pause per step (see the step loop of K1T16) */
 };
 
@@ -261,7 +262,9 @@ __host__ __device__ constexpr int tc16_smem_doubles_per_warp() { return D * kPZ1
  * drift apart and overlap the two phases.  Measured on C2: 4.93e9 -> 5.53e9 chain-steps/s (tools/bench_configs.py with
  * AMH_TC_WARPS=4 / 28).  A bound on the drift (no warp more than k steps ahead of the slowest) was tried to cut the
  * end-of-launch tail and LOSES throughput for every k (5.28e9 at k <= 16). */
-template <int D, int WARPS, bool MU_ZERO, bool IS_RW>
+/* COVD: the proposal covariance is diagonal (ScalMat / PDiagMat): v_i = sigma_i z_i needs no mat-vec, phase 1 is
+ * c = x + sigma_i z_i on the chain lanes (the contract's two roundings, proposal.jl:41-56 with a diagonal factor). */
+template <int D, int WARPS, bool MU_ZERO, bool IS_RW, bool COVD = false>
 __global__ void __launch_bounds__(32 * WARPS, 28 / WARPS)
 mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
 
@@ -317,6 +320,17 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
                 e = e_next;
             }
         }
+        if constexpr (COVD) {
+            /* every lane owns rows HR*half .. of its chain: the same tile entries it has just written */
+#pragma unroll
+            for (int i = 0; i < HR; ++i) {
+                const int row = HR * half + i;
+                const double t = __ldg(a.dscale + row) * ZC[row * kPZ16 + cl];
+                double c = t;
+                if (IS_RW) c = __ldcg(X + (long long)row * pitch + ch) + t;
+                ZC[row * kPZ16 + cl] = c;
+            }
+        } else {
         /* x in accumulator-fragment layout, software-pipelined two row blocks ahead of its use */
         double2 xf[NB][2];
         const double* xp = X + (long long)fr * pitch + cbase + 2 * fc;
@@ -376,6 +390,7 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
                 }
             }
         }
+        }   /* !COVD */
         __syncwarp();
         double q = 0.0;
         {
@@ -480,7 +495,9 @@ bool mh_tc_eligible(const amh_run& r) {
     const int d = r.dim;
     if (r.target->kind != AMH_TARGET_MVNORMAL) return false;
     if (!(d == 8 || d == 16 || d == 24 || d == 32)) return false;
-    if (s.d.cov_kind != AMH_COV_FULL || s.has_mean) return false;
+    if (s.has_mean || s.by_components()) return false;
+    if (s.d.cov_kind != AMH_COV_FULL && s.d.cov_kind != AMH_COV_DIAG && s.d.cov_kind != AMH_COV_SCALAR) return false;
+    if (s.d.cov_kind != AMH_COV_FULL && r.mh_path == 2) return false;          /* the 32-chains-per-warp variant is full-covariance only */
     if (s.d.kind == AMH_SAMPLER_STATIC && !s.d.symmetric) return false;      /* needs logq: generic path */
     if (r.pitch % 32) return false;
     return true;
@@ -493,11 +510,15 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     const amh_target& t = *r.target;
     if (!r.scratch) {
         std::vector<double> lf, uf, all;
-        build_frags(s.scale.data(), D, lf);
+        const bool covd0 = s.d.cov_kind != AMH_COV_FULL;
+        if (covd0) lf.assign((size_t)(D / 8) * (D / 8 + 1) * 32, 0.0);
+        else build_frags(s.scale.data(), D, lf);
         build_frags(t.blob.data() + 1 + D, D, uf);
         all = lf;
         all.insert(all.end(), uf.begin(), uf.end());
         all.insert(all.end(), t.blob.begin() + 1, t.blob.begin() + 1 + D);
+        for (int i = 0; i < D; ++i)                                             /* standard deviations of a diagonal proposal */
+            all.push_back(s.d.cov_kind == AMH_COV_DIAG ? s.scale[i] : s.d.cov_kind == AMH_COV_SCALAR ? s.scale[0] : 0.0);
         { const int rca = dmalloc(r.ctx, &r.scratch, all.size() * sizeof(double)); if (rca) return rca; }
         AMH_CUDA_TRY(cudaMemcpyAsync(r.scratch, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice, r.ctx->stream));
         AMH_CUDA_TRY(cudaStreamSynchronize(r.ctx->stream));     /* `all` is a stack temporary */
@@ -517,6 +538,8 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     a.Uf = a.Lf + (size_t)NT * 32;
     a.mu = a.Uf + (size_t)NT * 32;
     a.c0 = t.blob[0];
+    a.dscale = a.mu + D;
+    const bool covd = s.d.cov_kind != AMH_COV_FULL;
     {
         static const int pace_env = std::getenv("AMH_TC_PACE") ? std::atoi(std::getenv("AMH_TC_PACE")) : 0;
         a.pace = pace_env;
@@ -525,7 +548,7 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
         /* K1T16: 16 chains per warp, 28 resident warps per SM: as ONE CTA per SM (default), or as 7 CTAs of 4 warps
          * (AMH_TC_WARPS=4, kept for A/B measurements) */
         static const int w16_env = std::getenv("AMH_TC_WARPS") ? std::atoi(std::getenv("AMH_TC_WARPS")) : 28;
-        if (w16_env == 28) {
+        if (w16_env == 28 || covd) {
             constexpr int W28 = 28;
             const size_t smem28 = (size_t)W28 * tc16_smem_doubles_per_warp<D>() * sizeof(double);
             const unsigned grid28 = (unsigned)((r.n + 16 * W28 - 1) / (16 * W28));
@@ -538,11 +561,20 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
                     if (cv) AMH_CUDA_TRY(cudaFuncSetAttribute(mh_step_tc16_kernel<D, W28, __VA_ARGS__>, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(cv))); \
                 } while (0)
                 AMH_TC28_ATTR(true, true); AMH_TC28_ATTR(false, true); AMH_TC28_ATTR(true, false); AMH_TC28_ATTR(false, false);
+                AMH_TC28_ATTR(true, true, true); AMH_TC28_ATTR(false, true, true); AMH_TC28_ATTR(true, false, true); AMH_TC28_ATTR(false, false, true);
 #undef AMH_TC28_ATTR
                 r.ctx->configured.insert(key28);
             }
 #define AMH_TC28_GO(...) mh_step_tc16_kernel<D, W28, __VA_ARGS__><<<grid28, 32 * W28, smem28, r.ctx->stream>>>(a)
-            if (a.is_rw) {
+            if (covd) {
+                if (a.is_rw) {
+                    if (a.mu_zero) AMH_TC28_GO(true, true, true);
+                    else AMH_TC28_GO(false, true, true);
+                } else {
+                    if (a.mu_zero) AMH_TC28_GO(true, false, true);
+                    else AMH_TC28_GO(false, false, true);
+                }
+            } else if (a.is_rw) {
                 if (a.mu_zero) AMH_TC28_GO(true, true);
                 else AMH_TC28_GO(false, true);
             } else {

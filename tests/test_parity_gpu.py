@@ -31,7 +31,8 @@ def _seeds(n, s=0):
 
 
 @pytest.mark.parametrize("d,cov", [(1, "scalar"), (2, "scalar"), (2, "diag"), (3, "full"), (8, "full"), (8, "diag"), (13, "full"),
-                                   (16, "full"), (24, "full"), (32, "full"), (32, "scalar"), (40, "full")])
+                                   (16, "full"), (24, "full"), (32, "full"), (32, "scalar"), (40, "full"),
+                                   (8, "scalar"), (16, "diag"), (24, "scalar"), (32, "diag")])
 def test_rwmh_mvnormal_bit_exact(amh, cuda, oracle, d, cov):
     Sigma = make_spd(d, seed=d)
     target = amh.MvNormalTarget(np.linspace(-1, 1, d), Sigma)
@@ -607,3 +608,18 @@ def test_ram_warp_redo_path_with_ieee_operators_is_bit_exact(amh, cuda, oracle, 
             rg.steps(k, warmup=True, steps_per_launch=k)
             ro.steps(k, warmup=True)
         _assert_same_state(rg, ro, S=True)
+
+
+@pytest.mark.parametrize("cov", ["scalar", "diag"])
+def test_symmetric_static_mh_diagonal_proposal_on_the_tensor_path(amh, cuda, oracle, cov):
+    """StaticMH with issymmetric = true (Hastings term literal 0) and a diagonal proposal at a K1T16 dimension"""
+    d = 16
+    target = amh.MvNormalTarget(np.linspace(-0.5, 0.5, d), make_spd(d, seed=4, lo=0.5, hi=3.0))
+    dist = amh.MvNormal(np.zeros(d), 1.5 * amh.I) if cov == "scalar" else [amh.Normal(0, 1.0 + 0.05 * i) for i in range(d)]
+    spl = amh.MetropolisHastings(amh.SymmetricStaticProposal(dist))
+    n = 777
+    rg, ro = _pair(amh, cuda, oracle, target, spl, n, _seeds(n, 31))
+    _assert_same_state(rg, ro)
+    for k in (1, 2, 33):
+        rg.steps(k, steps_per_launch=k); ro.steps(k)
+        _assert_same_state(rg, ro)

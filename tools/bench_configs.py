@@ -61,6 +61,20 @@ def main():
             st = run.state()
             report(f"C2 RWMH MvNormal d={d} n={n}", n * (500 if os.environ.get("AMH_BENCH_LONG") else 200), ms, 2 * (d + 1) * 8, f"accept={st['naccept'].sum() / (n * st['step']):.3f}")
             run.close()
+    if "c2iso" in which:
+        # the isotropic / diagonal proposal variant of config 2: K1T16 with c = x + sigma_i z_i instead of the L z mat-vec
+        for d, kind in ((32, "scalar"), (32, "diag"), (16, "scalar")):
+            n = 65536
+            Sigma = spd(d, 32, 1.0, 100.0)
+            t = amh.MvNormalTarget(None, Sigma)
+            prop = amh.MvNormal(np.zeros(d), (1.2 ** 2 / d) * amh.I) if kind == "scalar" else \
+                [amh.Normal(0, 1.2 / np.sqrt(d) * (1 + 0.02 * i)) for i in range(d)]
+            s = amh.RWMH(prop)
+            run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), n, seeds(n, 1))
+            ms = timed(run, 500, spl=500)
+            st = run.state()
+            report(f"C2 RWMH MvNormal d={d} {kind} proposal", n * 500, ms, 2 * (d + 1) * 8, f"accept={st['naccept'].sum() / (n * st['step']):.3f}")
+            run.close()
     if "c3" in which:
         d, nw, ne = 10, 4096, 64
         t = amh.RosenbrockTarget(d)
