@@ -73,12 +73,21 @@ class AMHStateError(AMHError):
     """AMH_ERR_STATE -- e.g. MALA without initial parameters (MALA.jl:37)"""
 
 
+class PosDefException(ArithmeticError):
+    """LinearAlgebra.PosDefException: RAM's rank-1 downdate left the positive-definite cone
+    (`lowrankdowndate`, RobustAdaptiveMetropolis.jl:170).  The reference aborts `sample`; the device flags the chain
+    (amh_run_ram_failed) and the host raises after the run.  `.chain` is the first flagged chain, `.count` how many."""
+    def __init__(self, chain, count):
+        super().__init__(f"matrix is not positive definite; rank-1 downdate failed for {count} chain(s), first: chain {chain}")
+        self.chain, self.count = chain, count
+
+
 # every symbol include/amh.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
     "version", "last_error", "contract_version", "ctx_create", "ctx_destroy", "ctx_sync",
     "target_create", "target_create_source", "target_destroy", "sampler_create", "sampler_destroy",
     "run_create", "run_destroy", "run_steps", "run_sync", "run_sample", "run_sample_ld",
-    "run_get_state", "run_set_params", "run_set_state", "run_get_ram_adapt", "run_dim", "run_nchains", "run_launch_count",
+    "run_get_state", "run_set_params", "run_set_state", "run_get_ram_adapt", "run_set_ram_adapt", "run_ram_failed", "run_dim", "run_nchains", "run_launch_count",
     "run_kernel_time_ms", "host_alloc", "host_free",
 ]
 
@@ -133,6 +142,8 @@ class Engine:
         f("run_set_params").argtypes = [C.c_void_p, _dp]
         f("run_set_state").argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _u8p, _i64p, C.c_int64]
         f("run_get_ram_adapt").argtypes = [C.c_void_p, _dp, _dp]
+        f("run_set_ram_adapt").argtypes = [C.c_void_p, _dp, _dp, _u8p]
+        f("run_ram_failed").argtypes = [C.c_void_p, _i64p, _i64p, _u8p]
         f("run_kernel_time_ms").argtypes = [C.c_void_p, C.c_int32, _dp, _i64p]
         f("host_alloc").argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
         f("host_free").argtypes = [C.c_void_p]
@@ -336,7 +347,12 @@ class Run:
             g.ctypes.data_as(_dp) if g is not None else None,
             Sm.ctypes.data_as(_dp) if Sm is not None else None,
             acc.ctypes.data_as(_u8p), nacc.ctypes.data_as(_i64p), C.byref(step)))
-        return dict(x=x, lp=lp, grad=g, S=Sm, accepted=acc, naccept=nacc, step=step.value)
+        st = dict(x=x, lp=lp, grad=g, S=Sm, accepted=acc, naccept=nacc, step=step.value)
+        if self.sampler.kind == SAMPLER_RAM:
+            # the report-only fields of RobustAdaptiveMetropolisState (RAM :107-113) and the failed-downdate flags
+            st["logalpha"], st["eta"] = self.ram_adapt()
+            st["failed"] = self.ram_failed()[2]
+        return st
 
     def state_step(self):
         step = C.c_int64()
@@ -363,6 +379,10 @@ class Run:
             keep.append(a)
             return a.ctypes.data_as(ptr)
         step = state.get("step")
+        if self.sampler.kind == SAMPLER_RAM and any(state.get(k) is not None for k in ("logalpha", "eta", "failed")):
+            self.eng._check(self.eng._f("run_set_ram_adapt")(
+                self.h, arr("logalpha", (n,), np.float64, _dp), arr("eta", (n,), np.float64, _dp),
+                arr("failed", (n,), np.uint8, _u8p)))
         self.eng._check(self.eng._f("run_set_state")(
             self.h, arr("x", (d, n), np.float64, _dp), arr("lp", (n,), np.float64, _dp),
             arr("grad", (d, n), np.float64, _dp), arr("S", (d * (d + 1) // 2, n), np.float64, _dp),
@@ -374,6 +394,13 @@ class Run:
         la = np.empty(self.n); eta = np.empty(self.n)
         self.eng._check(self.eng._f("run_get_ram_adapt")(self.h, la.ctypes.data_as(_dp), eta.ctypes.data_as(_dp)))
         return la, eta
+
+    def ram_failed(self):
+        """(count, first global chain or -1, flags[n]) of chains whose rank-1 downdate failed (amh_run_ram_failed)"""
+        nf, first = C.c_int64(), C.c_int64()
+        flags = np.empty(self.n, dtype=np.uint8)
+        self.eng._check(self.eng._f("run_ram_failed")(self.h, C.byref(nf), C.byref(first), flags.ctypes.data_as(_u8p)))
+        return int(nf.value), int(first.value), flags
 
     def launch_count(self):
         return int(self.eng._f("run_launch_count")(self.h))

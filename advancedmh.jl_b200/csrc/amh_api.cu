@@ -41,6 +41,17 @@ int default_steps_per_launch(const amh_run& r) {
     default: return 64;
     }
 }
+/* amh_run_sample: the steps between two save points (a whole thinning interval) go into ONE launch where the kernel
+ * keeps its state on chip across fused steps (MH / MALA: the launch's only HBM traffic is the state at both ends);
+ * capped so that a launch stays in the millisecond range.  Stretch plans and K4W tiles are sized per launch length
+ * and keep their defaults. */
+static int sample_steps_per_launch(const amh_run& r, long long interval) {
+    switch (r.sampler->d.kind) {
+    case AMH_SAMPLER_STRETCH:
+    case AMH_SAMPLER_RAM: return default_steps_per_launch(r);
+    default: return (int)std::max<long long>(1, std::min<long long>(interval, 1024));
+    }
+}
 
 int dmalloc(amh_ctx* ctx, void** p, size_t bytes) {
     *p = nullptr;
@@ -599,12 +610,13 @@ int32_t amh_run_sample_ld(amh_run* run, int64_t N, int64_t discard_initial, int6
         sv.acc_out = dacc[b] ? dacc[b] + (size_t)slot * np : nullptr;
         sv.sum = r.sum;
         sv.sumsq = r.sumsq;
+        sv.inv_n = 1.0 / (double)(r.nsaved + 1);
         /* stateful step s (1-based, cumulative) is step_warmup iff s <= num_warmup */
         bool done = false;
         while (!done && !rc) {
             const bool wu = k > 0 && r.step < num_warmup;
             const long long m = wu ? std::min<long long>(k, num_warmup - r.step) : k;
-            rc = enqueue_steps(r, m, wu, 0, (m == k) ? &sv : nullptr);
+            rc = enqueue_steps(r, m, wu, sample_steps_per_launch(r, m), (m == k) ? &sv : nullptr);
             k -= m;
             done = (k == 0);
         }
@@ -633,17 +645,23 @@ int32_t amh_run_sample_ld(amh_run* run, int64_t N, int64_t discard_initial, int6
         double na = 0;
         for (long long c = 0; c < n; ++c) na += (double)ha[c];
         summary->accept_rate = r.step > 0 ? na / ((double)n * (double)r.step) : 0.0;
+        /* per-chain Welford (mean, M2) -> pooled moments (every chain holds n_saved samples): the pooled mean is the
+         * mean of the chain means, the pooled M2 is sum M2_c + n_saved * sum (mean_c - mean)^2  (Chan et al.) */
         for (int i = 0; i < d; ++i) {
-            double s1 = 0, s2 = 0;
+            double s1 = 0;
             for (long long c = 0; c < n; ++c) {
                 s1 += hs[(size_t)i * np + c];
-                s2 += hq[(size_t)i * np + c];
-                if (summary->chain_mean) summary->chain_mean[(size_t)i * n + c] = hs[(size_t)i * np + c] / (double)r.nsaved;
+                if (summary->chain_mean) summary->chain_mean[(size_t)i * n + c] = hs[(size_t)i * np + c];
             }
-            const double tot = (double)n * (double)r.nsaved;
-            const double m = s1 / tot;
+            const double m = s1 / (double)n;
+            double m2 = 0, dev = 0;
+            for (long long c = 0; c < n; ++c) {
+                const double dl = hs[(size_t)i * np + c] - m;
+                m2 += hq[(size_t)i * np + c];
+                dev = std::fma(dl, dl, dev);
+            }
             if (summary->mean) summary->mean[i] = m;
-            if (summary->var) summary->var[i] = s2 / tot - m * m;
+            if (summary->var) summary->var[i] = (m2 + (double)r.nsaved * dev) / ((double)n * (double)r.nsaved);
         }
     }
     return AMH_OK;
@@ -732,6 +750,36 @@ int32_t amh_run_get_ram_adapt(amh_run* run, double* logalpha, double* eta) {
     return AMH_OK;
 }
 
+int32_t amh_run_set_ram_adapt(amh_run* run, const double* logalpha, const double* eta, const uint8_t* failed) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    amh_run& r = *run;
+    if (r.sampler->d.kind != AMH_SAMPLER_RAM) return fail(AMH_ERR_INVALID, "not a RobustAdaptiveMetropolis run");
+    AMH_CUDA_TRY(cudaSetDevice(r.ctx->device));
+    cudaStream_t st = r.ctx->stream;
+    if (logalpha) AMH_CUDA_TRY(cudaMemcpyAsync(r.logalpha, logalpha, sizeof(double) * r.n, cudaMemcpyHostToDevice, st));
+    if (eta) AMH_CUDA_TRY(cudaMemcpyAsync(r.eta, eta, sizeof(double) * r.n, cudaMemcpyHostToDevice, st));
+    if (failed) AMH_CUDA_TRY(cudaMemcpyAsync(r.failed, failed, (size_t)r.n, cudaMemcpyHostToDevice, st));
+    AMH_CUDA_TRY(cudaStreamSynchronize(st));
+    return AMH_OK;
+}
+
+int32_t amh_run_ram_failed(amh_run* run, int64_t* nfailed, int64_t* first_chain, uint8_t* failed) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    amh_run& r = *run;
+    if (r.sampler->d.kind != AMH_SAMPLER_RAM) return fail(AMH_ERR_INVALID, "not a RobustAdaptiveMetropolis run");
+    AMH_CUDA_TRY(cudaSetDevice(r.ctx->device));
+    AMH_CUDA_TRY(cudaStreamSynchronize(r.ctx->stream));
+    std::vector<unsigned char> h((size_t)r.n);
+    AMH_CUDA_TRY(cudaMemcpy(h.data(), r.failed, (size_t)r.n, cudaMemcpyDeviceToHost));
+    long long nf = 0, first = -1;
+    for (long long c = 0; c < r.n; ++c)
+        if (h[c]) { if (first < 0) first = c; ++nf; }
+    if (nfailed) *nfailed = nf;
+    if (first_chain) *first_chain = first < 0 ? -1 : r.off + first;
+    if (failed) std::memcpy(failed, h.data(), (size_t)r.n);
+    return AMH_OK;
+}
+
 int32_t amh_run_set_params(amh_run* run, const double* x) {
     if (!run || !x) return fail(AMH_ERR_INVALID, "NULL argument");
     amh_run& r = *run;
@@ -744,7 +792,9 @@ int32_t amh_run_set_params(amh_run* run, const double* x) {
     if (r.sampler->d.kind != AMH_SAMPLER_RAM) {
         double* Ssave = r.S;
         r.S = nullptr;
+        r.keep_acc = true;               /* setparams!! builds Transition(model, params, t.accepted): the flag is kept */
         rc = launch_init(r, 0);
+        r.keep_acc = false;
         r.S = Ssave;
     }
     AMH_CUDA_TRY(cudaStreamSynchronize(r.ctx->stream));

@@ -104,8 +104,7 @@ mala_step_kernel(const __grid_constant__ MalaArgs a, const __grid_constant__ typ
             a.st.G[o] = sg[i * BLOCK + tid];
             if (a.sv.out) a.sv.out[(long long)i * a.sv.out_pitch + ch] = v;
             if (a.sv.sum) {
-                a.sv.sum[o] = a.sv.sum[o] + v;
-                a.sv.sumsq[o] = fma(v, v, a.sv.sumsq[o]);
+                save_moments(a.sv, o, v);
             }
         }
     a.st.lp[ch] = lp;

@@ -295,8 +295,7 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
             const double v = a.st.X[o];
             if (a.sv.out) a.sv.out[(long long)j * a.sv.out_pitch + ch] = v;
             if (a.sv.sum) {
-                a.sv.sum[o] = a.sv.sum[o] + v;
-                a.sv.sumsq[o] = fma(v, v, a.sv.sumsq[o]);
+                save_moments(a.sv, o, v);
             }
         }
     }

@@ -114,7 +114,7 @@ int launch_init_t(amh_run& r, int mode) {
     a.mode = mode;
     a.want_grad = s.d.kind == AMH_SAMPLER_MALA;
     a.want_lq = (s.d.kind == AMH_SAMPLER_STATIC && !s.d.symmetric);
-    a.init_acc = (s.d.kind == AMH_SAMPLER_RAM) ? 1 : 0;
+    a.init_acc = r.keep_acc ? -1 : (s.d.kind == AMH_SAMPLER_RAM) ? 1 : 0;
     a.n_walkers = s.d.n_walkers > 0 ? s.d.n_walkers : 1;
     a.prop = make_prop<0>(s);
     a.S = r.S;

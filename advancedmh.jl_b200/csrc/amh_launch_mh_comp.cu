@@ -104,8 +104,7 @@ mh_comp_kernel(const __grid_constant__ MhCompArgs a, const __grid_constant__ typ
         a.st.X[o] = v;
         if (a.sv.out) a.sv.out[(long long)i * a.sv.out_pitch + ch] = v;
         if (a.sv.sum) {
-            a.sv.sum[o] = a.sv.sum[o] + v;
-            a.sv.sumsq[o] = fma(v, v, a.sv.sumsq[o]);
+            save_moments(a.sv, o, v);
         }
     }
     a.st.lp[ch] = lp;

@@ -232,8 +232,7 @@ mh_step_tc_kernel(const __grid_constant__ MhTcArgs a) {
             const double v = X[o];
             if (a.sv.out) a.sv.out[(long long)i * a.sv.out_pitch + ch] = v;
             if (a.sv.sum) {
-                a.sv.sum[o] = a.sv.sum[o] + v;
-                a.sv.sumsq[o] = fma(v, v, a.sv.sumsq[o]);
+                save_moments(a.sv, o, v);
             }
         }
     }
@@ -464,8 +463,7 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
             const double v = X[o];
             if (a.sv.out) a.sv.out[(long long)i * a.sv.out_pitch + ch] = v;
             if (a.sv.sum) {
-                a.sv.sum[o] = a.sv.sum[o] + v;
-                a.sv.sumsq[o] = fma(v, v, a.sv.sumsq[o]);
+                save_moments(a.sv, o, v);
             }
         }
     }

@@ -162,8 +162,7 @@ ram_step_kernel(const __grid_constant__ RamArgs a, const __grid_constant__ typen
         a.st.X[o] = v;
         if (a.sv.out) a.sv.out[(long long)i * a.sv.out_pitch + ch] = v;
         if (a.sv.sum) {
-            a.sv.sum[o] = a.sv.sum[o] + v;
-            a.sv.sumsq[o] = fma(v, v, a.sv.sumsq[o]);
+            save_moments(a.sv, o, v);
         }
     }
     a.st.lp[ch] = lp;

@@ -450,8 +450,7 @@ ram_warp_kernel(const __grid_constant__ RamWArgs a) {
                 a.st.X[o] = x[r];
                 if (a.sv.out) a.sv.out[(long long)j * a.sv.out_pitch + ch] = x[r];
                 if (a.sv.sum) {
-                    a.sv.sum[o] = a.sv.sum[o] + x[r];
-                    a.sv.sumsq[o] = fma(x[r], x[r], a.sv.sumsq[o]);
+                    save_moments(a.sv, o, x[r]);
                 }
             }
         }

@@ -124,8 +124,7 @@ stretch_sweep_kernel(const __grid_constant__ StretchArgs a, const __grid_constan
                 if (a.sv.out) a.sv.out[(long long)j * a.sv.out_pitch + ch] = v;
                 if (a.sv.sum) {
                     const long long o = (long long)j * pitch + ch;
-                    a.sv.sum[o] = a.sv.sum[o] + v;
-                    a.sv.sumsq[o] = fma(v, v, a.sv.sumsq[o]);
+                    save_moments(a.sv, o, v);
                 }
             }
             if (a.sv.out) a.sv.out[(long long)d * a.sv.out_pitch + ch] = lpold[ch];
@@ -573,8 +572,7 @@ __device__ __forceinline__ void stretch_flow_body(const StretchArgs& a, const St
             a.st.X[o] = v;
             if (a.sv.out) a.sv.out[(long long)j * a.sv.out_pitch + ch] = v;
             if (a.sv.sum) {
-                a.sv.sum[o] = a.sv.sum[o] + v;
-                a.sv.sumsq[o] = fma(v, v, a.sv.sumsq[o]);
+                save_moments(a.sv, o, v);
             }
         }
         const double lpv = __ldcg(rec + d);

@@ -43,6 +43,9 @@ class MCMCB200:
     # GPU and driven by its own host thread: the host->device copy of one shard's initial parameters and the
     # device->host copy of its samples overlap the stepping kernels of the others.  Same results (global chain identity).
     streams: int = 1
+    # RAM: a failed rank-1 downdate raises PosDefException after the run, like the reference (RAM :170); True keeps the
+    # samples instead (the chain stopped adapting at that step, nothing else happened to it)
+    ignore_failed_downdates: bool = False
 
 
 # ---------------------------------------------------------------- chain types
@@ -150,6 +153,75 @@ def _dist_info():
     return 0, 1, None
 
 
+def _draw_seeds(rng, nchains: int, lo: int, hi: int):
+    """seeds[lo:hi] of `seeds = rand(rng, UInt, nchains)` (AbstractMCMC's per-chain seeding) WITHOUT drawing
+    the other ranks' seeds: chain c always gets raw 64-bit output number c of the generator, so the result does not
+    depend on the sharding, and a rank's host work is O(local chains).  Needs a jumpable bit generator (numpy's default
+    PCG64 family); any other generator falls back to drawing all of them.  The caller's rng ends up advanced by
+    `nchains` draws either way."""
+    bg = rng.bit_generator
+    if (lo, hi) != (0, nchains) and isinstance(bg, (np.random.PCG64, np.random.PCG64DXSM)):
+        st = bg.state
+        bg.advance(lo)
+        local = rng.integers(0, 2 ** 64, size=hi - lo, dtype=np.uint64)
+        bg.state = st
+        bg.advance(nchains)
+        return local
+    return rng.integers(0, 2 ** 64, size=nchains, dtype=np.uint64)[lo:hi]
+
+
+class SamplerState:
+    """What `callback(rng, model, sampler, sample, state, iteration)` receives as `state` (AbstractMCMC's callback
+    signature; test/RobustAdaptiveMetropolis.jl:11-28 records it per saved sample): the sampler state of ALL local
+    chains right after the saved step, chains on the last axis.  Fields follow the reference's state structs --
+    Transition (src/AdvancedMH.jl:61-65): params, lp, accepted; GradientTransition (MALA.jl:14-19): + gradient;
+    RobustAdaptiveMetropolisState (RAM :99-114): x, logprob, S, logalpha (`logα`), eta (`η`), iteration, isaccept."""
+    def __init__(self, st, dim, ram):
+        self.params = self.x = st["x"]
+        self.lp = self.logprob = st["lp"]
+        self.accepted = self.isaccept = st["accepted"].astype(bool)
+        self.gradient = st.get("grad")
+        self.naccept = st["naccept"]
+        self.step = st["step"]
+        self._S, self._dim = st.get("S"), dim
+        if ram:
+            self.logalpha, self.eta = st["logalpha"], st["eta"]
+            self.iteration = st["step"] + 1                  # state.iteration starts at 1 (RAM :211)
+            self.failed = st["failed"].astype(bool)
+
+    def S(self, chain=0):
+        """dense lower-triangular factor of one chain (RobustAdaptiveMetropolisState.S)"""
+        d = self._dim
+        out = np.zeros((d, d))
+        out[np.tril_indices(d)] = self._S[:, chain]
+        return out
+
+    def S_diag(self):
+        """eigvals(S) of every chain = the diagonal of the triangular factor (RAM :239-245): (dim, nchains)"""
+        d = self._dim
+        return self._S[[i * (i + 1) // 2 + i for i in range(d)], :]
+
+
+def _sample_with_callback(run, sampler, rng, model, N, discard_initial, thinning, num_warmup, callback, dim, out, acc):
+    """the AbstractMCMC schedule driven save point by save point, so that `callback` sees the real sampler state after
+    every saved step (one state read-back per saved sample: the price of the reference's per-sample callback)"""
+    is_ram, is_mala = isinstance(sampler, RobustAdaptiveMetropolis), isinstance(sampler, MALA)
+    for i in range(N):
+        k = discard_initial if i == 0 else thinning
+        while k > 0:
+            done = run.state_step()
+            wu = done < num_warmup
+            m = min(k, num_warmup - done) if wu else k
+            run.steps(m, warmup=wu)
+            k -= m
+        st = run.state(grad=is_mala, S=is_ram)
+        out[i, :dim, :] = st["x"]
+        out[i, dim, :] = st["lp"]
+        acc[i] = st["accepted"]
+        callback(rng, model, sampler, out[i], SamplerState(st, dim, is_ram), i + 1)
+    return out, acc
+
+
 def shard_bounds(nunits: int, rank: int, world: int):
     """contiguous block partition of `nunits` chains (or ensembles) over `world` ranks"""
     base, rem = divmod(nunits, world)
@@ -214,17 +286,22 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
         discard_initial = num_warmup          # AbstractMCMC default (RAM docstring :41-44)
     if isinstance(sampler, RobustAdaptiveMetropolis) and not hasattr(target, "kind"):
         raise ValueError("RobustAdaptiveMetropolis needs a LogDensityProblems-style target")
-    if rng is None:
-        rng = np.random.default_rng(seed)
-    nw = sampler.n_walkers if isinstance(sampler, Ensemble) else 1
-    # seeds = rand(rng, UInt, nchains): drawn for ALL chains so results do not depend on the sharding
-    seeds = rng.integers(0, 2 ** 64, size=nchains, dtype=np.uint64)
-    init = _initial_matrix(initial_params, sampler, dim, nchains, multi)
-
     rank, world, dist = (0, 1, None)
     if isinstance(parallel, MCMCB200):
         rank, world, dist = _dist_info()
+    if rng is None:
+        if seed is None and world > 1:
+            # every rank must key the SAME global seed vector: rank 0 draws the master seed, everybody gets it
+            box = [int(np.random.SeedSequence().entropy) if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            seed = box[0]
+        rng = np.random.default_rng(seed)
+    nw = sampler.n_walkers if isinstance(sampler, Ensemble) else 1
     lo, hi = shard_bounds(nchains, rank, world)
+    # seeds = rand(rng, UInt, nchains) with chain c <- draw number c, so results do not depend on the sharding;
+    # only this rank's block [lo, hi) is materialised
+    seeds = _draw_seeds(rng, nchains, lo, hi)
+    init = _initial_matrix(initial_params, sampler, dim, nchains, multi)
     eng = engine or default_engine(parallel.device if isinstance(parallel, MCMCB200) else None)
 
     n_local = (hi - lo) * nw
@@ -244,7 +321,7 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
         for k, e in enumerate(engs):
             a, b = shard_bounds(hi - lo, k, nstreams)
             ca, cb = (lo + a) * nw, (lo + b) * nw                      # global chain (walker) range of the shard
-            futs.append(_POOL.submit(_sample_block, e, target, sampler, dim, cb - ca, seeds[lo + a:lo + b],
+            futs.append(_POOL.submit(_sample_block, e, target, sampler, dim, cb - ca, seeds[a:b],
                                      None if init is None else init[:, ca:cb], ca, N, discard_initial, thinning, num_warmup,
                                      vals[:, :, ca - lo * nw:cb - lo * nw], accs[:, ca - lo * nw:cb - lo * nw]))
         launches = sum(f.result() for f in futs)
@@ -261,29 +338,38 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
             sl = slice(lo * nw, hi * nw)
             if initial_state is not None:
                 if "seeds" in initial_state:
-                    seeds = np.asarray(initial_state["seeds"], dtype=np.uint64)
-                    if seeds.shape != (nchains,):
+                    allseeds = np.asarray(initial_state["seeds"], dtype=np.uint64)
+                    if allseeds.shape != (nchains,):
                         raise ValueError("initial_state was saved for a different number of chains")
+                    seeds = allseeds[lo:hi]
                 init = np.asarray(initial_state["x"], dtype=np.float64)
                 if init.shape != (dim, nchains * nw):
                     raise ValueError(f"initial_state['x'] must have shape {(dim, nchains * nw)}")
-            run = eng.run(th, sh, n_local, seeds[lo:hi], None if init is None else init[:, sl], chain_offset=lo * nw)
+            run = eng.run(th, sh, n_local, seeds, None if init is None else init[:, sl], chain_offset=lo * nw)
             if initial_state is not None:
                 run.set_state({k: (v if k == "step" or v is None else np.asarray(v)[..., sl])
                                for k, v in initial_state.items() if k != "seeds"})
                 run.steps(1, warmup=run.state_step() < num_warmup)
-            out, acc, summ = run.sample(N, discard_initial, thinning, num_warmup, store=store,
-                                        store_accepted=store, summary=summary or not store, chain_means=False,
-                                        out=None if out is None else out[0], acc=None if out is None else out[1])
+            if callback is not None and store:
+                vals = np.empty((N, dim + 1, n_local)) if out is None else out[0]
+                accs = np.empty((N, n_local), dtype=np.uint8) if out is None else out[1]
+                out, acc = _sample_with_callback(run, sampler, rng, model, N, discard_initial, thinning, num_warmup,
+                                                 callback, dim, vals, accs)
+                summ = None
+            else:
+                out, acc, summ = run.sample(N, discard_initial, thinning, num_warmup, store=store,
+                                            store_accepted=store, summary=summary or not store, chain_means=False,
+                                            out=None if out is None else out[0], acc=None if out is None else out[1])
+            if isinstance(sampler, RobustAdaptiveMetropolis):
+                nfail, first, _ = run.ram_failed()
+                if nfail and not getattr(parallel, "ignore_failed_downdates", False):
+                    raise K.PosDefException(first, nfail)        # lowrankdowndate throws (RAM :170)
             info = dict(summary=summ, launches=run.launch_count(), rank=rank, world=world,
                         chains=(lo * nw, hi * nw))
             if save_state:
                 stt = run.state(grad=isinstance(sampler, MALA), S=isinstance(sampler, RobustAdaptiveMetropolis))
                 stt["seeds"] = seeds
                 info["state"] = stt
-            if callback is not None and store:
-                for i in range(N):
-                    callback(rng, model, sampler, out[i], None, i + 1)
         else:
             out = np.empty((N, dim + 1, 0)) if store else None
             acc = np.empty((N, 0), dtype=np.uint8) if store else None
@@ -303,7 +389,7 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
         parts = [None] * world
         dist.all_gather_object(parts, info.get("state"))
         parts = [p for p in parts if p is not None]
-        info["state"] = {k: (parts[0][k] if k in ("step", "seeds") else
+        info["state"] = {k: (parts[0][k] if k == "step" else
                              None if parts[0][k] is None else np.concatenate([p[k] for p in parts], axis=-1))
                          for k in parts[0]}
 

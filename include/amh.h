@@ -223,6 +223,16 @@ int32_t amh_run_set_state(amh_run* run, const double* x, const double* lp, const
 /* RAM: the state fields that only report the last step -- log acceptance ratio `log-alpha` and adaptation step size
  * `eta` (RAM :107-110), [nchains_local] each, either may be NULL (StatesExtractor, test/RobustAdaptiveMetropolis.jl:11-28) */
 int32_t amh_run_get_ram_adapt(amh_run* run, double* logalpha, double* eta);
+/* resume of a RAM run: installs the report-only fields read with amh_run_get_ram_adapt / amh_run_ram_failed, so that a
+ * resumed run reports the same `log-alpha` / `eta` as the uninterrupted one (RobustAdaptiveMetropolisState RAM :99-114).
+ * [nchains_local] each, any may be NULL. */
+int32_t amh_run_set_ram_adapt(amh_run* run, const double* logalpha, const double* eta, const uint8_t* failed);
+/* RAM: chains whose rank-1 downdate left the positive-definite cone.  In the reference `lowrankdowndate` throws
+ * `PosDefException` (RAM :170, SURVEY.md A.4: (v_i / A_ii)^2 > 1) and the whole `sample` call aborts; a lock-step
+ * kernel cannot throw, so the chain keeps its last good factor, stops nothing else, and raises a sticky per-chain flag.
+ * nfailed: number of flagged local chains; first_chain: GLOBAL index of the first one or -1; failed: [nchains_local]
+ * flags (any may be NULL).  The host layer turns nfailed > 0 into the reference's exception after the run. */
+int32_t amh_run_ram_failed(amh_run* run, int64_t* nfailed, int64_t* first_chain, uint8_t* failed);
 
 /* page-locked host memory for initial_params / sample buffers: host<->device copies of pinned buffers run at
  * full PCIe/C2C speed and asynchronously (Julia: unsafe_wrap(Array, Ptr{Float64}(p), dims)) */

@@ -28,6 +28,9 @@
  * Build: see oracle/Makefile  (g++ -O2 -ffp-contract=off, never -ffast-math).
  */
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <spawn.h>
+#include <sys/wait.h>
 #include <unistd.h>
 #include <cstdint>
 #include <cstdio>
@@ -42,6 +45,8 @@
 
 #include "../include/amh_contract.h"
 #include "../include/amh.h"
+
+extern char** environ;
 
 namespace {
 
@@ -67,7 +72,10 @@ struct Target {
     std::string user_so;
     ~Target() {
         if (user_lib) dlclose(user_lib);
-        if (!user_so.empty()) std::remove(user_so.c_str());
+        if (!user_so.empty()) {
+            std::remove(user_so.c_str());
+            rmdir(user_so.substr(0, user_so.rfind('/')).c_str());     /* its private mkdtemp directory */
+        }
     }
 
     /* Normal(mu, sigma) log-density of y: Distributions' normlogpdf
@@ -716,13 +724,19 @@ int do_steps(Run& r, int64_t nsteps, bool warmup) {
     return AMH_OK;
 }
 
+/* Welford running mean (r.sum) and M2 (r.sumsq) per (coordinate, chain) over the saved samples */
 void accumulate(Run& r) {
     const int64_t n = r.n;
+    const double inv_n = 1.0 / (double)(r.nsaved + 1);
     for (int i = 0; i < r.dim; ++i)
         for (int64_t c = 0; c < n; ++c) {
-            const double v = r.X[(int64_t)i * n + c];
-            r.sum[(int64_t)i * n + c] += v;
-            r.sumsq[(int64_t)i * n + c] = fma(v, v, r.sumsq[(int64_t)i * n + c]);
+            const int64_t o = (int64_t)i * n + c;
+            const double v = r.X[o];
+            const double m = r.sum[o];
+            const double dl = v - m;
+            const double m1 = fma(dl, inv_n, m);
+            r.sum[o] = m1;
+            r.sumsq[o] = fma(dl, v - m1, r.sumsq[o]);
         }
     r.nsaved += 1;
 }
@@ -796,23 +810,41 @@ int32_t amho_target_create_source(amh_ctx*, int32_t dim, const char* source, int
         const size_t k = p.rfind('/');
         incdir = (k == std::string::npos ? std::string(".") : p.substr(0, k)) + "/../include";
     }
+    /* a PRIVATE scratch directory (mkdtemp: mode 0700, unpredictable name) holds source, log and shared object, and the
+     * compiler is spawned without a shell, so neither a symlink race in /tmp nor AMHO_CXX can redirect what is loaded */
     char tmpl[] = "/tmp/amho_user_XXXXXX";
-    const int fd = mkstemp(tmpl);
-    if (fd < 0) return fail(AMH_ERR_STATE, "mkstemp failed");
-    close(fd);
-    const std::string base(tmpl), cpp = base + ".cpp", so = base + ".so", log = base + ".log";
+    if (!mkdtemp(tmpl)) return fail(AMH_ERR_STATE, "mkdtemp failed");
+    const std::string dir(tmpl), cpp = dir + "/target.cpp", so = dir + "/target.so", log = dir + "/build.log";
+    auto cleanup = [&](bool keep_so) {
+        std::remove(cpp.c_str()); std::remove(log.c_str());
+        if (!keep_so) { std::remove(so.c_str()); rmdir(dir.c_str()); }
+    };
     {
-        FILE* f = fopen(cpp.c_str(), "w");
-        if (!f) return fail(AMH_ERR_STATE, "cannot write the scratch source file");
+        FILE* f = fopen(cpp.c_str(), "wx");
+        if (!f) { cleanup(false); return fail(AMH_ERR_STATE, "cannot write the scratch source file"); }
         fputs("#include \"amh_user_target.h\"\n#line 1 \"amh_user_target.cu\"\n", f);
         fputs(source, f);
         fputs("\n", f);
         fclose(f);
     }
-    const char* cxx = getenv("AMHO_CXX");
-    const std::string cmd = std::string(cxx ? cxx : "g++") + " -O2 -std=c++17 -fPIC -shared -ffp-contract=off -fno-fast-math -mfma -I'" +
-                            incdir + "' -o '" + so + "' '" + cpp + "' > '" + log + "' 2>&1";
-    const int rc = system(cmd.c_str());
+    const char* cxx_env = getenv("AMHO_CXX");
+    const std::string cxx = cxx_env ? cxx_env : "g++", inc = "-I" + incdir;
+    int rc = -1;
+    {
+        const int lfd = open(log.c_str(), O_WRONLY | O_CREAT | O_EXCL, 0600);
+        posix_spawn_file_actions_t fa;
+        posix_spawn_file_actions_init(&fa);
+        if (lfd >= 0) { posix_spawn_file_actions_adddup2(&fa, lfd, 1); posix_spawn_file_actions_adddup2(&fa, lfd, 2); }
+        const char* argv[] = {cxx.c_str(), "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-mfma",
+                              inc.c_str(), "-o", so.c_str(), cpp.c_str(), nullptr};
+        pid_t pid = 0;
+        if (posix_spawnp(&pid, cxx.c_str(), &fa, nullptr, (char* const*)argv, environ) == 0) {
+            int status = 0;
+            if (waitpid(pid, &status, 0) == pid && WIFEXITED(status)) rc = WEXITSTATUS(status);
+        }
+        posix_spawn_file_actions_destroy(&fa);
+        if (lfd >= 0) close(lfd);
+    }
     std::string logtxt;
     if (FILE* f = fopen(log.c_str(), "r")) {
         char buf[4096];
@@ -820,8 +852,8 @@ int32_t amho_target_create_source(amh_ctx*, int32_t dim, const char* source, int
         while ((n = fread(buf, 1, sizeof(buf), f)) > 0) logtxt.append(buf, n);
         fclose(f);
     }
-    std::remove(cpp.c_str()); std::remove(log.c_str()); std::remove(base.c_str());
-    if (rc != 0) { std::remove(so.c_str()); return fail(AMH_ERR_INVALID, "the target source does not compile:\n" + logtxt); }
+    cleanup(rc == 0);
+    if (rc != 0) return fail(AMH_ERR_INVALID, "the target source does not compile:\n" + logtxt);
     Target* t = new Target();
     t->kind = AMH_TARGET_USER; t->dim = dim; t->ndata = ndata; t->user_so = so;
     if (ndata > 0) t->blob.assign(data, data + ndata);
@@ -1052,16 +1084,20 @@ int32_t amho_run_sample_ld(amh_run* run, int64_t N, int64_t discard_initial, int
         for (int64_t c = 0; c < n; ++c) na += (double)r.nacc[c];
         summary->accept_rate = r.step > 0 ? na / ((double)n * (double)r.step) : 0.0;
         for (int i = 0; i < d; ++i) {
-            double s1 = 0, s2 = 0;
+            double s1 = 0;
             for (int64_t c = 0; c < n; ++c) {
                 s1 += r.sum[(int64_t)i * n + c];
-                s2 += r.sumsq[(int64_t)i * n + c];
-                if (summary->chain_mean) summary->chain_mean[(int64_t)i * n + c] = r.sum[(int64_t)i * n + c] / (double)r.nsaved;
+                if (summary->chain_mean) summary->chain_mean[(int64_t)i * n + c] = r.sum[(int64_t)i * n + c];
             }
-            const double tot = (double)n * (double)r.nsaved;
-            const double m = s1 / tot;
+            const double m = s1 / (double)n;
+            double m2 = 0, dev = 0;
+            for (int64_t c = 0; c < n; ++c) {
+                const double dl = r.sum[(int64_t)i * n + c] - m;
+                m2 += r.sumsq[(int64_t)i * n + c];
+                dev = fma(dl, dl, dev);
+            }
             if (summary->mean) summary->mean[i] = m;
-            if (summary->var) summary->var[i] = s2 / tot - m * m;
+            if (summary->var) summary->var[i] = (m2 + (double)r.nsaved * dev) / ((double)n * (double)r.nsaved);
         }
     }
     return AMH_OK;
@@ -1118,6 +1154,29 @@ int32_t amho_run_get_ram_adapt(amh_run* run, double* logalpha, double* eta) {
     if (r.s->d.kind != AMH_SAMPLER_RAM) return fail(AMH_ERR_INVALID, "not a RobustAdaptiveMetropolis run");
     if (logalpha) std::memcpy(logalpha, r.logalpha.data(), sizeof(double) * r.logalpha.size());
     if (eta) std::memcpy(eta, r.eta.data(), sizeof(double) * r.eta.size());
+    return AMH_OK;
+}
+
+int32_t amho_run_set_ram_adapt(amh_run* run, const double* logalpha, const double* eta, const uint8_t* failed) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    Run& r = *(Run*)run;
+    if (r.s->d.kind != AMH_SAMPLER_RAM) return fail(AMH_ERR_INVALID, "not a RobustAdaptiveMetropolis run");
+    if (logalpha) std::memcpy(r.logalpha.data(), logalpha, sizeof(double) * r.logalpha.size());
+    if (eta) std::memcpy(r.eta.data(), eta, sizeof(double) * r.eta.size());
+    if (failed) std::memcpy(r.failed.data(), failed, r.failed.size());
+    return AMH_OK;
+}
+
+int32_t amho_run_ram_failed(amh_run* run, int64_t* nfailed, int64_t* first_chain, uint8_t* failed) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    Run& r = *(Run*)run;
+    if (r.s->d.kind != AMH_SAMPLER_RAM) return fail(AMH_ERR_INVALID, "not a RobustAdaptiveMetropolis run");
+    int64_t nf = 0, first = -1;
+    for (int64_t c = 0; c < r.n; ++c)
+        if (r.failed[c]) { if (first < 0) first = c; ++nf; }
+    if (nfailed) *nfailed = nf;
+    if (first_chain) *first_chain = first < 0 ? -1 : r.off + first;
+    if (failed) std::memcpy(failed, r.failed.data(), r.failed.size());
     return AMH_OK;
 }
 

@@ -1,0 +1,81 @@
+#!/usr/bin/env python3
+"""Small invocations of every hand-synchronised kernel, for `compute-sanitizer --tool racecheck|memcheck|synccheck`
+(sanitizers).  Each case is bit-compared with the oracle afterwards, so a sanitizer run is also a
+parity run.  Usage: python tools/sanitize_cases.py <case> ; cases:
+  c2     K1T16  RWMH d=32 full covariance                       (DMMA tiles in shared memory)
+  c3     K2F    stretch, 1-CTA sweep (AMH_STRETCH_CLUSTER=0)    (version flags in shared memory)
+  c3cl   K2F    stretch, 2-CTA cluster sweep                    (DSMEM mirrored flags)
+  c4     K3L    MALA logistic d=32, 200 rows                    (TMA producer warp + 10-stage mbarrier ring, wraps)
+  c5     K4W    RAM warm-up d=32                                (bulk load / store of the factor, roll-back)
+  c5redo K4W    same with the IEEE redo path forced on every step
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def spd(d, seed, lo, hi):
+    rng = np.random.default_rng(seed)
+    Q, _ = np.linalg.qr(rng.normal(size=(d, d)))
+    lam = np.exp(np.linspace(np.log(lo), np.log(hi), d))
+    S = (Q * lam) @ Q.T
+    return (S + S.T) / 2
+
+
+def main():
+    case = sys.argv[1]
+    if case == "c3":
+        os.environ["AMH_STRETCH_CLUSTER"] = "0"
+    if case == "c3cl":
+        os.environ["AMH_STRETCH_CLUSTER"] = "1"
+    if case == "c5redo":
+        os.environ["AMH_RAMW_FORCE_REDO"] = "1"
+    import amh_b200 as amh
+    gpu = amh.default_engine(0)
+    orc = amh.Engine(lib_path=os.path.join(ROOT, "oracle", "libamh_oracle.so"), prefix="amho_")
+    seeds = lambda n, s: np.random.default_rng(s).integers(0, 2 ** 64, size=n, dtype=np.uint64)
+    warm, nsteps, spl, init, keys = False, 8, 4, None, ["x", "lp", "accepted", "naccept"]
+    if case == "c2":
+        d, n = 32, 1024
+        Sg = spd(d, 32, 1.0, 100.0)
+        t, s, sd = amh.MvNormalTarget(None, Sg), amh.RWMH(amh.MvNormal(np.zeros(d), (2.38 ** 2 / d) * Sg)), seeds(n, 1)
+    elif case in ("c3", "c3cl"):
+        d, nw, ne = 10, 1024, 2
+        t = amh.RosenbrockTarget(d)
+        s = amh.Ensemble(nw, amh.StretchProposal(amh.MvNormal(np.zeros(d), amh.I)))
+        n, sd = nw * ne, seeds(ne, 2)
+    elif case == "c4":
+        d, rows, n = 32, 200, 64
+        rng = np.random.default_rng(5)
+        X = rng.normal(size=(rows, d)) / np.sqrt(d)
+        y = (rng.random(rows) < 0.5).astype(float)
+        t = amh.LogisticRegressionTarget(X, y, tau=10.0)
+        s = amh.MALA(lambda g: amh.MvNormal((0.05 / 2) * g, 0.05 * amh.I))
+        sd, init, nsteps, spl = seeds(n, 3), np.zeros((d, n)), 4, 2
+        keys = keys + ["grad"]
+    elif case in ("c5", "c5redo"):
+        d, n = 32, 256
+        Sg = spd(d, 64, 1e-2, 1.0)
+        t = amh.MvNormalTarget(None, Sg)
+        s = amh.RobustAdaptiveMetropolis(S=(2.38 / np.sqrt(d)) * np.linalg.cholesky(Sg))
+        sd, init, warm = seeds(n, 4), np.zeros((d, n)), True
+        keys = keys + ["S"]
+    else:
+        raise SystemExit(__doc__)
+    res = []
+    for eng in (gpu, orc):
+        run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), n, sd, init)
+        run.steps(nsteps, warmup=warm, steps_per_launch=spl)
+        res.append(run.state(grad="grad" in keys, S="S" in keys))
+        run.close()
+    for k in keys:
+        assert np.array_equal(res[0][k], res[1][k]), f"{case}: GPU and oracle differ in {k}"
+    print(f"{case}: ok, GPU == oracle bit for bit ({n} chains x {nsteps} steps)")
+
+
+if __name__ == "__main__":
+    main()
