@@ -88,12 +88,45 @@ ABI_SYMBOLS = [
     "target_create", "target_create_source", "target_destroy", "sampler_create", "sampler_destroy",
     "run_create", "run_destroy", "run_steps", "run_sync", "run_sample", "run_sample_ld",
     "run_get_state", "run_set_params", "run_set_state", "run_get_ram_adapt", "run_set_ram_adapt", "run_ram_failed", "run_dim", "run_nchains", "run_launch_count",
-    "run_kernel_time_ms", "host_alloc", "host_free",
+    "run_kernel_time_ms", "host_alloc", "host_free", "run_get_state_ld", "run_set_state_ld",
+    "job_create", "job_destroy", "job_ngpus", "job_target_create", "job_target_create_source", "job_broadcast_mode",
+    "job_broadcast_ms", "job_comm_init_ms", "job_sampler_create", "job_run_create", "job_run_destroy", "job_run_steps",
+    "job_run_sync", "job_run_sample", "job_run_get_state", "job_run_set_state", "job_run_get_ram_adapt",
+    "job_run_set_ram_adapt", "job_run_ram_failed", "job_run_shard", "job_run_launch_count", "job_run_kernel_time_ms",
 ]
 
 
 def _as_f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def sampler_desc(*, kind, dim, symmetric=False, cov_kind=COV_SCALAR, mean=None, scale=None,
+                 stretch_a=2.0, n_walkers=0, mala_sigma2=0.0, mala_drift=0.0,
+                 ram_alpha=0.234, ram_gamma=0.6, ram_eig_lo=0.0, ram_eig_hi=float("inf"), ram_S0=None,
+                 components=None):
+    """-> (amh_sampler_desc, objects that must stay alive while it is used).
+    components: list of (family, p0, p1, logc[, rw, symmetric]) -- one univariate law per coordinate"""
+    keep = []
+    def ptr(a):
+        if a is None:
+            return None
+        a = _as_f64(a).ravel()
+        keep.append(a)
+        return a.ctypes.data_as(_dp)
+    d = SamplerDesc(kind, dim, int(bool(symmetric)), cov_kind, ptr(mean), ptr(scale), float(stretch_a),
+                    int(n_walkers), float(mala_sigma2), float(mala_drift), float(ram_alpha), float(ram_gamma),
+                    float(ram_eig_lo), float(ram_eig_hi), ptr(ram_S0), None)
+    if components is not None:
+        if len(components) != dim:
+            raise AMHArgumentError(AMH_ERR_INVALID, f"need one component per coordinate ({dim}), got {len(components)}")
+        arr = (Component * dim)()
+        for i, c in enumerate(components):
+            fam, p0, p1, logc = c[:4]
+            rw, sym = (c[4], c[5]) if len(c) >= 6 else (0, 0)
+            arr[i] = Component(int(fam), int(bool(rw)), int(bool(sym)), 0, float(p0), float(p1), float(logc))
+        keep.append(arr)
+        d.components = C.cast(arr, C.POINTER(Component))
+    return d, keep
 
 
 class Engine:
@@ -147,6 +180,30 @@ class Engine:
         f("run_kernel_time_ms").argtypes = [C.c_void_p, C.c_int32, _dp, _i64p]
         f("host_alloc").argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
         f("host_free").argtypes = [C.c_void_p]
+        f("run_get_state_ld").argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, _u8p, _i64p, _i64p]
+        f("run_set_state_ld").argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, _u8p, _i64p, C.c_int64]
+        # multi-GPU job
+        f("job_create").argtypes = [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]
+        for n in ("job_destroy", "job_ngpus", "job_run_destroy", "job_run_sync", "job_run_launch_count", "job_broadcast_mode",
+                  "job_broadcast_ms", "job_comm_init_ms"):
+            f(n).argtypes = [C.c_void_p]
+        f("job_broadcast_mode").restype = C.c_char_p
+        f("job_broadcast_ms").restype = C.c_double
+        f("job_comm_init_ms").restype = C.c_double
+        f("job_run_launch_count").restype = C.c_int64
+        f("job_target_create").argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, C.c_int64]
+        f("job_target_create_source").argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, _dp, C.c_int64]
+        f("job_sampler_create").argtypes = [C.c_void_p, C.POINTER(SamplerDesc)]
+        f("job_run_create").argtypes = [C.c_void_p, C.c_int64, _u64p, _dp, C.c_int64]
+        f("job_run_steps").argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32]
+        f("job_run_sample").argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _dp, _u8p, C.POINTER(Summary)]
+        f("job_run_get_state").argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _u8p, _i64p, _i64p]
+        f("job_run_set_state").argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _u8p, _i64p, C.c_int64]
+        f("job_run_get_ram_adapt").argtypes = [C.c_void_p, _dp, _dp]
+        f("job_run_set_ram_adapt").argtypes = [C.c_void_p, _dp, _dp, _u8p]
+        f("job_run_ram_failed").argtypes = [C.c_void_p, _i64p, _i64p, _u8p]
+        f("job_run_shard").argtypes = [C.c_void_p, C.c_int32, _i64p, _i64p, C.POINTER(C.c_int32)]
+        f("job_run_kernel_time_ms").argtypes = [C.c_void_p, C.c_int32, _dp, _i64p]
 
     def _check(self, rc):
         if rc == AMH_OK:
@@ -208,34 +265,16 @@ class Engine:
             return self.target_source(t.dim, t.source, t.data, t.has_gradient)
         return self.target(t.kind, t.dim, t.blob())
 
-    def sampler(self, *, kind, dim, symmetric=False, cov_kind=COV_SCALAR, mean=None, scale=None,
-                stretch_a=2.0, n_walkers=0, mala_sigma2=0.0, mala_drift=0.0,
-                ram_alpha=0.234, ram_gamma=0.6, ram_eig_lo=0.0, ram_eig_hi=float("inf"), ram_S0=None,
-                components=None) -> "SamplerHandle":
-        """components: list of (family, p0, p1, logc[, rw, symmetric]) -- one univariate law per coordinate"""
-        keep = []
-        def ptr(a):
-            if a is None:
-                return None
-            a = _as_f64(a).ravel()
-            keep.append(a)
-            return a.ctypes.data_as(_dp)
-        d = SamplerDesc(kind, dim, int(bool(symmetric)), cov_kind, ptr(mean), ptr(scale), float(stretch_a),
-                        int(n_walkers), float(mala_sigma2), float(mala_drift), float(ram_alpha), float(ram_gamma),
-                        float(ram_eig_lo), float(ram_eig_hi), ptr(ram_S0), None)
-        if components is not None:
-            if len(components) != dim:
-                raise AMHArgumentError(AMH_ERR_INVALID, f"need one component per coordinate ({dim}), got {len(components)}")
-            arr = (Component * dim)()
-            for i, c in enumerate(components):
-                fam, p0, p1, logc = c[:4]
-                rw, sym = (c[4], c[5]) if len(c) >= 6 else (0, 0)
-                arr[i] = Component(int(fam), int(bool(rw)), int(bool(sym)), 0, float(p0), float(p1), float(logc))
-            keep.append(arr)
-            d.components = C.cast(arr, C.POINTER(Component))
+    def sampler(self, **kw) -> "SamplerHandle":
+        """keywords: see `sampler_desc`"""
+        d, keep = sampler_desc(**kw)
         h = C.c_void_p()
         self._check(self._f("sampler_create")(self.ctx, C.byref(d), C.byref(h)))
-        return SamplerHandle(self, h, kind, dim, int(n_walkers))
+        return SamplerHandle(self, h, d.kind, d.dim, int(d.n_walkers))
+
+    def job(self, ngpus: int, devices=None) -> "Job":
+        """amh_job_create: `ngpus` devices of this box behind one handle, in this process (MCMCB200(ngpus=k))"""
+        return Job(self, ngpus, devices)
 
     def run(self, target: "TargetHandle", sampler: "SamplerHandle", nchains: int, seeds, init=None,
             chain_offset: int = 0) -> "Run":
@@ -286,15 +325,20 @@ class SamplerHandle:
 
 
 class Run:
+    _p = "run_"            # entry-point family: amh_run_* (one device) or amh_job_run_* (JobRun)
+
     def __init__(self, eng, h, target, sampler, n):
         self.eng, self.h, self.target, self.sampler, self.n = eng, h, target, sampler, n
         self.dim = target.dim
 
+    def _r(self, name):
+        return self.eng._f(self._p + name)
+
     def steps(self, nsteps: int, warmup: bool = False, steps_per_launch: int = 0):
-        self.eng._check(self.eng._f("run_steps")(self.h, nsteps, int(warmup), steps_per_launch))
+        self.eng._check(self._r("steps")(self.h, nsteps, int(warmup), steps_per_launch))
 
     def sync(self):
-        self.eng._check(self.eng._f("run_sync")(self.h))
+        self.eng._check(self._r("sync")(self.h))
 
     def sample(self, N, discard_initial=0, thinning=1, num_warmup=0, store=True, store_accepted=True,
                summary=True, chain_means=False, out=None, acc=None):
@@ -325,15 +369,17 @@ class Run:
             cm = np.zeros((d, n)) if chain_means else None
             s = Summary(0, 0, 0.0, mean.ctypes.data_as(_dp), var.ctypes.data_as(_dp),
                         cm.ctypes.data_as(_dp) if cm is not None else None)
-        self.eng._check(self.eng._f("run_sample_ld")(
-            self.h, N, discard_initial, thinning, num_warmup,
-            C.cast(out.ctypes.data, _dp) if out is not None else None, out_ld,
-            C.cast(acc.ctypes.data, _u8p) if acc is not None else None, acc_ld,
-            C.byref(s) if s is not None else None))
+        self._sample_call(N, discard_initial, thinning, num_warmup,
+                          C.cast(out.ctypes.data, _dp) if out is not None else None, out_ld,
+                          C.cast(acc.ctypes.data, _u8p) if acc is not None else None, acc_ld,
+                          C.byref(s) if s is not None else None)
         if s is not None:
             summ = dict(n_saved=s.n_saved, n_steps=s.n_steps, accept_rate=s.accept_rate, mean=mean, var=var,
                         chain_mean=cm)
         return out, acc, summ
+
+    def _sample_call(self, N, discard_initial, thinning, num_warmup, out_p, out_ld, acc_p, acc_ld, summ_p):
+        self.eng._check(self._r("sample_ld")(self.h, N, discard_initial, thinning, num_warmup, out_p, out_ld, acc_p, acc_ld, summ_p))
 
     def state(self, grad=False, S=False):
         d, n = self.dim, self.n
@@ -342,7 +388,7 @@ class Run:
         Sm = np.empty((d * (d + 1) // 2, n)) if S else None
         acc = np.empty(n, dtype=np.uint8); nacc = np.empty(n, dtype=np.int64)
         step = C.c_int64()
-        self.eng._check(self.eng._f("run_get_state")(
+        self.eng._check(self._r("get_state")(
             self.h, x.ctypes.data_as(_dp), lp.ctypes.data_as(_dp),
             g.ctypes.data_as(_dp) if g is not None else None,
             Sm.ctypes.data_as(_dp) if Sm is not None else None,
@@ -356,13 +402,13 @@ class Run:
 
     def state_step(self):
         step = C.c_int64()
-        self.eng._check(self.eng._f("run_get_state")(self.h, None, None, None, None, None, None, C.byref(step)))
+        self.eng._check(self._r("get_state")(self.h, None, None, None, None, None, None, C.byref(step)))
         return step.value
 
     def set_params(self, x):
         x = _as_f64(x)
         assert x.shape == (self.dim, self.n)
-        self.eng._check(self.eng._f("run_set_params")(self.h, x.ctypes.data_as(_dp)))
+        self.eng._check(self._r("set_params")(self.h, x.ctypes.data_as(_dp)))
 
     def set_state(self, state):
         """resume from a dict returned by `state()` (AbstractMCMC's `initial_state`); missing / None entries keep
@@ -380,10 +426,10 @@ class Run:
             return a.ctypes.data_as(ptr)
         step = state.get("step")
         if self.sampler.kind == SAMPLER_RAM and any(state.get(k) is not None for k in ("logalpha", "eta", "failed")):
-            self.eng._check(self.eng._f("run_set_ram_adapt")(
+            self.eng._check(self._r("set_ram_adapt")(
                 self.h, arr("logalpha", (n,), np.float64, _dp), arr("eta", (n,), np.float64, _dp),
                 arr("failed", (n,), np.uint8, _u8p)))
-        self.eng._check(self.eng._f("run_set_state")(
+        self.eng._check(self._r("set_state")(
             self.h, arr("x", (d, n), np.float64, _dp), arr("lp", (n,), np.float64, _dp),
             arr("grad", (d, n), np.float64, _dp), arr("S", (d * (d + 1) // 2, n), np.float64, _dp),
             arr("accepted", (n,), np.uint8, _u8p), arr("naccept", (n,), np.int64, _i64p),
@@ -392,25 +438,137 @@ class Run:
     def ram_adapt(self):
         """(log-alpha, eta) of the last step of every chain -- RobustAdaptiveMetropolisState fields (RAM :107-110)"""
         la = np.empty(self.n); eta = np.empty(self.n)
-        self.eng._check(self.eng._f("run_get_ram_adapt")(self.h, la.ctypes.data_as(_dp), eta.ctypes.data_as(_dp)))
+        self.eng._check(self._r("get_ram_adapt")(self.h, la.ctypes.data_as(_dp), eta.ctypes.data_as(_dp)))
         return la, eta
 
     def ram_failed(self):
         """(count, first global chain or -1, flags[n]) of chains whose rank-1 downdate failed (amh_run_ram_failed)"""
         nf, first = C.c_int64(), C.c_int64()
         flags = np.empty(self.n, dtype=np.uint8)
-        self.eng._check(self.eng._f("run_ram_failed")(self.h, C.byref(nf), C.byref(first), flags.ctypes.data_as(_u8p)))
+        self.eng._check(self._r("ram_failed")(self.h, C.byref(nf), C.byref(first), flags.ctypes.data_as(_u8p)))
         return int(nf.value), int(first.value), flags
 
     def launch_count(self):
-        return int(self.eng._f("run_launch_count")(self.h))
+        return int(self._r("launch_count")(self.h))
 
     def kernel_time_ms(self, reset=False):
         ms = C.c_double(); nl = C.c_int64()
-        self.eng._check(self.eng._f("run_kernel_time_ms")(self.h, int(reset), C.byref(ms), C.byref(nl)))
+        self.eng._check(self._r("kernel_time_ms")(self.h, int(reset), C.byref(ms), C.byref(nl)))
         return ms.value, nl.value
 
     def close(self):
         if self.h:
-            self.eng._f("run_destroy")(self.h)
+            self._r("destroy")(self.h)
+            self.h = None
+
+
+class _JobPart:
+    """what Job.target*/sampler return: the job owns the object, closing is a no-op"""
+    def __init__(self, kind, dim, n_walkers=0):
+        self.kind, self.dim, self.n_walkers = kind, dim, n_walkers
+    def close(self):
+        pass
+
+
+class Job:
+    """amh_job: `ngpus` devices of one box in ONE process (include/amh.h "multi-GPU job").  Same surface as Engine for the
+    host mirrors -- target / target_source / target_of / sampler / run -- but every array is job-wide and the library
+    shards the chains, broadcasts the target and writes each device's column block of the output in place."""
+
+    def __init__(self, eng: "Engine", ngpus: int, devices=None):
+        self.eng, self.ngpus = eng, int(ngpus)
+        devs = None
+        if devices is not None:
+            if len(devices) != ngpus:
+                raise AMHArgumentError(AMH_ERR_INVALID, "need one device index per GPU of the job")
+            devs = (C.c_int32 * ngpus)(*[int(v) for v in devices])
+        h = C.c_void_p()
+        eng._check(eng._f("job_create")(C.c_int32(ngpus), devs, C.byref(h)))
+        self.h = h
+        self._target = self._sampler = None
+        self._keep = None
+
+    # Engine look-alikes used by samplers.lower / sampling
+    _check = property(lambda self: self.eng._check)
+    _f = property(lambda self: self.eng._f)
+    pinned_empty = property(lambda self: self.eng.pinned_empty)
+
+    def target(self, kind, dim, blob):
+        blob = _as_f64(blob).ravel()
+        self.eng._check(self.eng._f("job_target_create")(self.h, kind, dim, blob.ctypes.data_as(_dp), blob.size))
+        self._target = _JobPart(kind, dim)
+        return self._target
+
+    def target_source(self, dim, source, data=None, has_gradient=False):
+        data = np.zeros(0) if data is None else _as_f64(data).ravel()
+        self.eng._check(self.eng._f("job_target_create_source")(self.h, dim, source.encode(), int(bool(has_gradient)),
+                                                                data.ctypes.data_as(_dp) if data.size else None, data.size))
+        self._target = _JobPart(TARGET_USER, dim)
+        return self._target
+
+    def target_of(self, t):
+        if getattr(t, "kind", None) == TARGET_USER:
+            return self.target_source(t.dim, t.source, t.data, t.has_gradient)
+        return self.target(t.kind, t.dim, t.blob())
+
+    def sampler(self, **kw):
+        d, keep = sampler_desc(**kw)
+        self.eng._check(self.eng._f("job_sampler_create")(self.h, C.byref(d)))
+        self._sampler = _JobPart(d.kind, d.dim, int(d.n_walkers))
+        return self._sampler
+
+    def broadcast_info(self):
+        """(mode, ms of the last target broadcast, ms of the one-time communicator set-up)"""
+        return ((self.eng._f("job_broadcast_mode")(self.h) or b"").decode(), float(self.eng._f("job_broadcast_ms")(self.h)),
+                float(self.eng._f("job_comm_init_ms")(self.h)))
+
+    def run(self, target, sampler, nchains, seeds, init=None, chain_offset=0) -> "JobRun":
+        """seeds / init are JOB-WIDE: one seed per chain (per ensemble for Ensemble), init (dim, nchains)"""
+        if chain_offset:
+            raise AMHArgumentError(AMH_ERR_INVALID, "a job holds all chains: chain_offset must be 0")
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64).ravel()
+        init_p, init_ld = None, 0
+        if init is not None:
+            init = np.asarray(init)
+            if init.shape != (target.dim, nchains):
+                raise AMHArgumentError(AMH_ERR_INVALID, f"init must have shape (dim, nchains) = {(target.dim, nchains)}, got {init.shape}")
+            ok = (init.dtype == np.float64 and init.strides[1] == 8 and init.strides[0] % 8 == 0 and init.strides[0] >= 8 * nchains)
+            if not ok:
+                init = _as_f64(init)
+            init_ld = init.strides[0] // 8
+            init_p = C.cast(init.ctypes.data, _dp)
+        self.eng._check(self.eng._f("job_run_create")(self.h, nchains, seeds.ctypes.data_as(_u64p), init_p, init_ld))
+        return JobRun(self, target, sampler, nchains)
+
+    def shards(self):
+        """[(lo, hi, device)] of the current run"""
+        out = []
+        for k in range(self.ngpus):
+            lo, hi, dev = C.c_int64(), C.c_int64(), C.c_int32()
+            self.eng._check(self.eng._f("job_run_shard")(self.h, k, C.byref(lo), C.byref(hi), C.byref(dev)))
+            out.append((lo.value, hi.value, dev.value))
+        return out
+
+    def close(self):
+        if self.h:
+            self.eng._f("job_destroy")(self.h)
+            self.h = None
+
+
+class JobRun(Run):
+    """the run of a Job: the Run surface over amh_job_run_*, all arrays job-wide"""
+    _p = "job_run_"
+
+    def __init__(self, job, target, sampler, n):
+        super().__init__(job.eng, job.h, target, sampler, n)
+        self.job = job
+
+    def _sample_call(self, N, discard_initial, thinning, num_warmup, out_p, out_ld, acc_p, acc_ld, summ_p):
+        if out_ld != self.n or acc_ld != self.n:
+            raise AMHArgumentError(AMH_ERR_INVALID, "a job writes the whole C-contiguous (N, dim+1, nchains) array")
+        self.eng._check(self._r("sample")(self.h, N, discard_initial, thinning, num_warmup, out_p, acc_p, summ_p))
+
+    def close(self):
+        if self.h:
+            self._r("destroy")(self.h)      # releases the run, the job handle stays
             self.h = None

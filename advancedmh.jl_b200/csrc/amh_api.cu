@@ -235,6 +235,13 @@ int32_t amh_ctx_sync(amh_ctx* c) {
 
 int32_t amh_target_create(amh_ctx* ctx, int32_t kind, int32_t dim, const double* blob, int64_t nblob,
                           amh_target** out) {
+    return amhh::target_create_impl(ctx, kind, dim, blob, nblob, out, true);
+}
+}  /* extern "C" */
+
+/* upload_data == false: device memory is allocated but left for a broadcast to fill (amh_job.cu) */
+int amhh::target_create_impl(amh_ctx* ctx, int32_t kind, int32_t dim, const double* blob, int64_t nblob,
+                             amh_target** out, bool upload_data) {
     if (!ctx || !out) return fail(AMH_ERR_INVALID, "ctx/out is NULL");
     if (dim < 1) return fail(AMH_ERR_INVALID, "dim must be >= 1");
     if (nblob < 0 || (nblob > 0 && !blob)) return fail(AMH_ERR_INVALID, "blob is NULL");
@@ -266,11 +273,16 @@ int32_t amh_target_create(amh_ctx* ctx, int32_t kind, int32_t dim, const double*
     t->ctx = ctx; t->kind = kind; t->dim = dim; t->ndata = ndata;
     t->inv2tau2 = inv2tau2; t->invtau2 = invtau2;
     t->blob.assign(blob, blob + nblob);
-    const int rc = upload(ctx, &t->dblob, t->blob);
+    const int rc = upload_data ? upload(ctx, &t->dblob, t->blob) : dmalloc(ctx, (void**)&t->dblob, sizeof(double) * (size_t)nblob);
     if (rc) { delete t; return rc; }
     *out = t;
     return AMH_OK;
 }
+int amhh::target_create_empty(amh_ctx* ctx, int32_t kind, int32_t dim, const double* blob, int64_t nblob, amh_target** out) {
+    return target_create_impl(ctx, kind, dim, blob, nblob, out, false);
+}
+
+extern "C" {
 int32_t amh_target_create_source(amh_ctx* ctx, int32_t dim, const char* source, int32_t has_gradient,
                                  const double* data, int64_t ndata, amh_target** out) {
     if (!ctx || !out) return fail(AMH_ERR_INVALID, "ctx/out is NULL");
@@ -670,16 +682,23 @@ int32_t amh_run_sample_ld(amh_run* run, int64_t N, int64_t discard_initial, int6
 int32_t amh_run_get_state(amh_run* run, double* x, double* lp, double* grad, double* S, uint8_t* accepted,
                           int64_t* naccept, int64_t* step_counter) {
     if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    return amh_run_get_state_ld(run, run->n, x, lp, grad, S, accepted, naccept, step_counter);
+}
+
+int32_t amh_run_get_state_ld(amh_run* run, int64_t ld, double* x, double* lp, double* grad, double* S, uint8_t* accepted,
+                             int64_t* naccept, int64_t* step_counter) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
     amh_run& r = *run;
     const long long n = r.n, np = r.pitch;
     const int d = r.dim;
+    if (ld < n) return fail(AMH_ERR_INVALID, "ld must be >= nchains_local");
     AMH_CUDA_TRY(cudaSetDevice(r.ctx->device));
     AMH_CUDA_TRY(cudaStreamSynchronize(r.ctx->stream));
-    if (x) AMH_CUDA_TRY(cudaMemcpy2D(x, sizeof(double) * n, r.X, sizeof(double) * np, sizeof(double) * n, d, cudaMemcpyDeviceToHost));
+    if (x) AMH_CUDA_TRY(cudaMemcpy2D(x, sizeof(double) * ld, r.X, sizeof(double) * np, sizeof(double) * n, d, cudaMemcpyDeviceToHost));
     if (lp) AMH_CUDA_TRY(cudaMemcpy(lp, r.lp, sizeof(double) * n, cudaMemcpyDeviceToHost));
     if (grad) {
         if (!r.G) return fail(AMH_ERR_INVALID, "sampler keeps no gradient");
-        AMH_CUDA_TRY(cudaMemcpy2D(grad, sizeof(double) * n, r.G, sizeof(double) * np, sizeof(double) * n, d, cudaMemcpyDeviceToHost));
+        AMH_CUDA_TRY(cudaMemcpy2D(grad, sizeof(double) * ld, r.G, sizeof(double) * np, sizeof(double) * n, d, cudaMemcpyDeviceToHost));
     }
     if (S) {
         if (!r.S) return fail(AMH_ERR_INVALID, "sampler keeps no Cholesky factor");
@@ -691,7 +710,7 @@ int32_t amh_run_get_state(amh_run* run, double* x, double* lp, double* grad, dou
         if (!rc) {
             cudaError_t e = cudaStreamSynchronize(r.ctx->stream);
             if (e == cudaSuccess)
-                e = cudaMemcpy2D(S, sizeof(double) * n, tmp, sizeof(double) * np, sizeof(double) * n, nt, cudaMemcpyDeviceToHost);
+                e = cudaMemcpy2D(S, sizeof(double) * ld, tmp, sizeof(double) * np, sizeof(double) * n, nt, cudaMemcpyDeviceToHost);
             if (e != cudaSuccess) rc = cuda_fail(e, "copy S");
         }
         dfree(r.ctx, tmp);
@@ -706,16 +725,23 @@ int32_t amh_run_get_state(amh_run* run, double* x, double* lp, double* grad, dou
 int32_t amh_run_set_state(amh_run* run, const double* x, const double* lp, const double* grad, const double* S,
                           const uint8_t* accepted, const int64_t* naccept, int64_t step_counter) {
     if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    return amh_run_set_state_ld(run, run->n, x, lp, grad, S, accepted, naccept, step_counter);
+}
+
+int32_t amh_run_set_state_ld(amh_run* run, int64_t ld, const double* x, const double* lp, const double* grad, const double* S,
+                             const uint8_t* accepted, const int64_t* naccept, int64_t step_counter) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
     amh_run& r = *run;
     const long long n = r.n, np = r.pitch;
     const int d = r.dim;
+    if (ld < n) return fail(AMH_ERR_INVALID, "ld must be >= nchains_local");
     if (grad && !r.G) return fail(AMH_ERR_INVALID, "sampler keeps no gradient");
     if (S && !r.S) return fail(AMH_ERR_INVALID, "sampler keeps no Cholesky factor");
     AMH_CUDA_TRY(cudaSetDevice(r.ctx->device));
     cudaStream_t st = r.ctx->stream;
-    if (x) AMH_CUDA_TRY(cudaMemcpy2DAsync(r.X, sizeof(double) * np, x, sizeof(double) * n, sizeof(double) * n, d, cudaMemcpyHostToDevice, st));
+    if (x) AMH_CUDA_TRY(cudaMemcpy2DAsync(r.X, sizeof(double) * np, x, sizeof(double) * ld, sizeof(double) * n, d, cudaMemcpyHostToDevice, st));
     if (lp) AMH_CUDA_TRY(cudaMemcpyAsync(r.lp, lp, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    if (grad) AMH_CUDA_TRY(cudaMemcpy2DAsync(r.G, sizeof(double) * np, grad, sizeof(double) * n, sizeof(double) * n, d, cudaMemcpyHostToDevice, st));
+    if (grad) AMH_CUDA_TRY(cudaMemcpy2DAsync(r.G, sizeof(double) * np, grad, sizeof(double) * ld, sizeof(double) * n, d, cudaMemcpyHostToDevice, st));
     if (accepted) AMH_CUDA_TRY(cudaMemcpyAsync(r.acc, accepted, (size_t)n, cudaMemcpyHostToDevice, st));
     if (naccept) AMH_CUDA_TRY(cudaMemcpyAsync(r.nacc, naccept, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
     int rc = AMH_OK;
@@ -724,7 +750,7 @@ int32_t amh_run_set_state(amh_run* run, const double* x, const double* lp, const
         double* tmp = nullptr;
         rc = dmalloc(r.ctx, (void**)&tmp, sizeof(double) * nt * np);
         if (rc) return rc;
-        cudaError_t e = cudaMemcpy2DAsync(tmp, sizeof(double) * np, S, sizeof(double) * n, sizeof(double) * n, nt, cudaMemcpyHostToDevice, st);
+        cudaError_t e = cudaMemcpy2DAsync(tmp, sizeof(double) * np, S, sizeof(double) * ld, sizeof(double) * n, nt, cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) rc = cuda_fail(e, "copy S");
         if (!rc) rc = r.ram_warp ? ramw_import_S(r, tmp) : ram_scatter_S(r, tmp);
         dfree(r.ctx, tmp);
@@ -805,7 +831,7 @@ int32_t amh_host_alloc(size_t bytes, void** out) {
     if (!out) return fail(AMH_ERR_INVALID, "out is NULL");
     *out = nullptr;
     if (bytes == 0) return AMH_OK;
-    AMH_CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    AMH_CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocPortable));     /* pinned for every device of a multi-GPU job */
     return AMH_OK;
 }
 int32_t amh_host_free(void* p) {

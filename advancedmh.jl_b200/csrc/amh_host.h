@@ -112,6 +112,8 @@ int cuda_fail(cudaError_t e, const char* what);
     } while (0)
 
 amhd::ChainState chain_state(amh_run& r);
+int target_create_impl(amh_ctx* ctx, int32_t kind, int32_t dim, const double* blob, int64_t nblob, amh_target** out, bool upload_data);
+int target_create_empty(amh_ctx* ctx, int32_t kind, int32_t dim, const double* blob, int64_t nblob, amh_target** out);
 /* device memory from the context's stream-ordered pool (cudaMallocAsync): run handles are created and
  * destroyed per `sample` call, and the pool makes that cheap */
 int dmalloc(amh_ctx* ctx, void** p, size_t bytes);

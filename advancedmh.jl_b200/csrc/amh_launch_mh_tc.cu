@@ -364,7 +364,12 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
                     dmma(acc[mb][nb][0], acc[mb][nb][1], aq[t], bf);
                 }
                 if (psched(NB, t, true, 2) == 1) {
-                    /* both row blocks of the pair have read Z: their rows of C may now replace it */
+                    /* both row blocks of the pair have read Z: their rows of C may now replace it.  The reads feed
+                     * mma.sync.aligned instructions that every lane has executed before it gets here, so they have
+                     * completed warp-wide; the explicit warp barrier states that ordering for the memory model and for
+                     * racecheck (which reported a warning-level write-after-read hazard without it) and costs nothing
+                     * measurable: 5.641 / 5.643e9 without, 5.635 / 5.641e9 chain-steps/s with (profiles/r2_sanitizers.md) */
+                    __syncwarp();
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         const int mw = (u == 0) ? mb : ((mb & 1) == (NB & 1) ? mb + 1 : mb - 1);   /* the pair's other block */

@@ -39,6 +39,12 @@ class MCMCB200:
     across ranks; there is no per-step collective."""
     device: int | None = None
     gather: bool = True
+    # ngpus = k: ALL chains in THIS process on k devices of the box through the library's multi-GPU job (amh_job_*):
+    # the chains are sharded by the library, the target is broadcast once (NCCL over NVLink), every device writes its
+    # column block of the output array directly; no torch.distributed involved.  This is what the Julia shim's
+    # `MCMCB200(ngpus = 8)` lowers to.  `devices` optionally names the CUDA device indices.
+    ngpus: int | None = None
+    devices: tuple | None = None
     # this rank's chains as `streams` contiguous shards, each with its own context (stream, copy stream) on the same
     # GPU and driven by its own host thread: the host->device copy of one shard's initial parameters and the
     # device->host copy of its samples overlap the stepping kernels of the others.  Same results (global chain identity).
@@ -116,6 +122,16 @@ def default_engine(device: int | None = None) -> K.Engine:
 
 _STREAM_ENGINES: dict = {}
 _POOL = None
+_JOBS: dict = {}
+
+
+def _job_for(eng: K.Engine, ngpus: int, devices=None) -> K.Job:
+    """the multi-GPU job of this process for (library, device list): created once (communicator set-up is the expensive
+    part), reused by every `sample` call"""
+    key = (eng.path, eng.prefix, ngpus, None if devices is None else tuple(devices))
+    if key not in _JOBS:
+        _JOBS[key] = eng.job(ngpus, devices)
+    return _JOBS[key]
 
 
 def _stream_engines(eng: K.Engine, k: int):
@@ -229,6 +245,14 @@ def shard_bounds(nunits: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class LocalParams:
+    """`initial_params=LocalParams(block)`: the initial parameters of THIS rank's chains only, (dim, n_local) float64 in
+    the device layout (chains fastest; n_local counts walkers for an Ensemble).  Under torchrun every rank then builds
+    and uploads O(local chains) of host data instead of the whole (dim, nchains) matrix."""
+    def __init__(self, block):
+        self.block = block
+
+
 def _initial_matrix(initial_params, sampler, dim, nchains, multi):
     """-> (dim, nchains_total) float64 or None; mirrors AbstractMCMC: a multi-chain call takes one entry per
     chain.  Fast path: a (dim, nchains_total) float64 array in the device layout is used as is."""
@@ -287,7 +311,8 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
     if isinstance(sampler, RobustAdaptiveMetropolis) and not hasattr(target, "kind"):
         raise ValueError("RobustAdaptiveMetropolis needs a LogDensityProblems-style target")
     rank, world, dist = (0, 1, None)
-    if isinstance(parallel, MCMCB200):
+    in_process_job = isinstance(parallel, MCMCB200) and parallel.ngpus is not None
+    if isinstance(parallel, MCMCB200) and not in_process_job:
         rank, world, dist = _dist_info()
     if rng is None:
         if seed is None and world > 1:
@@ -301,12 +326,21 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
     # seeds = rand(rng, UInt, nchains) with chain c <- draw number c, so results do not depend on the sharding;
     # only this rank's block [lo, hi) is materialised
     seeds = _draw_seeds(rng, nchains, lo, hi)
-    init = _initial_matrix(initial_params, sampler, dim, nchains, multi)
+    if isinstance(initial_params, LocalParams):
+        init = np.asarray(initial_params.block)
+        if init.shape != (dim, (hi - lo) * nw):
+            raise ValueError(f"LocalParams block must have shape {(dim, (hi - lo) * nw)}, got {init.shape}")
+    else:
+        init = _initial_matrix(initial_params, sampler, dim, nchains, multi)
+        if init is not None:
+            init = init[:, lo * nw:hi * nw]                    # this rank's column block (a view: no copy)
     eng = engine or default_engine(parallel.device if isinstance(parallel, MCMCB200) else None)
+    if in_process_job:
+        eng = _job_for(eng, int(parallel.ngpus), parallel.devices)     # same surface as an Engine, arrays job-wide
 
     n_local = (hi - lo) * nw
     nstreams = parallel.streams if isinstance(parallel, MCMCB200) else 1
-    if (nstreams > 1 and hi - lo >= nstreams and store and not summary and initial_state is None and not save_state
+    if (nstreams > 1 and not in_process_job and hi - lo >= nstreams and store and not summary and initial_state is None and not save_state
             and callback is None and getattr(target, "kind", None) != K.TARGET_USER):
         # shards of this rank's chains on separate streams of the GPU, one host thread each
         global _POOL
@@ -322,7 +356,7 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
             a, b = shard_bounds(hi - lo, k, nstreams)
             ca, cb = (lo + a) * nw, (lo + b) * nw                      # global chain (walker) range of the shard
             futs.append(_POOL.submit(_sample_block, e, target, sampler, dim, cb - ca, seeds[a:b],
-                                     None if init is None else init[:, ca:cb], ca, N, discard_initial, thinning, num_warmup,
+                                     None if init is None else init[:, ca - lo * nw:cb - lo * nw], ca, N, discard_initial, thinning, num_warmup,
                                      vals[:, :, ca - lo * nw:cb - lo * nw], accs[:, ca - lo * nw:cb - lo * nw]))
         launches = sum(f.result() for f in futs)
         out, acc = vals, accs
@@ -345,7 +379,8 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
                 init = np.asarray(initial_state["x"], dtype=np.float64)
                 if init.shape != (dim, nchains * nw):
                     raise ValueError(f"initial_state['x'] must have shape {(dim, nchains * nw)}")
-            run = eng.run(th, sh, n_local, seeds, None if init is None else init[:, sl], chain_offset=lo * nw)
+                init = init[:, sl]
+            run = eng.run(th, sh, n_local, seeds, init, chain_offset=lo * nw)
             if initial_state is not None:
                 run.set_state({k: (v if k == "step" or v is None else np.asarray(v)[..., sl])
                                for k, v in initial_state.items() if k != "seeds"})

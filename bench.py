@@ -12,6 +12,11 @@ the 17 MB chain state is L2 resident.  `e2e` is the same step through the public
 HOST buffers: initial parameters, seeds and target go host->device, two saved samples of every chain
 come device->host, handle creation and destruction included.
 
+The same line carries `configs.{c3,c4,c5}`: short runs of the other BASELINE configs through the C ABI (value, algorithmic
+bytes, roofline fraction; C4 also the FP64-pipe fraction, C5 warm-up at 1 and 16 fused steps per launch from S = I and from
+an adapted S0), every rank running its own copy (weak scaling: C5 at 8 GPUs = 262 144 chains), so that a driver run observes
+all five configs.
+
   python bench.py [--gpus N] [--steps K] [--warmup W]            # this engine
   python bench.py --impl reference ...                           # the CPU arm (oracle port; Julia is not installed)
 
@@ -90,24 +95,143 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
-def cpu_baseline(amh, d, spl, seconds=12.0, nchains=2048):
-    """the oracle port timed on this box's host cores on a bounded sample of the same workload"""
+def workload_config(d, n, spl, world, flush=True):
+    """the `config` object: identical for this engine and for --impl reference (same workload, same sizes)"""
+    return {"workload": f"C2: RWMH MvNormal d={d}, {n} chains per GPU, full-Cholesky proposal, fp64",
+            "chains_per_gpu": n, "mcmc_steps_per_launch": spl,
+            "l2": "state L2-resident by nature; L2 flushed (512 MB rewrite) between timed steps" if flush else "no flush",
+            "parallelism": f"chains sharded x{world}, no per-step collective"}
+
+
+def cpu_baseline(amh, d, spl, seconds=12.0, nchains=65536):
+    """the oracle port timed on this box's host cores on a bounded sample of the same workload: the SAME 65 536 chains,
+    fewer MCMC steps (about `seconds` of CPU work)"""
     orc = amh.Engine(lib_path=os.path.join(ROOT, "oracle", "libamh_oracle.so"), prefix="amho_")
     cores = int(orc.lib.amho_get_threads())
     target, sampler, Sigma = make_problem(amh, d)
     seeds = np.random.default_rng(7).integers(0, 2 ** 64, size=nchains, dtype=np.uint64)
     run = orc.run(orc.target(target.kind, d, target.blob()), sampler.lower(orc, d), nchains, seeds)
-    run.steps(5)
+    run.steps(2)
+    chunk = 20
     t0 = time.perf_counter()
     steps = 0
     while time.perf_counter() - t0 < seconds:
-        run.steps(spl)
-        steps += spl
+        run.steps(chunk)
+        steps += chunk
     dt = time.perf_counter() - t0
     run.close()
     return {"value": nchains * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{nchains} chains x {steps} MCMC steps of the same d={d} workload, C++ oracle (restatement of "
                       f"mh-core.jl:92-117; Julia is not installed), std::thread over chains"}
+
+
+# ---------------------------------------------------------------- the other BASELINE configs, as sub-records
+def _spd(d, seed, lo, hi):
+    rng = np.random.default_rng(seed)
+    Q, _ = np.linalg.qr(rng.normal(size=(d, d)))
+    lam = np.exp(np.linspace(np.log(lo), np.log(hi), d))
+    S = (Q * lam) @ Q.T
+    return (S + S.T) / 2
+
+
+def _timed(run, nsteps, warmup=False, spl=0, reps=3, warm=1):
+    """mean device time (CUDA events on the launching stream, inside the library) of `nsteps` MCMC steps"""
+    for _ in range(warm):
+        run.steps(nsteps, warmup=warmup, steps_per_launch=spl)
+    run.sync()
+    run.kernel_time_ms(reset=True)
+    for _ in range(reps):
+        run.steps(nsteps, warmup=warmup, steps_per_launch=spl)
+    run.sync()
+    ms, _ = run.kernel_time_ms(reset=True)
+    return ms / reps
+
+
+# FP64-pipe cycles of one 16-chain warp-step of K1T16 by dimension (contract v1 instruction mix; DESIGN.md 5)
+PIPE_MODEL = {32: 80 * 16.2 + 398 * 2.07 + 182 * 4.1}
+
+FP64_TFLOPS_PEAK = 148 * 64 * 2 * 1.965e9 / 1e12      # 64 FP64 FMA / clk / SM (DMMA or DFMA, one shared datapath) at 1965 MHz = 37.2
+
+
+def _rec(chain_steps, ms, bytes_per, peak, **extra):
+    v = chain_steps / (ms * 1e-3)
+    out = {"value": v, "unit": UNIT, "ms": ms, "algorithmic_bytes_per_chain_step": bytes_per,
+           "achieved_gbs": v * bytes_per / 1e9, "frac": v * bytes_per / 1e9 / peak}
+    out.update(extra)
+    return out
+
+
+def bench_c3(amh, eng, peak, seed=2):
+    d, nw, ne = 10, 4096, 64
+    t = amh.RosenbrockTarget(d)
+    s = amh.Ensemble(nw, amh.StretchProposal(amh.MvNormal(np.zeros(d), amh.I)))
+    sd = np.random.default_rng(seed).integers(0, 2 ** 64, size=ne, dtype=np.uint64)
+    run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), nw * ne, sd)
+    ms = _timed(run, 64, spl=16)
+    st = run.state()
+    out = _rec(nw * ne * 64, ms, 2 * (d + 1) * 8, peak, workload=f"C3: Ensemble(4096, StretchProposal) Rosenbrock d=10, {ne} ensembles per GPU, exact sequential sweep",
+               kernel="stretch_plan_kernel + stretch_sweep_flow2_kernel (K2F, 2-CTA cluster per ensemble)",
+               accept_rate=float(st["naccept"].sum() / (nw * ne * st["step"])), sweeps_timed=64 * 3)
+    run.close()
+    return out
+
+
+def bench_c4(amh, eng, peak, seed=3, n=16384):
+    d, nrows = 128, 10000
+    rng = np.random.default_rng(128)
+    X = rng.normal(size=(nrows, d)) / np.sqrt(d)
+    beta = rng.normal(size=d)
+    y = (rng.random(nrows) < 1 / (1 + np.exp(-X @ beta))).astype(float)
+    t = amh.LogisticRegressionTarget(X, y, tau=10.0)
+    s2 = 3.3e-2
+    s = amh.MALA(lambda g: amh.MvNormal((s2 / 2) * g, s2 * amh.I))
+    sd = np.random.default_rng(seed).integers(0, 2 ** 64, size=n, dtype=np.uint64)
+    run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), n, sd, np.zeros((d, n)))
+    run.steps(60, steps_per_launch=4)                  # from zeros to the posterior mode region
+    st0 = run.state()
+    ms = _timed(run, 4, spl=2, reps=2, warm=1)
+    st = run.state()
+    tf = 4.0 * nrows * d * n * 4 / (ms * 1e-3) / 1e12  # two 10 000 x 128 mat-vecs per chain-step = 5.12 MFLOP
+    out = _rec(n * 4, ms, 2 * (2 * d + 1) * 8, peak, workload=f"C4: MALA logistic regression d=128, 10 000 rows, {n} chains per GPU, analytic device gradient",
+               kernel="mala_logistic_kernel<128> (K3L: TMA ring + two chained FP64 DMMA GEMMs)", bound="fp64 tensor",
+               fp64_tflops=tf, fp64_pipe_frac=tf / FP64_TFLOPS_PEAK, fp64_tflops_peak=FP64_TFLOPS_PEAK,
+               accept_rate_recent=float((st["naccept"].sum() - st0["naccept"].sum()) / (n * (st["step"] - st0["step"]))))
+    run.close()
+    return out
+
+
+def bench_c5(amh, eng, peak, seed=4, n=32768):
+    d = 64
+    Sigma = _spd(d, 64, 1e-4, 1.0)
+    t = amh.MvNormalTarget(None, Sigma)
+    out = {"workload": f"C5: RobustAdaptiveMetropolis ill-conditioned Gaussian d=64 (eigenvalues 1e-4..1), {n} chains per GPU",
+           "kernel": "ram_warp_kernel (K4W: warp per chain, factor in shared memory via bulk copies)", "bound": "hbm"}
+    Bw, Bs = 2 * (d + 1) * 8 + d * (d + 1) * 8, 2 * (d + 1) * 8 + d * (d + 1) // 2 * 8
+    sd = np.random.default_rng(seed).integers(0, 2 ** 64, size=n, dtype=np.uint64)
+    for tag, S0 in (("from_identity", None), ("from_adapted_S0", (2.38 / np.sqrt(d)) * np.linalg.cholesky(Sigma))):
+        # S = I is the reference default (RAM :198-199); on this target it does not get moving within any affordable
+        # warm-up (acceptance 0: every step is a downdate), so the stationary mix of updates and downdates is timed from
+        # the usual 2.38/sqrt(d) scaling of the target's factor as well.  Both are reported.
+        s = amh.RobustAdaptiveMetropolis() if S0 is None else amh.RobustAdaptiveMetropolis(S=S0)
+        run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), n, sd, np.zeros((d, n)))
+        run.steps(128, warmup=True, steps_per_launch=16)
+        st0 = run.state()
+        rec = {}
+        for spl in (1, 16):
+            ms = _timed(run, 32, warmup=True, spl=spl)
+            rec[f"warmup_{spl}_per_launch"] = _rec(n * 32, ms, Bw, peak)
+        st1 = run.state()
+        rec["accept_rate_recent"] = float((st1["naccept"].sum() - st0["naccept"].sum()) / (n * max(1, st1["step"] - st0["step"])))
+        for spl in (1, 16):
+            ms = _timed(run, 32, warmup=False, spl=spl)
+            rec[f"sampling_{spl}_per_launch"] = _rec(n * 32, ms, Bs, peak)
+        rec["failed_downdates"] = int(run.ram_failed()[0])
+        out[tag] = rec
+        run.close()
+    # the headline figure of the sub-record: warm-up, one kernel per MCMC step (the genuinely HBM-bound case), adapted start
+    h = out["from_adapted_S0"]["warmup_1_per_launch"]
+    out.update(value=h["value"], unit=UNIT, frac=h["frac"], algorithmic_bytes_per_chain_step=Bw)
+    return out
 
 
 def run_reference(args):
@@ -120,7 +244,7 @@ def run_reference(args):
     d, spl = args.dim, args.mcmc_steps_per_launch
     orc = amh.Engine(lib_path=os.path.join(ROOT, "oracle", "libamh_oracle.so"), prefix="amho_")
     cores = int(orc.lib.amho_get_threads())
-    nchains = args.ref_chains
+    nchains = args.ref_chains if args.ref_chains > 0 else args.chains
     target, sampler, _ = make_problem(amh, d)
     seeds = np.random.default_rng(7).integers(0, 2 ** 64, size=nchains, dtype=np.uint64)
     run = orc.run(orc.target(target.kind, d, target.blob()), sampler.lower(orc, d), nchains, seeds)
@@ -131,14 +255,13 @@ def run_reference(args):
         run.steps(spl)
     dt = time.perf_counter() - t0
     value = nchains * spl * args.steps / dt
-    sample = (f"{nchains} chains x {spl} MCMC steps per bench step (bounded sample of the 65536-chain workload; "
-              f"chain-steps/s is chain-count independent once every core is busy)")
+    sample = (f"{nchains} chains x {spl} MCMC steps per bench step: the whole per-GPU workload of this engine's arm, C++ oracle "
+              f"(restatement of mh-core.jl:92-117; Julia is not installed), std::thread over chains")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C2: RWMH MvNormal d={d}, full-Cholesky proposal", "sampler": "RWMH",
-                   "chains_timed": nchains, "mcmc_steps_per_launch": spl},
+        "config": workload_config(d, args.chains, spl, args.gpus, not args.no_flush), "chains_timed": nchains,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -154,7 +277,8 @@ def main():
     ap.add_argument("--dim", type=int, default=32)
     ap.add_argument("--chains", type=int, default=65536, help="chains per GPU")
     ap.add_argument("--mcmc-steps-per-launch", type=int, default=500)
-    ap.add_argument("--ref-chains", type=int, default=16384)
+    ap.add_argument("--ref-chains", type=int, default=0, help="chains of the --impl reference run (0 = --chains: the same config)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C3/C4/C5 sub-records")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
@@ -195,11 +319,12 @@ def main():
     eng = amh.default_engine(local)
     th = eng.target(target.kind, d, blob.cpu().numpy())
     sh = sampler.lower(eng, d)
-    # global chain identity: seeds are drawn for ALL chains, rank r owns [r*n, (r+1)*n)
-    seeds_all = np.random.default_rng(20261017).integers(0, 2 ** 64, size=n * world, dtype=np.uint64)
+    # global chain identity: chain c is keyed by draw number c of one generator; rank r materialises only its block
+    # [r*n, (r+1)*n) (jumpable PCG64): per-rank host work is O(local chains)
+    seeds = amh.sampling._draw_seeds(np.random.default_rng(20261017), n * world, rank * n, (rank + 1) * n)
     L = np.linalg.cholesky(Sigma)
     init = np.ascontiguousarray(L @ np.random.default_rng(100 + rank).normal(size=(d, n)))
-    run = eng.run(th, sh, n, seeds_all[rank * n:(rank + 1) * n], init, chain_offset=rank * n)
+    run = eng.run(th, sh, n, seeds, init, chain_offset=rank * n)
 
     flush_buf = None if args.no_flush else torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
@@ -244,19 +369,19 @@ def main():
     # ---- e2e: the public sample() call, host buffers in, host samples out --------------------
     e2e = None
     if args.e2e_steps > 0:
-        init_all = np.concatenate([L @ np.random.default_rng(100 + r).normal(size=(d, n)) for r in range(world)], axis=1)
-        hinit = eng.pinned_empty((d, n * world))
-        hinit[...] = init_all
+        hinit = eng.pinned_empty((d, n))                # this rank's block of the initial parameters, page-locked
+        hinit[...] = init
+        linit = amh.LocalParams(hinit)
         pout = eng.pinned_empty((2, d + 1, n))          # this rank's shard of the two saved samples
         pacc = eng.pinned_empty((2, n), dtype=np.uint8)
         model = amh.DensityModel(target)
-        amh.sample(model, sampler, amh.MCMCB200(device=local, gather=False, streams=args.e2e_streams), 2, n * world, initial_params=hinit,
+        amh.sample(model, sampler, amh.MCMCB200(device=local, gather=False, streams=args.e2e_streams), 2, n * world, initial_params=linit,
                    thinning=spl, chain_type=amh.Chains, seed=99, out=(pout, pacc))          # warm-up call
         barrier()
         t0 = time.perf_counter()
         for i in range(args.e2e_steps):
             ch = amh.sample(model, sampler, amh.MCMCB200(device=local, gather=False, streams=args.e2e_streams), 2, n * world,
-                            initial_params=hinit, thinning=spl, chain_type=amh.Chains, seed=i, out=(pout, pacc))
+                            initial_params=linit, thinning=spl, chain_type=amh.Chains, seed=i, out=(pout, pacc))
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -279,19 +404,54 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     # per-rank achieved bandwidth of the step kernel (algorithmic bytes / mean launch duration)
     achieved = B * float(n) * spl / (ms / max(1, nl) * 1e-3) / 1e9
-    traffic = None
+    # DRAM bytes of one launch: only quoted when the committed ncu --set full capture is of THIS launch shape
+    # (same chains, same fused steps); anything else is not a measurement of the timed launch -> null
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic_mh_step.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            if int(tj.get("mcmc_steps_in_captured_launch", -1)) == spl and int(tj.get("chains", 65536)) == n and int(tj.get("dim", 32)) == d:
+                traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("capture")
         except Exception:
             traffic = None
+    # what really bounds the kernel: the shared FP64 datapath.  Pipe cycles one 16-chain warp-step needs, from the
+    # instruction mix of the kernel (ncu source page) x the per-instruction pipe costs measured with tools/ubench/issue_probe.cu
+    # (profiles/r1_issue_probe_b200.txt: DMMA 16.2, DFMA-class 2.07, IMAD.WIDE/HI 4.1 cycles of a scheduler's FP64 pipe)
+    pipe_cycles_per_warp_step = PIPE_MODEL.get(d)
+    fp64_pipe = None
+    if pipe_cycles_per_warp_step is not None and n % 16 == 0:
+        sm_hz = 1e6 * float(peaks.get("sm_max_mhz", 1965.0))
+        us_step = 1e3 * (ms / max(1, nl)) / spl
+        warp_steps_per_sched = (n / 16.0) / (148 * 4)
+        floor_us = warp_steps_per_sched * pipe_cycles_per_warp_step / sm_hz * 1e6
+        fp64_pipe = {"frac": floor_us / us_step, "floor_us_per_mcmc_step": floor_us, "measured_us_per_mcmc_step": us_step,
+                     "pipe_cycles_per_16_chain_warp_step": pipe_cycles_per_warp_step,
+                     "model": "80 DMMA x 16.2 + 398 DFMA-class x 2.07 + 182 IMAD.WIDE x 4.1 cycles (profiles/r1_issue_probe_b200.txt, DESIGN.md 5)"}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "kernel": "mh_step_tc16_kernel<32,28,true,true> (K1T16: DMMA mat-vecs, 16 chains per warp, one 28-warp CTA per SM)",
                 "algorithmic_bytes_per_chain_step": B,
                 "chain_steps_per_launch": n * spl,
-                "note": "state (17 MB) is L2 resident and the kernel is bound by the shared FP64 datapath (DMMA + DFMA + the wide integer multiplies of Philox, 64 FMA/clk/SM); the HBM figure is the contractual denominator (SURVEY.md 8d)"}
+                "fp64_pipe_frac": None if fp64_pipe is None else fp64_pipe["frac"], "fp64_pipe": fp64_pipe,
+                "note": "state (17 MB) is L2 resident and the kernel is bound by the shared FP64 datapath (DMMA + DFMA + the wide integer multiplies of Philox, 64 FMA/clk/SM): fp64_pipe_frac is the honest utilisation figure; the HBM figure is the contractual denominator (SURVEY.md 8d)"}
+
+    # ---- the other BASELINE configs (every rank runs its own copy: weak scaling; rank 0 reports the max-time aggregate) ----
+    configs = None
+    if not args.no_configs:
+        configs = {}
+        for name, fn in (("c3", bench_c3), ("c4", bench_c4), ("c5", bench_c5)):
+            barrier()
+            rec = fn(amh, eng, peak, seed=10 * (rank + 1) + len(configs))
+            if dist is not None:
+                # whole-job value: every rank processed the same number of units; time = max over ranks
+                tm = torch.tensor([rec["value"]], dtype=torch.float64, device=dev)
+                dist.all_reduce(tm, op=dist.ReduceOp.MIN)
+                rec["value_per_gpu_min"] = float(tm.item())
+                rec["value"] = float(tm.item()) * world
+                rec["n_gpus"] = world
+            configs[name] = rec
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -302,12 +462,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C2: RWMH MvNormal d={d}, {n} chains per GPU, full-Cholesky proposal, fp64",
-                       "chains_per_gpu": n, "mcmc_steps_per_launch": spl,
-                       "l2": "state L2-resident by nature; L2 flushed (512 MB rewrite) between timed steps" if not args.no_flush else "no flush",
-                       "parallelism": f"chains sharded x{world}, no per-step collective"},
+            "config": workload_config(d, n, spl, world, not args.no_flush),
             "clocks": clk.result(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "wall_s_timed_region": t_wall,
+            "cpu_baseline": cpu, "configs": configs, "wall_s_timed_region": t_wall,
         }
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())

@@ -125,6 +125,7 @@ typedef struct amh_ctx     amh_ctx;
 typedef struct amh_target  amh_target;
 typedef struct amh_sampler amh_sampler;
 typedef struct amh_run     amh_run;
+typedef struct amh_job     amh_job;
 
 #ifndef AMH_RTC   /* (the NVRTC translation unit of user-supplied targets needs the constants and structs only) */
 /* handshake, diagnostics */
@@ -210,6 +211,10 @@ int32_t amh_run_sample_ld(amh_run* run, int64_t N, int64_t discard_initial, int6
  * S:[dim(dim+1)/2][n] packed rows (RAM) accepted:[n] naccept:[n] */
 int32_t amh_run_get_state(amh_run* run, double* x, double* lp, double* grad, double* S,
                           uint8_t* accepted, int64_t* naccept, int64_t* step_counter);
+/* the same into COLUMN BLOCKS of job-wide arrays: every 2-d array has row stride `ld` >= nchains_local (x, grad:
+ * [dim][ld]; S: [dim(dim+1)/2][ld]); the 1-d arrays are written at the pointer given */
+int32_t amh_run_get_state_ld(amh_run* run, int64_t ld, double* x, double* lp, double* grad, double* S,
+                             uint8_t* accepted, int64_t* naccept, int64_t* step_counter);
 /* setparams!!: replaces x and recomputes lp (and the gradient for MALA) on the device */
 int32_t amh_run_set_params(amh_run* run, const double* x);
 /* resume: installs a state read earlier with amh_run_get_state, so that a new run continues an old one bit for bit
@@ -220,6 +225,8 @@ int32_t amh_run_set_params(amh_run* run, const double* x);
  * MH's cached proposal log-density of the state (a pure function of x). */
 int32_t amh_run_set_state(amh_run* run, const double* x, const double* lp, const double* grad, const double* S,
                           const uint8_t* accepted, const int64_t* naccept, int64_t step_counter);
+int32_t amh_run_set_state_ld(amh_run* run, int64_t ld, const double* x, const double* lp, const double* grad, const double* S,
+                             const uint8_t* accepted, const int64_t* naccept, int64_t step_counter);
 /* RAM: the state fields that only report the last step -- log acceptance ratio `log-alpha` and adaptation step size
  * `eta` (RAM :107-110), [nchains_local] each, either may be NULL (StatesExtractor, test/RobustAdaptiveMetropolis.jl:11-28) */
 int32_t amh_run_get_ram_adapt(amh_run* run, double* logalpha, double* eta);
@@ -248,6 +255,48 @@ int64_t amh_run_launch_count(amh_run* run);
  * The first call switches event recording on for this run (off by default: two
  * event records per amh_run_steps call are not free at one launch per step). */
 int32_t amh_run_kernel_time_ms(amh_run* run, int32_t reset, double* ms, int64_t* launches);
+
+/* ---- multi-GPU job: N devices of one box behind ONE handle, in ONE process ---------------------------------------
+ * The multi-chain call of the reference is `sample(model, sampler, MCMCThreads() | MCMCDistributed(), N, nchains)`
+ * (src/AdvancedMH.jl:30 re-export; README.md:135-148; test/runtests.jl:96-110): one keyword turns on chain-level data
+ * parallelism.  Here that keyword is `MCMCB200(ngpus = k)` and the job handle is what it lowers to: the caller passes
+ * JOB-WIDE arrays (seeds[nchains], init[dim][nchains], out[N][dim+1][nchains], state arrays) and the library shards
+ * the chains in contiguous blocks over the devices (an ensemble stays on one device), drives every device from its own
+ * host thread, broadcasts the target's fixed data once (ncclBroadcast over NVLink when libnccl can be loaded, else peer
+ * copies; no per-step collective), lets every device write its column block of `out` directly, and pools the
+ * summaries.  Results are bit-identical to a one-device run of the same seeds (global chain identity).
+ * A job owns at most one target, one sampler and one run at a time; creating a new one releases the old. */
+int32_t amh_job_create(int32_t ngpus, const int32_t* devices /* [ngpus] or NULL = 0..ngpus-1 */, amh_job** out);
+int32_t amh_job_destroy(amh_job* job);
+int32_t amh_job_ngpus(amh_job* job);
+int32_t amh_job_target_create(amh_job* job, int32_t kind, int32_t dim, const double* blob, int64_t nblob);
+int32_t amh_job_target_create_source(amh_job* job, int32_t dim, const char* source, int32_t has_gradient,
+                                     const double* data, int64_t ndata);
+/* how the last target reached the devices ("nccl", "peer", "h2d", "source") and how long it took (host clock, ms) */
+const char* amh_job_broadcast_mode(amh_job* job);
+double      amh_job_broadcast_ms(amh_job* job);
+double      amh_job_comm_init_ms(amh_job* job);     /* one-time cost of ncclCommInitAll at amh_job_create (0 without NCCL) */
+int32_t amh_job_sampler_create(amh_job* job, const amh_sampler_desc* desc);
+/* nchains counts walkers for an Ensemble; seeds: one per chain (per ensemble for STRETCH); init: [dim][init_ld] or NULL */
+int32_t amh_job_run_create(amh_job* job, int64_t nchains, const uint64_t* seeds, const double* init, int64_t init_ld);
+int32_t amh_job_run_destroy(amh_job* job);
+int32_t amh_job_run_steps(amh_job* job, int64_t nsteps, int32_t warmup, int32_t steps_per_launch);
+int32_t amh_job_run_sync(amh_job* job);
+/* out: [N][dim+1][nchains], accepted_out: [N][nchains], summary pooled over all devices (any may be NULL) */
+int32_t amh_job_run_sample(amh_job* job, int64_t N, int64_t discard_initial, int64_t thinning, int64_t num_warmup,
+                           double* out, uint8_t* accepted_out, amh_summary* summary);
+int32_t amh_job_run_get_state(amh_job* job, double* x, double* lp, double* grad, double* S, uint8_t* accepted,
+                              int64_t* naccept, int64_t* step_counter);
+int32_t amh_job_run_set_state(amh_job* job, const double* x, const double* lp, const double* grad, const double* S,
+                              const uint8_t* accepted, const int64_t* naccept, int64_t step_counter);
+int32_t amh_job_run_get_ram_adapt(amh_job* job, double* logalpha, double* eta);
+int32_t amh_job_run_set_ram_adapt(amh_job* job, const double* logalpha, const double* eta, const uint8_t* failed);
+int32_t amh_job_run_ram_failed(amh_job* job, int64_t* nfailed, int64_t* first_chain, uint8_t* failed);
+/* which chains device number k of the job holds: [lo, hi) and the CUDA device index */
+int32_t amh_job_run_shard(amh_job* job, int32_t k, int64_t* lo, int64_t* hi, int32_t* device);
+int64_t amh_job_run_launch_count(amh_job* job);
+/* device time of the stepping kernels: max over the devices (they run concurrently), launches summed */
+int32_t amh_job_run_kernel_time_ms(amh_job* job, int32_t reset, double* ms, int64_t* launches);
 #endif /* AMH_RTC */
 
 #ifdef __cplusplus

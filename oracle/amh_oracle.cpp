@@ -1103,19 +1103,30 @@ int32_t amho_run_sample_ld(amh_run* run, int64_t N, int64_t discard_initial, int
     return AMH_OK;
 }
 
+static void copy_rows(double* dst, int64_t dld, const double* src, int64_t sld, int64_t rows, int64_t n) {
+    for (int64_t i = 0; i < rows; ++i) std::memcpy(dst + i * dld, src + i * sld, sizeof(double) * n);
+}
+int32_t amho_run_get_state_ld(amh_run* run, int64_t ld, double* x, double* lp, double* grad, double* S,
+                              uint8_t* accepted, int64_t* naccept, int64_t* step_counter);
 int32_t amho_run_get_state(amh_run* run, double* x, double* lp, double* grad, double* S,
                            uint8_t* accepted, int64_t* naccept, int64_t* step_counter) {
     if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    return amho_run_get_state_ld(run, ((Run*)run)->n, x, lp, grad, S, accepted, naccept, step_counter);
+}
+int32_t amho_run_get_state_ld(amh_run* run, int64_t ld, double* x, double* lp, double* grad, double* S,
+                              uint8_t* accepted, int64_t* naccept, int64_t* step_counter) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
     Run& r = *(Run*)run;
-    if (x) std::memcpy(x, r.X.data(), sizeof(double) * r.X.size());
+    if (ld < r.n) return fail(AMH_ERR_INVALID, "ld must be >= nchains_local");
+    if (x) copy_rows(x, ld, r.X.data(), r.n, r.dim, r.n);
     if (lp) std::memcpy(lp, r.lp.data(), sizeof(double) * r.lp.size());
     if (grad) {
         if (r.G.empty()) return fail(AMH_ERR_INVALID, "sampler keeps no gradient");
-        std::memcpy(grad, r.G.data(), sizeof(double) * r.G.size());
+        copy_rows(grad, ld, r.G.data(), r.n, r.dim, r.n);
     }
     if (S) {
         if (r.S.empty()) return fail(AMH_ERR_INVALID, "sampler keeps no Cholesky factor");
-        std::memcpy(S, r.S.data(), sizeof(double) * r.S.size());
+        copy_rows(S, ld, r.S.data(), r.n, (int64_t)r.dim * (r.dim + 1) / 2, r.n);
     }
     if (accepted) std::memcpy(accepted, r.acc.data(), r.acc.size());
     if (naccept) std::memcpy(naccept, r.nacc.data(), sizeof(int64_t) * r.nacc.size());
@@ -1123,18 +1134,26 @@ int32_t amho_run_get_state(amh_run* run, double* x, double* lp, double* grad, do
     return AMH_OK;
 }
 
+int32_t amho_run_set_state_ld(amh_run* run, int64_t ld, const double* x, const double* lp, const double* grad, const double* S,
+                              const uint8_t* accepted, const int64_t* naccept, int64_t step_counter);
 int32_t amho_run_set_state(amh_run* run, const double* x, const double* lp, const double* grad, const double* S,
                            const uint8_t* accepted, const int64_t* naccept, int64_t step_counter) {
+    if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
+    return amho_run_set_state_ld(run, ((Run*)run)->n, x, lp, grad, S, accepted, naccept, step_counter);
+}
+int32_t amho_run_set_state_ld(amh_run* run, int64_t ld, const double* x, const double* lp, const double* grad, const double* S,
+                              const uint8_t* accepted, const int64_t* naccept, int64_t step_counter) {
     if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
     Run& r = *(Run*)run;
     const int d = r.dim;
     const int64_t n = r.n;
+    if (ld < n) return fail(AMH_ERR_INVALID, "ld must be >= nchains_local");
     if (grad && r.G.empty()) return fail(AMH_ERR_INVALID, "sampler keeps no gradient");
     if (S && r.S.empty()) return fail(AMH_ERR_INVALID, "sampler keeps no Cholesky factor");
-    if (x) std::memcpy(r.X.data(), x, sizeof(double) * r.X.size());
+    if (x) copy_rows(r.X.data(), n, x, ld, d, n);
     if (lp) std::memcpy(r.lp.data(), lp, sizeof(double) * r.lp.size());
-    if (grad) std::memcpy(r.G.data(), grad, sizeof(double) * r.G.size());
-    if (S) std::memcpy(r.S.data(), S, sizeof(double) * r.S.size());
+    if (grad) copy_rows(r.G.data(), n, grad, ld, d, n);
+    if (S) copy_rows(r.S.data(), n, S, ld, (int64_t)d * (d + 1) / 2, n);
     if (accepted) std::memcpy(r.acc.data(), accepted, r.acc.size());
     if (naccept) std::memcpy(r.nacc.data(), naccept, sizeof(int64_t) * r.nacc.size());
     if (step_counter >= 0) r.step = step_counter;
@@ -1260,3 +1279,50 @@ void amho_probe_target_grad(amh_target* t, const double* x, double* lp, double* 
 }
 
 }  /* extern "C" */
+
+/* ---- the multi-device job layer (amh_job_*): the product's sharding logic (advancedmh.jl_b200/csrc/amh_job_impl.h)
+ * instantiated over the oracle's own entry points, so that the CPU tests exercise the same code path the GPU job runs:
+ * "devices" are just shards here. ---- */
+#include "../advancedmh.jl_b200/csrc/amh_job_impl.h"
+
+namespace {
+struct OracleBackend {
+    struct Shared {};
+    static std::string last_error() { return amho_last_error(); }
+    static int fail(int code, const std::string& m) { return ::fail(code, m); }
+    static int ctx_create(int dev, amh_ctx** out) { return amho_ctx_create(dev, out); }
+    static int ctx_destroy(amh_ctx* c) { return amho_ctx_destroy(c); }
+    static int target_destroy(amh_target* t) { return amho_target_destroy(t); }
+    static int target_create_source(amh_ctx* c, int32_t dim, const char* src, int32_t g, const double* data, int64_t nd, amh_target** out) {
+        return amho_target_create_source(c, dim, src, g, data, nd, out);
+    }
+    static int sampler_create(amh_ctx* c, const amh_sampler_desc* d, amh_sampler** out) { return amho_sampler_create(c, d, out); }
+    static int sampler_destroy(amh_sampler* s) { return amho_sampler_destroy(s); }
+    static int run_create(amh_ctx* c, amh_target* t, amh_sampler* s, int64_t n, int64_t off, const uint64_t* seeds, const double* init,
+                          int64_t ld, amh_run** out) { return amho_run_create(c, t, s, n, off, seeds, init, ld, out); }
+    static int run_destroy(amh_run* r) { return amho_run_destroy(r); }
+    static int run_steps(amh_run* r, int64_t n, int32_t w, int32_t spl) { return amho_run_steps(r, n, w, spl); }
+    static int run_sync(amh_run* r) { return amho_run_sync(r); }
+    static int run_sample_ld(amh_run* r, int64_t N, int64_t di, int64_t th, int64_t nw, double* out, int64_t old, uint8_t* acc, int64_t ald,
+                             amh_summary* s) { return amho_run_sample_ld(r, N, di, th, nw, out, old, acc, ald, s); }
+    static int run_get_state_ld(amh_run* r, int64_t ld, double* x, double* lp, double* g, double* S, uint8_t* a, int64_t* na, int64_t* st) {
+        return amho_run_get_state_ld(r, ld, x, lp, g, S, a, na, st);
+    }
+    static int run_set_state_ld(amh_run* r, int64_t ld, const double* x, const double* lp, const double* g, const double* S, const uint8_t* a,
+                                const int64_t* na, int64_t st) { return amho_run_set_state_ld(r, ld, x, lp, g, S, a, na, st); }
+    static int run_get_ram_adapt(amh_run* r, double* la, double* eta) { return amho_run_get_ram_adapt(r, la, eta); }
+    static int run_set_ram_adapt(amh_run* r, const double* la, const double* eta, const uint8_t* f) { return amho_run_set_ram_adapt(r, la, eta, f); }
+    static int run_ram_failed(amh_run* r, int64_t* nf, int64_t* first, uint8_t* f) { return amho_run_ram_failed(r, nf, first, f); }
+    static int64_t run_launch_count(amh_run* r) { return amho_run_launch_count(r); }
+    static int run_kernel_time_ms(amh_run* r, int32_t reset, double* ms, int64_t* l) { return amho_run_kernel_time_ms(r, reset, ms, l); }
+    static int shared_init(amhjob::Job<OracleBackend>&) { return AMH_OK; }
+    static void shared_destroy(amhjob::Job<OracleBackend>&) {}
+    static int target_broadcast(amhjob::Job<OracleBackend>& j, int32_t kind, int32_t dim, const double* blob, int64_t nblob) {
+        j.bcast_mode = "copy";
+        return j.each([&](int k) { return (int)amho_target_create(j.ctx[k], kind, dim, blob, nblob, &j.target[k]); });
+    }
+};
+}  // namespace
+
+AMH_DEFINE_JOB_ABI(amho_, OracleBackend)
+extern "C" double amho_job_comm_init_ms(amh_job*) { return 0.0; }

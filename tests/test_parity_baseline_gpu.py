@@ -1,0 +1,202 @@
+"""T1 parity at the BASELINE.json sizes: the CUDA engine against the CPU oracle, bit for bit,
+on the shapes the bench lines are quoted on -- not only on the small cases of test_parity_gpu.py:
+
+  C2  RWMH, MvNormal d=32, 65 536 chains x 1 000 steps            (">= 10^3 steps x 65 536 chains identical")
+  C3  stretch move, Rosenbrock d=10, 64 ensembles x 4 096 walkers, 2-CTA cluster sweep, planned-ahead launches
+  C4  MALA, logistic regression d=128 x 10 000 rows (1 250 ring blocks = 125 wraps of the 10-stage TMA ring)
+  C5  RAM warm-up d=64 x 4 096 chains, 16 fused steps per launch, from S = I and from an adapted S0
+
+plus the reference semantics added in round 2 (failed-downdate flag, resume of log-alpha / eta, Welford summaries,
+callback states, setparams!! keeping `accepted`)."""
+import numpy as np
+import pytest
+
+from conftest import make_spd
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(cuda, oracle, target, sampler, n, seeds, init=None):
+    runs = []
+    for eng in (cuda, oracle):
+        th = eng.target(target.kind, target.dim, target.blob())
+        sh = sampler.lower(eng, target.dim)
+        runs.append(eng.run(th, sh, n, seeds, init))
+    return runs
+
+
+def _same(rg, ro, keys=("x", "lp", "accepted", "naccept"), **kw):
+    sg, so = rg.state(**kw), ro.state(**kw)
+    for k in keys:
+        assert np.array_equal(sg[k], so[k], equal_nan=True), f"{k} differs in {np.count_nonzero(sg[k] != so[k])} entries"
+    assert sg["step"] == so["step"]
+    return sg
+
+
+def _seeds(n, s=0):
+    return np.random.default_rng(s).integers(0, 2 ** 64, size=n, dtype=np.uint64)
+
+
+def test_c2_full_size_65536_chains_x_1000_steps_bit_exact(amh, cuda, oracle):
+    d, n = 32, 65536
+    Sigma = make_spd(d, seed=32)
+    target = amh.MvNormalTarget(None, Sigma)
+    spl = amh.RWMH(amh.MvNormal(np.zeros(d), (2.38 ** 2 / d) * Sigma))
+    rg, ro = _pair(cuda, oracle, target, spl, n, _seeds(n, 2026))
+    _same(rg, ro)                                  # first step: 65 536 draws from the proposal
+    rg.steps(1000, steps_per_launch=500)           # the bench's launch shape: 500 fused steps
+    ro.steps(1000)
+    sg = _same(rg, ro)
+    assert 0.2 < sg["naccept"].sum() / (n * 1000) < 0.3
+    # and through the sampling schedule (thinning interval = one launch), with the Welford summaries
+    og, ag, smg = rg.sample(3, discard_initial=100, thinning=200, chain_means=True)
+    oo, ao, smo = ro.sample(3, discard_initial=100, thinning=200, chain_means=True)
+    assert np.array_equal(og, oo) and np.array_equal(ag, ao)
+    for k in ("mean", "var", "chain_mean"):
+        assert np.array_equal(smg[k], smo[k]), k
+
+
+def test_c3_full_size_64_ensembles_x_4096_walkers_cluster_sweep_bit_exact(amh, cuda, oracle):
+    d, nw, ne = 10, 4096, 64
+    target = amh.RosenbrockTarget(d)
+    spl = amh.Ensemble(nw, amh.StretchProposal(amh.MvNormal(np.zeros(d), amh.I)))
+    rg, ro = _pair(cuda, oracle, target, spl, nw * ne, _seeds(ne, 3))
+    _same(rg, ro)
+    rg.steps(6, steps_per_launch=3)                # two launches: the second one runs on a plan made ahead
+    ro.steps(6)
+    sg = _same(rg, ro)
+    assert 0.2 < sg["naccept"].sum() / (nw * ne * 6) < 0.9
+    og, ag, _ = rg.sample(2, discard_initial=1, thinning=2)
+    oo, ao, _ = ro.sample(2, discard_initial=1, thinning=2)
+    assert np.array_equal(og, oo) and np.array_equal(ag, ao)
+
+
+def test_c4_full_size_10000_rows_d128_bit_exact(amh, cuda, oracle):
+    d, rows, n = 128, 10000, 24                    # 24 chains = 3 warps' worth; rows are what the ring wraps over
+    rng = np.random.default_rng(128)
+    X = rng.normal(size=(rows, d)) / np.sqrt(d)
+    beta = rng.normal(size=d)
+    y = (rng.random(rows) < 1 / (1 + np.exp(-X @ beta))).astype(float)
+    target = amh.LogisticRegressionTarget(X, y, tau=10.0)
+    s2 = 3.3e-2                                    # tools/bench_configs.py: acceptance ~0.57 on this posterior
+    spl = amh.MALA(lambda g: amh.MvNormal((s2 / 2) * g, s2 * amh.I))
+    init = 0.05 * rng.normal(size=(d, n))
+    rg, ro = _pair(cuda, oracle, target, spl, n, _seeds(n, 4), init)
+    _same(rg, ro, keys=("x", "lp", "grad", "accepted", "naccept"), grad=True)
+    rg.steps(3, steps_per_launch=2)
+    ro.steps(3)
+    _same(rg, ro, keys=("x", "lp", "grad", "accepted", "naccept"), grad=True)
+    og, ag, _ = rg.sample(3, discard_initial=1, thinning=2)
+    oo, ao, _ = ro.sample(3, discard_initial=1, thinning=2)
+    assert np.array_equal(og, oo) and np.array_equal(ag, ao)
+    _same(rg, ro, keys=("x", "lp", "grad", "accepted", "naccept"), grad=True)
+
+
+@pytest.mark.parametrize("start", ["identity", "adapted"])
+def test_c5_ram_warmup_d64_4096_chains_16_fused_steps_bit_exact(amh, cuda, oracle, start):
+    d, n = 64, 4096
+    Sigma = make_spd(d, 64, 1e-4, 1.0)
+    target = amh.MvNormalTarget(None, Sigma)
+    S0 = None if start == "identity" else (2.38 / np.sqrt(d)) * np.linalg.cholesky(Sigma)
+    spl = amh.RobustAdaptiveMetropolis() if S0 is None else amh.RobustAdaptiveMetropolis(S=S0)
+    rg, ro = _pair(cuda, oracle, target, spl, n, _seeds(n, 5), np.zeros((d, n)))
+    keys = ("x", "lp", "S", "accepted", "naccept", "logalpha", "eta", "failed")
+    _same(rg, ro, keys=keys, S=True)
+    rg.steps(32, warmup=True, steps_per_launch=16)
+    ro.steps(32, warmup=True)
+    sg = _same(rg, ro, keys=keys, S=True)
+    rg.steps(8, warmup=False, steps_per_launch=8)
+    ro.steps(8, warmup=False)
+    _same(rg, ro, keys=keys, S=True)
+    if start == "adapted":
+        assert 0.02 < sg["naccept"].sum() / (n * 32) < 0.5
+    assert rg.ram_failed()[0] == ro.ram_failed()[0] == 0
+
+
+# ------------------------------------------------------------------ round-2 semantics
+def test_ram_failed_downdate_is_flagged_exported_and_raised_like_the_reference(amh, cuda, oracle):
+    """RAM :165-171: lowrankdowndate throws PosDefException when (v_i / A_ii)^2 > 1.  With gamma = 0 (eta = 1) and
+    alpha close to 1 a rejected step asks for a downdate by almost the whole factor; rounding pushes some chains over."""
+    d, n = 8, 2048
+    target = amh.MvNormalTarget(None, make_spd(d, 7, 1e-6, 1e-4))       # tiny target: proposals from S = I are rejected
+    spl = amh.RobustAdaptiveMetropolis(alpha=1.0 - 2.0 ** -53, gamma=0.0)
+    rg, ro = _pair(cuda, oracle, target, spl, n, _seeds(n, 6), np.zeros((d, n)))
+    rg.steps(4, warmup=True)
+    ro.steps(4, warmup=True)
+    keys = ("x", "lp", "S", "accepted", "naccept", "logalpha", "eta", "failed")
+    sg = _same(rg, ro, keys=keys, S=True)
+    ng, fg, flg = rg.ram_failed()
+    no, fo, flo = ro.ram_failed()
+    assert (ng, fg) == (no, fo) and np.array_equal(flg, flo)
+    if ng == 0:
+        pytest.skip("no downdate failed with this seed set (the flag path is covered by the oracle comparison above)")
+    assert fg == int(np.flatnonzero(flg)[0])
+    with pytest.raises(amh.PosDefException) as ei:
+        amh.sample(target, spl, amh.MCMCB200(), 3, n, num_warmup=4, initial_params=np.zeros((d, n)), seed=1, chain_type=amh.Chains)
+    assert ei.value.count > 0
+    ch = amh.sample(target, spl, amh.MCMCB200(ignore_failed_downdates=True), 3, n, num_warmup=4, initial_params=np.zeros((d, n)),
+                    seed=1, chain_type=amh.Chains)
+    assert ch.value.shape == (3, d + 1, n)
+
+
+def test_ram_resume_carries_logalpha_eta_and_failed(amh, cuda, oracle):
+    d, n = 16, 200
+    target = amh.MvNormalTarget(None, make_spd(d, 8, 0.05, 2.0))
+    spl = amh.RobustAdaptiveMetropolis(S=0.3 * np.eye(d))
+    seeds = _seeds(n, 9)
+    ra, _ = _pair(cuda, oracle, target, spl, n, seeds, np.zeros((d, n)))
+    ra.steps(20, warmup=True)
+    st = ra.state(S=True)
+    rb, _ = _pair(cuda, oracle, target, spl, n, seeds, np.zeros((d, n)))
+    rb.set_state(st)
+    sb = rb.state(S=True)
+    for k in ("x", "lp", "S", "logalpha", "eta", "failed", "accepted", "naccept"):
+        assert np.array_equal(st[k], sb[k]), k           # a resumed run REPORTS what the uninterrupted one reports
+    ra.steps(5, warmup=False); rb.steps(5, warmup=False)
+    sa, sb = ra.state(S=True), rb.state(S=True)
+    for k in ("x", "lp", "S", "logalpha", "eta", "accepted", "naccept"):
+        assert np.array_equal(sa[k], sb[k]), k
+
+
+def test_set_params_recomputes_lp_and_keeps_accepted(amh, cuda, oracle):
+    """setparams!!(model, t, params) = Transition(model, params, t.accepted)  (src/AdvancedMH.jl:151-157)"""
+    d, n = 3, 64
+    target = amh.MvNormalTarget(None, make_spd(d, 3, 0.5, 2.0))
+    spl = amh.RWMH(amh.MvNormal(np.zeros(d), 0.5 * amh.I))
+    rg, ro = _pair(cuda, oracle, target, spl, n, _seeds(n, 10))
+    rg.steps(5); ro.steps(5)
+    before = rg.state()
+    assert 0 < before["accepted"].sum() < n
+    xnew = np.random.default_rng(0).normal(size=(d, n))
+    rg.set_params(xnew); ro.set_params(xnew)
+    sg = _same(rg, ro)
+    assert np.array_equal(sg["accepted"], before["accepted"]) and np.array_equal(sg["x"], xnew)
+    assert not np.array_equal(sg["lp"], before["lp"])
+
+
+def test_callback_receives_the_sampler_state_of_every_saved_sample(amh, cuda, oracle):
+    """test/RobustAdaptiveMetropolis.jl:11-28,46-71: StatesExtractor records `state` per saved sample and the test checks
+    eigvals(S) against the bounds at every one of them"""
+    d, n, lo, hi = 2, 16, 0.9, 1.1
+    target = amh.MvNormalTarget(None, np.diag([10.0, 10.0]))
+    spl = amh.RobustAdaptiveMetropolis(gamma=0.51, eigenvalue_lower_bound=lo, eigenvalue_upper_bound=hi)
+    seen = []
+    def extractor(rng, model, sampler, sample, state, iteration):
+        seen.append((iteration, state.S_diag().copy(), state.logalpha.copy(), state.eta.copy(), state.iteration, sample.copy(),
+                     state.isaccept.copy()))
+    N = 60
+    ch = amh.sample(target, spl, amh.MCMCB200(), N, n, num_warmup=N, discard_initial=0, callback=extractor, seed=3,
+                    initial_params=np.zeros((d, n)), chain_type=amh.Chains)
+    assert [s[0] for s in seen] == list(range(1, N + 1))
+    assert [s[4] for s in seen] == list(range(1, N + 1))            # state.iteration: 1 after the first step (RAM :211)
+    diag = np.stack([s[1] for s in seen])
+    assert (diag >= lo).all() and (diag <= hi).all()                 # every eigenvalue of every state within the bounds
+    assert diag.max() == pytest.approx(hi, abs=0.05)                 # sigma^2 = 10: the upper bound is reached
+    assert all((s[2] <= 0).all() for s in seen)
+    np.testing.assert_allclose(seen[-1][3], float(N - 1) ** -0.51)   # eta of the last adaptation: iteration^-gamma
+    assert np.array_equal(np.stack([s[5] for s in seen]), ch.value)
+    assert np.array_equal(np.stack([s[6] for s in seen]), ch.accepted.astype(bool))
+    # and the stored samples are what the plain (no-callback) schedule returns
+    ch2 = amh.sample(target, spl, amh.MCMCB200(), N, n, num_warmup=N, discard_initial=0, seed=3,
+                     initial_params=np.zeros((d, n)), chain_type=amh.Chains)
+    assert np.array_equal(ch.value, ch2.value) and np.array_equal(ch.accepted, ch2.accepted)
