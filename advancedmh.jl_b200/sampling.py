@@ -10,6 +10,8 @@ thinning, num_warmup, chain_type, param_names, progress (ignored), callback."""
 from __future__ import annotations
 
 import os
+import sys
+import time
 from dataclasses import dataclass
 
 import numpy as np
@@ -18,6 +20,8 @@ from . import _capi as K
 from .models import as_target
 from .samplers import Ensemble, MALA, MHSampler, RobustAdaptiveMetropolis
 
+
+_TRACE = os.environ.get("AMH_TRACE") is not None     # phase timings of `sample` on stderr (the library prints its own)
 
 # ------------------------------------------------------------------ parallel
 class MCMCSerial:
@@ -290,6 +294,12 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
     `initial_state=` (AbstractMCMC keyword): a state dict of ALL chains as returned in `info["state"]` by a call with
     `save_state=True`; the run then continues the old one bit for bit -- its first sample is one `step` from that
     state, the step counter (hence the noise stream, RAM's `iteration` and the warm-up boundary) carries on."""
+    _t = [time.perf_counter()] if _TRACE else None
+    def lap(what):
+        if _TRACE:
+            now = time.perf_counter()
+            print(f"[amh.py] sample {what:22s} +{(now - _t[-1]) * 1e3:7.3f} ms", file=sys.stderr)
+            _t.append(now)
     args = list(args)
     if args and isinstance(args[0], np.random.Generator):
         rng = args.pop(0)
@@ -338,6 +348,7 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
     if in_process_job:
         eng = _job_for(eng, int(parallel.ngpus), parallel.devices)     # same surface as an Engine, arrays job-wide
 
+    lap("seeds + init + engine")
     n_local = (hi - lo) * nw
     nstreams = parallel.streams if isinstance(parallel, MCMCB200) else 1
     if (nstreams > 1 and not in_process_job and hi - lo >= nstreams and store and not summary and initial_state is None and not save_state
@@ -380,7 +391,9 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
                 if init.shape != (dim, nchains * nw):
                     raise ValueError(f"initial_state['x'] must have shape {(dim, nchains * nw)}")
                 init = init[:, sl]
+            lap("target + sampler")
             run = eng.run(th, sh, n_local, seeds, init, chain_offset=lo * nw)
+            lap("run_create")
             if initial_state is not None:
                 run.set_state({k: (v if k == "step" or v is None else np.asarray(v)[..., sl])
                                for k, v in initial_state.items() if k != "seeds"})
@@ -395,6 +408,7 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
                 out, acc, summ = run.sample(N, discard_initial, thinning, num_warmup, store=store,
                                             store_accepted=store, summary=summary or not store, chain_means=False,
                                             out=None if out is None else out[0], acc=None if out is None else out[1])
+            lap("run.sample")
             if isinstance(sampler, RobustAdaptiveMetropolis):
                 nfail, first, _ = run.ram_failed()
                 if nfail and not getattr(parallel, "ignore_failed_downdates", False):
@@ -417,6 +431,7 @@ def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None
         if th is not None:
             th.close()
 
+    lap("close")
     if world > 1 and isinstance(parallel, MCMCB200) and parallel.gather and store:
         out, acc = _gather_samples(dist, out, acc, nchains * nw, world, nw)
     if world > 1 and isinstance(parallel, MCMCB200) and parallel.gather and save_state:

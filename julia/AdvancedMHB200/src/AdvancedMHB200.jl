@@ -6,11 +6,12 @@
 # maintainer would review, not as verified code.
 #
 # What it adds to an unmodified AdvancedMH.jl:
-#   * `MCMCB200 <: AbstractMCMC.AbstractMCMCEnsemble`: sample(model, sampler, MCMCB200(), N, nchains; kw...)
+#   * `MCMCB200 <: AbstractMCMC.AbstractMCMCEnsemble`: sample(model, sampler, MCMCB200(ngpus = 8), N, nchains; kw...)
+#     -- one process, N GPUs, through the library's multi-GPU job (amh_job_*, include/amh.h)
 #   * catalogue targets (`MvNormalTarget`, ...) that ALSO implement LogDensityProblems, so the same object runs
-#     through stock MCMCThreads() for CPU comparison
-#   * `PhiloxRNG <: Random.AbstractRNG`: makes stock AdvancedMH consume the contract stream (include/amh_contract.h)
-#     so a CPU run can be compared step by step with the GPU (parity tier T3 of SURVEY.md 8c)
+#     through stock MCMCThreads() for CPU comparison (bench/ref_mcmcthreads.jl)
+# NOT in this module: `PhiloxRNG`, the AbstractRNG that makes stock AdvancedMH consume the contract stream for the T3
+# parity run.  It calls the CPU oracle's probes, i.e. it is test infrastructure, and lives in test/PhiloxRNG.jl.
 module AdvancedMHB200
 
 using AbstractMCMC, AdvancedMH, Distributions, LinearAlgebra, LogDensityProblems, Random
@@ -19,7 +20,7 @@ const libamh = get(ENV, "AMH_B200_LIB", "libamh_b200")
 
 # ---------------------------------------------------------------- ABI constants (include/amh.h)
 const AMH_OK = Int32(0)
-const TARGET_IID_NORMAL, TARGET_MVNORMAL, TARGET_ROSENBROCK, TARGET_LOGISTIC, TARGET_GAUSS_PREC = Int32.(1:5)
+const TARGET_IID_NORMAL, TARGET_MVNORMAL, TARGET_ROSENBROCK, TARGET_LOGISTIC, TARGET_GAUSS_PREC, TARGET_NIG_TOY, TARGET_NIG_TOY_LOG = Int32.(1:7)
 const TARGET_USER = Int32(100)
 const SAMPLER_STATIC, SAMPLER_RW, SAMPLER_STRETCH, SAMPLER_MALA, SAMPLER_RAM, SAMPLER_MIXED = Int32.(1:6)
 const COV_SCALAR, COV_DIAG, COV_FULL, COV_COMPONENTS = Int32.(1:4)
@@ -38,6 +39,11 @@ struct SamplerDesc            # struct amh_sampler_desc, field for field
     ram_alpha::Float64; ram_gamma::Float64; ram_eig_lo::Float64; ram_eig_hi::Float64
     ram_S0::Ptr{Float64}
     components::Ptr{Component}
+end
+
+struct Summary                # struct amh_summary
+    n_saved::Int64; n_steps::Int64; accept_rate::Float64
+    mean::Ptr{Float64}; var::Ptr{Float64}; chain_mean::Ptr{Float64}
 end
 
 function check(rc::Int32)
@@ -100,6 +106,49 @@ LogDensityProblems.logdensity(t::RosenbrockTarget, x) =
 LogDensityProblems.dimension(t::RosenbrockTarget) = t.dim
 LogDensityProblems.capabilities(::Type{RosenbrockTarget}) = LogDensityProblems.LogDensityOrder{0}()
 
+"""Bayesian logistic regression, prior N(0, tau^2 I): sum_i [y_i eta_i - log1pexp(eta_i)] - |beta|^2 / (2 tau^2), eta = X beta
+(BASELINE config 4); blob = [tau, X row-major, y]"""
+struct LogisticRegressionTarget <: DeviceTarget
+    X::Matrix{Float64}      # n x d
+    y::Vector{Float64}
+    tau::Float64
+end
+LogisticRegressionTarget(X, y; tau=10.0) = LogisticRegressionTarget(Matrix{Float64}(X), collect(Float64, y), Float64(tau))
+kind(::LogisticRegressionTarget) = TARGET_LOGISTIC
+blob(t::LogisticRegressionTarget) = vcat(t.tau, vec(permutedims(t.X)), t.y)
+log1pexp(x) = x > 0 ? x + log1p(exp(-x)) : log1p(exp(x))
+function LogDensityProblems.logdensity(t::LogisticRegressionTarget, b)
+    eta = t.X * b
+    sum(t.y .* eta .- log1pexp.(eta)) - dot(b, b) / (2 * t.tau^2)
+end
+LogDensityProblems.dimension(t::LogisticRegressionTarget) = size(t.X, 2)
+LogDensityProblems.capabilities(::Type{LogisticRegressionTarget}) = LogDensityProblems.LogDensityOrder{1}()
+function LogDensityProblems.logdensity_and_gradient(t::LogisticRegressionTarget, b)
+    eta = t.X * b
+    (sum(t.y .* eta .- log1pexp.(eta)) - dot(b, b) / (2 * t.tau^2), t.X' * (t.y .- 1 ./ (1 .+ exp.(-eta))) .- b ./ t.tau^2)
+end
+
+"""The emcee example of the reference's tests: s ~ InverseGamma(alpha, beta), m ~ N(0, s), y_i ~ N(m, s)
+(test/emcee.jl:5-15), or in (log s, m) with the Jacobian term (`log_space = true`, test/emcee.jl:46-56)"""
+struct NormalInverseGammaToy <: DeviceTarget
+    obs::Vector{Float64}
+    alpha::Float64
+    beta::Float64
+    log_space::Bool
+end
+NormalInverseGammaToy(obs=[1.5, 2.0]; alpha=2.0, beta=3.0, log_space=false) =
+    NormalInverseGammaToy(collect(Float64, obs), Float64(alpha), Float64(beta), log_space)
+kind(t::NormalInverseGammaToy) = t.log_space ? TARGET_NIG_TOY_LOG : TARGET_NIG_TOY
+blob(t::NormalInverseGammaToy) = vcat(t.alpha, t.beta, t.alpha * log(t.beta) - first(logabsgamma(t.alpha)), t.obs)
+function LogDensityProblems.logdensity(t::NormalInverseGammaToy, th)
+    s, m = t.log_space ? (exp(th[1]), th[2]) : (th[1], th[2])
+    s > 0 || return -Inf
+    lp = logpdf(InverseGamma(t.alpha, t.beta), s) + logpdf(Normal(0, sqrt(s)), m) + sum(logpdf.(Normal(m, sqrt(s)), t.obs))
+    t.log_space ? lp + th[1] : lp
+end
+LogDensityProblems.dimension(::NormalInverseGammaToy) = 2
+LogDensityProblems.capabilities(::Type{NormalInverseGammaToy}) = LogDensityProblems.LogDensityOrder{0}()
+
 """
     SourceTarget(dim, source; data = Float64[], gradient = false, logdensity = nothing)
 
@@ -124,17 +173,17 @@ LogDensityProblems.logdensity(t::SourceTarget, x) =
 LogDensityProblems.dimension(t::SourceTarget) = t.dim
 LogDensityProblems.capabilities(::Type{<:SourceTarget}) = LogDensityProblems.LogDensityOrder{0}()
 
-# handle creation: catalogue entry (kind, blob) or source text
-function create_target(ctx, target::DeviceTarget, d, tg)
+# the job's target: catalogue entry (kind, blob) or source text; the library broadcasts it to every device of the job
+function create_target(job, target::DeviceTarget, d)
     b = blob(target)
-    GC.@preserve b check(ccall((:amh_target_create, libamh), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Int64, Ptr{Ptr{Cvoid}}),
-                               ctx, kind(target), d, b, length(b), tg))
+    GC.@preserve b check(ccall((:amh_job_target_create, libamh), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Int64),
+                               job, kind(target), d, b, length(b)))
 end
-function create_target(ctx, target::SourceTarget, d, tg)
+function create_target(job, target::SourceTarget, d)
     b = target.data
-    GC.@preserve b check(ccall((:amh_target_create_source, libamh), Int32,
-                               (Ptr{Cvoid}, Int32, Cstring, Int32, Ptr{Float64}, Int64, Ptr{Ptr{Cvoid}}),
-                               ctx, d, target.source, target.gradient, isempty(b) ? C_NULL : pointer(b), length(b), tg))
+    GC.@preserve b check(ccall((:amh_job_target_create_source, libamh), Int32,
+                               (Ptr{Cvoid}, Int32, Cstring, Int32, Ptr{Float64}, Int64),
+                               job, d, target.source, target.gradient, isempty(b) ? C_NULL : pointer(b), length(b)))
 end
 
 # a DensityModel / LogDensityModel must wrap a catalogue target; anything else cannot run on the device
@@ -221,13 +270,26 @@ function lower(spl::AdvancedMH.Ensemble, d)
 end
 
 function lower(spl::AdvancedMH.MALA, d)
-    # recover (sigma2, drift) of g -> MvNormal(drift*g, sigma2*I) by probing the closure on the host
+    # recover (sigma2, drift) of g -> MvNormal(drift*g, sigma2*I) by probing the closure on the host: p(0) gives sigma2,
+    # p(e_i) the drift coefficient of every coordinate, p(2 e_i) checks linearity; anything else cannot be lowered
+    # (same checks as the Python mirror, samplers.py MALA.probe)
     f = spl.proposal.proposal
-    p0 = f(zeros(d)); e1 = zeros(d); e1[1] = 1.0
-    p1 = f(e1)
-    (p0 isa MvNormal && p0.Σ isa Distributions.PDMats.ScalMat) ||
-        throw(ArgumentError("MALA on the device needs proposal(g) = MvNormal(c*g, sigma2*I)"))
-    Lowered(SamplerDesc(SAMPLER_MALA, d, 0, COV_SCALAR, C_NULL, C_NULL, 2.0, 0, p0.Σ.value, mean(p1)[1],
+    bad() = throw(ArgumentError("MALA on the device needs proposal(g) = MvNormal(c*g, sigma2*I)"))
+    scal(p) = p isa MvNormal && p.Σ isa Distributions.PDMats.ScalMat && length(p) == d
+    p0 = f(zeros(d))
+    (scal(p0) && all(iszero, mean(p0))) || bad()
+    sigma2 = p0.Σ.value
+    c = nothing
+    for i in 1:d
+        e = zeros(d); e[i] = 1.0
+        p1, p2 = f(e), f(2 .* e)
+        (scal(p1) && scal(p2) && p1.Σ.value == sigma2) || bad()
+        m1, m2 = mean(p1), mean(p2)
+        ci = m1[i]
+        (all(iszero, m1[1:d .!= i]) && abs(m2[i] - 2ci) <= 1e-12 * max(1.0, abs(ci))) || bad()
+        c === nothing ? (c = ci) : (ci == c || bad())
+    end
+    Lowered(SamplerDesc(SAMPLER_MALA, d, 0, COV_SCALAR, C_NULL, C_NULL, 2.0, 0, sigma2, c,
                         0.234, 0.6, 0.0, Inf, C_NULL, C_NULL), Any[])
 end
 
@@ -241,14 +303,39 @@ end
 
 # ---------------------------------------------------------------- the ensemble type
 """
-    MCMCB200(; device = 0)
+    MCMCB200(; ngpus = 1, devices = nothing, ignore_failed_downdates = false)
 
-Run all chains in lock-step on a B200.  `sample(model, sampler, MCMCB200(), N, nchains; kw...)` keeps AbstractMCMC's
-keywords: `initial_params` (one entry per chain), `discard_initial`, `thinning`, `num_warmup`, `chain_type`,
-`param_names`.
+Run all chains in lock-step on `ngpus` B200s of this box, from this one process: the drop-in for `MCMCThreads()` /
+`MCMCDistributed()` (AdvancedMH.jl src/AdvancedMH.jl:30, README.md:135-148).  The library shards the chains in contiguous
+blocks (an `Ensemble` stays on one GPU), broadcasts the target's fixed data once (NCCL over NVLink), steps every block on
+its own stream without any per-step collective, and every GPU writes its column block of the result array directly.
+`sample(model, sampler, MCMCB200(ngpus = 8), N, nchains; kw...)` keeps AbstractMCMC's keywords: `initial_params` (one
+entry per chain), `discard_initial`, `thinning`, `num_warmup`, `chain_type`, `param_names`.
 """
 Base.@kwdef struct MCMCB200 <: AbstractMCMC.AbstractMCMCEnsemble
-    device::Int = 0
+    ngpus::Int = 1
+    devices::Union{Nothing,Vector{Int32}} = nothing       # CUDA device indices, default 0:ngpus-1
+    ignore_failed_downdates::Bool = false                 # RAM: keep the samples instead of throwing PosDefException
+end
+
+# (n, d) column-major == the device layout X[dim][chain] with chains fastest.  One entry per chain; for an Ensemble an
+# entry is the vector of its n_walkers walker positions (emcee.jl:29-34 returns exactly that shape).
+function initial_matrix(initial_params, nchains, nw, d)
+    initial_params === nothing && return nothing
+    length(initial_params) == nchains || throw(ArgumentError("initial_params must have one entry per chain"))
+    init = Matrix{Float64}(undef, nchains * nw, d)
+    for (c, p) in enumerate(initial_params)
+        if nw == 1
+            length(p) == d || throw(ArgumentError("initial_params entry has length $(length(p)), model dimension is $d"))
+            init[c, :] .= p
+        else
+            length(p) == nw || throw(ArgumentError("an Ensemble needs n_walkers initial positions per chain"))
+            for (w, q) in enumerate(p)
+                init[(c - 1) * nw + w, :] .= q
+            end
+        end
+    end
+    init
 end
 
 function AbstractMCMC.mcmcsample(rng::Random.AbstractRNG, model::AbstractMCMC.AbstractModel,
@@ -262,57 +349,47 @@ function AbstractMCMC.mcmcsample(rng::Random.AbstractRNG, model::AbstractMCMC.Ab
     n = nchains * nw
     seeds = rand(rng, UInt64, nchains)                         # exactly AbstractMCMC's per-chain seeding
     low = lower(sampler, d)
-    b = blob(target)
-    # device layout: X[dim][chain], chains fastest == Julia Matrix(undef, nchains, dim) (column-major)
-    init = initial_params === nothing ? nothing : permutedims(reduce(hcat, [vec(collect(Float64, p)) for p in initial_params]))
-    out = Array{Float64}(undef, n, d + 1, N)                   # C order [N][d+1][n]
+    init = initial_matrix(initial_params, nchains, nw, d)
+    out = Array{Float64}(undef, n, d + 1, N)                   # C order [N][d+1][n]: every GPU fills its block of columns
     acc = Array{UInt8}(undef, n, N)
-    ctx = Ref{Ptr{Cvoid}}(); tg = Ref{Ptr{Cvoid}}(); sp = Ref{Ptr{Cvoid}}(); run = Ref{Ptr{Cvoid}}()
-    GC.@preserve low b seeds init out acc begin
-        check(ccall((:amh_ctx_create, libamh), Int32, (Int32, Ptr{Ptr{Cvoid}}), par.device, ctx))
+    devs = par.devices === nothing ? C_NULL : pointer(par.devices)
+    job = Ref{Ptr{Cvoid}}(C_NULL)
+    nfailed = Ref{Int64}(0); first_failed = Ref{Int64}(-1)
+    GC.@preserve low seeds init out acc par begin
+        check(ccall((:amh_job_create, libamh), Int32, (Int32, Ptr{Int32}, Ptr{Ptr{Cvoid}}), par.ngpus, devs, job))
         try
-            create_target(ctx[], target, d, tg)
-            check(ccall((:amh_sampler_create, libamh), Int32, (Ptr{Cvoid}, Ref{SamplerDesc}, Ptr{Ptr{Cvoid}}), ctx[], low.desc, sp))
-            check(ccall((:amh_run_create, libamh), Int32,
-                        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{UInt64}, Ptr{Float64}, Int64, Ptr{Ptr{Cvoid}}),
-                        ctx[], tg[], sp[], n, 0, seeds, init === nothing ? C_NULL : pointer(init), 0, run))
-            check(ccall((:amh_run_sample, libamh), Int32,
-                        (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ptr{Float64}, Ptr{UInt8}, Ptr{Cvoid}),
-                        run[], N, discard_initial, thinning, num_warmup, out, acc, C_NULL))
+            create_target(job[], target, d)
+            check(ccall((:amh_job_sampler_create, libamh), Int32, (Ptr{Cvoid}, Ref{SamplerDesc}), job[], low.desc))
+            check(ccall((:amh_job_run_create, libamh), Int32, (Ptr{Cvoid}, Int64, Ptr{UInt64}, Ptr{Float64}, Int64),
+                        job[], n, seeds, init === nothing ? C_NULL : pointer(init), 0))
+            check(ccall((:amh_job_run_sample, libamh), Int32,
+                        (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ptr{Float64}, Ptr{UInt8}, Ptr{Summary}),
+                        job[], N, discard_initial, thinning, num_warmup, out, acc, C_NULL))
+            if sampler isa AdvancedMH.RobustAdaptiveMetropolis
+                check(ccall((:amh_job_run_ram_failed, libamh), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{UInt8}),
+                            job[], nfailed, first_failed, C_NULL))
+            end
         finally
-            run[] == C_NULL || ccall((:amh_run_destroy, libamh), Int32, (Ptr{Cvoid},), run[])
-            sp[] == C_NULL || ccall((:amh_sampler_destroy, libamh), Int32, (Ptr{Cvoid},), sp[])
-            tg[] == C_NULL || ccall((:amh_target_destroy, libamh), Int32, (Ptr{Cvoid},), tg[])
-            ccall((:amh_ctx_destroy, libamh), Int32, (Ptr{Cvoid},), ctx[])
+            ccall((:amh_job_destroy, libamh), Int32, (Ptr{Cvoid},), job[])       # releases run, sampler, target, contexts
         end
     end
-    # hand the arrays to the reference's own bundling: one Vector{Transition} per chain, then bundle_samples +
-    # chainsstack exactly like AbstractMCMC does (src/AdvancedMH.jl:80-123, ext/AdvancedMHMCMCChainsExt.jl)
+    # lowrankdowndate throws PosDefException and aborts `sample` (RobustAdaptiveMetropolis.jl:170); so does this path
+    if nfailed[] > 0 && !par.ignore_failed_downdates
+        throw(LinearAlgebra.PosDefException(Int(first_failed[]) + 1))
+    end
+    # hand the arrays to the reference's own bundling, then chainsstack exactly like AbstractMCMC does
+    # (src/AdvancedMH.jl:80-123, ext/AdvancedMHMCMCChainsExt.jl).  An Ensemble sample is the Vector of ALL its walkers'
+    # Transitions (emcee.jl:14-24), which is what the Chains extension bundles (:80-121).
+    transition(col, i) = AdvancedMH.Transition(out[col, 1:d, i], out[col, d + 1, i], acc[col, i] != 0)
     chains = map(1:nchains) do c
-        ts = [AdvancedMH.Transition(out[(c - 1) * nw + 1, 1:d, i], out[(c - 1) * nw + 1, d + 1, i], acc[(c - 1) * nw + 1, i] != 0)
-              for i in 1:N]
+        ts = nw == 1 ? [transition(c, i) for i in 1:N] :
+                       [[transition((c - 1) * nw + w, i) for w in 1:nw] for i in 1:N]
         AbstractMCMC.bundle_samples(ts, model, sampler, nothing, chain_type; discard_initial, thinning, kwargs...)
     end
     return AbstractMCMC.chainsstack(AbstractMCMC.tighten_eltype(chains))
 end
 
-# ---------------------------------------------------------------- contract RNG for CPU-side parity runs
-"""
-    PhiloxRNG(seed)
-
-Sequential consumer of the contract stream (include/amh_contract.h): `randn`, `randexp`, `rand` are served from
-Philox4x32-10 blocks with the per-step layout of the kernels, so `sample(rng = PhiloxRNG(seed), ...)` with stock
-AdvancedMH reproduces the device chain seeded `seed`, provided it is re-positioned (`seekstep!`) at every step start.
-The transcendental functions must be the contract's (ccall into the oracle's `amho_probe_*`), not Base's.
-"""
-mutable struct PhiloxRNG <: Random.AbstractRNG
-    seed::UInt64
-    block::UInt64
-    word::Int
-end
-PhiloxRNG(seed::Integer) = PhiloxRNG(UInt64(seed), 0, 0)
-seekstep!(r::PhiloxRNG, k::Integer, d::Integer) = (r.block = UInt64(k) * UInt64(cld(d, 2) + 1); r.word = 0; r)
-
-export MCMCB200, MvNormalTarget, GaussianPrecisionTarget, IIDNormalTarget, RosenbrockTarget, PhiloxRNG, seekstep!
+export MCMCB200, MvNormalTarget, GaussianPrecisionTarget, IIDNormalTarget, RosenbrockTarget, LogisticRegressionTarget,
+       NormalInverseGammaToy, SourceTarget
 
 end # module
