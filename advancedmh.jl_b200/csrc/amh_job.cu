@@ -2,12 +2,16 @@
  * process, which is what a Julia host needs (`MCMCB200(ngpus = 8)`; north star: "chains shard across the 8 GPUs of one
  * box with only a one-time NCCL broadcast of the target's fixed data ... no per-step collective").
  *
- * Broadcast of the target blob (AMH_JOB_BCAST = nccl | peer | h2d, default: nccl when libnccl can be loaded):
- *   nccl  host -> device 0, then ONE ncclBroadcast over NVLink / NVSwitch (communicators from ncclCommInitAll at job
- *         creation; libnccl.so.2 is dlopen'ed -- no link-time dependency, and inside a process that already holds an
- *         NCCL, e.g. PyTorch's, the loaded copy is reused)
+ * Broadcast of the target blob (AMH_JOB_BCAST = auto | nccl | peer | h2d):
+ *   nccl  host -> device 0, then ONE ncclBroadcast over NVLink / NVSwitch (communicators from ncclCommInitAll, created
+ *         lazily at the first broadcast; libnccl.so.2 is dlopen'ed -- no link-time dependency, and inside a process
+ *         that already holds an NCCL, e.g. PyTorch's, the loaded copy is reused)
  *   peer  host -> device 0, then cudaMemcpyPeerAsync 0 -> k over NVLink
- *   h2d   N host -> device copies
+ *   h2d   N host -> device copies, one per PCIe link, in parallel
+ *   auto  (default) by MEASUREMENT on 8 x B200 (profiles/r2_job_check_8gpu.txt), BASELINE config 4's 10.3 MB blob:
+ *         h2d 2.5 ms, nccl 7.1 ms (+ 1.8 s of one-time communicator set-up, 309 ms for the first call), peer 8.8 ms --
+ *         every GPU has its own PCIe link, so N parallel host copies beat a staged fan-out until the blob is large
+ *         enough for host-memory bandwidth to matter: h2d up to 256 MB, above that device 0 + NVLink peer copies.
  * Samples never cross NVLink: every device writes its column block of the caller's host array directly. */
 #include <dlfcn.h>
 #include <nccl.h>
@@ -99,25 +103,25 @@ struct CudaBackend {
                 if (e != cudaSuccess) cudaGetLastError();                 /* cudaErrorPeerAccessAlreadyEnabled */
             }
         }
-        if (want == "h2d" || want == "peer") { sh.mode = want; return AMH_OK; }
+        if (want == "h2d" || want == "peer" || want == "nccl") sh.mode = want;
+        else sh.mode = "auto";
+        if (sh.mode == "nccl" && !nccl_api().ok())
+            return fail(AMH_ERR_UNSUPPORTED, "AMH_JOB_BCAST=nccl but libnccl.so.2 could not be loaded");
+        return AMH_OK;
+    }
+    /* communicators are only built when a broadcast really goes through NCCL (1.8 s for 8 GPUs) */
+    static int nccl_init(amhjob::Job<CudaBackend>& j) {
+        Shared& sh = j.shared;
+        if (!sh.comms.empty()) return AMH_OK;
         NcclApi& api = nccl_api();
-        if (!api.ok()) {
-            if (want == "nccl") return fail(AMH_ERR_UNSUPPORTED, "AMH_JOB_BCAST=nccl but libnccl.so.2 could not be loaded");
-            sh.mode = "peer";
-            return AMH_OK;
-        }
         const auto t0 = std::chrono::steady_clock::now();
         sh.comms.assign(j.ngpus, nullptr);
         const ncclResult_t r = api.CommInitAll(sh.comms.data(), j.ngpus, j.devices.data());
         sh.comm_init_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (r != ncclSuccess) {
             sh.comms.clear();
-            if (want == "nccl")
-                return fail(AMH_ERR_CUDA, std::string("ncclCommInitAll failed: ") + (api.GetErrorString ? api.GetErrorString(r) : "?"));
-            sh.mode = "peer";
-            return AMH_OK;
+            return fail(AMH_ERR_CUDA, std::string("ncclCommInitAll failed: ") + (api.GetErrorString ? api.GetErrorString(r) : "?"));
         }
-        sh.mode = "nccl";
         return AMH_OK;
     }
     static void shared_destroy(amhjob::Job<CudaBackend>& j) {
@@ -129,15 +133,19 @@ struct CudaBackend {
     /* target blob: host -> device 0, then device 0 -> the others */
     static int target_broadcast(amhjob::Job<CudaBackend>& j, int32_t kind, int32_t dim, const double* blob, int64_t nblob) {
         Shared& sh = j.shared;
-        j.bcast_mode = sh.mode;
-        if (sh.mode == "h2d" || nblob == 0)
+        const size_t bytes = sizeof(double) * (size_t)nblob;
+        std::string mode = sh.mode;
+        if (mode == "auto") mode = (j.ngpus == 1 || bytes <= (256ull << 20)) ? "h2d" : "peer";
+        j.bcast_mode = mode;
+        if (mode == "h2d" || nblob == 0)
             return j.each([&](int k) { return (int)amh_target_create(j.ctx[k], kind, dim, blob, nblob, &j.target[k]); });
+        if (mode == "nccl")
+            if (int rc0 = nccl_init(j)) return rc0;
         int rc = amh_target_create(j.ctx[0], kind, dim, blob, nblob, &j.target[0]);        /* validates, uploads, syncs */
         if (rc) return rc;
         for (int k = 1; k < j.ngpus && !rc; ++k) rc = amhh::target_create_empty(j.ctx[k], kind, dim, blob, nblob, &j.target[k]);
         if (rc) return rc;
-        const size_t bytes = sizeof(double) * (size_t)nblob;
-        if (sh.mode == "nccl") {
+        if (mode == "nccl") {
             NcclApi& api = nccl_api();
             ncclResult_t r = api.GroupStart();
             for (int k = 0; k < j.ngpus && r == ncclSuccess; ++k)
