@@ -48,6 +48,7 @@ class SamplerDesc(C.Structure):
         ("ram_eig_lo", C.c_double), ("ram_eig_hi", C.c_double),
         ("ram_S0", _dp),
         ("components", C.POINTER(Component)),
+        ("contract", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -87,13 +88,32 @@ ABI_SYMBOLS = [
     "version", "last_error", "contract_version", "ctx_create", "ctx_destroy", "ctx_sync",
     "target_create", "target_create_source", "target_destroy", "sampler_create", "sampler_destroy",
     "run_create", "run_destroy", "run_steps", "run_sync", "run_sample", "run_sample_ld",
-    "run_get_state", "run_set_params", "run_set_state", "run_get_ram_adapt", "run_set_ram_adapt", "run_ram_failed", "run_dim", "run_nchains", "run_launch_count",
+    "run_get_state", "run_set_params", "run_set_state", "run_get_ram_adapt", "run_set_ram_adapt", "run_ram_failed", "run_contract", "run_dim", "run_nchains", "run_launch_count",
     "run_kernel_time_ms", "host_alloc", "host_free", "run_get_state_ld", "run_set_state_ld",
     "job_create", "job_destroy", "job_ngpus", "job_target_create", "job_target_create_source", "job_broadcast_mode",
     "job_broadcast_ms", "job_comm_init_ms", "job_sampler_create", "job_run_create", "job_run_destroy", "job_run_steps",
     "job_run_sync", "job_run_sample", "job_run_get_state", "job_run_set_state", "job_run_get_ram_adapt",
-    "job_run_set_ram_adapt", "job_run_ram_failed", "job_run_shard", "job_run_launch_count", "job_run_kernel_time_ms",
+    "job_run_set_ram_adapt", "job_run_ram_failed", "job_run_contract", "job_run_shard", "job_run_launch_count", "job_run_kernel_time_ms",
 ]
+
+
+# contract version new samplers are lowered with when the caller does not say (0 = the library's default, v2);
+# tests pin v1 with `with contract(1): ...`
+DEFAULT_CONTRACT = 0
+
+
+class contract:
+    """context manager: lower samplers under numerical-contract version `v` inside the block"""
+    def __init__(self, v):
+        self.v = int(v)
+    def __enter__(self):
+        global DEFAULT_CONTRACT
+        self.old, DEFAULT_CONTRACT = DEFAULT_CONTRACT, self.v
+        return self
+    def __exit__(self, *exc):
+        global DEFAULT_CONTRACT
+        DEFAULT_CONTRACT = self.old
+        return False
 
 
 def _as_f64(a):
@@ -103,9 +123,10 @@ def _as_f64(a):
 def sampler_desc(*, kind, dim, symmetric=False, cov_kind=COV_SCALAR, mean=None, scale=None,
                  stretch_a=2.0, n_walkers=0, mala_sigma2=0.0, mala_drift=0.0,
                  ram_alpha=0.234, ram_gamma=0.6, ram_eig_lo=0.0, ram_eig_hi=float("inf"), ram_S0=None,
-                 components=None):
+                 components=None, contract=None):
     """-> (amh_sampler_desc, objects that must stay alive while it is used).
-    components: list of (family, p0, p1, logc[, rw, symmetric]) -- one univariate law per coordinate"""
+    components: list of (family, p0, p1, logc[, rw, symmetric]) -- one univariate law per coordinate
+    contract: version of the numerical contract (include/amh_contract.h); None = `DEFAULT_CONTRACT` (0 = library default)"""
     keep = []
     def ptr(a):
         if a is None:
@@ -115,7 +136,8 @@ def sampler_desc(*, kind, dim, symmetric=False, cov_kind=COV_SCALAR, mean=None, 
         return a.ctypes.data_as(_dp)
     d = SamplerDesc(kind, dim, int(bool(symmetric)), cov_kind, ptr(mean), ptr(scale), float(stretch_a),
                     int(n_walkers), float(mala_sigma2), float(mala_drift), float(ram_alpha), float(ram_gamma),
-                    float(ram_eig_lo), float(ram_eig_hi), ptr(ram_S0), None)
+                    float(ram_eig_lo), float(ram_eig_hi), ptr(ram_S0), None,
+                    int(DEFAULT_CONTRACT if contract is None else contract), 0)
     if components is not None:
         if len(components) != dim:
             raise AMHArgumentError(AMH_ERR_INVALID, f"need one component per coordinate ({dim}), got {len(components)}")
@@ -156,7 +178,7 @@ class Engine:
         f("last_error").restype = C.c_char_p
         f("run_nchains").restype = C.c_int64
         f("run_launch_count").restype = C.c_int64
-        for n in ("run_nchains", "run_launch_count", "run_dim", "run_sync", "run_destroy", "ctx_sync",
+        for n in ("run_nchains", "run_launch_count", "run_dim", "run_contract", "run_sync", "run_destroy", "ctx_sync",
                   "ctx_destroy", "target_destroy", "sampler_destroy"):
             f(n).argtypes = [C.c_void_p]
         f("ctx_create").argtypes = [C.c_int32, C.POINTER(C.c_void_p)]
@@ -184,7 +206,7 @@ class Engine:
         f("run_set_state_ld").argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, _u8p, _i64p, C.c_int64]
         # multi-GPU job
         f("job_create").argtypes = [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]
-        for n in ("job_destroy", "job_ngpus", "job_run_destroy", "job_run_sync", "job_run_launch_count", "job_broadcast_mode",
+        for n in ("job_destroy", "job_ngpus", "job_run_contract", "job_run_destroy", "job_run_sync", "job_run_launch_count", "job_broadcast_mode",
                   "job_broadcast_ms", "job_comm_init_ms"):
             f(n).argtypes = [C.c_void_p]
         f("job_broadcast_mode").restype = C.c_char_p
@@ -447,6 +469,10 @@ class Run:
         flags = np.empty(self.n, dtype=np.uint8)
         self.eng._check(self._r("ram_failed")(self.h, C.byref(nf), C.byref(first), flags.ctypes.data_as(_u8p)))
         return int(nf.value), int(first.value), flags
+
+    def contract(self):
+        """the numerical-contract version this run was created under"""
+        return int(self._r("contract")(self.h))
 
     def launch_count(self):
         return int(self._r("launch_count")(self.h))

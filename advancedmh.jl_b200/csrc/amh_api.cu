@@ -30,7 +30,7 @@ amhd::ChainState chain_state(amh_run& r) {
     amhd::ChainState st;
     st.X = r.X; st.lp = r.lp; st.lq = r.lq; st.G = r.G;
     st.acc = r.acc; st.nacc = r.nacc; st.seeds = r.seeds;
-    st.n = r.n; st.pitch = r.pitch;
+    st.n = r.n; st.pitch = r.pitch; st.cv = r.cv;
     return st;
 }
 
@@ -386,6 +386,11 @@ int32_t amh_sampler_create(amh_ctx* ctx, const amh_sampler_desc* desc, amh_sampl
         return bad("unknown sampler kind");
     }
     s->d.mean = nullptr; s->d.scale = nullptr; s->d.ram_S0 = nullptr; s->d.components = nullptr;
+    if (s->d.contract == 0) {
+        const char* ev = std::getenv("AMH_CONTRACT");
+        s->d.contract = ev ? std::atoi(ev) : AMH_CONTRACT_VERSION;
+    }
+    if (s->d.contract != AMH_CONTRACT_V1 && s->d.contract != AMH_CONTRACT_V2) return bad("unknown contract version");
     cudaSetDevice(ctx->device);
     int rc = upload(ctx, &s->dmean, s->mean);
     if (!rc && !s->comps.empty()) {
@@ -442,6 +447,7 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
     amh_run* r = new amh_run();
     r->ctx = ctx; r->target = target; r->sampler = sampler;
     r->n = n; r->off = off; r->dim = d; r->nseeds = nseeds;
+    r->cv = sampler->d.contract;
     r->pitch = (n + 31) / 32 * 32;          /* rows start 256-byte aligned; a warp's 32 chains never straddle a row end */
     if (const char* ev = std::getenv("AMH_PITCH_PAD")) r->pitch += 32ll * std::atoll(ev);      /* experiment switch */
     {
@@ -840,6 +846,7 @@ int32_t amh_host_free(void* p) {
 }
 
 int32_t amh_run_dim(amh_run* run) { return run ? run->dim : -1; }
+int32_t amh_run_contract(amh_run* run) { return run ? run->cv : -1; }
 int64_t amh_run_nchains(amh_run* run) { return run ? run->n : -1; }
 int64_t amh_run_launch_count(amh_run* run) { return run ? run->launches : -1; }
 

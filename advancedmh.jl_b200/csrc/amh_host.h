@@ -89,6 +89,7 @@ struct amh_run {
     long long plan_step0[2] = {-1, -1};              /* what buffer b holds: first step and number of sweeps            */
     int plan_nsteps[2] = {0, 0};
     int plan_layout_nsteps = -1;                     /* launch length the two plan buffers are laid out for            */
+    int cv = AMH_CONTRACT_VERSION;  /* contract version of the step noise (amh_sampler_desc.contract) */
     bool keep_acc = false;         /* launch_init leaves Transition.accepted alone (amh_run_set_params) */
     bool ram_warp = false;         /* RAM: S stored [chain][column-packed] and stepped by K4W */
     int mh_path = 0;               /* 0 = choose (tensor-core K1T when eligible), 1 = force the per-thread DFMA kernel K1 */

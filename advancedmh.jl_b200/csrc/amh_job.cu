@@ -87,6 +87,7 @@ struct CudaBackend {
     static int run_set_ram_adapt(amh_run* r, const double* la, const double* eta, const uint8_t* f) { return amh_run_set_ram_adapt(r, la, eta, f); }
     static int run_ram_failed(amh_run* r, int64_t* nf, int64_t* first, uint8_t* f) { return amh_run_ram_failed(r, nf, first, f); }
     static int64_t run_launch_count(amh_run* r) { return amh_run_launch_count(r); }
+    static int run_contract(amh_run* r) { return amh_run_contract(r); }
     static int run_kernel_time_ms(amh_run* r, int32_t reset, double* ms, int64_t* l) { return amh_run_kernel_time_ms(r, reset, ms, l); }
 
     static int shared_init(amhjob::Job<CudaBackend>& j) {

@@ -479,6 +479,13 @@ int job_run_kernel_time_ms(Job<B>* j, int32_t reset, double* ms, int64_t* launch
     int32_t AMH_JOB_CAT(P, job_run_shard)(amh_job* j, int32_t k, int64_t* lo, int64_t* hi, int32_t* device) {                      \
         return amhjob::job_run_shard<B>((amhjob::Job<B>*)j, k, lo, hi, device);                                                    \
     }                                                                                                                              \
+    int32_t AMH_JOB_CAT(P, job_run_contract)(amh_job* j) {                                                                         \
+        amhjob::Job<B>* q = (amhjob::Job<B>*)j;                                                                                    \
+        if (!q) return -1;                                                                                                         \
+        for (int k = 0; k < q->ngpus; ++k)                                                                                         \
+            if (q->run[k]) return B::run_contract(q->run[k]);                                                                      \
+        return -1;                                                                                                                 \
+    }                                                                                                                              \
     int64_t AMH_JOB_CAT(P, job_run_launch_count)(amh_job* j) { return amhjob::job_run_launch_count<B>((amhjob::Job<B>*)j); }       \
     int32_t AMH_JOB_CAT(P, job_run_kernel_time_ms)(amh_job* j, int32_t reset, double* ms, int64_t* launches) {                     \
         return amhjob::job_run_kernel_time_ms<B>((amhjob::Job<B>*)j, reset, ms, launches);                                         \

@@ -56,7 +56,8 @@ mh_step_kernel(const __grid_constant__ MhArgs<DMAX> a,
     for (int i = 0; i < top; ++i)
         if (i < d) sx[i * BLOCK + tid] = a.st.X[(long long)i * a.st.pitch + ch];
 
-    const unsigned long long B = (unsigned long long)((d + 1) / 2 + 1);
+    const int cv = a.st.cv;
+    const unsigned long long B = amh::blocks_per_step_cv(cv, d);
     double z[CAP];
     for (int s = 0; s < a.nsteps; ++s) {
         /* untaken by default, kept on purpose: with this branch at the top of the step ptxas orders the loop body
@@ -67,11 +68,10 @@ mh_step_kernel(const __grid_constant__ MhArgs<DMAX> a,
         const unsigned long long blk0 = k * B;
         double e;
         if constexpr (D::fixed) {
-            step_noise_fixed<DMAX>(seed, blk0, z, e);
+            step_noise_fixed_cv<DMAX>(cv, seed, k, z, e);
         } else {
-            step_normals<DMAX>(seed, blk0, d, z);
-            const amh::Block be = amh::stream_block(seed, blk0 + (unsigned long long)((d + 1) / 2), 0u);
-            e = amh::exponential(be.v[0], be.v[1]);
+            step_normals<DMAX>(cv, seed, blk0, d, z);
+            e = amh::step_exponential_cv(cv, seed, blk0, d);
         }
         draw_inplace<DMAX>(z, d, a.prop);
         if (a.is_rw) {
@@ -174,7 +174,7 @@ init_kernel(const __grid_constant__ InitArgs a, const __grid_constant__ typename
         if (a.comps) draw_components(x, d, a.comps, seed, (unsigned long long)w * (unsigned long long)d);
         else draw_inplace<0>(x, d, a.prop);
     } else {
-        step_normals<0>(a.st.seeds[ch], 0ull, d, x);
+        step_normals<0>(a.st.cv, a.st.seeds[ch], 0ull, d, x);
         if (a.mode == 1) {
             if (a.comps) draw_components(x, d, a.comps, a.st.seeds[ch], 0ull);
             else draw_inplace<0>(x, d, a.prop);

@@ -49,18 +49,18 @@ mala_step_kernel(const __grid_constant__ MalaArgs a, const __grid_constant__ typ
             sx[i * BLOCK + tid] = a.st.X[(long long)i * a.st.pitch + ch];
             sg[i * BLOCK + tid] = a.st.G[(long long)i * a.st.pitch + ch];
         }
-    const unsigned long long B = (unsigned long long)((d + 1) / 2 + 1);
+    const int cv = a.st.cv;
+    const unsigned long long B = amh::blocks_per_step_cv(cv, d);
     double c[CAP], gc[CAP];
     for (int s = 0; s < a.nsteps; ++s) {
         const unsigned long long k = a.step0 + (unsigned long long)s + 1ull;
         const unsigned long long blk0 = k * B;
         double e;
         if constexpr (D::fixed) {
-            step_noise_fixed<DMAX>(seed, blk0, c, e);
+            step_noise_fixed_cv<DMAX>(cv, seed, k, c, e);
         } else {
-            step_normals<DMAX>(seed, blk0, d, c);
-            const amh::Block be = amh::stream_block(seed, blk0 + (unsigned long long)((d + 1) / 2), 0u);
-            e = amh::exponential(be.v[0], be.v[1]);
+            step_normals<DMAX>(cv, seed, blk0, d, c);
+            e = amh::step_exponential_cv(cv, seed, blk0, d);
         }
         /* candidate = state + rand(MvNormal(drift*grad, sigma2*I))  (MALA.jl:70 -> proposal.jl:49-56) */
 #pragma unroll UNR

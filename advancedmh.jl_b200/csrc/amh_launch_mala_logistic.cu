@@ -159,12 +159,25 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
         double e = 0.0;
         {
             double z[2 * NPP];
+            if (a.st.cv == AMH_CONTRACT_V2) {
+                /* contract v2: four normals per block -> D/16 blocks per lane part, the exponential in block D/4 */
+                constexpr int NB2 = D / 16;
+                constexpr unsigned long long B2 = (unsigned long long)(D / 4 + 1);
+                const unsigned long long b0 = k * B2 + (unsigned long long)(NB2 * part);
+                if constexpr (NB2 > 4) {
+                    noise_group<4, false, 2>(seed, b0, 0ull, z, e);
+                    noise_group<NB2 - 4, true, 2>(seed, b0 + 4, k * B2 + (unsigned long long)(D / 4), z + 16, e);
+                } else {
+                    noise_group<NB2, true, 2>(seed, b0, k * B2 + (unsigned long long)(D / 4), z, e);
+                }
+            } else {
             const unsigned long long b0 = k * B + (unsigned long long)(NPP * part);
             if constexpr (NPP > 8) {
                 noise_group<8, false>(seed, b0, 0ull, z, e);
                 noise_group<NPP - 8, true>(seed, b0 + 8, k * B + (unsigned long long)(D / 2), z + 16, e);
             } else {
                 noise_group<NPP, true>(seed, b0, k * B + (unsigned long long)(D / 2), z, e);
+            }
             }
 #pragma unroll
             for (int i = 0; i < 2 * NPP; ++i) {

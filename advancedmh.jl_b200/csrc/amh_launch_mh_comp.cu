@@ -42,13 +42,14 @@ mh_comp_kernel(const __grid_constant__ MhCompArgs a, const __grid_constant__ typ
     unsigned char accepted = a.st.acc[ch];
     for (int i = 0; i < d; ++i) sx[i * BLOCK + tid] = a.st.X[(long long)i * a.st.pitch + ch];
 
-    const unsigned long long B = (unsigned long long)((d + 1) / 2 + 1);
+    const int cv = a.st.cv;
+    const unsigned long long B = amh::blocks_per_step_cv(cv, d);
     double z[CAP];
     for (int s = 0; s < a.nsteps; ++s) {
         const unsigned long long k = a.step0 + (unsigned long long)s + 1ull;
         const unsigned long long blk0 = k * B;
-        step_normals<0>(seed, blk0, d, z);
-        const amh::Block be = amh::stream_block(seed, blk0 + (unsigned long long)((d + 1) / 2), 0u);
+        step_normals<0>(cv, seed, blk0, d, z);
+        const amh::Block be = amh::step_block(cv, seed, blk0 + (unsigned long long)amh::normal_blocks(cv, d));
         const double e = amh::exponential(be.v[0], be.v[1]);
         draw_components(z, d, a.comps, seed, k * (unsigned long long)d);
         for (int i = 0; i < d; ++i) {

@@ -263,13 +263,14 @@ __host__ __device__ constexpr int tc16_smem_doubles_per_warp() { return D * kPZ1
  * end-of-launch tail and LOSES throughput for every k (5.28e9 at k <= 16). */
 /* COVD: the proposal covariance is diagonal (ScalMat / PDiagMat): v_i = sigma_i z_i needs no mat-vec, phase 1 is
  * c = x + sigma_i z_i on the chain lanes (the contract's two roundings, proposal.jl:41-56 with a diagonal factor). */
-template <int D, int WARPS, bool MU_ZERO, bool IS_RW, bool COVD = false>
+template <int D, int WARPS, bool MU_ZERO, bool IS_RW, bool COVD = false, int CV = 1>
 __global__ void __launch_bounds__(32 * WARPS, 28 / WARPS)
 mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
 
-    static_assert(D % 8 == 0 && D >= 8 && D <= 32, "row blocks of 8; D/4 noise blocks per lane half");
+    static_assert(D % 8 == 0 && D >= 8 && D <= 32, "row blocks of 8; D/4 (v1) or D/8 (v2) noise blocks per lane half");
     constexpr int NB = D / 8;
-    constexpr int NPH = D / 4;                 /* Philox blocks per half-chain lane */
+    constexpr int NPB = (CV == 2) ? 4 : 2;     /* normals per Philox block (contract v1 / v2) */
+    constexpr int NPH = D / (2 * NPB);         /* Philox blocks per half-chain lane */
     constexpr int HR = D / 2;                  /* rows of Z / X owned by a half      */
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31;
@@ -289,7 +290,7 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
     double lp = active ? a.st.lp[ch] : 0.0;
     unsigned nacc = 0u;                         /* accepted moves of this launch */
     unsigned char accepted = active ? a.st.acc[ch] : (unsigned char)0;
-    constexpr unsigned long long B = (unsigned long long)((D + 1) / 2 + 1);
+    constexpr unsigned long long B = (unsigned long long)(D / NPB + 1);
     double e_next = 0.0;
 
     for (int s = 0; s < a.nsteps; ++s) {
@@ -303,19 +304,19 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
         {
             const unsigned long long b0 = k * B + (unsigned long long)(NPH * half);
             double* zt = ZC + (HR * half) * kPZ16 + cl;            /* Z[HR half + j][cl] */
-            constexpr int G1 = (NPH >= 6) ? NPH / 2 : 0;           /* two lock-step batches when there are enough blocks */
-            if constexpr (G1 > 0) noise_group<(G1 > 0 ? G1 : 1), false>(seed, b0, 0ull, zt, e, amh::amh_log_tab_dev, kPZ16);
+            constexpr int G1 = (NPH * NPB >= 12) ? NPH / 2 : 0;    /* two lock-step batches when there are >= 6 pairs */
+            if constexpr (G1 > 0) noise_group<(G1 > 0 ? G1 : 1), false, CV>(seed, b0, 0ull, zt, e, amh::amh_log_tab_dev, kPZ16);
             /* the exponential: both lanes of a chain run the same instructions, so on even steps of the launch lane half
              * h draws the exponential of step k + h, and odd steps draw none */
             if ((s & 1) == 0) {
                 double eh;
-                noise_group<NPH - G1, true>(seed, b0 + G1, (k + (unsigned long long)half) * B + (unsigned long long)(D / 2),
-                                            zt + 2 * G1 * kPZ16, eh, amh::amh_log_tab_dev, kPZ16);
+                noise_group<NPH - G1, true, CV>(seed, b0 + G1, (k + (unsigned long long)half) * B + (unsigned long long)(D / NPB),
+                                                zt + NPB * G1 * kPZ16, eh, amh::amh_log_tab_dev, kPZ16);
                 e = __shfl_sync(0xffffffffu, eh, cl);
                 e_next = __shfl_sync(0xffffffffu, eh, cl + 16);
             } else {
                 double dummy;
-                noise_group<NPH - G1, false>(seed, b0 + G1, 0ull, zt + 2 * G1 * kPZ16, dummy, amh::amh_log_tab_dev, kPZ16);
+                noise_group<NPH - G1, false, CV>(seed, b0 + G1, 0ull, zt + NPB * G1 * kPZ16, dummy, amh::amh_log_tab_dev, kPZ16);
                 e = e_next;
             }
         }
@@ -547,11 +548,12 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
         static const int pace_env = std::getenv("AMH_TC_PACE") ? std::atoi(std::getenv("AMH_TC_PACE")) : 0;
         a.pace = pace_env;
     }
-    if (r.mh_path != 2) {
+    const bool v2 = r.cv == AMH_CONTRACT_V2;
+    if (r.mh_path != 2 || v2) {
         /* K1T16: 16 chains per warp, 28 resident warps per SM: as ONE CTA per SM (default), or as 7 CTAs of 4 warps
-         * (AMH_TC_WARPS=4, kept for A/B measurements) */
+         * (AMH_TC_WARPS=4, kept for A/B measurements; contract v1 only, like the 32-chain kernel K1T) */
         static const int w16_env = std::getenv("AMH_TC_WARPS") ? std::atoi(std::getenv("AMH_TC_WARPS")) : 28;
-        if (w16_env == 28 || covd) {
+        if (w16_env == 28 || covd || v2) {
             constexpr int W28 = 28;
             const size_t smem28 = (size_t)W28 * tc16_smem_doubles_per_warp<D>() * sizeof(double);
             const unsigned grid28 = (unsigned)((r.n + 16 * W28 - 1) / (16 * W28));
@@ -565,11 +567,29 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
                 } while (0)
                 AMH_TC28_ATTR(true, true); AMH_TC28_ATTR(false, true); AMH_TC28_ATTR(true, false); AMH_TC28_ATTR(false, false);
                 AMH_TC28_ATTR(true, true, true); AMH_TC28_ATTR(false, true, true); AMH_TC28_ATTR(true, false, true); AMH_TC28_ATTR(false, false, true);
+                AMH_TC28_ATTR(true, true, false, 2); AMH_TC28_ATTR(false, true, false, 2); AMH_TC28_ATTR(true, false, false, 2); AMH_TC28_ATTR(false, false, false, 2);
+                AMH_TC28_ATTR(true, true, true, 2); AMH_TC28_ATTR(false, true, true, 2); AMH_TC28_ATTR(true, false, true, 2); AMH_TC28_ATTR(false, false, true, 2);
 #undef AMH_TC28_ATTR
                 r.ctx->configured.insert(key28);
             }
 #define AMH_TC28_GO(...) mh_step_tc16_kernel<D, W28, __VA_ARGS__><<<grid28, 32 * W28, smem28, r.ctx->stream>>>(a)
-            if (covd) {
+            if (v2) {
+                if (covd) {
+                    if (a.is_rw) {
+                        if (a.mu_zero) AMH_TC28_GO(true, true, true, 2);
+                        else AMH_TC28_GO(false, true, true, 2);
+                    } else {
+                        if (a.mu_zero) AMH_TC28_GO(true, false, true, 2);
+                        else AMH_TC28_GO(false, false, true, 2);
+                    }
+                } else if (a.is_rw) {
+                    if (a.mu_zero) AMH_TC28_GO(true, true, false, 2);
+                    else AMH_TC28_GO(false, true, false, 2);
+                } else {
+                    if (a.mu_zero) AMH_TC28_GO(true, false, false, 2);
+                    else AMH_TC28_GO(false, false, false, 2);
+                }
+            } else if (covd) {
                 if (a.is_rw) {
                     if (a.mu_zero) AMH_TC28_GO(true, true, true);
                     else AMH_TC28_GO(false, true, true);

@@ -57,7 +57,8 @@ ram_step_kernel(const __grid_constant__ RamArgs a, const __grid_constant__ typen
     unsigned long long nacc = a.st.nacc[ch];
     unsigned char accepted = a.st.acc[ch], failed = a.failed[ch], flag = a.sflag[ch];
     for (int i = 0; i < d; ++i) sx[i * BLOCK] = a.st.X[(long long)i * pitch + ch];
-    const unsigned long long B = (unsigned long long)((d + 1) / 2 + 1);
+    const int cv = a.st.cv;
+    const unsigned long long B = amh::blocks_per_step_cv(cv, d);
 
     for (int s = 0; s < a.nsteps; ++s) {
         const unsigned long long k = a.step0 + (unsigned long long)s + 1ull;   /* = state.iteration */
@@ -65,12 +66,24 @@ ram_step_kernel(const __grid_constant__ RamArgs a, const __grid_constant__ typen
         const double* __restrict__ Sc = (flag ? a.S2 : a.S) + ch;
         double* __restrict__ Sn = (flag ? a.S : a.S2) + ch;
         /* U = randn(rng, d)  (:135) */
-        for (int j = 0; 2 * j < d; ++j) {
-            const amh::Block b = amh::stream_block(seed, blk0 + (unsigned long long)j, 0u);
-            double z0, z1;
-            amh::normal_pair(b, z0, z1);
-            su[(2 * j) * BLOCK] = z0;
-            if (2 * j + 1 < d) su[(2 * j + 1) * BLOCK] = z1;
+        if (cv == AMH_CONTRACT_V2) {
+            for (int j = 0; 4 * j < d; ++j) {
+                const amh::Block b = amh::stream_block7(seed, blk0 + (unsigned long long)j, 0u);
+                double q0, q1, q2, q3;
+                amh::normal_quad(b, q0, q1, q2, q3);
+                su[(4 * j) * BLOCK] = q0;
+                if (4 * j + 1 < d) su[(4 * j + 1) * BLOCK] = q1;
+                if (4 * j + 2 < d) su[(4 * j + 2) * BLOCK] = q2;
+                if (4 * j + 3 < d) su[(4 * j + 3) * BLOCK] = q3;
+            }
+        } else {
+            for (int j = 0; 2 * j < d; ++j) {
+                const amh::Block b = amh::stream_block(seed, blk0 + (unsigned long long)j, 0u);
+                double z0, z1;
+                amh::normal_pair(b, z0, z1);
+                su[(2 * j) * BLOCK] = z0;
+                if (2 * j + 1 < d) su[(2 * j + 1) * BLOCK] = z1;
+            }
         }
         /* S U (row by row); x_new = muladd(S, U, x)  (:136) */
         double nu2 = 0.0;
@@ -94,7 +107,7 @@ ram_step_kernel(const __grid_constant__ RamArgs a, const __grid_constant__ typen
         const double lp_new = T::template logp<0>(xl, d, tp);
         const double dl = lp_new - lp;
         logalpha = (dl != dl) ? dl : (dl < 0.0 ? dl : 0.0);    /* min(lp_new - lp, 0)  (:147) */
-        const amh::Block be = amh::stream_block(seed, blk0 + (unsigned long long)((d + 1) / 2), 0u);
+        const amh::Block be = amh::step_block(cv, seed, blk0 + (unsigned long long)amh::normal_blocks(cv, d));
         const double e = amh::exponential(be.v[0], be.v[1]);
         const bool isaccept = e > -logalpha;                   /* (:148) */
         if (a.warmup) {

@@ -271,8 +271,10 @@ ram_warp_kernel(const __grid_constant__ RamWArgs a) {
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(Vs + 32 * RPL);
     const unsigned sbytes = (unsigned)(ntp * sizeof(double));   /* bulk copies move multiples of 16 bytes */
     const long long pitch = a.st.pitch;
-    const unsigned long long B = (unsigned long long)((d + 1) / 2 + 1);
-    const int npb = (d + 1) / 2;
+    const int cv = a.st.cv;
+    const unsigned long long B = amh::blocks_per_step_cv(cv, d);
+    const int npb = (d + 1) / 2;                         /* normal PAIRS of a step */
+    const int nbe = amh::normal_blocks(cv, d);           /* block of the exponential */
     if (lane == 0) mbar_init(bar, 1);
     __syncwarp();
     unsigned phase = 0;
@@ -302,14 +304,26 @@ ram_warp_kernel(const __grid_constant__ RamWArgs a) {
             const unsigned long long k = a.step0 + (unsigned long long)s + 1ull;   /* = state.iteration */
             const unsigned long long blk0 = k * B;
             /* U = randn(rng, d)  (:135): lane l draws blocks l, l+32, ...; every lane draws the exponential */
-            for (int jb = lane; jb < npb; jb += 32) {
-                const amh::Block b = amh::stream_block(seed, blk0 + (unsigned long long)jb, 0u);
-                double z0, z1;
-                amh::normal_pair(b, z0, z1);
-                Us[2 * jb] = z0;
-                if (2 * jb + 1 < d) Us[2 * jb + 1] = z1;
+            if (cv == AMH_CONTRACT_V2) {
+                /* contract v2: pair p = normals 2p, 2p+1 comes from words (2(p&1), 2(p&1)+1) of block p >> 1; two lanes
+                 * run the same 7-round block and keep one pair each (shorter critical path than one lane doing both) */
+                for (int p = lane; p < npb; p += 32) {
+                    const amh::Block b = amh::stream_block7(seed, blk0 + (unsigned long long)(p >> 1), 0u);
+                    double z0, z1;
+                    amh::normal_pair32((p & 1) ? b.v[2] : b.v[0], (p & 1) ? b.v[3] : b.v[1], z0, z1);
+                    Us[2 * p] = z0;
+                    if (2 * p + 1 < d) Us[2 * p + 1] = z1;
+                }
+            } else {
+                for (int jb = lane; jb < npb; jb += 32) {
+                    const amh::Block b = amh::stream_block(seed, blk0 + (unsigned long long)jb, 0u);
+                    double z0, z1;
+                    amh::normal_pair(b, z0, z1);
+                    Us[2 * jb] = z0;
+                    if (2 * jb + 1 < d) Us[2 * jb + 1] = z1;
+                }
             }
-            const amh::Block be = amh::stream_block(seed, blk0 + (unsigned long long)npb, 0u);
+            const amh::Block be = amh::step_block(cv, seed, blk0 + (unsigned long long)nbe);
             const double e = amh::exponential(be.v[0], be.v[1]);
             __syncwarp();
             /* y = S U by columns; x_new = muladd(S, U, x)  (:136) */

@@ -147,8 +147,10 @@ def _timed(run, nsteps, warmup=False, spl=0, reps=3, warm=1):
     return ms / reps
 
 
-# FP64-pipe cycles of one 16-chain warp-step of K1T16 by dimension (contract v1 instruction mix)
-PIPE_MODEL = {32: 80 * 16.2 + 398 * 2.07 + 182 * 4.1}
+# FP64-pipe cycles of one 16-chain warp-step of K1T16 at d = 32, by contract version (instruction mix from the ncu source
+# page x per-instruction pipe costs of tools/ubench/issue_probe.cu): (DMMA, DFMA-class, IMAD.WIDE/HI)
+PIPE_MIX = {1: (80, 398, 182), 2: (80, 398, 75)}
+PIPE_COST = (16.2, 2.07, 4.1)
 
 FP64_TFLOPS_PEAK = 148 * 64 * 2 * 1.965e9 / 1e12      # 64 FP64 FMA / clk / SM (DMMA or DFMA, one shared datapath) at 1965 MHz = 37.2
 
@@ -411,14 +413,17 @@ def main():
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            if int(tj.get("mcmc_steps_in_captured_launch", -1)) == spl and int(tj.get("chains", 65536)) == n and int(tj.get("dim", 32)) == d:
+            if (int(tj.get("mcmc_steps_in_captured_launch", -1)) == spl and int(tj.get("chains", 65536)) == n and int(tj.get("dim", 32)) == d
+                    and int(tj.get("contract_version", 1)) == cv):
                 traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("capture")
         except Exception:
             traffic = None
     # what really bounds the kernel: the shared FP64 datapath.  Pipe cycles one 16-chain warp-step needs, from the
     # instruction mix of the kernel (ncu source page) x the per-instruction pipe costs measured with tools/ubench/issue_probe.cu
     # (profiles/r1_issue_probe_b200.txt: DMMA 16.2, DFMA-class 2.07, IMAD.WIDE/HI 4.1 cycles of a scheduler's FP64 pipe)
-    pipe_cycles_per_warp_step = PIPE_MODEL.get(d)
+    cv = run.contract()
+    mix = PIPE_MIX.get(cv) if d == 32 else None
+    pipe_cycles_per_warp_step = None if mix is None else sum(m * c for m, c in zip(mix, PIPE_COST))
     fp64_pipe = None
     if pipe_cycles_per_warp_step is not None and n % 16 == 0:
         sm_hz = 1e6 * float(peaks.get("sm_max_mhz", 1965.0))
@@ -427,7 +432,7 @@ def main():
         floor_us = warp_steps_per_sched * pipe_cycles_per_warp_step / sm_hz * 1e6
         fp64_pipe = {"frac": floor_us / us_step, "floor_us_per_mcmc_step": floor_us, "measured_us_per_mcmc_step": us_step,
                      "pipe_cycles_per_16_chain_warp_step": pipe_cycles_per_warp_step,
-                     "model": "80 DMMA x 16.2 + 398 DFMA-class x 2.07 + 182 IMAD.WIDE x 4.1 cycles (profiles/r1_issue_probe_b200.txt, DESIGN.md 5)"}
+                     "model": f"{mix[0]} DMMA x 16.2 + {mix[1]} DFMA-class x 2.07 + {mix[2]} IMAD.WIDE x 4.1 cycles (profiles/r1_issue_probe_b200.txt, DESIGN.md 5)"}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
@@ -461,7 +466,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f64", "data": "synthetic", "contract_version": cv,
             "config": workload_config(d, n, spl, world, not args.no_flush),
             "clocks": clk.result(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "configs": configs, "wall_s_timed_region": t_wall,

@@ -109,6 +109,10 @@ typedef struct amh_sampler_desc {
     double  ram_eig_hi;      /* RAM.eigenvalue_upper_bound = Inf (:86)                          */
     const double* ram_S0;    /* RAM.S: dense dim x dim row-major (lower triangle used), NULL = I (:82,198-207) */
     const amh_component* components;  /* [dim], cov_kind == AMH_COV_COMPONENTS or kind == AMH_SAMPLER_MIXED, else NULL */
+    int32_t contract;        /* version of the numerical contract the run's step noise follows (include/amh_contract.h):
+                                0 = the library default (AMH_CONTRACT_VERSION, or the environment variable AMH_CONTRACT),
+                                1 = v1, 2 = v2.  The oracle takes the same field, so parity is per version.           */
+    int32_t reserved;
 } amh_sampler_desc;
 
 /* pooled and per-chain summaries accumulated on the device over SAVED samples */
@@ -246,6 +250,7 @@ int32_t amh_run_ram_failed(amh_run* run, int64_t* nfailed, int64_t* first_chain,
 int32_t amh_host_alloc(size_t bytes, void** out);
 int32_t amh_host_free(void* p);
 
+int32_t amh_run_contract(amh_run* run);      /* the contract version this run was created under (1 or 2) */
 int32_t amh_run_dim(amh_run* run);
 int64_t amh_run_nchains(amh_run* run);
 /* number of kernel launches issued by this run so far (bench.py's gpu_launches) */
@@ -294,6 +299,7 @@ int32_t amh_job_run_set_ram_adapt(amh_job* job, const double* logalpha, const do
 int32_t amh_job_run_ram_failed(amh_job* job, int64_t* nfailed, int64_t* first_chain, uint8_t* failed);
 /* which chains device number k of the job holds: [lo, hi) and the CUDA device index */
 int32_t amh_job_run_shard(amh_job* job, int32_t k, int64_t* lo, int64_t* hi, int32_t* device);
+int32_t amh_job_run_contract(amh_job* job);
 int64_t amh_job_run_launch_count(amh_job* job);
 /* device time of the stepping kernels: max over the devices (they run concurrently), launches summed */
 int32_t amh_job_run_kernel_time_ms(amh_job* job, int32_t reset, double* ms, int64_t* launches);

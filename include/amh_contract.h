@@ -32,7 +32,19 @@
 #define AMH_HD static inline
 #endif
 
-#define AMH_CONTRACT_VERSION 1   /* v1 + univariate families (additive: no v1 stream or result changed) */
+/* Contract versions.  A run is created under ONE version (amh_sampler_desc.contract; 0 = AMH_CONTRACT_VERSION) and
+ * keeps it for life; kernels and oracle implement both, bit for bit.
+ *   v1  every normal PAIR consumes one Philox4x32-10 block: 64-bit uniforms for radius and angle.
+ *   v2  the step noise of MH / MALA / RAM (the d normals and the exponential of a step, stream 0) comes from
+ *       Philox4x32-7 blocks -- the Crush-resistant round count of Salmon et al. (SC'11, table 2) -- and one block
+ *       yields FOUR normals (two Box-Muller pairs, 32-bit radius and angle words).  Why: on B200 the 32x32->64
+ *       multiplies of Philox (IMAD.WIDE) issue on the FP64 datapath and cost a quarter of the d = 32 step
+ *       (tools/ubench/issue_probe.cu); v2 needs 63 of them per 16 normals instead of 170.  Everything else
+ *       -- the stretch move's partner / uniform / exponential words, the univariate families' sub-streams, initial
+ *       ensemble draws, every transcendental function -- is v1's, unchanged. */
+#define AMH_CONTRACT_V1 1
+#define AMH_CONTRACT_V2 2
+#define AMH_CONTRACT_VERSION 2   /* the default of new runs */
 
 namespace amh {
 
@@ -64,14 +76,15 @@ AMH_HD double make_double(uint32_t hi, uint32_t lo) {
  * (SC'11).  Pinned in tests against the Random123 known-answer vectors. */
 struct Block { uint32_t v[4]; };
 
-AMH_HD Block philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                           uint32_t k0, uint32_t k1) {
+template <int ROUNDS>
+AMH_HD Block philox4x32_r(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                          uint32_t k0, uint32_t k1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
     const uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
         const uint64_t p0 = (uint64_t)M0 * c0;
         const uint64_t p1 = (uint64_t)M1 * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -82,12 +95,27 @@ AMH_HD Block philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
     Block b; b.v[0] = c0; b.v[1] = c1; b.v[2] = c2; b.v[3] = c3;
     return b;
 }
+AMH_HD Block philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    return philox4x32_r<10>(c0, c1, c2, c3, k0, k1);
+}
+AMH_HD Block philox4x32_7(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    return philox4x32_r<7>(c0, c1, c2, c3, k0, k1);
+}
 
 /* Block `blk` of the stream of the chain whose 64-bit seed is `seed`.
  * key = (lo32(seed), hi32(seed)); counter = (lo32(blk), hi32(blk), stream, 0). */
 AMH_HD Block stream_block(uint64_t seed, uint64_t blk, uint32_t stream) {
     return philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), stream, 0u,
                          (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+/* the same with 7 rounds: the step-noise blocks of contract v2 */
+AMH_HD Block stream_block7(uint64_t seed, uint64_t blk, uint32_t stream) {
+    return philox4x32_7((uint32_t)blk, (uint32_t)(blk >> 32), stream, 0u,
+                        (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+/* step-noise block of a run under contract `cv` */
+AMH_HD Block step_block(int cv, uint64_t seed, uint64_t blk) {
+    return cv == AMH_CONTRACT_V2 ? stream_block7(seed, blk, 0u) : stream_block(seed, blk, 0u);
 }
 
 /* --------------------------------------------------------------- uniform
@@ -96,6 +124,11 @@ AMH_HD Block stream_block(uint64_t seed, uint64_t blk, uint32_t stream) {
 AMH_HD double u01(uint32_t wlo, uint32_t whi) {
     const double d = make_double(0x3FF00000u | (whi >> 12), (whi << 20) | (wlo >> 12));
     return d - 0x1.fffffffffffffp-1;   /* d - (1 - 2^-53) */
+}
+/* 32-bit word -> u = (w + 1/2) * 2^-32, strictly in (0,1), exact (contract v2 radius) */
+AMH_HD double u01_32(uint32_t w) {
+    const double d = make_double(0x3FF00000u | (w >> 12), w << 20);
+    return d - 0x1.ffffffffp-1;        /* d - (1 - 2^-33) */
 }
 
 /* ------------------------------------------------------------------- log
@@ -207,14 +240,9 @@ AMH_HD double exponential(uint32_t wlo, uint32_t whi) {
  *   (z0, z1) = rad (cos theta, sin theta)
  * sin/cos(pi/2 g) come from near-minimax polynomials on |g| <= 1/2; the
  * quadrant q is applied exactly by swap + sign flips. */
-AMH_HD void normal_pair(const Block& b, double& z0, double& z1) {
-    const double nl = neglog_normal(u01(b.v[0], b.v[1]));
+AMH_HD void box_muller(double u, uint32_t q, double g, double& z0, double& z1) {
+    const double nl = neglog_normal(u);
     const double rad = sqrt(nl + nl);
-    const uint32_t whi = b.v[3], wlo = b.v[2];
-    const uint32_t q = whi >> 30;
-    /* 52 fraction bits = bits 61..10 of the word */
-    const double g = make_double(0x3FF00000u | ((whi >> 10) & 0x000FFFFFu),
-                                 (whi << 22) | (wlo >> 10)) - 1.5;
     const double y = g * g;
     double s = fma(y, AMH_SIN_S6, AMH_SIN_S5);
     s = fma(y, s, AMH_SIN_S4);
@@ -240,6 +268,24 @@ AMH_HD void normal_pair(const Block& b, double& z0, double& z1) {
     const double cb = make_double(hi32(bb) ^ sb, lo32(bb));
     z0 = rad * ca;
     z1 = rad * cb;
+}
+AMH_HD void normal_pair(const Block& b, double& z0, double& z1) {
+    const uint32_t whi = b.v[3], wlo = b.v[2];
+    /* 52 fraction bits = bits 61..10 of the word */
+    const double g = make_double(0x3FF00000u | ((whi >> 10) & 0x000FFFFFu),
+                                 (whi << 22) | (wlo >> 10)) - 1.5;
+    box_muller(u01(b.v[0], b.v[1]), whi >> 30, g, z0, z1);
+}
+/* contract v2: one Box-Muller pair from two 32-bit words (radius word wr, angle word wa: quadrant = top 2 bits,
+ * g = its other 30 bits as a fraction, minus 1/2); the arithmetic after that is v1's */
+AMH_HD void normal_pair32(uint32_t wr, uint32_t wa, double& z0, double& z1) {
+    const double g = make_double(0x3FF00000u | ((wa >> 10) & 0x000FFFFFu), wa << 22) - 1.5;
+    box_muller(u01_32(wr), wa >> 30, g, z0, z1);
+}
+/* contract v2: the four normals of one step-noise block: (v0, v1) -> z[0], z[1]; (v2, v3) -> z[2], z[3] */
+AMH_HD void normal_quad(const Block& b, double& z0, double& z1, double& z2, double& z3) {
+    normal_pair32(b.v[0], b.v[1], z0, z1);
+    normal_pair32(b.v[2], b.v[3], z2, z3);
 }
 
 /* -------------------------------------------------------- bounded integer
@@ -358,6 +404,39 @@ AMH_HD double family_logpdf(int fam, double p0, double p1, double logc, double x
  * stream: block 0 word 0 -> partner index, word 1 -> uniform for z;
  *         block 1 word 0 -> exponential. */
 AMH_HD uint64_t blocks_per_step(int d) { return (uint64_t)((d + 1) / 2 + 1); }
+
+/* the same under contract `cv`: v2 packs four normals into a block, B = ceil(d/4) + 1, block ceil(d/4) word 0 (64 bits)
+ * -> the exponential */
+AMH_HD int normal_blocks(int cv, int d) { return cv == AMH_CONTRACT_V2 ? (d + 3) / 4 : (d + 1) / 2; }
+AMH_HD uint64_t blocks_per_step_cv(int cv, int d) { return (uint64_t)(normal_blocks(cv, d) + 1); }
+
+/* z[0..d-1] of the step whose first block is blk0 (generic form: one block after the other) */
+AMH_HD void step_normals_cv(int cv, uint64_t seed, uint64_t blk0, int d, double* z) {
+    if (cv == AMH_CONTRACT_V2) {
+        for (int j = 0; 4 * j < d; ++j) {
+            const Block b = stream_block7(seed, blk0 + (uint64_t)j, 0u);
+            double q0, q1, q2, q3;
+            normal_quad(b, q0, q1, q2, q3);
+            z[4 * j] = q0;
+            if (4 * j + 1 < d) z[4 * j + 1] = q1;
+            if (4 * j + 2 < d) z[4 * j + 2] = q2;
+            if (4 * j + 3 < d) z[4 * j + 3] = q3;
+        }
+    } else {
+        for (int j = 0; 2 * j < d; ++j) {
+            const Block b = stream_block(seed, blk0 + (uint64_t)j, 0u);
+            double z0, z1;
+            normal_pair(b, z0, z1);
+            z[2 * j] = z0;
+            if (2 * j + 1 < d) z[2 * j + 1] = z1;
+        }
+    }
+}
+/* the exponential of that step */
+AMH_HD double step_exponential_cv(int cv, uint64_t seed, uint64_t blk0, int d) {
+    const Block b = step_block(cv, seed, blk0 + (uint64_t)normal_blocks(cv, d));
+    return exponential(b.v[0], b.v[1]);
+}
 
 }  /* namespace amh */
 

@@ -39,7 +39,14 @@ struct SamplerDesc            # struct amh_sampler_desc, field for field
     ram_alpha::Float64; ram_gamma::Float64; ram_eig_lo::Float64; ram_eig_hi::Float64
     ram_S0::Ptr{Float64}
     components::Ptr{Component}
+    contract::Int32; reserved::Int32
 end
+"version of the numerical contract new runs are created under: 0 = the library default (v2), 1 = v1, 2 = v2"
+const CONTRACT = Ref(Int32(0))
+SamplerDesc(kind, dim, symmetric, cov_kind, mean, scale, stretch_a, n_walkers, mala_sigma2, mala_drift, ram_alpha, ram_gamma,
+            ram_eig_lo, ram_eig_hi, ram_S0, components) =
+    SamplerDesc(kind, dim, symmetric, cov_kind, mean, scale, stretch_a, n_walkers, mala_sigma2, mala_drift, ram_alpha, ram_gamma,
+                ram_eig_lo, ram_eig_hi, ram_S0, components, CONTRACT[], Int32(0))
 
 struct Summary                # struct amh_summary
     n_saved::Int64; n_steps::Int64; accept_rate::Float64

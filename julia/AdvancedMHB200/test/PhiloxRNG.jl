@@ -11,8 +11,10 @@
 #   rand    src/emcee.jl:81 (uniform), src/emcee.jl:48,52 (Random.Sampler(rng, 1:n-1))
 #
 # Stream layout (amh_contract.h "stream word budget"), per chain seeded `seed`:
-#   MH / MALA / RAM, dimension d, B = cld(d,2)+1 blocks per step: step k (k = 0 is the initial draw) owns blocks
-#     [kB, (k+1)B): block j -> normals z[2j], z[2j+1]; block cld(d,2), word 0 -> the step's exponential.
+#   MH / MALA / RAM, dimension d.  Contract v1: B = cld(d,2)+1 Philox4x32-10 blocks per step; step k (k = 0 is the initial
+#     draw) owns blocks [kB, (k+1)B): block j -> normals z[2j], z[2j+1]; block cld(d,2), word 0 -> the step's exponential.
+#     Contract v2 (the library default): B = cld(d,4)+1 Philox4x32-7 blocks; block j -> normals z[4j..4j+3] (two Box-Muller
+#     pairs from its 32-bit words); block cld(d,4), 64-bit word 0 -> the exponential.
 #     The reference draws d normals then ONE exponential per step and only normals at initialisation, so a sequential
 #     consumer advances to the next step after `randexp`, or when a (d+1)-th normal is requested (initial draw -> step 1).
 #   stretch move, per ENSEMBLE: initial draw of walker w from stream 1, blocks w*cld(d,2) + j; move i of sweep k owns
@@ -29,6 +31,17 @@ philox(blk::UInt64, stream::UInt32, seed::UInt64) = begin
     ccall((:amho_probe_philox, liboracle), Cvoid, (UInt32, UInt32, UInt32, UInt32, UInt32, UInt32, Ptr{UInt32}),
           blk % UInt32, (blk >> 32) % UInt32, stream, UInt32(0), seed % UInt32, (seed >> 32) % UInt32, out)
     out
+end
+philox7(blk::UInt64, stream::UInt32, seed::UInt64) = begin          # the step-noise blocks of contract v2
+    out = Vector{UInt32}(undef, 4)
+    ccall((:amho_probe_philox7, liboracle), Cvoid, (UInt32, UInt32, UInt32, UInt32, UInt32, UInt32, Ptr{UInt32}),
+          blk % UInt32, (blk >> 32) % UInt32, stream, UInt32(0), seed % UInt32, (seed >> 32) % UInt32, out)
+    out
+end
+function normal_pair32(wr::UInt32, wa::UInt32)
+    a, b = Ref(wr), Ref(wa); z0, z1 = Ref(0.0), Ref(0.0)
+    ccall((:amho_probe_normal_pair32, liboracle), Cvoid, (Ptr{UInt32}, Ptr{UInt32}, Ptr{Float64}, Ptr{Float64}, Int64), a, b, z0, z1, 1)
+    z0[], z1[]
 end
 word(b, i) = UInt64(b[2i + 1]) | (UInt64(b[2i + 2]) << 32)          # 64-bit word i (0 or 1) of a block
 
@@ -49,33 +62,42 @@ function u01(w::UInt64)
 end
 
 """
-    PhiloxRNG(seed, d)                       # MetropolisHastings / MALA / RobustAdaptiveMetropolis, dimension d
+    PhiloxRNG(seed, d; contract = 2)         # MetropolisHastings / MALA / RobustAdaptiveMetropolis, dimension d
     PhiloxRNG(seed, d; n_walkers = nw)       # Ensemble(nw, StretchProposal(...)); `seed` is the ENSEMBLE's seed
 """
 mutable struct PhiloxRNG <: Random.AbstractRNG
     seed::UInt64
     d::Int
+    cv::Int            # contract version of the step noise (1 or 2)
     nw::Int            # 0: chain layout, > 0: ensemble layout
     step::UInt64       # chain layout: current step k; ensemble layout: moves consumed so far (k*nw + i), after the initial draws
     pos::Int           # chain layout: normals consumed in this step; ensemble layout: normals consumed in the initial draw
     init_done::Bool    # ensemble layout: the nw initial draws are over
     cache::Float64     # second normal of the current Box-Muller pair
 end
-PhiloxRNG(seed::Integer, d::Integer; n_walkers::Integer=0) = PhiloxRNG(UInt64(seed), Int(d), Int(n_walkers), 0, 0, false, NaN)
+PhiloxRNG(seed::Integer, d::Integer; n_walkers::Integer=0, contract::Integer=2) =
+    PhiloxRNG(UInt64(seed), Int(d), Int(contract), Int(n_walkers), 0, 0, false, NaN)
 
 "re-position at the start of step k (chain layout): the hook a step-by-step comparison uses"
 seekstep!(r::PhiloxRNG, k::Integer) = (r.step = UInt64(k); r.pos = 0; r)
 
-blocks_per_step(r::PhiloxRNG) = UInt64(cld(r.d, 2) + 1)
+normal_blocks(r::PhiloxRNG) = r.cv == 2 ? cld(r.d, 4) : cld(r.d, 2)
+blocks_per_step(r::PhiloxRNG) = UInt64(normal_blocks(r) + 1)
+step_block(r::PhiloxRNG, blk::UInt64) = r.cv == 2 ? philox7(blk, UInt32(0), r.seed) : philox(blk, UInt32(0), r.seed)
 
 function Random.randn(r::PhiloxRNG, ::Type{Float64}=Float64)
     if r.nw == 0
         if r.pos == r.d                         # a (d+1)-th normal: the initial draw is over, this is step + 1
             r.step += 1; r.pos = 0
         end
-        j = r.pos ÷ 2
         if iseven(r.pos)
-            z0, z1 = normal_pair(philox(r.step * blocks_per_step(r) + UInt64(j), UInt32(0), r.seed))
+            if r.cv == 2                        # pair (pos % 4) / 2 of block pos / 4: words (0,1) or (2,3)
+                b = step_block(r, r.step * blocks_per_step(r) + UInt64(r.pos ÷ 4))
+                h = (r.pos % 4) ÷ 2
+                z0, z1 = normal_pair32(b[2h + 1], b[2h + 2])
+            else
+                z0, z1 = normal_pair(step_block(r, r.step * blocks_per_step(r) + UInt64(r.pos ÷ 2)))
+            end
             r.cache = z1; r.pos += 1
             return z0
         end
@@ -97,7 +119,7 @@ function Random.randexp(r::PhiloxRNG, ::Type{Float64}=Float64)
     if r.nw == 0
         r.pos == r.d || r.step == 0 && r.pos == 0 ||
             error("PhiloxRNG: randexp after $(r.pos) of $(r.d) normals -- not the reference's per-step consumption")
-        e = exponential(word(philox(r.step * blocks_per_step(r) + UInt64(cld(r.d, 2)), UInt32(0), r.seed), 0))
+        e = exponential(word(step_block(r, r.step * blocks_per_step(r) + UInt64(normal_blocks(r))), 0))
         r.step += 1; r.pos = 0                  # the exponential closes the step (mh-core.jl:108)
         return e
     else

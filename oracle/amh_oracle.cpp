@@ -353,13 +353,20 @@ struct Run {
     std::vector<uint8_t> acc, failed;
     std::vector<int64_t> nacc;
     int64_t step = 0;          /* stateful steps taken so far */
+    int cv = AMH_CONTRACT_VERSION;   /* contract version of the step noise (amh_sampler_desc.contract) */
     /* saved-sample moments */
     std::vector<double> sum, sumsq;
     int64_t nsaved = 0;
 };
 
-void normals(uint64_t seed, uint64_t step, uint32_t stream, int d, double* z) {
-    const uint64_t B = (stream == 0) ? amh::blocks_per_step(d) : (uint64_t)((d + 1) / 2);
+/* the d standard normals of step `step`: stream 0 = the chain's step noise under contract `cv`; stream 1 = the initial
+ * draws of an ensemble's walkers (always the v1 layout: one block per pair) */
+void normals(int cv, uint64_t seed, uint64_t step, uint32_t stream, int d, double* z) {
+    if (stream == 0) {
+        amh::step_normals_cv(cv, seed, step * amh::blocks_per_step_cv(cv, d), d, z);
+        return;
+    }
+    const uint64_t B = (uint64_t)((d + 1) / 2);
     const uint64_t b0 = step * B;
     for (int j = 0; 2 * j < d; ++j) {
         const amh::Block b = amh::stream_block(seed, b0 + j, stream);
@@ -370,10 +377,8 @@ void normals(uint64_t seed, uint64_t step, uint32_t stream, int d, double* z) {
     }
 }
 
-double step_exponential(uint64_t seed, uint64_t step, int d) {
-    const uint64_t B = amh::blocks_per_step(d);
-    const amh::Block b = amh::stream_block(seed, step * B + (uint64_t)((d + 1) / 2), 0);
-    return amh::exponential(b.v[0], b.v[1]);
+double step_exponential(int cv, uint64_t seed, uint64_t step, int d) {
+    return amh::step_exponential_cv(cv, seed, step * amh::blocks_per_step_cv(cv, d), d);
 }
 
 template <class F>
@@ -407,7 +412,7 @@ void mh_steps(Run& r, int64_t a, int64_t b, int64_t nsteps) {
         uint8_t accepted = r.acc[ch];
         for (int64_t s = 0; s < nsteps; ++s) {
             const uint64_t k = (uint64_t)(r.step + s + 1);
-            normals(seed, k, 0, d, z.data());
+            normals(r.cv, seed, k, 0, d, z.data());
             sp.draw(z.data(), v.data());
             /* candidate = t + rand(rng, proposal) (proposal.jl:49-56) | rand(rng, proposal) (:70-77) */
             for (int i = 0; i < d; ++i) c[i] = is_rw ? x[i] + v[i] : v[i];
@@ -431,7 +436,7 @@ void mh_steps(Run& r, int64_t a, int64_t b, int64_t nsteps) {
                 }
             }
             const double loga = (lp_c - lp) + logratio;
-            const double e = step_exponential(seed, k, d);
+            const double e = step_exponential(r.cv, seed, k, d);
             if (-e < loga) {                       /* mh-core.jl:108 (strict) */
                 for (int i = 0; i < d; ++i) x[i] = c[i];
                 lp = lp_c; lq = lq_c; accepted = 1; ++nacc;
@@ -462,7 +467,7 @@ void mh_component_steps(Run& r, int64_t a, int64_t b, int64_t nsteps) {
         uint8_t accepted = r.acc[ch];
         for (int64_t s = 0; s < nsteps; ++s) {
             const uint64_t k = (uint64_t)(r.step + s + 1);
-            normals(seed, k, 0, d, z.data());
+            normals(r.cv, seed, k, 0, d, z.data());
             sp.draw_components(z.data(), seed, k * (uint64_t)d, v.data());
             for (int i = 0; i < d; ++i) {
                 const bool rw_i = mixed ? sp.comps[i].rw != 0 : is_rw;
@@ -493,7 +498,7 @@ void mh_component_steps(Run& r, int64_t a, int64_t b, int64_t nsteps) {
                 }
             }
             const double loga = (lp_c - lp) + logratio;
-            const double e = step_exponential(seed, k, d);
+            const double e = step_exponential(r.cv, seed, k, d);
             if (-e < loga) {                       /* mh-core.jl:108 (strict; NaN rejects) */
                 for (int i = 0; i < d; ++i) x[i] = c[i];
                 lp = lp_c; accepted = 1; ++nacc;
@@ -520,7 +525,7 @@ void mala_steps(Run& r, int64_t a, int64_t b, int64_t nsteps) {
         uint8_t accepted = r.acc[ch];
         for (int64_t s = 0; s < nsteps; ++s) {
             const uint64_t k = (uint64_t)(r.step + s + 1);
-            normals(seed, k, 0, d, z.data());
+            normals(r.cv, seed, k, 0, d, z.data());
             /* state + rand(MvNormal(drift*grad, sigma2*I)) (MALA.jl:70 -> proposal.jl:49-56) */
             for (int i = 0; i < d; ++i) c[i] = x[i] + (sigma * z[i] + drift * g[i]);
             double lp_c;
@@ -535,7 +540,7 @@ void mala_steps(Run& r, int64_t a, int64_t b, int64_t nsteps) {
             }
             const double logratio = (-0.5 * (A / sigma2)) - (-0.5 * (B / sigma2));
             const double loga = (lp_c - lp) + logratio;
-            const double e = step_exponential(seed, k, d);
+            const double e = step_exponential(r.cv, seed, k, d);
             if (-e < loga) {
                 x = c; g = gc; lp = lp_c; accepted = 1; ++nacc;
             } else {
@@ -566,7 +571,7 @@ void ram_steps(Run& r, int64_t a, int64_t b, int64_t nsteps, bool warmup) {
         for (int64_t s = 0; s < nsteps; ++s) {
             const uint64_t k = (uint64_t)(r.step + s + 1);
             const int64_t iteration = r.step + s + 1;     /* state.iteration (starts at 1, RAM :211) */
-            normals(seed, k, 0, d, U.data());
+            normals(r.cv, seed, k, 0, d, U.data());
             /* x_new = muladd(S, U, x)  (RAM :136) */
             for (int i = 0; i < d; ++i) {
                 double t = S[tri(i, 0)] * U[0];
@@ -577,7 +582,7 @@ void ram_steps(Run& r, int64_t a, int64_t b, int64_t nsteps, bool warmup) {
             const double lp_new = r.t->logp(xn.data());
             const double dl = lp_new - lp;
             logalpha = (dl != dl) ? dl : (dl < 0.0 ? dl : 0.0);    /* min(lp_new - lp, 0)  (:147) */
-            const double e = step_exponential(seed, k, d);
+            const double e = step_exponential(r.cv, seed, k, d);
             const bool isaccept = e > -logalpha;                     /* (:148) */
             if (warmup) {
                 /* ram_adapt (:153-173) */
@@ -941,6 +946,11 @@ int32_t amho_sampler_create(amh_ctx*, const amh_sampler_desc* desc, amh_sampler*
         return bad("unknown sampler kind");
     }
     s->d.mean = nullptr; s->d.scale = nullptr; s->d.ram_S0 = nullptr; s->d.components = nullptr;
+    if (s->d.contract == 0) {
+        const char* ev = getenv("AMH_CONTRACT");
+        s->d.contract = ev ? atoi(ev) : AMH_CONTRACT_VERSION;
+    }
+    if (s->d.contract != AMH_CONTRACT_V1 && s->d.contract != AMH_CONTRACT_V2) { delete s; return fail(AMH_ERR_INVALID, "unknown contract version"); }
     *out = (amh_sampler*)s;
     return AMH_OK;
 }
@@ -972,6 +982,7 @@ int32_t amho_run_create(amh_ctx*, amh_target* target, amh_sampler* sampler, int6
         return fail(AMH_ERR_INVALID, "stretch move without init needs an initial-draw proposal");
     Run* r = new Run();
     r->t = t; r->s = s; r->n = n; r->off = off; r->dim = d;
+    r->cv = s->d.contract;
     r->seeds.assign(seeds, seeds + nseeds);
     r->X.assign((size_t)d * n, 0.0);
     r->lp.assign(n, 0.0); r->lq.assign(n, 0.0);
@@ -990,15 +1001,15 @@ int32_t amho_run_create(amh_ctx*, amh_target* target, amh_sampler* sampler, int6
             if (init) {
                 for (int i = 0; i < d; ++i) x[i] = init[(int64_t)i * init_ld + ch];
             } else if (kind == AMH_SAMPLER_RAM) {
-                normals(r->seeds[ch], 0, 0, d, x.data());            /* randn(rng, T, d)  (:193) */
+                normals(r->cv, r->seeds[ch], 0, 0, d, x.data());     /* randn(rng, T, d)  (:193) */
             } else if (kind == AMH_SAMPLER_STRETCH) {
                 /* n_walkers draws from the inner proposal (emcee.jl:29-34): stream 1 of the ensemble */
                 const int64_t en = ch / s->d.n_walkers, w = ch % s->d.n_walkers;
-                normals(r->seeds[en], (uint64_t)w, 1, d, z.data());
+                normals(r->cv, r->seeds[en], (uint64_t)w, 1, d, z.data());
                 if (s->by_components()) s->draw_components(z.data(), r->seeds[en], (uint64_t)w * (uint64_t)d, x.data());
                 else s->draw(z.data(), x.data());
             } else {
-                normals(r->seeds[ch], 0, 0, d, z.data());
+                normals(r->cv, r->seeds[ch], 0, 0, d, z.data());
                 if (s->by_components()) s->draw_components(z.data(), r->seeds[ch], 0ull, x.data());   /* proposal.jl:132-140 */
                 else s->draw(z.data(), x.data());                    /* propose(rng, sampler, model) */
             }
@@ -1270,8 +1281,20 @@ void amho_probe_normal_pair(const uint64_t* w0, const uint64_t* w1, double* z0, 
 }
 /* the d standard normals and the exponential of step `step` of the chain seeded `seed` */
 void amho_probe_step_noise(uint64_t seed, uint64_t step, int32_t d, double* z, double* e) {
-    normals(seed, step, 0, d, z);
-    *e = step_exponential(seed, step, d);
+    normals(AMH_CONTRACT_V1, seed, step, 0, d, z);
+    *e = step_exponential(AMH_CONTRACT_V1, seed, step, d);
+}
+void amho_probe_step_noise_cv(int32_t cv, uint64_t seed, uint64_t step, int32_t d, double* z, double* e) {
+    normals(cv, seed, step, 0, d, z);
+    *e = step_exponential(cv, seed, step, d);
+}
+void amho_probe_philox7(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out4) {
+    const amh::Block b = amh::philox4x32_7(c0, c1, c2, c3, k0, k1);
+    for (int i = 0; i < 4; ++i) out4[i] = b.v[i];
+}
+int32_t amho_run_contract(amh_run* run) { return run ? ((Run*)run)->cv : -1; }
+void amho_probe_normal_pair32(const uint32_t* wr, const uint32_t* wa, double* z0, double* z1, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) amh::normal_pair32(wr[i], wa[i], z0[i], z1[i]);
 }
 double amho_probe_target_logp(amh_target* t, const double* x) { return ((Target*)t)->logp(x); }
 void amho_probe_target_grad(amh_target* t, const double* x, double* lp, double* g) {
@@ -1314,6 +1337,7 @@ struct OracleBackend {
     static int run_set_ram_adapt(amh_run* r, const double* la, const double* eta, const uint8_t* f) { return amho_run_set_ram_adapt(r, la, eta, f); }
     static int run_ram_failed(amh_run* r, int64_t* nf, int64_t* first, uint8_t* f) { return amho_run_ram_failed(r, nf, first, f); }
     static int64_t run_launch_count(amh_run* r) { return amho_run_launch_count(r); }
+    static int run_contract(amh_run* r) { return amho_run_contract(r); }
     static int run_kernel_time_ms(amh_run* r, int32_t reset, double* ms, int64_t* l) { return amho_run_kernel_time_ms(r, reset, ms, l); }
     static int shared_init(amhjob::Job<OracleBackend>&) { return AMH_OK; }
     static void shared_destroy(amhjob::Job<OracleBackend>&) {}

@@ -31,7 +31,7 @@ def test_product_library_exports_every_declared_symbol():
     major, minor = C.c_int32(), C.c_int32()
     assert lib.amh_version(C.byref(major), C.byref(minor)) == 0
     assert (major.value, minor.value) == (0, 1)
-    assert lib.amh_contract_version() == 1
+    assert lib.amh_contract_version() == 2
 
 
 def test_oracle_exports_the_same_abi_under_its_own_prefix(oracle):

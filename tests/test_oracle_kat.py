@@ -30,6 +30,59 @@ PHILOX_KAT = [   # ctr[4], key[2] -> out[4]   (Random123 kat_vectors: "philox4x3
 ]
 
 
+PHILOX7_KAT = [   # Random123 kat_vectors: "philox4x32 7 ..." -- the round count of contract v2's step-noise blocks
+    ((0, 0, 0, 0), (0, 0), (0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48)),
+    ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662)),
+    ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+     (0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a)),
+]
+
+
+def test_philox4x32_7_known_answers(oracle):
+    out = (C.c_uint32 * 4)()
+    for ctr, key, want in PHILOX7_KAT:
+        oracle.lib.amho_probe_philox7(*[C.c_uint32(v) for v in ctr], *[C.c_uint32(v) for v in key], out)
+        assert tuple(out) == want
+
+
+def test_contract_v2_step_noise_layout_and_distribution(oracle):
+    """contract v2 (include/amh_contract.h): block j of a step -> normals 4j..4j+3 from its four 32-bit words (radius word,
+    angle word) x 2, Philox4x32-7; the exponential from the 64-bit word 0 of block ceil(d/4).  Rebuilt here from the raw
+    Philox probe with numpy, then checked for normality / independence."""
+    import scipy.stats as st
+    dp = C.POINTER(C.c_double)
+    out = (C.c_uint32 * 4)()
+    def block(seed, blk):
+        oracle.lib.amho_probe_philox7(C.c_uint32(blk & 0xffffffff), C.c_uint32(blk >> 32), C.c_uint32(0), C.c_uint32(0),
+                                      C.c_uint32(seed & 0xffffffff), C.c_uint32(seed >> 32), out)
+        return [int(v) for v in out]
+    for seed, step, d in ((12345678901234567, 3, 7), (2 ** 63 + 11, 2 ** 33 + 1, 32), (5, 0, 1)):
+        z = np.empty(d); e = C.c_double()
+        oracle.lib.amho_probe_step_noise_cv(2, C.c_uint64(seed), C.c_uint64(step), d, z.ctypes.data_as(dp), C.byref(e))
+        nb = (d + 3) // 4
+        want = []
+        for j in range(nb):
+            v = block(seed, step * (nb + 1) + j)
+            for wr, wa in ((v[0], v[1]), (v[2], v[3])):
+                u = (wr + 0.5) * 2.0 ** -32
+                ang = (np.pi / 2) * ((wa >> 30) + ((wa & 0x3fffffff) * 2.0 ** -30 - 0.5))
+                r = np.sqrt(-2.0 * np.log(u))
+                want += [r * np.cos(ang), r * np.sin(ang)]
+        np.testing.assert_allclose(z, np.array(want)[:d], rtol=1e-13, atol=1e-15)
+        v = block(seed, step * (nb + 1) + nb)
+        assert e.value == pytest.approx(-np.log((((v[1] << 32 | v[0]) >> 12) + 0.5) * 2.0 ** -52), rel=1e-14)
+    zs, es = [], []
+    z = np.empty(32); e = C.c_double()
+    for seed in _seeds(6000, 77):
+        oracle.lib.amho_probe_step_noise_cv(2, C.c_uint64(int(seed)), C.c_uint64(9), 32, z.ctypes.data_as(dp), C.byref(e))
+        zs.append(z.copy()); es.append(e.value)
+    zs = np.array(zs)
+    assert st.kstest(zs.ravel(), "norm").pvalue > 1e-3 and st.kstest(es, "expon").pvalue > 1e-3
+    assert abs(zs.var() - 1) < 0.01 and abs(st.kurtosis(zs.ravel())) < 0.05
+    cm = np.corrcoef(zs.T)
+    assert np.abs(cm - np.eye(32)).max() < 0.06          # no correlation inside or across blocks (6000 samples: sd 0.013)
+
+
 def test_philox4x32_10_known_answers(oracle):
     out = (C.c_uint32 * 4)()
     for ctr, key, want in PHILOX_KAT:

@@ -42,10 +42,11 @@ def _grad(oracle, th, x):
     return lp.value, g
 
 
-def _noise(oracle, seed, step, d):
+def _noise(oracle, seed, step, d, cv=2):
+    """the d normals and the exponential of a step under contract version `cv` (the default of new runs is 2)"""
     z = np.empty(d)
     e = C.c_double()
-    oracle.lib.amho_probe_step_noise(C.c_uint64(int(seed)), C.c_uint64(step), d, z.ctypes.data_as(dp), C.byref(e))
+    oracle.lib.amho_probe_step_noise_cv(cv, C.c_uint64(int(seed)), C.c_uint64(step), d, z.ctypes.data_as(dp), C.byref(e))
     return z, e.value
 
 
@@ -146,7 +147,7 @@ def test_mh_step_candidate_logalpha_and_decision_vs_scipy(amh, oracle, kind):
     s1 = run.state()
     n_acc = 0
     for c in range(n):
-        z, e = _noise(oracle, seeds[c], 1, d)
+        z, e = _noise(oracle, seeds[c], 1, d, run.contract())
         v = pm + L @ z                                             # rand(rng, MvNormal): mu + L z
         x = x0[:, c]
         cand = x + v if kind.startswith("rw") else v
@@ -187,7 +188,7 @@ def test_mala_step_vs_scipy_logpdfs(amh, oracle):
     s1 = run.state(grad=True)
     n_acc = 0
     for c in range(n):
-        z, e = _noise(oracle, seeds[c], 1, d)
+        z, e = _noise(oracle, seeds[c], 1, d, run.contract())
         x = x0[:, c]
         lpx, gx = lp_grad(x)
         np.testing.assert_allclose(s0["grad"][:, c], gx, rtol=1e-10, atol=1e-11)
@@ -272,7 +273,7 @@ def test_ram_adaptation_is_the_rank_one_cholesky_update_or_downdate(amh, oracle,
         run.steps(1, warmup=True)
         cur = run.state(S=True)
         for c in range(n):
-            U, e = _noise(oracle, seeds[c], k, d)
+            U, e = _noise(oracle, seeds[c], k, d, run.contract())
             S = np.zeros((d, d)); S[tril] = prev["S"][:, c]
             S1 = np.zeros((d, d)); S1[tril] = cur["S"][:, c]
             x = prev["x"][:, c]

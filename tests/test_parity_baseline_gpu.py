@@ -200,3 +200,57 @@ def test_callback_receives_the_sampler_state_of_every_saved_sample(amh, cuda, or
     ch2 = amh.sample(target, spl, amh.MCMCB200(), N, n, num_warmup=N, discard_initial=0, seed=3,
                      initial_params=np.zeros((d, n)), chain_type=amh.Chains)
     assert np.array_equal(ch.value, ch2.value) and np.array_equal(ch.accepted, ch2.accepted)
+
+
+# ------------------------------------------------------------------ contract versions
+@pytest.mark.parametrize("cv", [1, 2])
+def test_both_contract_versions_on_every_tuned_kernel_bit_exact(amh, cuda, oracle, cv):
+    """the default contract is v2 (Philox4x32-7, four normals per block); v1 stays selectable per run and every kernel
+    implements both: K1T16 (d = 8, 16, 24, 32; full and diagonal proposals), K1 fixed / generic dimensions, K3L, K4W, K4"""
+    with amh.contract(cv):
+        for d, cov in ((8, "full"), (16, "full"), (24, "full"), (32, "full"), (32, "diag"), (10, "full"), (13, "full"), (40, "full")):
+            Sg = make_spd(d, seed=d)
+            target = amh.MvNormalTarget(np.linspace(-1, 1, d), Sg)
+            prop = amh.MvNormal(np.zeros(d), (2.38 ** 2 / d) * Sg) if cov == "full" else [amh.Normal(0, 0.5 + 0.1 * i) for i in range(d)]
+            n = 777
+            rg, ro = _pair(cuda, oracle, target, amh.RWMH(prop), n, _seeds(n, d))
+            assert rg.contract() == ro.contract() == cv
+            _same(rg, ro)
+            for k, spl in ((1, 1), (9, 4), (33, 0)):
+                rg.steps(k, steps_per_launch=spl); ro.steps(k)
+                _same(rg, ro)
+        # static MH on the tensor path (odd / even launch steps share the exponential draw between the two lanes of a chain)
+        d = 16
+        Sg = make_spd(d, 5, 0.5, 3.0)
+        rg, ro = _pair(cuda, oracle, amh.MvNormalTarget(None, Sg), amh.MetropolisHastings(amh.StaticProposal(amh.MvNormal(np.zeros(d), 1.3 * Sg))),
+                       300, _seeds(300, 6))
+        rg.steps(7, steps_per_launch=3); ro.steps(7)
+        _same(rg, ro)
+        # K3L d = 32 / 64 / 128
+        for d, rows, n in ((32, 100, 50), (64, 72, 24), (128, 203, 70)):
+            rng = np.random.default_rng(d)
+            X = rng.normal(size=(rows, d)) / np.sqrt(d)
+            y = (rng.random(rows) < 0.5).astype(float)
+            s2 = 0.02
+            rg, ro = _pair(cuda, oracle, amh.LogisticRegressionTarget(X, y, tau=5.0), amh.MALA(lambda g: amh.MvNormal((s2 / 2) * g, s2 * amh.I)),
+                           n, _seeds(n, 300 + d), 0.1 * rng.normal(size=(d, n)))
+            rg.steps(6, steps_per_launch=2); ro.steps(6)
+            _same(rg, ro, keys=("x", "lp", "grad", "accepted", "naccept"), grad=True)
+        # MALA on the per-thread kernel (fixed and generic dimension), RAM on K4W and on K4
+        for d in (5, 16):
+            Sg = make_spd(d, 9, 0.5, 3.0)
+            s2 = 0.1
+            rg, ro = _pair(cuda, oracle, amh.MvNormalTarget(None, Sg), amh.MALA(lambda g: amh.MvNormal((s2 / 2) * g, s2 * amh.I)), 200, _seeds(200, 7),
+                           np.zeros((d, 200)))
+            rg.steps(9); ro.steps(9)
+            _same(rg, ro, keys=("x", "lp", "grad", "accepted", "naccept"), grad=True)
+        for d in (2, 20, 33, 64):
+            Sg = make_spd(d, 11, 0.05, 2.0)
+            rg, ro = _pair(cuda, oracle, amh.MvNormalTarget(None, Sg), amh.RobustAdaptiveMetropolis(S=0.3 * np.eye(d)), 150, _seeds(150, 8))
+            rg.steps(12, warmup=True, steps_per_launch=5); ro.steps(12, warmup=True)
+            _same(rg, ro, keys=("x", "lp", "S", "accepted", "naccept", "logalpha", "eta"), S=True)
+        # arrays of univariate laws: Normal components read the step's Box-Muller slots
+        comp = amh.MetropolisHastings(amh.StaticProposal([amh.Normal(0, 1), amh.InverseGamma(2, 3), amh.Normal(1, 2)]))
+        rg, ro = _pair(cuda, oracle, amh.MvNormalTarget(np.array([0.0, 1.5, 1.0]), np.eye(3)), comp, 100, _seeds(100, 9))
+        rg.steps(15); ro.steps(15)
+        _same(rg, ro)
