@@ -474,10 +474,12 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
         chk(dev_alloc(ctx, &r->lp2, np));
     }
     if (kind == AMH_SAMPLER_RAM) {
-        r->ram_warp = ram_warp_eligible(*r) && !(std::getenv("AMH_RAM_PATH") && std::strcmp(std::getenv("AMH_RAM_PATH"), "thread") == 0);
+        const char* rp = std::getenv("AMH_RAM_PATH");          /* A/B switch: thread forces K4 */
+        r->ram_warp = ram_warp_eligible(*r) && !(rp && std::strcmp(rp, "thread") == 0);
     }
     if (kind == AMH_SAMPLER_RAM && r->ram_warp) {
-        chk(dev_alloc(ctx, &r->S, ((nt + 1) & ~(size_t)1) * (size_t)n));   /* [chain][column-packed, padded to 16 B], single buffer */
+        chk(dev_alloc(ctx, &r->S, ((nt + 1) & ~(size_t)1) * (size_t)n));   /* [chain][column-packed, padded to 16 B] */
+
         chk(dev_alloc(ctx, &r->logalpha, np));
         chk(dev_alloc(ctx, &r->eta, np));
     } else if (kind == AMH_SAMPLER_RAM) {
@@ -502,7 +504,7 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
     if (r->logalpha) cu(cudaMemsetAsync(r->logalpha, 0, sizeof(double) * np, st), "memset logalpha");
     if (r->eta) cu(cudaMemsetAsync(r->eta, 0, sizeof(double) * np, st), "memset eta");
     if (r->sflag) cu(cudaMemsetAsync(r->sflag, 0, np, st), "memset sflag");
-    if (r->S2) cu(cudaMemsetAsync(r->S2, 0, sizeof(double) * nt * np, st), "memset S2");
+    if (r->S2 && !r->ram_warp) cu(cudaMemsetAsync(r->S2, 0, sizeof(double) * nt * np, st), "memset S2");
     cu(cudaMemcpyAsync(r->seeds, seeds, sizeof(uint64_t) * nseeds, cudaMemcpyHostToDevice, st), "copy seeds");
     int mode;
     if (init) {

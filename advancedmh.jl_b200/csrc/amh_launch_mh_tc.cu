@@ -299,12 +299,17 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
          * it at the top of the step ptxas schedules the whole loop body differently, and that schedule is 8 % faster
          * (C2: 5.18e9 -> 5.60e9 chain-steps/s, same box, A/B of two builds, profiles/r1_k1t16_cta_shape_ab.txt); an
          * asm memory clobber or a __syncwarp at the same place do not have this effect. */
-        if (a.pace > 0) __nanosleep((unsigned)a.pace);
+        /* (contract v1 only: the v2 kernel -- the default -- is 1.6 % FASTER without the branch, 6.39e9 vs 6.28e9 chain-steps/s,
+         * profiles/r2_k1t16_v2_ab.txt, so the default path no longer depends on this scheduling accident) */
+        if constexpr (CV == 1) {
+            if (a.pace > 0) __nanosleep((unsigned)a.pace);
+        }
         double e;
         {
             const unsigned long long b0 = k * B + (unsigned long long)(NPH * half);
             double* zt = ZC + (HR * half) * kPZ16 + cl;            /* Z[HR half + j][cl] */
-            constexpr int G1 = (NPH * NPB >= 12) ? NPH / 2 : 0;    /* two lock-step batches when there are >= 6 pairs */
+            /* two lock-step batches when there are >= 6 pairs (v2, d = 32: 2 + 2 blocks; one batch of 4 blocks measured 2.5 % slower) */
+            constexpr int G1 = (NPH * NPB >= 12) ? NPH / 2 : 0;
             if constexpr (G1 > 0) noise_group<(G1 > 0 ? G1 : 1), false, CV>(seed, b0, 0ull, zt, e, amh::amh_log_tab_dev, kPZ16);
             /* the exponential: both lanes of a chain run the same instructions, so on even steps of the launch lane half
              * h draws the exponential of step k + h, and odd steps draw none */

@@ -21,28 +21,10 @@
 #include <cstdlib>
 #include "amh_params.cuh"
 #include "amh_fastmath.cuh"
+#include "amh_ram_common.cuh"
 
 namespace amhh {
 using namespace amhd;
-
-struct RamWArgs {
-    ChainState st;
-    SaveArgs sv;
-    int d;
-    int nsteps;
-    int warmup;
-    unsigned long long step0;
-    double* S;                 /* [chain][nt] column-packed lower factor */
-    unsigned char* failed;
-    double* logalpha;
-    double* eta;
-    double alpha, gamma, lo, hi;
-    int check;
-    const double* Utc;         /* target factor, column-packed [nt] */
-    int force_redo;            /* test switch: treat every speculative sweep as out of range (exercises the redo path) */
-    const double* mu;          /* [d] */
-    double c0;
-};
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -78,17 +60,11 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__host__ __device__ __forceinline__ int colstart(int i, int d) { return i * d - (i * (i - 1)) / 2; }
-
 template <int RPL>
 __host__ __device__ constexpr int ramw_doubles_per_warp(int d) {
     /* S tile (padded to 16 bytes) + U, V vectors */
     return ((d * (d + 1) / 2 + 1) & ~1) + 2 * 32 * RPL + 2;
 }
-
-/* out-of-line IEEE operators for the operands the branch-free sequences of amh_fastmath.cuh do not cover */
-__device__ __noinline__ double div_slow(double a, double b) { return a / b; }
-
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Rank-1 Cholesky up/down-date of the warp's tile (LinearAlgebra lowrankupdate / lowrankdowndate).
@@ -103,14 +79,6 @@ __device__ __noinline__ double div_slow(double a, double b) { return a / b; }
  *   - split by row block (the compile-time `rb` loop), so that v[] is never indexed dynamically (it stays in
  *     registers) and rows above the diagonal block cost no predicate.
  * Results are bit-identical to the operators (tools/ubench/fdiv_probe.cu; RAM parity tests). */
-/* range bookkeeping of the speculative sweeps: instead of testing every operand against the exponent range of the
- * straight-line sequences, the loops keep a running minimum / maximum of the operands' HIGH WORDS (for doubles of one
- * sign the integer order of the high words is the order of the values; a negative value gives a negative word, NaN and
- * Inf large positive ones) -- two integer min/max per operand, off the fp64 pipe and off the critical path */
-constexpr int kHiLo = 0x2B800000;          /* high word of 2^-327 ~ 3.7e-99  */
-constexpr int kHiHi = 0x54B00000;          /* high word of 2^332  ~ 8.7e99   */
-__device__ __forceinline__ int hi_abs(double x) { return __double2hiint(x) & 0x7fffffff; }
-
 template <int RPL, bool CHECK>
 __device__ __forceinline__ bool givens_update_fast(double* __restrict__ Sb, int d, int lane, double (&v)[RPL],
                                                    double lo, double hi, bool& out_of_bounds) {
@@ -484,17 +452,19 @@ ram_warp_kernel(const __grid_constant__ RamWArgs a) {
 }
 
 /* ---- layout conversion: [chain][column-packed] <-> the ABI's [row-packed tri][chain] ---- */
-__global__ void ramw_export_S_kernel(const double* Sw, double* dst, long long n, long long pitch, int d) {
+__global__ void ramw_export_S_kernel(const double* S1, const double* S2, const unsigned char* sflag, double* dst, long long n, long long pitch, int d) {
     const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= n) return;
     const int ntp = (d * (d + 1) / 2 + 1) & ~1;
+    const double* Sw = (sflag && sflag[ch]) ? S2 : S1;          /* K4S: the chain's current buffer */
     for (int i = 0; i < d; ++i)
         for (int j = 0; j <= i; ++j) dst[(long long)tri(i, j) * pitch + ch] = Sw[(size_t)ch * ntp + colstart(j, d) + (i - j)];
 }
-__global__ void ramw_import_S_kernel(double* Sw, const double* src, long long n, long long pitch, int d) {
+__global__ void ramw_import_S_kernel(double* S1, double* S2, const unsigned char* sflag, const double* src, long long n, long long pitch, int d) {
     const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= n) return;
     const int ntp = (d * (d + 1) / 2 + 1) & ~1;
+    double* Sw = (sflag && sflag[ch]) ? S2 : S1;
     for (int i = 0; i < d; ++i)
         for (int j = 0; j <= i; ++j) Sw[(size_t)ch * ntp + colstart(j, d) + (i - j)] = src[(long long)tri(i, j) * pitch + ch];
 }
@@ -527,7 +497,7 @@ int ramw_init_S(amh_run& r) {
 
 int ramw_export_S(amh_run& r, double* dst) {
     const unsigned grid = (unsigned)((r.n + 127) / 128);
-    ramw_export_S_kernel<<<grid, 128, 0, r.ctx->stream>>>(r.S, dst, r.n, r.pitch, r.dim);
+    ramw_export_S_kernel<<<grid, 128, 0, r.ctx->stream>>>(r.S, r.S2, r.sflag, dst, r.n, r.pitch, r.dim);
     AMH_CUDA_TRY(cudaGetLastError());
     r.launches += 1;
     return AMH_OK;
@@ -535,7 +505,7 @@ int ramw_export_S(amh_run& r, double* dst) {
 
 int ramw_import_S(amh_run& r, const double* src) {
     const unsigned grid = (unsigned)((r.n + 127) / 128);
-    ramw_import_S_kernel<<<grid, 128, 0, r.ctx->stream>>>(r.S, src, r.n, r.pitch, r.dim);
+    ramw_import_S_kernel<<<grid, 128, 0, r.ctx->stream>>>(r.S, r.S2, r.sflag, src, r.n, r.pitch, r.dim);
     AMH_CUDA_TRY(cudaGetLastError());
     r.launches += 1;
     return AMH_OK;
