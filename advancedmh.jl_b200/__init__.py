@@ -4,7 +4,7 @@ multi-chain path, over the hand-written sm_100a engine in libamh_b200.so.
 Importable as `advancedmh_jl_b200` through the loader `amh_b200.py` at the
 repository root (the directory name contains a dot)."""
 from . import _capi
-from ._capi import AMHArgumentError, AMHError, AMHStateError, Engine, PosDefException, contract
+from ._capi import AMHArgumentError, AMHError, AMHStateError, Engine, PosDefException, contract, precision
 from .distributions import (Exponential, Gamma, I, InverseGamma, LogNormal, MvNormal, Normal, Uniform, Zeros)
 from .models import (DensityModel, DeviceTarget, GaussianPrecisionTarget, IIDNormalTarget,
                      LogisticRegressionTarget, MvNormalTarget, NormalInverseGammaToy, RosenbrockTarget, SourceTarget)

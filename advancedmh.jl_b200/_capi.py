@@ -48,7 +48,7 @@ class SamplerDesc(C.Structure):
         ("ram_eig_lo", C.c_double), ("ram_eig_hi", C.c_double),
         ("ram_S0", _dp),
         ("components", C.POINTER(Component)),
-        ("contract", C.c_int32), ("reserved", C.c_int32),
+        ("contract", C.c_int32), ("precision", C.c_int32),
     ]
 
 
@@ -116,6 +116,28 @@ class contract:
         return False
 
 
+# arithmetic of the design-matrix contractions: 0 = fp64 (bit-exact, default), 1 = split-bf16 tensor-core GEMMs (opt-in,
+# stated tolerance; MALA x logistic target x dim 128 only).  `with precision("bf16x2"): ...` or MCMCB200(dtype="bf16x2").
+PRECISION_FP64, PRECISION_BF16X2 = 0, 1
+DEFAULT_PRECISION = 0
+
+
+class precision:
+    """context manager: lower samplers with `amh_sampler_desc.precision` = p ("fp64" / "bf16x2" or 0 / 1) inside the block"""
+    def __init__(self, p):
+        self.p = {"fp64": 0, "f64": 0, "bf16x2": 1}.get(p, p)
+        if self.p not in (0, 1):
+            raise ValueError("precision must be 'fp64' or 'bf16x2'")
+    def __enter__(self):
+        global DEFAULT_PRECISION
+        self.old, DEFAULT_PRECISION = DEFAULT_PRECISION, self.p
+        return self
+    def __exit__(self, *exc):
+        global DEFAULT_PRECISION
+        DEFAULT_PRECISION = self.old
+        return False
+
+
 def _as_f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
@@ -123,7 +145,7 @@ def _as_f64(a):
 def sampler_desc(*, kind, dim, symmetric=False, cov_kind=COV_SCALAR, mean=None, scale=None,
                  stretch_a=2.0, n_walkers=0, mala_sigma2=0.0, mala_drift=0.0,
                  ram_alpha=0.234, ram_gamma=0.6, ram_eig_lo=0.0, ram_eig_hi=float("inf"), ram_S0=None,
-                 components=None, contract=None):
+                 components=None, contract=None, precision=None):
     """-> (amh_sampler_desc, objects that must stay alive while it is used).
     components: list of (family, p0, p1, logc[, rw, symmetric]) -- one univariate law per coordinate
     contract: version of the numerical contract (include/amh_contract.h); None = `DEFAULT_CONTRACT` (0 = library default)"""
@@ -137,7 +159,8 @@ def sampler_desc(*, kind, dim, symmetric=False, cov_kind=COV_SCALAR, mean=None, 
     d = SamplerDesc(kind, dim, int(bool(symmetric)), cov_kind, ptr(mean), ptr(scale), float(stretch_a),
                     int(n_walkers), float(mala_sigma2), float(mala_drift), float(ram_alpha), float(ram_gamma),
                     float(ram_eig_lo), float(ram_eig_hi), ptr(ram_S0), None,
-                    int(DEFAULT_CONTRACT if contract is None else contract), 0)
+                    int(DEFAULT_CONTRACT if contract is None else contract),
+                    int(DEFAULT_PRECISION if precision is None else precision))
     if components is not None:
         if len(components) != dim:
             raise AMHArgumentError(AMH_ERR_INVALID, f"need one component per coordinate ({dim}), got {len(components)}")

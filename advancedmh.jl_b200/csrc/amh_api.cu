@@ -164,8 +164,9 @@ static void free_run(amh_run* r) {
         }
     }
     void* ptrs[] = {r->X, r->X2, r->lp, r->lp2, r->lq, r->G, r->S, r->S2, r->logalpha, r->eta, r->acc, r->failed,
-                    r->sflag, r->nacc, r->seeds, r->sum, r->sumsq, r->scratch};
+                    r->sflag, r->nacc, r->seeds, r->sum, r->sumsq, r->scratch, r->scratch2};
     for (void* p : ptrs) dfree(r->ctx, p);
+    mala_tensor_release(*r);
     for (auto& pr : r->pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto& pr : r->pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     delete r;
@@ -443,6 +444,11 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
     }
     if (kind == AMH_SAMPLER_STRETCH && !init && sampler->scale.empty() && !sampler->by_components())
         return fail(AMH_ERR_INVALID, "stretch move without init needs an initial-draw proposal");
+    if (sampler->d.precision != AMH_PRECISION_FP64 &&
+        !(sampler->d.precision == AMH_PRECISION_BF16X2 && kind == AMH_SAMPLER_MALA && target->kind == AMH_TARGET_LOGISTIC && d == 128 &&
+          target->ndata >= 64))
+        return fail(AMH_ERR_UNSUPPORTED, "precision bf16x2 (split-bf16 tensor-core path) exists for MALA on the logistic target with dim = 128 "
+                                         "and >= 64 rows; every other combination runs in fp64");
     AMH_CUDA_TRY(cudaSetDevice(ctx->device));
     amh_run* r = new amh_run();
     r->ctx = ctx; r->target = target; r->sampler = sampler;

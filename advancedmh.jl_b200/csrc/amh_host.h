@@ -77,6 +77,8 @@ struct amh_run {
     double* sum = nullptr;
     double* sumsq = nullptr;
     void* scratch = nullptr;       /* sampler / kernel specific device buffer */
+    void* scratch2 = nullptr;      /* K3T: bf16 operand slices, candidate / gradient scratch */
+    void* tensor_state = nullptr;  /* K3T: host-side state (tensor maps), amh_launch_mala_tensor.cu */
     size_t scratch_bytes = 0;
     long long step = 0;
     long long nsaved = 0;
@@ -127,6 +129,10 @@ int launch_mh_comp(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 bool mh_tc_eligible(const amh_run& r);        /* K1T: both mat-vecs on the FP64 tensor cores */
 int launch_mh_tc(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_mala(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
+/* K3T: the same on the tcgen05 tensor cores as split-bf16 GEMMs, opt-in (amh_launch_mala_tensor.cu) */
+bool mala_tensor_eligible(const amh_run& r);
+int launch_mala_tensor(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
+void mala_tensor_release(amh_run& r);
 /* K3L: MALA on the many-row logistic target as two chained DMMA GEMMs (amh_launch_mala_logistic.cu) */
 bool mala_logistic_eligible(const amh_run& r);
 int launch_mala_logistic(amh_run& r, int nsteps, const amhd::SaveArgs& sv);

@@ -162,6 +162,7 @@ int launch_mala_dim(amh_run& r, int nsteps, const SaveArgs& sv) {
 
 int launch_mala(amh_run& r, int nsteps, const SaveArgs& sv) {
     static const bool scalar_only = std::getenv("AMH_MALA_PATH") && std::strcmp(std::getenv("AMH_MALA_PATH"), "scalar") == 0;
+    if (nsteps > 0 && mala_tensor_eligible(r)) return launch_mala_tensor(r, nsteps, sv);      /* opt-in: precision bf16x2 */
     if (!scalar_only && mala_logistic_eligible(r)) return launch_mala_logistic(r, nsteps, sv);
     switch (r.target->kind) {
     case AMH_TARGET_MVNORMAL: return launch_mala_dim<TMvNormal>(r, nsteps, sv);

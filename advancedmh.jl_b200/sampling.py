@@ -49,6 +49,10 @@ class MCMCB200:
     # `MCMCB200(ngpus = 8)` lowers to.  `devices` optionally names the CUDA device indices.
     ngpus: int | None = None
     devices: tuple | None = None
+    # "fp64" (default): every kernel bit-exact against the oracle.  "bf16x2": OPT-IN tensor-core arithmetic with a stated
+    # tolerance -- MALA on the many-row logistic target (dim 128) runs its design-matrix contractions as split-bf16
+    # tcgen05 GEMMs; anything else raises.
+    dtype: str = "fp64"
     # this rank's chains as `streams` contiguous shards, each with its own context (stream, copy stream) on the same
     # GPU and driven by its own host thread: the host->device copy of one shard's initial parameters and the
     # device->host copy of its samples overlap the stepping kernels of the others.  Same results (global chain identity).
@@ -287,7 +291,16 @@ def _initial_matrix(initial_params, sampler, dim, nchains, multi):
     return np.ascontiguousarray(np.concatenate(cols, axis=1))
 
 
-def sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None, thinning=1, num_warmup=0,
+def sample(*args, **kw):
+    """see `_sample`; `MCMCB200(dtype=...)` selects the arithmetic the samplers are lowered with"""
+    par = next((a for a in args if isinstance(a, MCMCB200)), None)
+    if par is not None and par.dtype != "fp64":
+        with K.precision(par.dtype):
+            return _sample(*args, **kw)
+    return _sample(*args, **kw)
+
+
+def _sample(*args, rng=None, seed=None, initial_params=None, discard_initial=None, thinning=1, num_warmup=0,
            chain_type=None, param_names=None, progress=False, callback=None, engine=None, store=True,
            summary=False, steps_per_launch=0, out=None, initial_state=None, save_state=False):
     """See module docstring.  Extra device-side keywords (never on the samplers): `engine`

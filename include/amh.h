@@ -112,8 +112,14 @@ typedef struct amh_sampler_desc {
     int32_t contract;        /* version of the numerical contract the run's step noise follows (include/amh_contract.h):
                                 0 = the library default (AMH_CONTRACT_VERSION, or the environment variable AMH_CONTRACT),
                                 1 = v1, 2 = v2.  The oracle takes the same field, so parity is per version.           */
-    int32_t reserved;
+    int32_t precision;       /* AMH_PRECISION_FP64 (0, default): fp64 throughout, bit-exact against the oracle.
+                                AMH_PRECISION_BF16X2 (1): OPT-IN tensor-core path with a stated tolerance -- MALA on the
+                                logistic target with dim = 128 runs its two design-matrix contractions as split-bf16
+                                tcgen05 GEMMs with fp32 accumulation (csrc/amh_launch_mala_tensor.cu); every other
+                                sampler / target combination rejects it with AMH_ERR_UNSUPPORTED                      */
 } amh_sampler_desc;
+#define AMH_PRECISION_FP64   0
+#define AMH_PRECISION_BF16X2 1
 
 /* pooled and per-chain summaries accumulated on the device over SAVED samples */
 typedef struct amh_summary {

@@ -39,7 +39,7 @@ struct SamplerDesc            # struct amh_sampler_desc, field for field
     ram_alpha::Float64; ram_gamma::Float64; ram_eig_lo::Float64; ram_eig_hi::Float64
     ram_S0::Ptr{Float64}
     components::Ptr{Component}
-    contract::Int32; reserved::Int32
+    contract::Int32; precision::Int32     # precision: 0 = fp64 (bit-exact), 1 = split-bf16 tensor path (MALA x logistic, opt-in)
 end
 "version of the numerical contract new runs are created under: 0 = the library default (v2), 1 = v1, 2 = v2"
 const CONTRACT = Ref(Int32(0))

@@ -254,3 +254,68 @@ def test_both_contract_versions_on_every_tuned_kernel_bit_exact(amh, cuda, oracl
         rg, ro = _pair(cuda, oracle, amh.MvNormalTarget(np.array([0.0, 1.5, 1.0]), np.eye(3)), comp, 100, _seeds(100, 9))
         rg.steps(15); ro.steps(15)
         _same(rg, ro)
+
+
+# ------------------------------------------------------------------ K3T: the opt-in split-bf16 tcgen05 path (tolerance, not bit-exact)
+def _logistic(rows, d, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(rows, d)) / np.sqrt(d)
+    y = (rng.random(rows) < 1 / (1 + np.exp(-X @ rng.normal(size=d)))).astype(float)
+    return X, y
+
+
+@pytest.mark.parametrize("rows,n", [(1000, 200), (64, 128), (10000, 300)])
+def test_mala_tensor_path_one_step_within_stated_tolerance(amh, cuda, oracle, rows, n):
+    """precision = bf16x2 (csrc/amh_launch_mala_tensor.cu): eta = X c and X'r as split-bf16 tcgen05 GEMMs with fp32
+    accumulation, everything else fp64.  STATED TOLERANCE against the fp64 oracle, one step from the same state:
+      * the candidate is fp64 and identical, so accepted chains hold bit-identical x;
+      * log-density of the new state: |lp - lp_oracle| <= 2e-3 + 2e-6 |lp|   (observed ~1e-4);
+      * gradient: max_j |g_j - g_j_oracle| <= 2e-3 * max(1, max_j |g_j|);
+      * accept / reject decisions agree except when |log-alpha + e| is inside that tolerance (<= 1 % of the chains here)."""
+    d = 128
+    X, y = _logistic(rows, d, rows)
+    target = amh.LogisticRegressionTarget(X, y, tau=10.0)
+    s2 = 3.3e-2 if rows >= 5000 else 0.2
+    spl = amh.MALA(lambda g: amh.MvNormal((s2 / 2) * g, s2 * amh.I))
+    init = 0.05 * np.random.default_rng(1).normal(size=(d, n))
+    seeds = _seeds(n, 11)
+    with amh.precision("bf16x2"):
+        rg = cuda.run(cuda.target_of(target), spl.lower(cuda, d), n, seeds, init)
+    ro = oracle.run(oracle.target_of(target), spl.lower(oracle, d), n, seeds, init)
+    s0g, s0o = rg.state(grad=True), ro.state(grad=True)
+    for k in ("x", "lp", "grad"):
+        assert np.array_equal(s0g[k], s0o[k]), k              # the first step (initial lp / gradient) is the fp64 init kernel
+    rg.steps(1); ro.steps(1)
+    sg, so = rg.state(grad=True), ro.state(grad=True)
+    agree = sg["accepted"] == so["accepted"]
+    assert agree.mean() >= 0.99, f"accept decisions differ for {(~agree).sum()} of {n} chains"
+    both = agree & (sg["accepted"] == 1)
+    assert both.sum() > 0.3 * n
+    assert np.array_equal(sg["x"][:, both], so["x"][:, both])                     # fp64 candidates, identical
+    dlp = np.abs(sg["lp"][agree] - so["lp"][agree])
+    assert dlp.max() <= 2e-3 + 2e-6 * np.abs(so["lp"]).max(), dlp.max()
+    gmax = max(1.0, np.abs(so["grad"]).max())
+    assert np.abs(sg["grad"][:, agree] - so["grad"][:, agree]).max() <= 2e-3 * gmax
+    rg.close(); ro.close()
+
+
+def test_mala_tensor_path_long_run_statistics_and_api(amh, cuda, oracle):
+    """many steps: the chains decouple from the fp64 ones at the first knife-edge decision, so the comparison is
+    statistical -- acceptance rate and posterior means of the fp64 engine (K3L) and of the tensor path agree"""
+    d, rows, n = 128, 2000, 1024
+    X, y = _logistic(rows, d, 5)
+    target = amh.LogisticRegressionTarget(X, y, tau=10.0)
+    s2 = 0.12
+    spl = amh.MALA(lambda g: amh.MvNormal((s2 / 2) * g, s2 * amh.I))
+    init = np.zeros((d, n))
+    kw = dict(initial_params=init, discard_initial=60, thinning=5, seed=3, chain_type=amh.Chains)
+    a = amh.sample(target, spl, amh.MCMCB200(), 8, n, **kw)
+    b = amh.sample(target, spl, amh.MCMCB200(dtype="bf16x2"), 8, n, **kw)
+    assert abs(a.accepted[1:].mean() - b.accepted[1:].mean()) < 0.02
+    ma, mb = a.value[1:, :d, :].mean(axis=(0, 2)), b.value[1:, :d, :].mean(axis=(0, 2))
+    sd = a.value[1:, :d, :].std(axis=(0, 2))
+    assert np.abs(ma - mb).max() < 0.1 * sd.max()                                  # 7 x 1024 draws: standard error ~0.012 sd
+    assert np.abs(a.value[1:, d, :].mean() - b.value[1:, d, :].mean()) < 0.5      # mean log-density (std of lp ~ 8)
+    # only MALA x logistic x dim 128 has this path; everything else says so instead of silently running fp64
+    with pytest.raises(amh.AMHArgumentError, match="bf16x2"):
+        amh.sample(amh.MvNormalTarget(None, np.eye(4)), amh.RWMH(4), amh.MCMCB200(dtype="bf16x2"), 3, 8)

@@ -103,6 +103,27 @@ def main():
             report(f"C4 MALA logistic d=128 rows=10k n={n}", n * 4, ms, 2 * (2 * d + 1) * 8,
                    f"accept(recent)={acc:.3f}  {5.12e6 * n * 4 / (ms * 1e-3) / 1e12:.2f} TFLOP/s fp64")
             run.close()
+    if "c4t" in which:
+        # config 4 on the opt-in split-bf16 tcgen05 path (K3T, stated tolerance; csrc/amh_launch_mala_tensor.cu)
+        d, nrows = 128, 10000
+        rng = np.random.default_rng(128)
+        X = rng.normal(size=(nrows, d)) / np.sqrt(d)
+        beta = rng.normal(size=d)
+        y = (rng.random(nrows) < 1 / (1 + np.exp(-X @ beta))).astype(float)
+        t = amh.LogisticRegressionTarget(X, y, tau=10.0)
+        s2 = float(os.environ.get("AMH_C4_S2", "3.3e-2"))
+        s = amh.MALA(lambda g: amh.MvNormal((s2 / 2) * g, s2 * amh.I))
+        for n in (16384,):
+            with amh.precision("bf16x2"):
+                run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), n, seeds(n, 3), np.zeros((d, n)))
+            run.steps(60)
+            st0 = run.state()
+            ms = timed(run, 20, reps=2, warm=1)
+            st = run.state()
+            acc = (st['naccept'].sum() - st0['naccept'].sum()) / (n * (st['step'] - st0['step']))
+            report(f"C4 MALA logistic d=128 rows=10k n={n} bf16x2 tcgen05", n * 20, ms, 2 * (2 * d + 1) * 8,
+                   f"accept(recent)={acc:.3f}  {5.12e6 * n * 20 / (ms * 1e-3) / 1e12:.2f} TFLOP/s fp64-equivalent, {3 * 5.12e6 * n * 20 / (ms * 1e-3) / 1e12:.1f} TFLOP/s bf16 issued")
+            run.close()
     if "c5" in which:
         d = 64
         Sigma = spd(d, 64, 1e-4, 1.0)
