@@ -92,6 +92,10 @@ __device__ __forceinline__ void t_ld16(unsigned taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+/* MUFU approximations without the denormal fix-ups of __expf / __logf (arguments here are never denormal) */
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 /* 8 consecutive K elements (one 16-byte chunk) of operand row `row` in a [rows x 64] K-block tile, SWIZZLE_128B */
 __device__ __forceinline__ void store_chunk(unsigned char* tile, int row, int chunk, const unsigned (&e)[4]) {
     *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = make_uint4(e[0], e[1], e[2], e[3]);
@@ -103,21 +107,28 @@ constexpr int kOffX = 65536;                      /* [stage 2][slice 2][kblock 2
 constexpr int kOffXT = 131072;                    /* [stage 2][slice 2][128 features x 128 B]         65 536 */
 constexpr int kOffR = 196608;                     /* [slice 2][128 chains x 128 B]                    32 768 */
 constexpr int kOffBar = 229376;
-constexpr int kSmemT = kOffBar + 128;
-enum { BAR_FULL = 0, BAR_EMPTY = 2, BAR_A1FULL = 4, BAR_A1EMPTY = 6, BAR_RFULL = 8, BAR_REMPTY = 9, BAR_A2FULL = 10, BAR_CREADY = 11 };
+constexpr int kSmemT = kOffBar + 160;
+enum { BAR_FULL = 0, BAR_EMPTY = 2, BAR_A1FULL = 4, BAR_A1EMPTY = 6, BAR_RFULL = 8, BAR_REMPTY = 9, BAR_A2FULL = 10, BAR_CREADY = 11,
+       BAR_FULLT = 12, BAR_EMPTYT = 14, BAR_COUNT = 16 };     /* FULL / EMPTY: the X half of a stage; FULLT / EMPTYT: the X^T half */
 
 __global__ void __launch_bounds__(320, 1)
 mala_tensor_kernel(const __grid_constant__ MalaTArgs a, const __grid_constant__ CUtensorMap mapXhi, const __grid_constant__ CUtensorMap mapXlo,
                    const __grid_constant__ CUtensorMap mapXThi, const __grid_constant__ CUtensorMap mapXTlo) {
     extern __shared__ __align__(1024) unsigned char tsm[];
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(tsm + kOffBar);
-    unsigned* tmem_ptr = reinterpret_cast<unsigned*>(tsm + kOffBar + 12 * 8);
+    unsigned* tmem_ptr = reinterpret_cast<unsigned*>(tsm + kOffBar + BAR_COUNT * 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = a.ntiles;
+    /* every CTA walks the row tiles in its own rotation: the sums over tiles do not care about the order, and 128 CTAs
+     * asking L2 for the SAME 64 KB at the same moment serialise on its slices (ncu: the epilogue warps spent 21 % of their
+     * stall samples waiting for GEMM1, i.e. for the tile's TMA) */
+    const int trot = (int)((37u * blockIdx.x) % (unsigned)T);
 
     if (threadIdx.x == 0) {
         t_mbar_init(bars + BAR_FULL, 1); t_mbar_init(bars + BAR_FULL + 1, 1);
         t_mbar_init(bars + BAR_EMPTY, 1); t_mbar_init(bars + BAR_EMPTY + 1, 1);
+        t_mbar_init(bars + BAR_FULLT, 1); t_mbar_init(bars + BAR_FULLT + 1, 1);
+        t_mbar_init(bars + BAR_EMPTYT, 1); t_mbar_init(bars + BAR_EMPTYT + 1, 1);
         t_mbar_init(bars + BAR_A1FULL, 1); t_mbar_init(bars + BAR_A1FULL + 1, 1);
         t_mbar_init(bars + BAR_A1EMPTY, 8); t_mbar_init(bars + BAR_A1EMPTY + 1, 8);
         t_mbar_init(bars + BAR_RFULL, 8);
@@ -140,16 +151,21 @@ mala_tensor_kernel(const __grid_constant__ MalaTArgs a, const __grid_constant__ 
         if (lane == 0) {
             for (int t = 0; t < T; ++t) {
                 const int s = t & 1, u = t >> 1;
-                t_mbar_wait(bars + BAR_EMPTY + s, (unsigned)((u & 1) ^ 1));
-                t_mbar_expect_tx(bars + BAR_FULL + s, 65536u);
+                int tt = t + trot; if (tt >= T) tt -= T;
+                /* the X half (GEMM1's B) is released as soon as GEMM1 of tile t-2 has completed, the X^T half (GEMM2's B)
+                 * after GEMM2 of tile t-2: two barrier pairs per stage keep the loads off the GEMM2 -> GEMM1 chain */
                 unsigned char* dx = tsm + kOffX + s * 32768;
                 unsigned char* dxt = tsm + kOffXT + s * 32768;
+                t_mbar_wait(bars + BAR_EMPTY + s, (unsigned)((u & 1) ^ 1));
+                t_mbar_expect_tx(bars + BAR_FULL + s, 32768u);
                 for (int kb = 0; kb < 2; ++kb) {
-                    t_tma_2d(dx + kb * 8192, &mapXhi, kb * 64, t * kTRows, bars + BAR_FULL + s);
-                    t_tma_2d(dx + 16384 + kb * 8192, &mapXlo, kb * 64, t * kTRows, bars + BAR_FULL + s);
+                    t_tma_2d(dx + kb * 8192, &mapXhi, kb * 64, tt * kTRows, bars + BAR_FULL + s);
+                    t_tma_2d(dx + 16384 + kb * 8192, &mapXlo, kb * 64, tt * kTRows, bars + BAR_FULL + s);
                 }
-                t_tma_2d(dxt, &mapXThi, t * kTRows, 0, bars + BAR_FULL + s);
-                t_tma_2d(dxt + 16384, &mapXTlo, t * kTRows, 0, bars + BAR_FULL + s);
+                t_mbar_wait(bars + BAR_EMPTYT + s, (unsigned)((u & 1) ^ 1));
+                t_mbar_expect_tx(bars + BAR_FULLT + s, 32768u);
+                t_tma_2d(dxt, &mapXThi, tt * kTRows, 0, bars + BAR_FULLT + s);
+                t_tma_2d(dxt + 16384, &mapXTlo, tt * kTRows, 0, bars + BAR_FULLT + s);
             }
         }
     } else if (warp == 1) {
@@ -159,6 +175,7 @@ mala_tensor_kernel(const __grid_constant__ MalaTArgs a, const __grid_constant__ 
             const unsigned acc2 = tmem + 128;
             auto gemm2 = [&](int tt) {
                 const int s = tt & 1;
+                t_mbar_wait(bars + BAR_FULLT + s, (unsigned)((tt >> 1) & 1));
                 t_mbar_wait(bars + BAR_RFULL, (unsigned)(tt & 1));
                 t_fence_after();
                 const unsigned char* sr = tsm + kOffR;
@@ -171,7 +188,7 @@ mala_tensor_kernel(const __grid_constant__ MalaTArgs a, const __grid_constant__ 
                     t_umma(acc2, t_desc(sr + 16384 + kk * 32), t_desc(sxt + kk * 32), id2, 1u);
                 }
                 t_commit(bars + BAR_REMPTY);            /* R may be overwritten */
-                t_commit(bars + BAR_EMPTY + s);         /* the stage's X / X^T may be overwritten */
+                t_commit(bars + BAR_EMPTYT + s);        /* the stage's X^T half may be overwritten */
             };
             t_mbar_wait(bars + BAR_CREADY, 0u);
             t_fence_after();
@@ -194,6 +211,7 @@ mala_tensor_kernel(const __grid_constant__ MalaTArgs a, const __grid_constant__ 
                         t_umma(acc1, t_desc(sc + 32768 + oc), t_desc(sx + ox), id1, 1u);
                     }
                 t_commit(bars + BAR_A1FULL + s);
+                t_commit(bars + BAR_EMPTY + s);         /* the stage's X half may be overwritten */
                 if (t >= 1) gemm2(t - 1);
             }
             gemm2(T - 1);
@@ -258,52 +276,54 @@ mala_tensor_kernel(const __grid_constant__ MalaTArgs a, const __grid_constant__ 
             const int s = t & 1, u = t >> 1;
             t_mbar_wait(bars + BAR_A1FULL + s, (unsigned)(u & 1));
             t_fence_after();
+            /* the tile's 32 columns of this thread, processed STAGE BY STAGE over all 32 values (straight-line code: 32
+             * independent dependency chains for the scheduler; the MUFU latencies overlap instead of adding up) */
+            float eta[32];
+            t_ld16(tmem + ((unsigned)(32 * lg) << 16) + (unsigned)(s * 64 + 32 * h), *reinterpret_cast<float(*)[16]>(&eta[0]));
+            t_ld16(tmem + ((unsigned)(32 * lg) << 16) + (unsigned)(s * 64 + 32 * h + 16), *reinterpret_cast<float(*)[16]>(&eta[16]));
+            int tt = t + trot; if (tt >= T) tt -= T;
+            const int row0 = tt * kTRows + 32 * h;
+            float ys[32];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 yv = __ldg(reinterpret_cast<const float4*>(a.y + row0 + i));
+                ys[i] = yv.x; ys[i + 1] = yv.y; ys[i + 2] = yv.z; ys[i + 3] = yv.w;
+            }
+            float ex[32], w[32], iw[32], lw[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ex[i] = ex2_approx(-1.4426950408889634f * fabsf(eta[i]));   /* e^-|eta| */
+#pragma unroll
+            for (int i = 0; i < 32; ++i) w[i] = 1.0f + ex[i];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { iw[i] = rcp_approx(w[i]); lw[i] = lg2_approx(w[i]); }
+            float rv[32];
             float llt = 0.0f;
-            bool r_free = false;
+            const int nlive = a.nrows - row0;                                   /* rows beyond the data are padding */
 #pragma unroll
-            for (int cc = 0; cc < 32; cc += 16) {
-                const int c0 = 32 * h + cc;
-                float eta[16];
-                t_ld16(tmem + ((unsigned)(32 * lg) << 16) + (unsigned)(s * 64 + c0), eta);
-                unsigned rh[8], rl[8];
-                const int row0 = t * kTRows + c0;
+            for (int i = 0; i < 32; ++i) {
+                const float l1p = fmaf(lw[i], 0.6931471805599453f, fmaxf(eta[i], 0.0f));    /* log1pexp(eta) */
+                const float sg = eta[i] >= 0.0f ? iw[i] : ex[i] * iw[i];                    /* sigmoid(eta)  */
+                const bool live = i < nlive;
+                llt += live ? fmaf(ys[i], eta[i], -l1p) : 0.0f;
+                rv[i] = live ? (ys[i] - sg) : 0.0f;
+            }
+            unsigned rh[16], rl[16];
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    const float4 yv = __ldg(reinterpret_cast<const float4*>(a.y + row0 + i));
-                    const float ys[4] = {yv.x, yv.y, yv.z, yv.w};
-                    float rv[4];
+            for (int i = 0; i < 32; i += 2) {
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(rv[i], rv[i + 1]);
+                const float2 hf = __bfloat1622float2(hh);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(rv[i] - hf.x, rv[i + 1] - hf.y);
+                rh[i >> 1] = *reinterpret_cast<const unsigned*>(&hh);
+                rl[i >> 1] = *reinterpret_cast<const unsigned*>(&l2);
+            }
+            /* only now does R have to be free: GEMM2 of the previous tile ran under the arithmetic above */
+            t_mbar_wait(bars + BAR_REMPTY, (unsigned)((t & 1) ^ 1));
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float x = eta[i + e];
-                        const float ex = __expf(-fabsf(x));
-                        const float w = 1.0f + ex;
-                        const float iw = __fdividef(1.0f, w);
-                        const float l1p = fmaxf(x, 0.0f) + __logf(w);            /* log1pexp(eta) */
-                        const float sg = x >= 0.0f ? iw : ex * iw;               /* sigmoid(eta)  */
-                        const bool live = row0 + i + e < a.nrows;
-                        llt += live ? (ys[e] * x - l1p) : 0.0f;
-                        rv[e] = live ? (ys[e] - sg) : 0.0f;
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; e += 2) {
-                        const __nv_bfloat162 hh = __floats2bfloat162_rn(rv[e], rv[e + 1]);
-                        const float2 hf = __bfloat1622float2(hh);
-                        const __nv_bfloat162 l2 = __floats2bfloat162_rn(rv[e] - hf.x, rv[e + 1] - hf.y);
-                        rh[(i + e) >> 1] = *reinterpret_cast<const unsigned*>(&hh);
-                        rl[(i + e) >> 1] = *reinterpret_cast<const unsigned*>(&l2);
-                    }
-                }
-                if (!r_free) {                           /* GEMM2 of the previous tile has finished reading R */
-                    t_mbar_wait(bars + BAR_REMPTY, (unsigned)((t & 1) ^ 1));
-                    r_free = true;
-                }
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const unsigned eh[4] = {rh[4 * g], rh[4 * g + 1], rh[4 * g + 2], rh[4 * g + 3]};
-                    const unsigned el[4] = {rl[4 * g], rl[4 * g + 1], rl[4 * g + 2], rl[4 * g + 3]};
-                    store_chunk(tsm + kOffR, m, (c0 >> 3) + g, eh);
-                    store_chunk(tsm + kOffR + 16384, m, (c0 >> 3) + g, el);
-                }
+            for (int g = 0; g < 4; ++g) {
+                const unsigned eh[4] = {rh[4 * g], rh[4 * g + 1], rh[4 * g + 2], rh[4 * g + 3]};
+                const unsigned el[4] = {rl[4 * g], rl[4 * g + 1], rl[4 * g + 2], rl[4 * g + 3]};
+                store_chunk(tsm + kOffR, m, 4 * h + g, eh);
+                store_chunk(tsm + kOffR + 16384, m, 4 * h + g, el);
             }
             ll += (double)llt;
             t_fence_before();                            /* this thread's TMEM reads of the accumulator are done */

@@ -149,7 +149,7 @@ def _timed(run, nsteps, warmup=False, spl=0, reps=3, warm=1):
 
 # FP64-pipe cycles of one 16-chain warp-step of K1T16 at d = 32, by contract version (instruction mix from the ncu source
 # page x per-instruction pipe costs of tools/ubench/issue_probe.cu): (DMMA, DFMA-class, IMAD.WIDE/HI)
-PIPE_MIX = {1: (80, 398, 182), 2: (80, 398, 75)}
+PIPE_MIX = {1: (80, 398, 182), 2: (80, 377, 62)}        # v2 measured: profiles/r2_k1t16_v2_ncu_summary.txt
 PIPE_COST = (16.2, 2.07, 4.1)
 
 FP64_TFLOPS_PEAK = 148 * 64 * 2 * 1.965e9 / 1e12      # 64 FP64 FMA / clk / SM (DMMA or DFMA, one shared datapath) at 1965 MHz = 37.2
@@ -178,7 +178,7 @@ def bench_c3(amh, eng, peak, seed=2):
     return out
 
 
-def bench_c4(amh, eng, peak, seed=3, n=16384):
+def bench_c4(amh, eng, peak, seed=3, n=16384, bf16_peak=1403.9):
     d, nrows = 128, 10000
     rng = np.random.default_rng(128)
     X = rng.normal(size=(nrows, d)) / np.sqrt(d)
@@ -198,6 +198,24 @@ def bench_c4(amh, eng, peak, seed=3, n=16384):
                kernel="mala_logistic_kernel<128> (K3L: TMA ring + two chained FP64 DMMA GEMMs)", bound="fp64 tensor",
                fp64_tflops=tf, fp64_pipe_frac=tf / FP64_TFLOPS_PEAK, fp64_tflops_peak=FP64_TFLOPS_PEAK,
                accept_rate_recent=float((st["naccept"].sum() - st0["naccept"].sum()) / (n * (st["step"] - st0["step"]))))
+    run.close()
+    # the same config on the OPT-IN split-bf16 tcgen05 path (K3T): not bit-exact, tolerance stated in DESIGN.md / the tests
+    with amh.precision("bf16x2"):
+        run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), n, sd, np.zeros((d, n)))
+    run.steps(60)
+    st0 = run.state()
+    ms = _timed(run, 20, reps=2, warm=1)
+    st = run.state()
+    v = n * 20 / (ms * 1e-3)
+    issued = 3 * 4.0 * nrows * d * v / 1e12            # three bf16 slice products per contraction
+    out["tensor_bf16x2"] = {
+        "value": v, "unit": UNIT, "ms": ms, "speedup_vs_fp64_path": v / out["value"],
+        "kernel": "mala_tensor_kernel (K3T: tcgen05.mma kind::f16, TMEM accumulators, TMA-staged split-bf16 operands, fp32 link function)",
+        "fp64_equivalent_tflops": 4.0 * nrows * d * v / 1e12, "bf16_tflops_issued": issued, "bf16_peak_tflops_sustained": bf16_peak,
+        "tensor_frac": issued / bf16_peak, "bit_exact": False,
+        "tolerance": "one step from the same state: |d lp| <= 2e-3 + 2e-6 |lp|, |d grad| <= 2e-3 max|grad|, identical fp64 candidates; "
+                     "acceptance rate and posterior means agree with the fp64 path (tests/test_parity_baseline_gpu.py::test_mala_tensor_*)",
+        "accept_rate_recent": float((st["naccept"].sum() - st0["naccept"].sum()) / (n * (st["step"] - st0["step"])))}
     run.close()
     return out
 
@@ -448,7 +466,7 @@ def main():
         configs = {}
         for name, fn in (("c3", bench_c3), ("c4", bench_c4), ("c5", bench_c5)):
             barrier()
-            rec = fn(amh, eng, peak, seed=10 * (rank + 1) + len(configs))
+            rec = fn(amh, eng, peak, seed=10 * (rank + 1) + len(configs), **({"bf16_peak": float(peaks.get("bf16_tflops_sustained", 1403.9))} if name == "c4" else {}))
             if dist is not None:
                 # whole-job value: every rank processed the same number of units; time = max over ranks
                 tm = torch.tensor([rec["value"]], dtype=torch.float64, device=dev)
@@ -456,6 +474,10 @@ def main():
                 rec["value_per_gpu_min"] = float(tm.item())
                 rec["value"] = float(tm.item()) * world
                 rec["n_gpus"] = world
+                if "tensor_bf16x2" in rec:
+                    tm = torch.tensor([rec["tensor_bf16x2"]["value"]], dtype=torch.float64, device=dev)
+                    dist.all_reduce(tm, op=dist.ReduceOp.MIN)
+                    rec["tensor_bf16x2"]["value"] = float(tm.item()) * world
             configs[name] = rec
 
     cpu = None

@@ -43,10 +43,12 @@ struct SamplerDesc            # struct amh_sampler_desc, field for field
 end
 "version of the numerical contract new runs are created under: 0 = the library default (v2), 1 = v1, 2 = v2"
 const CONTRACT = Ref(Int32(0))
+"arithmetic of the design-matrix contractions: 0 = fp64 (bit-exact, default), 1 = split-bf16 tensor path (opt-in; MALA x logistic x dim 128)"
+const PRECISION = Ref(Int32(0))
 SamplerDesc(kind, dim, symmetric, cov_kind, mean, scale, stretch_a, n_walkers, mala_sigma2, mala_drift, ram_alpha, ram_gamma,
             ram_eig_lo, ram_eig_hi, ram_S0, components) =
     SamplerDesc(kind, dim, symmetric, cov_kind, mean, scale, stretch_a, n_walkers, mala_sigma2, mala_drift, ram_alpha, ram_gamma,
-                ram_eig_lo, ram_eig_hi, ram_S0, components, CONTRACT[], Int32(0))
+                ram_eig_lo, ram_eig_hi, ram_S0, components, CONTRACT[], PRECISION[])
 
 struct Summary                # struct amh_summary
     n_saved::Int64; n_steps::Int64; accept_rate::Float64
@@ -323,6 +325,7 @@ Base.@kwdef struct MCMCB200 <: AbstractMCMC.AbstractMCMCEnsemble
     ngpus::Int = 1
     devices::Union{Nothing,Vector{Int32}} = nothing       # CUDA device indices, default 0:ngpus-1
     ignore_failed_downdates::Bool = false                 # RAM: keep the samples instead of throwing PosDefException
+    dtype::Symbol = :fp64                                 # :bf16x2 = opt-in tensor-core arithmetic with a stated tolerance (MALA x logistic)
 end
 
 # (n, d) column-major == the device layout X[dim][chain] with chains fastest.  One entry per chain; for an Ensemble an
@@ -355,6 +358,7 @@ function AbstractMCMC.mcmcsample(rng::Random.AbstractRNG, model::AbstractMCMC.Ab
     nw = sampler isa AdvancedMH.Ensemble ? sampler.n_walkers : 1
     n = nchains * nw
     seeds = rand(rng, UInt64, nchains)                         # exactly AbstractMCMC's per-chain seeding
+    PRECISION[] = par.dtype === :bf16x2 ? Int32(1) : Int32(0)
     low = lower(sampler, d)
     init = initial_matrix(initial_params, nchains, nw, d)
     out = Array{Float64}(undef, n, d + 1, N)                   # C order [N][d+1][n]: every GPU fills its block of columns
