@@ -247,7 +247,7 @@ stretch_plan_kernel(StretchPlan o, const unsigned long long* __restrict__ seeds,
         m[0] = start[lcap - 1];                               /* padded slots of the parallel levels */
         m[1] = start[lcap - 1];                               /* overflow bucket [lo, hi) */
         m[2] = start[lcap - 1] + hist[lcap - 1];
-        m[3] = 0;
+        m[3] = min(wsum[BLOCK / 32 - 1], fcap);               /* forwarding slots in use */
     }
     /* sentinels in the padding of every level */
     for (int l = tid >> 5; l < kStretchLevels; l += BLOCK >> 5) {
@@ -308,8 +308,17 @@ struct StretchSmem {
     unsigned char* accs;                  /* [nw] last accept flag */
     /* 2-CTA cluster variant (one ensemble on two SMs): every CTA keeps its own copy of `fwd` and `ver`, the mover of a
      * walker writes both (the peer's through distributed shared memory); naccs / accs live in rank 0 only */
-    double* fwd_peer;
     volatile unsigned short* ver_peer;
+    /* forwarded values cross the cluster WITHOUT a cluster-scope fence (fence.acq_rel.cluster = MEMBAR.ALL.GPU + an L1
+     * invalidation on the acquire side: ~3 000 cycles on the critical path of every level of the dependency forest):
+     * every forwarding slot has one mbarrier per CTA that completes exactly once per sweep.  The mover of the walker
+     * completes its OWN CTA's with a plain arrive (release.cta orders its st.shared of the value) and the PEER's with a
+     * remote arrive.expect_tx followed by st.async of the value -- the async stores carry complete_tx, so the peer's
+     * barrier completes when, and only when, all bytes have landed in the peer's copy of the slot.  Readers only ever
+     * wait on a barrier of their own CTA.  Shared-memory addresses below are 32-bit shared::cta / shared::cluster. */
+    unsigned bar_l;                       /* this CTA's barriers [fmax] */
+    unsigned bar_r;                       /* the peer's */
+    unsigned fwd_r;                       /* the peer's copy of `fwd` */
 };
 
 __device__ __forceinline__ unsigned cluster_ctarank() {
@@ -334,6 +343,37 @@ __device__ __forceinline__ P* map_cta(P* p, unsigned rank) {
     unsigned long long in = (unsigned long long)p, out;
     asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"(in), "r"(rank));
     return (P*)out;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned map_cta_u32(unsigned addr, unsigned rank) {
+    unsigned out;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(addr), "r"(rank));
+    return out;
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {                 /* release.cta: orders this thread's st.shared */
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_peer(unsigned bar_cluster, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" :: "r"(bar_cluster), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void st_async_peer(unsigned dst_cluster, double a, unsigned bar_cluster) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];"
+                 :: "r"(dst_cluster), "d"(a), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void st_async_peer2(unsigned dst_cluster, double a, double b, unsigned bar_cluster) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1,%2}, [%3];"
+                 :: "r"(dst_cluster), "d"(a), "d"(b), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {  /* acquire.cta; try_wait sleeps in hardware */
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
 }
 
 /* one stretch move (emcee.jl:70-102) of walker `i` with partner `idx`.  `w` = the walker's own record (already loaded);
@@ -396,16 +436,20 @@ __device__ __forceinline__ void stretch_move(const typename T::template Params<D
             for (int j = 0; j < d; ++j) ps[j] = w[j];
         }
         if constexpr (CL == 2) {
-            double* pp = sm.fwd_peer + (size_t)sslot * d;
-            if constexpr (D::fixed) {
+            /* the peer's copy first (the longer trip): expect_tx + async stores that complete the peer's barrier */
+            const unsigned rb = sm.bar_r + sslot * 8u;
+            const unsigned rf = sm.fwd_r + sslot * (unsigned)d * 8u;
+            mbar_arrive_expect_tx_peer(rb, (unsigned)d * 8u);
+            if constexpr (D::fixed && (DMAX % 2 == 0)) {
 #pragma unroll
-                for (int j = 0; j < DMAX; ++j) pp[j] = w[j];
+                for (int j = 0; j < DMAX; j += 2) st_async_peer2(rf + j * 8u, w[j], w[j + 1], rb);
+            } else if constexpr (D::fixed) {
+#pragma unroll
+                for (int j = 0; j < DMAX; ++j) st_async_peer(rf + j * 8u, w[j], rb);
             } else {
-                for (int j = 0; j < d; ++j) pp[j] = w[j];
+                for (int j = 0; j < d; ++j) st_async_peer(rf + j * 8u, w[j], rb);
             }
-            fence_cluster();
-            sm.ver[i] = want;
-            sm.ver_peer[i] = want;
+            mbar_arrive(sm.bar_l + sslot * 8u);              /* own CTA's barrier: after the st.shared above */
         } else {
             __threadfence_block();
             sm.ver[i] = want;
@@ -459,16 +503,19 @@ __device__ __forceinline__ void stretch_flow_body(const StretchArgs& a, const St
     const int d = D::fixed ? DMAX : a.d;
     StretchSmem sm;
     sm.fwd = smem_fl;
-    sm.naccs = reinterpret_cast<unsigned*>(sm.fwd + (size_t)fcap * d);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm.fwd + (size_t)fcap * d);    /* [fcap], cluster variant only */
+    sm.naccs = reinterpret_cast<unsigned*>(bars + (CL == 2 ? fcap : 0));
     unsigned short* ver_nv = reinterpret_cast<unsigned short*>(sm.naccs + nw);
     sm.ver = ver_nv;
     sm.accs = reinterpret_cast<unsigned char*>(ver_nv + nw);
-    sm.fwd_peer = nullptr;
     sm.ver_peer = nullptr;
+    sm.bar_l = sm.bar_r = sm.fwd_r = 0u;
     const unsigned rank = (CL == 2) ? cluster_ctarank() : 0u;
     if constexpr (CL == 2) {
-        sm.fwd_peer = map_cta(sm.fwd, rank ^ 1u);
         sm.ver_peer = map_cta(ver_nv, rank ^ 1u);
+        sm.bar_l = smem_u32(bars);
+        sm.bar_r = map_cta_u32(sm.bar_l, rank ^ 1u);
+        sm.fwd_r = map_cta_u32(smem_u32(sm.fwd), rank ^ 1u);
         if (rank != 0u) {
             sm.naccs = map_cta(sm.naccs, 0u);
             sm.accs = map_cta(sm.accs, 0u);
@@ -483,8 +530,13 @@ __device__ __forceinline__ void stretch_flow_body(const StretchArgs& a, const St
     const int rs = D::fixed ? Rec<DMAX>::cap : Rec<DMAX>::size(d);
     double* Rold = RA;  double* Rnew = RB;
     /* prologue: [dim][chain] state -> records */
-    if constexpr (CL == 2)
+    int fmax = 0;                                                         /* forwarding slots any sweep of this launch uses */
+    if constexpr (CL == 2) {
         for (int i = tid; i < nw; i += BLOCK) ver_nv[i] = 0;              /* every CTA clears its own copy */
+        for (int s = 0; s < a.nsteps; ++s) fmax = max(fmax, plan.meta[((size_t)s * nens + en) * 4 + 3]);
+        for (int q = tid; q < fmax; q += BLOCK) mbar_init(sm.bar_l + q * 8u, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     for (int i = tid + (int)rank * BLOCK; i < nw; i += CL * BLOCK) {
         ver_nv[i] = 0;
         sm.naccs[i] = 0u;
@@ -496,17 +548,19 @@ __device__ __forceinline__ void stretch_flow_body(const StretchArgs& a, const St
     }
     const int* __restrict__ meta0 = plan.meta + (size_t)en * 4;
     int npar = a.nsteps > 0 ? meta0[0] : 0, olo = a.nsteps > 0 ? meta0[1] : 0, ohi = a.nsteps > 0 ? meta0[2] : 0;
+    int nfwd = a.nsteps > 0 ? meta0[3] : 0;
     if constexpr (CL == 2) { __threadfence(); cluster_sync_all(); } else __syncthreads();
 
     for (int s = 0; s < a.nsteps; ++s) {
         const size_t off = ((size_t)s * nens + en) * (size_t)plan.nwp;
         const unsigned short want = (unsigned short)(s + 1);
         /* the next sweep's meta data, long before it is needed */
-        int npar_n = 0, olo_n = 0, ohi_n = 0;
+        int npar_n = 0, olo_n = 0, ohi_n = 0, nfwd_n = 0;
         if (s + 1 < a.nsteps) {
             const int* __restrict__ mn = plan.meta + ((size_t)(s + 1) * nens + en) * 4;
-            npar_n = mn[0]; olo_n = mn[1]; ohi_n = mn[2];
+            npar_n = mn[0]; olo_n = mn[1]; ohi_n = mn[2]; nfwd_n = mn[3];
         }
+        const unsigned par = (unsigned)s & 1u;                          /* every slot barrier completes once per sweep */
         /* plan entries one chunk ahead: they do not depend on the walkers */
         int q = ((int)rank * NWARP + warp) * 32 + lane;
         unsigned pr = kStretchSentinel, fw = 0xffffffffu;
@@ -530,13 +584,27 @@ __device__ __forceinline__ void stretch_flow_body(const StretchArgs& a, const St
                 const int i = (int)(pr_c & 0xffffu), idx = (int)(pr_c >> 16);
                 double w[Rec<DMAX>::cap];
                 stretch_load_own<DMAX>(w, Rold, base, i, d);             /* in flight while the lane waits */
-                if (idx < i) {
-                    while (sm.ver[idx] != want) { }                      /* the partner's new value (emcee.jl:53) */
-                    if constexpr (CL == 2) (void)ld_acquire_cluster_u16(sm.ver + idx); else __threadfence_block();
+                if (idx < i) {                                           /* the partner's new value (emcee.jl:53) */
+                    if (CL == 2 && (fw_c >> 16) != 0xffffu) {
+                        mbar_wait(sm.bar_l + (fw_c >> 16) * 8u, par);        /* forwarded: this CTA's barrier of the slot */
+                    } else {
+                        while (sm.ver[idx] != want) { }
+                        if constexpr (CL == 2) (void)ld_acquire_cluster_u16(sm.ver + idx); else __threadfence_block();
+                    }
                 }
                 stretch_move<DMAX, T, CL>(tp, d, base, i, idx, fw_c & 0xffffu, fw_c >> 16, z_c, am_c, ex_c, w, Rold, Rnew, sm, want);
             }
         }
+        /* cluster variant: before anybody may start the next sweep every slot barrier of this CTA must have completed
+         * its phase -- used slots by their mover (wait: the peer's async stores may still be in flight), unused ones here */
+        auto close_slots = [&]() {
+            if constexpr (CL == 2) {
+                for (int q = tid; q < fmax; q += BLOCK) {
+                    if (q < nfwd) mbar_wait(sm.bar_l + q * 8u, par); else mbar_arrive(sm.bar_l + q * 8u);
+                }
+            }
+        };
+        if (ohi <= olo) close_slots();
         if constexpr (CL == 2) { __threadfence(); cluster_sync_all(); } else __syncthreads();
         /* overflow bucket: in increasing walker order by one thread = the reference's own loop */
         if (ohi > olo) {
@@ -551,16 +619,22 @@ __device__ __forceinline__ void stretch_flow_body(const StretchArgs& a, const St
                     const unsigned po = plan.pair[off + bq], fo = plan.fwd[off + bq];
                     double w[Rec<DMAX>::cap];
                     stretch_load_own<DMAX>(w, Rold, base, (int)(po & 0xffffu), d);
+                    if (CL == 2 && (int)(po >> 16) < (int)(po & 0xffffu) && (fo >> 16) != 0xffffu)
+                        mbar_wait(sm.bar_l + (fo >> 16) * 8u, par);     /* a value the peer forwarded may still be landing */
                     stretch_move<DMAX, T, CL>(tp, d, base, (int)(po & 0xffffu), (int)(po >> 16), fo & 0xffffu, fo >> 16,
                                               plan.zf[off + bq], plan.am[off + bq], plan.ex[off + bq], w, Rold, Rnew, sm, want);
                     __threadfence_block();
                     last = best;
                 }
             }
-            if constexpr (CL == 2) { __threadfence(); cluster_sync_all(); } else __syncthreads();
+            if constexpr (CL == 2) {
+                __syncthreads();                                        /* the bucket's own forwarding is done */
+                close_slots();
+                __threadfence(); cluster_sync_all();
+            } else __syncthreads();
         }
         double* tR = Rold; Rold = Rnew; Rnew = tR;
-        npar = npar_n; olo = olo_n; ohi = ohi_n;
+        npar = npar_n; olo = olo_n; ohi = ohi_n; nfwd = nfwd_n;
     }
     /* epilogue: records -> [dim][chain] state (always the run's primary buffers), counters, save point outputs */
     for (int i = tid + (int)rank * BLOCK; i < nw; i += CL * BLOCK) {
@@ -604,6 +678,10 @@ stretch_sweep_flow2_kernel(const __grid_constant__ StretchArgs a, const __grid_c
 }
 
 /* @rtc-end */
+}  // namespace amhh
+#include "amh_launch_stretch_res.cuh"
+namespace amhh {
+
 template <int DMAX, class T>
 int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     constexpr int BLOCK = 1024;
@@ -619,6 +697,10 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     a.n_walkers = s.d.n_walkers;
     a.a = s.d.stretch_a;
     const auto tp = make_tp<T, DMAX>(*r.target);
+    if constexpr (DMAX > 0 && T::kind != AMH_TARGET_USER) {          /* K2R: the ensemble resident in a 2-CTA cluster */
+        int rc = AMH_OK;
+        if (launch_stretch_res_t<DMAX, T>(r, nsteps, a, tp, &rc)) return rc;
+    }
     if (a.n_walkers <= 16384 && nsteps < 65535) {   /* 16-bit walker indices / sweep versions, 8 B of shared memory per walker */
         const long long nens = r.n / a.n_walkers;
         StretchPlan plan;
@@ -675,9 +757,14 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
             const int v = std::atoi(ev);
             if (v == 768 || v == 1024) blk = v;
         }
-        /* forwarding slots: what is left of 200 KB of shared memory beside the per-walker flags and counters */
+        static const char* cl_env = std::getenv("AMH_STRETCH_CLUSTER");                                     /* A/B switch: 0 / 1 */
+        const bool use_cluster = T::kind != AMH_TARGET_USER && blk == 512 &&
+                                 (cl_env ? std::atoi(cl_env) != 0 : (2 * nens <= r.ctx->sm_count && a.n_walkers >= 1024));
+        /* forwarding slots: what is left of 200 KB of shared memory beside the per-walker flags and counters
+         * (cluster variant: + one 8-byte mbarrier per slot) */
         const size_t fixed_sm = (size_t)a.n_walkers * (sizeof(unsigned) + sizeof(unsigned short) + 1) + 32;
-        long long fcap = ((long long)(200 * 1024) - (long long)fixed_sm) / (long long)(sizeof(double) * r.dim);
+        const size_t slot_sm = sizeof(double) * r.dim + (use_cluster ? 8 : 0);
+        long long fcap = ((long long)(200 * 1024) - (long long)fixed_sm) / (long long)slot_sm;
         fcap = std::max<long long>(0, std::min<long long>(fcap, 65534));
         if (const char* ev = std::getenv("AMH_STRETCH_FWD")) fcap = std::min<long long>(fcap, std::atoll(ev));   /* test switch */
         static const bool no_ahead = std::getenv("AMH_STRETCH_NO_AHEAD") != nullptr;                              /* A/B switch */
@@ -712,7 +799,7 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
         } else {
             plan = plan_at(0);
         }
-        const size_t smemv = (size_t)fcap * r.dim * sizeof(double) + fixed_sm;
+        const size_t smemv = (size_t)fcap * slot_sm + fixed_sm;
         if constexpr (T::kind == AMH_TARGET_USER) {
             static_assert(DMAX == 0, "RK_FLOW* name stretch_sweep_flow_kernel<0, TUser, BL>");
             int fcap_i = (int)fcap;
@@ -721,9 +808,7 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
                                       (unsigned)blk, smemv, params);
             if (rc) return rc;
         } else {
-            static const char* cl_env = std::getenv("AMH_STRETCH_CLUSTER");                                 /* A/B switch: 0 / 1 */
-            const bool use_cluster = cl_env ? std::atoi(cl_env) != 0 : (2 * nens <= r.ctx->sm_count && a.n_walkers >= 1024);
-            if (use_cluster && blk == 512) {
+            if (use_cluster) {
                 auto kf2 = stretch_sweep_flow2_kernel<DMAX, T, 512>;
                 if (smemv > 48 * 1024)
                     AMH_CUDA_TRY(cudaFuncSetAttribute(kf2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv));

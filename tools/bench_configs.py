@@ -76,7 +76,7 @@ def main():
             report(f"C2 RWMH MvNormal d={d} {kind} proposal", n * 500, ms, 2 * (d + 1) * 8, f"accept={st['naccept'].sum() / (n * st['step']):.3f}")
             run.close()
     if "c3" in which:
-        d, nw, ne = 10, 4096, 64
+        d, nw, ne = 10, int(os.environ.get("AMH_C3_NW", "4096")), int(os.environ.get("AMH_C3_NE", "64"))
         t = amh.RosenbrockTarget(d)
         s = amh.Ensemble(nw, amh.StretchProposal(amh.MvNormal(np.zeros(d), amh.I)))
         run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), nw * ne, seeds(ne, 2))
