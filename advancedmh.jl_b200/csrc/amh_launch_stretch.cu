@@ -600,7 +600,8 @@ __device__ __forceinline__ void stretch_flow_body(const StretchArgs& a, const St
         auto close_slots = [&]() {
             if constexpr (CL == 2) {
                 for (int q = tid; q < fmax; q += BLOCK) {
-                    if (q < nfwd) mbar_wait(sm.bar_l + q * 8u, par); else mbar_arrive(sm.bar_l + q * 8u);
+                    if (q >= nfwd) mbar_arrive(sm.bar_l + q * 8u);       /* unused in this sweep: completes the phase at once */
+                    mbar_wait(sm.bar_l + q * 8u, par);
                 }
             }
         };

@@ -46,15 +46,22 @@ constexpr unsigned kResNoSlot = 0xfffu;
  * 26 = a later walker of this CTA reads the new value in this sweep (raise the version flag),
  * 27 = a later walker of the OTHER CTA reads it and there was no slot left (cluster-scope release before the flag) */
 struct StretchPlanR {
-    unsigned* pair;            /* [nsteps][n_ensembles][2][nwp] self | partner << 16, or the sentinel */
-    unsigned* info;
-    double* zf;
-    double* am;
-    double* ex;
+    double* ent;               /* [nsteps][n_ensembles][2][nwp][4] one 32-byte entry per slot: bits(self | partner << 16 | info << 32)
+                                  (self | partner = the sentinel in padding slots), z, (d-1) log z, the exponential */
     int* meta;                 /* [nsteps][n_ensembles][2][kResMeta]: 0 level-0 walkers, 1 windows, 2/3 dataflow slots [lo, hi),
                                   4/5 overflow slots [lo, hi), 6 forwarding slots of this CTA in use, 8.. window starts */
     long long nwp;             /* slots per (sweep, ensemble, cta) */
 };
+
+struct ResEntry { unsigned pair, info; double z, am, ex; };
+__device__ __forceinline__ ResEntry res_entry_load(const double* __restrict__ ent, size_t slot) {
+    double e0, e1, e2, e3;
+    ld256(ent + slot * 4, e0, e1, e2, e3);
+    const unsigned long long b = (unsigned long long)__double_as_longlong(e0);
+    ResEntry r;
+    r.pair = (unsigned)b; r.info = (unsigned)(b >> 32); r.z = e1; r.am = e2; r.ex = e3;
+    return r;
+}
 
 __host__ __device__ inline long long res_nwp(long long nw) { return (((nw + 1) / 2 + 31) & ~31ll) + 32 * (kStretchLevels + 1); }
 
@@ -208,7 +215,8 @@ stretch_plan_res_kernel(StretchPlanR o, const unsigned long long* __restrict__ s
         const int p = pl / kStretchLevels, l = pl % kStretchLevels;
         const int cntl = l == 0 ? (int)((tot >> (16 * p)) & 0xffffu) : hist[p][l];
         const int q = start[p][l] + cntl + (tid & 31);
-        if (q < start[p][l + 1]) o.pair[(blk_se * 2 + p) * (size_t)o.nwp + q] = kStretchSentinel;
+        if (q < start[p][l + 1])
+            st256(o.ent + ((blk_se * 2 + p) * (size_t)o.nwp + q) * 4, __longlong_as_double((long long)kStretchSentinel), 0.0, 0.0, 0.0);
     }
     for (int i = tid; i < nw; i += BLOCK) {
         const unsigned long long blk = (k * (unsigned long long)nw + (unsigned long long)i) * 2ull;
@@ -226,11 +234,9 @@ stretch_plan_res_kernel(StretchPlanR o, const unsigned long long* __restrict__ s
         }
         const unsigned sslot = (lv >= 1 && push[i] < 0xfffe) ? push[i] : kResNoSlot;
         const unsigned fl = (lv >= 1 && wl[i] ? 1u << 26 : 0u) | (lv >= 1 && push[i] == 0xfffe ? 1u << 27 : 0u);
-        o.pair[slot] = (unsigned)i | ((unsigned)pj << 16);
-        o.info[slot] = pslot | (sslot << 12) | (rk << 24) | fl;
-        o.zf[slot] = z;
-        o.am[slot] = (double)(d - 1) * amh::log_(z);
-        o.ex[slot] = amh::exponential(b1.v[0], b1.v[1]);
+        const unsigned long long w0 = (unsigned long long)((unsigned)i | ((unsigned)pj << 16)) |
+                                      ((unsigned long long)(pslot | (sslot << 12) | (rk << 24) | fl) << 32);
+        st256(o.ent + slot * 4, __longlong_as_double((long long)w0), z, (double)(d - 1) * amh::log_(z), amh::exponential(b1.v[0], b1.v[1]));
     }
 }
 
@@ -330,6 +336,7 @@ stretch_sweep_res_kernel(const __grid_constant__ StretchArgs a, const __grid_con
                          const __grid_constant__ typename T::template Params<DMAX> tp, double* Gall, int fcap) {
     static_assert(DMAX > 0, "K2R has exact-dimension instantiations only");
     constexpr int RS = DMAX + 1;
+    constexpr int GS = res_gs(DMAX);
     constexpr int NWARP = BLOCK / 32;
     extern __shared__ __align__(16) double smem_rs[];
     const int nw = (int)a.n_walkers;
@@ -354,7 +361,7 @@ stretch_sweep_res_kernel(const __grid_constant__ StretchArgs a, const __grid_con
     const long long nens = a.st.n / nw;
     const long long base = en * nw;
     const size_t pl_stride = (size_t)plan.nwp;
-    sm.G = Gall + (size_t)base * res_gs(DMAX);
+    sm.G = Gall + (size_t)base * GS;
     /* prologue: [dim][chain] state -> records of the own walkers */
     int fmax = 0;
     for (int s = 0; s < a.nsteps; ++s) fmax = max(fmax, plan.meta[(((size_t)s * nens + en) * 2 + rank) * kResMeta + 6]);
@@ -373,84 +380,112 @@ stretch_sweep_res_kernel(const __grid_constant__ StretchArgs a, const __grid_con
         for (int j = 0; j < RS; ++j) w0[j] = rec[j];
         res_store_mirror<DMAX>(sm, 2 * li + (int)rank, w0);
     }
+    /* what a sweep needs before it can start, fetched one sweep ahead (three dependent L2 round trips otherwise) */
+    struct SweepHead {
+        int nwin, dlo, dhi, olo, ohi, nfwd, olo2, ohi2, w0, w1, w2;
+        ResEntry e_w, e_w2;                                     /* this thread's entries of the first two windows */
+    };
+    auto no_entry = [] { ResEntry x; x.pair = kStretchSentinel; x.info = 0u; x.z = x.am = x.ex = 0.0; return x; };
+    auto load_head = [&](int s) {
+        SweepHead h;
+        const size_t pse = ((size_t)s * nens + en) * 2 + rank;
+        const int* __restrict__ m = plan.meta + pse * kResMeta;
+        const int* __restrict__ m2 = plan.meta + (pse ^ 1) * kResMeta;
+        h.nwin = m[1]; h.dlo = m[2]; h.dhi = m[3]; h.olo = m[4]; h.ohi = m[5]; h.nfwd = m[6];
+        h.olo2 = m2[4]; h.ohi2 = m2[5];
+        h.w0 = m[8]; h.w1 = m[9]; h.w2 = m[10];
+        const double* __restrict__ ent = plan.ent + pse * pl_stride * 4;
+        h.e_w = h.e_w2 = no_entry();
+        if (h.nwin > 0 && h.w0 + tid < h.w1) h.e_w = res_entry_load(ent, (size_t)(h.w0 + tid));
+        if (h.nwin > 1 && h.w1 + tid < h.w2) h.e_w2 = res_entry_load(ent, (size_t)(h.w1 + tid));
+        return h;
+    };
+    SweepHead hd;
+    if (a.nsteps > 0) hd = load_head(0);
     cluster_arrive(); cluster_wait();
 
     for (int s = 0; s < a.nsteps; ++s) {
         const size_t pse = ((size_t)s * nens + en) * 2 + rank;
         const int* __restrict__ meta = plan.meta + pse * kResMeta;
-        const size_t off = pse * pl_stride;
+        const double* __restrict__ ent = plan.ent + pse * pl_stride * 4;
         const unsigned short want = (unsigned short)(s + 1);
         const unsigned par = (unsigned)s & 1u;
-        const int nwin = meta[1], dlo = meta[2], dhi = meta[3], olo = meta[4], ohi = meta[5], nfwd = meta[6];
+        const int nwin = hd.nwin, dhi = hd.dhi, olo = hd.olo, ohi = hd.ohi, nfwd = hd.nfwd, olo2 = hd.olo2, ohi2 = hd.ohi2;
         if (nwin < 0) __trap();                                  /* more level-0 windows than the plan can describe: the host sizes them so that this cannot happen */
-        /* the first dataflow chunk's plan entries, long before they are needed */
-        int q = dlo + warp * 32 + lane;
-        unsigned pr = kStretchSentinel, inf = 0u;
-        double z = 0.0, am = 0.0, ex = 0.0;
-        if (q < dhi) {
-            pr = __ldg(plan.pair + off + q); inf = __ldg(plan.info + off + q); z = __ldg(plan.zf + off + q);
-            am = __ldg(plan.am + off + q);   ex = __ldg(plan.ex + off + q);
-        }
-        /* ---- level 0: windows of ascending walker index; reads | barrier | writes ---- */
+        int q = hd.dlo + warp * 32 + lane;
+        ResEntry e = no_entry(), e2 = no_entry();
+        /* ---- level 0: windows of ascending walker index; reads | barrier | writes.  Everything that comes from L2 is
+         * fetched ahead: plan entries two windows ahead, the other CTA's partners (global mirror) one window ahead (a
+         * window only reads walkers that no earlier window writes), and the mirror copy of a window's accepted moves is
+         * stored after the NEXT window's arrive, so that no arrive waits for a store acknowledgement from L2 ---- */
         {
-            int w0 = meta[8];
-            /* plan entries one window ahead */
-            unsigned p0n = kStretchSentinel;
-            double z0n = 0.0, am0n = 0.0, ex0n = 0.0;
-            if (nwin > 0 && w0 + tid < meta[9]) {
-                const int q0 = w0 + tid;
-                p0n = __ldg(plan.pair + off + q0);
-                z0n = __ldg(plan.zf + off + q0); am0n = __ldg(plan.am + off + q0); ex0n = __ldg(plan.ex + off + q0);
-            }
-            for (int w = 0; w < nwin; ++w) {
-                const int w1 = meta[9 + w];
-                const unsigned p0 = p0n;
-                const double z0 = z0n, am0 = am0n, ex0 = ex0n;
-                const bool have = p0 != kStretchSentinel;
-                p0n = kStretchSentinel;
-                if (w + 1 < nwin && w1 + tid < meta[10 + w]) {
-                    const int q1 = w1 + tid;
-                    p0n = __ldg(plan.pair + off + q1);
-                    z0n = __ldg(plan.zf + off + q1); am0n = __ldg(plan.am + off + q1); ex0n = __ldg(plan.ex + off + q1);
+            ResEntry ew = hd.e_w, ew2 = hd.e_w2;
+            int w2 = hd.w2;                                     /* end of window w + 1 */
+            double og[DMAX];                                    /* partner of the current window's move when it lives in the other CTA */
+            auto fetch_remote = [&](const ResEntry& x) {
+                if (x.pair != kStretchSentinel && (((x.pair >> 16) & 1u) != rank)) {
+                    const double* g = sm.G + (size_t)(x.pair >> 16) * GS;
+                    double t[GS];
+#pragma unroll
+                    for (int j = 0; j < ((DMAX + 3) & ~3); j += 4) ld256(g + j, t[j], t[j + 1], t[j + 2], t[j + 3]);
+#pragma unroll
+                    for (int j = 0; j < DMAX; ++j) og[j] = t[j];
                 }
+            };
+            fetch_remote(ew);
+            for (int w = 0; w < nwin; ++w) {
+                const ResEntry ec = ew;
+                const bool have = ec.pair != kStretchSentinel;
+                const int i0 = (int)(ec.pair & 0xffffu), idx0 = (int)(ec.pair >> 16), li = i0 >> 1;
                 double wr[RS], o[DMAX];
-                int li = 0, i0 = 0;
                 if (have) {
-                    i0 = (int)(p0 & 0xffffu);
-                    li = i0 >> 1;
                     const double* rec = sm.rec + (size_t)li * RS;
 #pragma unroll
                     for (int j = 0; j < RS; ++j) wr[j] = rec[j];
-                    res_load_partner<DMAX>(o, sm, rank, (int)(p0 >> 16));          /* the OLD value (idx > i) */
+                    if (((unsigned)idx0 & 1u) == rank) {                            /* the OLD value (idx > i) */
+                        const double* pr = sm.rec + (size_t)(idx0 >> 1) * RS;
+#pragma unroll
+                        for (int j = 0; j < DMAX; ++j) o[j] = pr[j];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < DMAX; ++j) o[j] = og[j];
+                    }
                 }
                 cluster_arrive();                                                   /* my reads of this window are done */
+                /* next window: its entry was loaded a window ago, its remote partner starts its trip now */
+                ew = ew2;
+                fetch_remote(ew);
+                ew2 = no_entry();
+                const int w3 = (w + 2 < nwin) ? meta[11 + w] : w2;
+                if (w + 2 < nwin && w2 + tid < w3) ew2 = res_entry_load(ent, (size_t)(w2 + tid));
+                w2 = w3;
                 bool acc = false;
-                if (have) acc = res_move<DMAX, T>(tp, wr, o, z0, am0, ex0);
+                if (have) acc = res_move<DMAX, T>(tp, wr, o, ec.z, ec.am, ec.ex);
                 cluster_wait();                                                     /* everybody's are */
                 if (have) {
                     if (acc) { res_store_record<DMAX>(sm, i0, wr); res_store_mirror<DMAX>(sm, i0, wr); }
                     const unsigned c = sm.nacc[li] & 0x7fffffffu;
                     sm.nacc[li] = acc ? ((c + 1u) | 0x80000000u) : c;
                 }
-                w0 = w1;
             }
-            cluster_arrive(); cluster_wait();                                       /* level 0 is written, cluster wide */
+            cluster_arrive();
+            /* the first two dataflow chunks' entries of this lane while the barrier completes */
+            if (q < dhi) e = res_entry_load(ent, (size_t)q);
+            if (q + NWARP * 32 < dhi) e2 = res_entry_load(ent, (size_t)(q + NWARP * 32));
+            cluster_wait();                                                         /* level 0 is written, cluster wide */
         }
         /* ---- levels >= 1: dataflow ---- */
 #pragma unroll 1
         for (; q - lane < dhi; q += NWARP * 32) {
-            const unsigned pr_c = pr, inf_c = inf;
-            const double z_c = z, am_c = am, ex_c = ex;
-            const int qn = q + NWARP * 32;
-            if (qn < dhi) {
-                pr = __ldg(plan.pair + off + qn); inf = __ldg(plan.info + off + qn); z = __ldg(plan.zf + off + qn);
-                am = __ldg(plan.am + off + qn);   ex = __ldg(plan.ex + off + qn);
-            } else {
-                pr = kStretchSentinel;
-            }
-            if (pr_c != kStretchSentinel) {
-                const int i = (int)(pr_c & 0xffffu), idx = (int)(pr_c >> 16);
+            const ResEntry ec = e;
+            e = e2;                                                              /* loaded an iteration ago */
+            const int qn = q + 2 * NWARP * 32;
+            e2.pair = kStretchSentinel;
+            if (qn < dhi) e2 = res_entry_load(ent, (size_t)qn);
+            if (ec.pair != kStretchSentinel) {
+                const int i = (int)(ec.pair & 0xffffu), idx = (int)(ec.pair >> 16);
                 const int li = i >> 1;
+                const unsigned inf_c = ec.info;
                 const unsigned rk = (inf_c >> 24) & 3u;
                 double wr[RS], o[DMAX];
                 double* rec = sm.rec + (size_t)li * RS;
@@ -471,7 +506,7 @@ stretch_sweep_res_kernel(const __grid_constant__ StretchArgs a, const __grid_con
                     }
                     res_load_partner<DMAX>(o, sm, rank, idx, rk == 3u);
                 }
-                const bool acc = res_move<DMAX, T>(tp, wr, o, z_c, am_c, ex_c);
+                const bool acc = res_move<DMAX, T>(tp, wr, o, ec.z, ec.am, ec.ex);
                 const unsigned ss = (inf_c >> 12) & 0xfffu;
                 if (ss != kResNoSlot) {                                             /* a reader in the other CTA */
                     const unsigned rb = sm.bar_r + ss * 8u, rf = sm.fwd_r + ss * (unsigned)(DMAX * 8);
@@ -494,41 +529,44 @@ stretch_sweep_res_kernel(const __grid_constant__ StretchArgs a, const __grid_con
                 sm.nacc[li] = acc ? ((c + 1u) | 0x80000000u) : c;
             }
         }
+        /* the next sweep's head while this one drains */
+        if (s + 1 < a.nsteps) hd = load_head(s + 1);
         /* every slot barrier of this CTA completes exactly one phase per sweep: used slots by their mover in the other
          * CTA (wait: its async stores may still be in flight), unused ones here */
         for (int qs = tid; qs < fmax; qs += BLOCK) {
-            if (qs < nfwd) mbar_wait(sm.bar + qs * 8u, par); else mbar_arrive(sm.bar + qs * 8u);
+            if (qs >= nfwd) mbar_arrive(sm.bar + qs * 8u);       /* unused in this sweep: completes the phase at once */
+            mbar_wait(sm.bar + qs * 8u, par);
         }
         cluster_arrive(); cluster_wait();
         /* overflow bucket: one thread, increasing walker order over both CTAs' lists = the reference's own loop */
-        const int* __restrict__ meta_o = plan.meta + (pse ^ 1) * kResMeta;
-        const int olo2 = meta_o[4], ohi2 = meta_o[5];
         if (ohi > olo || ohi2 > olo2) {
             if (tid == 0 && rank == 0u) {
-                const size_t off2 = (pse ^ 1) * pl_stride;
+                const double* __restrict__ ent2 = plan.ent + (pse ^ 1) * pl_stride * 4;
                 int last = -1;
                 for (int c = 0; c < (ohi - olo) + (ohi2 - olo2); ++c) {
-                    int best = 0x7fffffff; size_t bq = 0;
+                    int best = 0x7fffffff;
+                    ResEntry be;
                     for (int qq = olo; qq < ohi; ++qq) {
-                        const int self = (int)(plan.pair[off + qq] & 0xffffu);
-                        if (self > last && self < best) { best = self; bq = off + qq; }
+                        const ResEntry x = res_entry_load(ent, (size_t)qq);
+                        const int self = (int)(x.pair & 0xffffu);
+                        if (self > last && self < best) { best = self; be = x; }
                     }
                     for (int qq = olo2; qq < ohi2; ++qq) {
-                        const int self = (int)(plan.pair[off2 + qq] & 0xffffu);
-                        if (self > last && self < best) { best = self; bq = off2 + qq; }
+                        const ResEntry x = res_entry_load(ent2, (size_t)qq);
+                        const int self = (int)(x.pair & 0xffffu);
+                        if (self > last && self < best) { best = self; be = x; }
                     }
-                    const int i = best, idx = (int)(plan.pair[bq] >> 16);
+                    const int i = best, idx = (int)(be.pair >> 16);
                     double* recg = map_cta(sm.rec, (unsigned)(i & 1)) + (size_t)(i >> 1) * RS;      /* generic, either CTA */
                     double wr[RS], o[DMAX];
 #pragma unroll
                     for (int j = 0; j < RS; ++j) wr[j] = recg[j];
                     res_load_partner<DMAX>(o, sm, 0u, idx, true);
-                    const bool acc = res_move<DMAX, T>(tp, wr, o, plan.zf[bq], plan.am[bq], plan.ex[bq]);
+                    const bool acc = res_move<DMAX, T>(tp, wr, o, be.z, be.am, be.ex);
                     if (acc) {
-                        constexpr int GS = res_gs(DMAX);
 #pragma unroll
                         for (int j = 0; j < RS; ++j) recg[j] = wr[j];
-                        for (int j = 0; j < GS; ++j) sm.G[(size_t)i * GS + j] = j < RS ? wr[j < RS ? j : 0] : 0.0;
+                        res_store_mirror<DMAX>(sm, i, wr);
                     }
                     unsigned* na = map_cta(sm.nacc, (unsigned)(i & 1)) + (i >> 1);
                     const unsigned cc = *na & 0x7fffffffu;
@@ -562,12 +600,13 @@ stretch_sweep_res_kernel(const __grid_constant__ StretchArgs a, const __grid_con
     cluster_arrive(); cluster_wait();                        /* shared memory must outlive the other CTA's reads */
 }
 
-
 /* host side: returns true when K2R took the launch (rc = its status) */
 template <int DMAX, class T>
 bool launch_stretch_res_t(amh_run& r, int nsteps, const StretchArgs& a, const typename T::template Params<DMAX>& tp, int* rc) {
-    constexpr int BLOCK = 512;
     constexpr int PB = 1024;
+    /* threads of a sweep CTA: 384 = 12 warps x 168 registers.  512 x 128 spills the one-window-ahead loads (8.7e9 vs 1.05e10
+     * moves/s on config 3); the level-1 chunks of config 3 need two rounds with 12 as with 16 warps */
+    constexpr int BLOCK = 384;
     static const char* res_env = std::getenv("AMH_STRETCH_RES");                       /* A/B / test switch: 0 = K2F, 1 = K2R whenever it fits */
     const long long nw = a.n_walkers;
     if (nw < 64 || nw > 16384 || nsteps >= 65535) return false;
@@ -600,7 +639,7 @@ bool launch_stretch_res_t(amh_run& r, int nsteps, const StretchArgs& a, const ty
         StretchPlanR plan;
         plan.nwp = res_nwp(nw);
         const size_t slots = (size_t)nsteps * nens * 2 * plan.nwp;
-        const size_t pbytes = (slots * (3 * sizeof(double) + 2 * sizeof(unsigned)) + (size_t)nsteps * nens * 2 * kResMeta * sizeof(int) + 255) & ~(size_t)255;
+        const size_t pbytes = (slots * 4 * sizeof(double) + (size_t)nsteps * nens * 2 * kResMeta * sizeof(int) + 255) & ~(size_t)255;
         const size_t gbytes = ((size_t)r.n * res_gs(DMAX) * sizeof(double) + 255) & ~(size_t)255;
         const size_t need = 256 + gbytes + 2 * pbytes;
         if (!r.aux_stream) {
@@ -630,12 +669,8 @@ bool launch_stretch_res_t(amh_run& r, int nsteps, const StretchArgs& a, const ty
         auto plan_at = [&](int b) {
             StretchPlanR q = plan;
             char* p0 = pbase + (size_t)b * pbytes;
-            q.zf = (double*)p0;
-            q.am = q.zf + slots;
-            q.ex = q.am + slots;
-            q.pair = (unsigned*)(q.ex + slots);
-            q.info = q.pair + slots;
-            q.meta = (int*)(q.info + slots);
+            q.ent = (double*)p0;
+            q.meta = (int*)(q.ent + slots * 4);
             return q;
         };
         const size_t smemp = (size_t)nw * 24 + 16;

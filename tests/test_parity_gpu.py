@@ -557,6 +557,31 @@ def test_stretch_level_schedule_configs_and_overflow_bucket(amh, cuda, oracle, m
     assert np.array_equal(out_g, out_o) and np.array_equal(acc_g, acc_o)
 
 
+@pytest.mark.parametrize("d,nw,ne", [(10, 333, 3), (3, 256, 2), (16, 130, 2)])
+@pytest.mark.parametrize("win,fwd,levels", [(None, None, None), ("7", None, None), ("100", "0", None), (None, "20", "4"),
+                                              ("33", "5", "3")])
+def test_stretch_resident_cluster_sweep_paths(amh, cuda, oracle, monkeypatch, d, nw, ne, win, fwd, levels):
+    """K2R (amh_launch_stretch_res.cuh): the ensemble resident in the shared memory of a 2-CTA cluster, updated in place.
+    Forced on for small ensembles (AMH_STRETCH_RES=1) and driven through every hand-off path: many small level-0
+    windows, no / too few forwarding slots (remote version flag + distributed-shared-memory read), the ordered overflow
+    bucket, odd walker counts and an odd dimension (scalar st.async) -- each reproduces the sequential sweep of
+    emcee.jl:39-58 bit for bit"""
+    monkeypatch.setenv("AMH_STRETCH_RES", "1")
+    for k, v in (("AMH_STRETCH_WIN", win), ("AMH_STRETCH_FWD", fwd), ("AMH_STRETCH_LEVELS", levels)):
+        if v is not None:
+            monkeypatch.setenv(k, v)
+    target = amh.RosenbrockTarget(d)
+    spl = amh.Ensemble(nw, amh.StretchProposal(amh.MvNormal(np.zeros(d), amh.I)))
+    rg, ro = _pair(amh, cuda, oracle, target, spl, nw * ne, _seeds(ne, 91))
+    for k, spl_ in [(1, 1), (6, 4), (21, 0)]:
+        rg.steps(k, steps_per_launch=spl_)
+        ro.steps(k)
+        _assert_same_state(rg, ro)
+    out_g, acc_g, _ = rg.sample(5, 2, 3)
+    out_o, acc_o, _ = ro.sample(5, 2, 3)
+    assert np.array_equal(out_g, out_o) and np.array_equal(acc_g, acc_o)
+
+
 def test_sample_on_four_streams_equals_one_stream_and_the_oracle(amh, cuda, oracle):
     d, n = 8, 4096 + 37
     Sigma = make_spd(d, seed=2)

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 sum=gpurun_out/sanitizer_${tag}_summary.txt
 : > $sum
 for tool in memcheck racecheck synccheck; do
-  for c in c2 c3 c3cl c4 c4t c5 c5redo; do
+  for c in ${SAN_CASES:-c2 c3 c3cl c3r c3rs c4 c4t c5 c5redo}; do
     log=gpurun_out/sanitizer_${tag}_${tool}_${c}.log
     start=$(date +%s)
     timeout 600 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_cases.py $c > $log 2>&1

@@ -4,7 +4,9 @@
 parity run.  Usage: python tools/sanitize_cases.py <case> ; cases:
   c2     K1T16  RWMH d=32 full covariance                       (DMMA tiles in shared memory)
   c3     K2F    stretch, 1-CTA sweep (AMH_STRETCH_CLUSTER=0)    (version flags in shared memory)
-  c3cl   K2F    stretch, 2-CTA cluster sweep                    (DSMEM mirrored flags)
+  c3cl   K2F    stretch, 2-CTA cluster sweep                    (values pushed into the peer with st.async + mbarriers)
+  c3r    K2R    stretch, ensemble resident in a 2-CTA cluster   (in-place records, cluster-barrier windows, st.async pushes)
+  c3rs   K2R    same with 100-walker windows, 20 forwarding slots and 4 levels: remote-flag hand-off, overflow bucket
   c4     K3L    MALA logistic d=32, 200 rows                    (TMA producer warp + 10-stage mbarrier ring, wraps)
   c5     K4W    RAM warm-up d=32                                (bulk load / store of the factor, roll-back)
   c5redo K4W    same with the IEEE redo path forced on every step
@@ -31,9 +33,17 @@ def spd(d, seed, lo, hi):
 def main():
     case = sys.argv[1]
     if case == "c3":
+        os.environ["AMH_STRETCH_RES"] = "0"
         os.environ["AMH_STRETCH_CLUSTER"] = "0"
     if case == "c3cl":
+        os.environ["AMH_STRETCH_RES"] = "0"
         os.environ["AMH_STRETCH_CLUSTER"] = "1"
+    if case in ("c3r", "c3rs"):
+        os.environ["AMH_STRETCH_RES"] = "1"
+    if case == "c3rs":
+        os.environ["AMH_STRETCH_WIN"] = "100"
+        os.environ["AMH_STRETCH_FWD"] = "20"
+        os.environ["AMH_STRETCH_LEVELS"] = "4"
     if case == "c5redo":
         os.environ["AMH_RAMW_FORCE_REDO"] = "1"
     import amh_b200 as amh
@@ -45,7 +55,7 @@ def main():
         d, n = 32, 1024
         Sg = spd(d, 32, 1.0, 100.0)
         t, s, sd = amh.MvNormalTarget(None, Sg), amh.RWMH(amh.MvNormal(np.zeros(d), (2.38 ** 2 / d) * Sg)), seeds(n, 1)
-    elif case in ("c3", "c3cl"):
+    elif case in ("c3", "c3cl", "c3r", "c3rs"):
         d, nw, ne = 10, 1024, 2
         t = amh.RosenbrockTarget(d)
         s = amh.Ensemble(nw, amh.StretchProposal(amh.MvNormal(np.zeros(d), amh.I)))
