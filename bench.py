@@ -172,7 +172,8 @@ def bench_c3(amh, eng, peak, seed=2):
     ms = _timed(run, 64, spl=16)
     st = run.state()
     out = _rec(nw * ne * 64, ms, 2 * (d + 1) * 8, peak, workload=f"C3: Ensemble(4096, StretchProposal) Rosenbrock d=10, {ne} ensembles per GPU, exact sequential sweep",
-               kernel="stretch_plan_kernel + stretch_sweep_flow2_kernel (K2F, 2-CTA cluster per ensemble)",
+               kernel="stretch_plan_res_kernel + stretch_sweep_res_kernel (K2R: ensemble resident in the shared memory of a 2-CTA cluster, "
+                      "in-place records, st.async + mbarrier hand-off; plan made ahead on a second stream)",
                accept_rate=float(st["naccept"].sum() / (nw * ne * st["step"])), sweeps_timed=64 * 3)
     run.close()
     return out
