@@ -134,7 +134,10 @@ AMH_HD double u01_32(uint32_t w) {
 /* ------------------------------------------------------------------- log
  * Table-driven: z = x / 2^k in [0.6875, 1.375), r = z/c_i - 1 with |r| < 2^-7,
  * ln x = k ln2 - ln(1/c_i) + ln(1+r).  The two intervals adjacent to 1 use
- * c = 1 exactly, so ln(u) keeps full relative accuracy for u -> 1. */
+ * c = 1 exactly, so ln(u) keeps full relative accuracy for u -> 1.
+ * Attribution: the scheme (offset 0x3FE6..., 128-entry invc / logc table, r = z * invc - 1, polynomial in r) is the one
+ * of the ARM Optimized Routines / glibc double-precision log (Szabolcs Nagy, MIT / LGPL); a third-party algorithm, not
+ * the reference's.  The table here is regenerated by tools/gen_contract_tables.py with mpmath, not copied. */
 struct alignas(16) LogTabEntry { double invc, nlogc; };
 
 #if defined(__CUDACC__)
