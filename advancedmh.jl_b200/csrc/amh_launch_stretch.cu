@@ -680,6 +680,7 @@ stretch_sweep_flow2_kernel(const __grid_constant__ StretchArgs a, const __grid_c
 
 /* @rtc-end */
 }  // namespace amhh
+#include "amh_fastmath.cuh"
 #include "amh_launch_stretch_res.cuh"
 namespace amhh {
 
@@ -769,7 +770,7 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
         fcap = std::max<long long>(0, std::min<long long>(fcap, 65534));
         if (const char* ev = std::getenv("AMH_STRETCH_FWD")) fcap = std::min<long long>(fcap, std::atoll(ev));   /* test switch */
         static const bool no_ahead = std::getenv("AMH_STRETCH_NO_AHEAD") != nullptr;                              /* A/B switch */
-        constexpr int PB = 1024;
+        constexpr int PB = 512;                   /* two plan CTAs per SM: one computes while the other sits at a barrier */
         const size_t smemp = (size_t)a.n_walkers * 3 * sizeof(int);
         auto kp = stretch_plan_kernel<PB>;
         if (smemp > 40 * 1024) AMH_CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp));

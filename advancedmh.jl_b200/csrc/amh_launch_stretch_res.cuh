@@ -218,13 +218,18 @@ stretch_plan_res_kernel(StretchPlanR o, const unsigned long long* __restrict__ s
         if (q < start[p][l + 1])
             st256(o.ent + ((blk_se * 2 + p) * (size_t)o.nwp + q) * 4, __longlong_as_double((long long)kStretchSentinel), 0.0, 0.0, 0.0);
     }
+    /* z = t^2 / a for every move: one reciprocal refinement of `a` per thread + Markstein's correction (amh_fastmath.cuh;
+     * t^2 is in [1, a^2], so only `a` needs the range check) */
+    const bool zfast = fast_div_ok(1.0, aa) && fast_div_ok(aa * aa, aa);
+    const double raa = zfast ? rcp_refined(aa) : 0.0;
     for (int i = tid; i < nw; i += BLOCK) {
         const unsigned long long blk = (k * (unsigned long long)nw + (unsigned long long)i) * 2ull;
         const amh::Block b1 = amh::stream_block(seed, blk + 1ull, 0u);
         const int p = i & 1, lv = lvl[i];
         const size_t slot = (blk_se * 2 + p) * (size_t)o.nwp + start[p][lv] + slotof[i];
         const double tt = (aa - 1.0) * ubuf[i] + 1.0;
-        const double z = (tt * tt) / aa;
+        const double t2 = tt * tt;
+        const double z = zfast ? div_with_rcp(t2, aa, raa) : t2 / aa;   /* the correctly rounded quotient either way */
         const int pj = partner[i];
         unsigned rk = 0u, pslot = 0u;
         if (pj < i && lv < lcap - 1 && lvl[pj] >= 1) {
@@ -603,7 +608,7 @@ stretch_sweep_res_kernel(const __grid_constant__ StretchArgs a, const __grid_con
 /* host side: returns true when K2R took the launch (rc = its status) */
 template <int DMAX, class T>
 bool launch_stretch_res_t(amh_run& r, int nsteps, const StretchArgs& a, const typename T::template Params<DMAX>& tp, int* rc) {
-    constexpr int PB = 1024;
+    constexpr int PB = 512;                      /* two plan CTAs per SM: one computes while the other sits at a barrier */
     /* threads of a sweep CTA: 384 = 12 warps x 168 registers.  512 x 128 spills the one-window-ahead loads (8.7e9 vs 1.05e10
      * moves/s on config 3); the level-1 chunks of config 3 need two rounds with 12 as with 16 warps */
     constexpr int BLOCK = 384;
