@@ -111,7 +111,9 @@ constexpr int kSmemT = kOffBar + 160;
 enum { BAR_FULL = 0, BAR_EMPTY = 2, BAR_A1FULL = 4, BAR_A1EMPTY = 6, BAR_RFULL = 8, BAR_REMPTY = 9, BAR_A2FULL = 10, BAR_CREADY = 11,
        BAR_FULLT = 12, BAR_EMPTYT = 14, BAR_COUNT = 16 };     /* FULL / EMPTY: the X half of a stage; FULLT / EMPTYT: the X^T half */
 
-__global__ void __launch_bounds__(320, 1)
+/* NQ = threads per chain = epilogue warps per TMEM lane group (2: 8 epilogue warps, 4: 16) */
+template <int NQ>
+__global__ void __launch_bounds__(64 + 128 * NQ, 1)
 mala_tensor_kernel(const __grid_constant__ MalaTArgs a, const __grid_constant__ CUtensorMap mapXhi, const __grid_constant__ CUtensorMap mapXlo,
                    const __grid_constant__ CUtensorMap mapXThi, const __grid_constant__ CUtensorMap mapXTlo) {
     extern __shared__ __align__(1024) unsigned char tsm[];
@@ -130,11 +132,11 @@ mala_tensor_kernel(const __grid_constant__ MalaTArgs a, const __grid_constant__ 
         t_mbar_init(bars + BAR_FULLT, 1); t_mbar_init(bars + BAR_FULLT + 1, 1);
         t_mbar_init(bars + BAR_EMPTYT, 1); t_mbar_init(bars + BAR_EMPTYT + 1, 1);
         t_mbar_init(bars + BAR_A1FULL, 1); t_mbar_init(bars + BAR_A1FULL + 1, 1);
-        t_mbar_init(bars + BAR_A1EMPTY, 8); t_mbar_init(bars + BAR_A1EMPTY + 1, 8);
-        t_mbar_init(bars + BAR_RFULL, 8);
+        t_mbar_init(bars + BAR_A1EMPTY, 4 * NQ); t_mbar_init(bars + BAR_A1EMPTY + 1, 4 * NQ);
+        t_mbar_init(bars + BAR_RFULL, 4 * NQ);
         t_mbar_init(bars + BAR_REMPTY, 1);
         t_mbar_init(bars + BAR_A2FULL, 1);
-        t_mbar_init(bars + BAR_CREADY, 8);
+        t_mbar_init(bars + BAR_CREADY, 4 * NQ);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -218,9 +220,10 @@ mala_tensor_kernel(const __grid_constant__ MalaTArgs a, const __grid_constant__ 
             t_commit(bars + BAR_A2FULL);
         }
     } else {
-        /* ===== 8 warps, two threads per chain: candidate, link function, tail of the step =====
-         * TMEM lane group lg = warp % 4 (hardware rule); the two warps of a lane group split everything in halves:
-         * h = 0 takes dimensions 0..63 / tile columns 0..31, h = 1 dimensions 64..127 / columns 32..63 */
+        /* ===== 4 NQ warps, NQ threads per chain: candidate, link function, tail of the step =====
+         * TMEM lane group lg = warp % 4 (hardware rule); the NQ warps of a lane group split everything in equal parts:
+         * part h takes dimensions [DW h, DW (h + 1)) and tile columns [CW h, CW (h + 1)) */
+        constexpr int DW = kTD / NQ, CW = kTRows / NQ;
         const int lg = warp & 3;
         const int h = (warp - 2) >> 2;
         const int m = 32 * lg + lane;                    /* chain of the CTA = TMEM lane = operand row */
@@ -232,19 +235,19 @@ mala_tensor_kernel(const __grid_constant__ MalaTArgs a, const __grid_constant__ 
         const unsigned long long blk0 = a.step * amh::blocks_per_step_cv(cv, kTD);
         /* ---- candidate = x + (sigma z + drift grad)  (MALA.jl:70 -> proposal.jl:49-56), fp64, contract noise ---- */
         {
-            double z[64];                                /* the normals of dimensions 64h .. 64h+63 */
+            double z[DW];                                /* the normals of dimensions DW h .. DW h + DW - 1 */
             if (cv == AMH_CONTRACT_V2) {
-                for (int jb = 0; jb < 16; ++jb) {
-                    const amh::Block b = amh::stream_block7(seed, blk0 + (unsigned long long)(16 * h + jb), 0u);
+                for (int jb = 0; jb < DW / 4; ++jb) {
+                    const amh::Block b = amh::stream_block7(seed, blk0 + (unsigned long long)(DW / 4 * h + jb), 0u);
                     amh::normal_quad(b, z[4 * jb], z[4 * jb + 1], z[4 * jb + 2], z[4 * jb + 3]);
                 }
             } else {
-                for (int jb = 0; jb < 32; ++jb) {
-                    const amh::Block b = amh::stream_block(seed, blk0 + (unsigned long long)(32 * h + jb), 0u);
+                for (int jb = 0; jb < DW / 2; ++jb) {
+                    const amh::Block b = amh::stream_block(seed, blk0 + (unsigned long long)(DW / 2 * h + jb), 0u);
                     amh::normal_pair(b, z[2 * jb], z[2 * jb + 1]);
                 }
             }
-            for (int j0 = 0; j0 < 64; j0 += 8) {
+            for (int j0 = 0; j0 < DW; j0 += 8) {
                 unsigned hi[4], lo[4];
 #pragma unroll
                 for (int i = 0; i < 8; i += 2) {
@@ -252,7 +255,7 @@ mala_tensor_kernel(const __grid_constant__ MalaTArgs a, const __grid_constant__ 
                     if (active) {
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            const long long o = (long long)(64 * h + j0 + i + e) * pitch + ch;
+                            const long long o = (long long)(DW * h + j0 + i + e) * pitch + ch;
                             c[e] = a.st.X[o] + (a.sigma * z[j0 + i + e] + a.drift * a.st.G[o]);
                             a.Xc[o] = c[e];
                         }
@@ -263,81 +266,100 @@ mala_tensor_kernel(const __grid_constant__ MalaTArgs a, const __grid_constant__ 
                     hi[i >> 1] = *reinterpret_cast<const unsigned*>(&hh);
                     lo[i >> 1] = *reinterpret_cast<const unsigned*>(&ll2);
                 }
-                store_chunk(tsm + kOffC + h * 16384, m, j0 >> 3, hi);                 /* K block = h */
-                store_chunk(tsm + kOffC + 32768 + h * 16384, m, j0 >> 3, lo);
+                const int dim0 = DW * h + j0;                                          /* K block = dim0 / 64, chunk = (dim0 % 64) / 8 */
+                store_chunk(tsm + kOffC + (dim0 >> 6) * 16384, m, (dim0 & 63) >> 3, hi);
+                store_chunk(tsm + kOffC + 32768 + (dim0 >> 6) * 16384, m, (dim0 & 63) >> 3, lo);
             }
         }
         t_fence_async_smem();
         __syncwarp();
         if (lane == 0) t_mbar_arrive(bars + BAR_CREADY);
-        /* ---- per tile: eta -> (log-likelihood terms, residuals), columns 32h .. 32h+31 ---- */
+        /* ---- per tile: eta -> (log-likelihood terms, residuals), columns CW h .. CW h + CW - 1 ---- */
         double ll = 0.0;
+        /* the responses of a tile's rows come from L2: fetched one tile ahead (they were the top stall of the epilogue) */
+        float ysn[CW];
+        auto load_y = [&](int t) {
+            int tq = t + trot; if (tq >= T) tq -= T;
+            const float* yp = a.y + tq * kTRows + CW * h;
+#pragma unroll
+            for (int i = 0; i < CW; i += 4) {
+                const float4 yv = __ldg(reinterpret_cast<const float4*>(yp + i));
+                ysn[i] = yv.x; ysn[i + 1] = yv.y; ysn[i + 2] = yv.z; ysn[i + 3] = yv.w;
+            }
+        };
+        load_y(0);
         for (int t = 0; t < T; ++t) {
             const int s = t & 1, u = t >> 1;
+            float ysc[CW];
+#pragma unroll
+            for (int i = 0; i < CW; ++i) ysc[i] = ysn[i];
+            if (t + 1 < T) load_y(t + 1);
             t_mbar_wait(bars + BAR_A1FULL + s, (unsigned)(u & 1));
             t_fence_after();
-            /* the tile's 32 columns of this thread, processed STAGE BY STAGE over all 32 values (straight-line code: 32
-             * independent dependency chains for the scheduler; the MUFU latencies overlap instead of adding up) */
-            float eta[32];
-            t_ld16(tmem + ((unsigned)(32 * lg) << 16) + (unsigned)(s * 64 + 32 * h), *reinterpret_cast<float(*)[16]>(&eta[0]));
-            t_ld16(tmem + ((unsigned)(32 * lg) << 16) + (unsigned)(s * 64 + 32 * h + 16), *reinterpret_cast<float(*)[16]>(&eta[16]));
+            /* the tile's CW columns of this thread, processed STAGE BY STAGE over 16 values at a time (straight-line code:
+             * 16 independent dependency chains for the scheduler; the MUFU latencies overlap instead of adding up) */
             int tt = t + trot; if (tt >= T) tt -= T;
-            const int row0 = tt * kTRows + 32 * h;
-            float ys[32];
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const float4 yv = __ldg(reinterpret_cast<const float4*>(a.y + row0 + i));
-                ys[i] = yv.x; ys[i + 1] = yv.y; ys[i + 2] = yv.z; ys[i + 3] = yv.w;
-            }
-            float ex[32], w[32], iw[32], lw[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) ex[i] = ex2_approx(-1.4426950408889634f * fabsf(eta[i]));   /* e^-|eta| */
-#pragma unroll
-            for (int i = 0; i < 32; ++i) w[i] = 1.0f + ex[i];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { iw[i] = rcp_approx(w[i]); lw[i] = lg2_approx(w[i]); }
-            float rv[32];
-            float llt = 0.0f;
+            const int row0 = tt * kTRows + CW * h;
             const int nlive = a.nrows - row0;                                   /* rows beyond the data are padding */
+            unsigned rh[CW / 2], rl[CW / 2];
+            float llt = 0.0f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float l1p = fmaf(lw[i], 0.6931471805599453f, fmaxf(eta[i], 0.0f));    /* log1pexp(eta) */
-                const float sg = eta[i] >= 0.0f ? iw[i] : ex[i] * iw[i];                    /* sigmoid(eta)  */
-                const bool live = i < nlive;
-                llt += live ? fmaf(ys[i], eta[i], -l1p) : 0.0f;
-                rv[i] = live ? (ys[i] - sg) : 0.0f;
-            }
-            unsigned rh[16], rl[16];
+            for (int c0 = 0; c0 < CW; c0 += 16) {
+                float eta[16];
+                t_ld16(tmem + ((unsigned)(32 * lg) << 16) + (unsigned)(s * 64 + CW * h + c0), eta);
+                float ys[16];
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-                const __nv_bfloat162 hh = __floats2bfloat162_rn(rv[i], rv[i + 1]);
-                const float2 hf = __bfloat1622float2(hh);
-                const __nv_bfloat162 l2 = __floats2bfloat162_rn(rv[i] - hf.x, rv[i + 1] - hf.y);
-                rh[i >> 1] = *reinterpret_cast<const unsigned*>(&hh);
-                rl[i >> 1] = *reinterpret_cast<const unsigned*>(&l2);
+                for (int i = 0; i < 16; ++i) ys[i] = ysc[c0 + i];
+                float ex[16], w[16], iw[16], lw[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) ex[i] = ex2_approx(-1.4426950408889634f * fabsf(eta[i]));   /* e^-|eta| */
+#pragma unroll
+                for (int i = 0; i < 16; ++i) w[i] = 1.0f + ex[i];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { iw[i] = rcp_approx(w[i]); lw[i] = lg2_approx(w[i]); }
+                /* rows beyond the data need no mask: their design-matrix rows and responses are zero, so eta = 0 exactly,
+                 * their residual (-1/2) meets a zero row in GEMM2, and their log-likelihood term is -log1pexp(0) = -ln 2
+                 * each, which is added back once per tile below */
+                float rv[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float l1p = fmaf(lw[i], 0.6931471805599453f, fmaxf(eta[i], 0.0f));    /* log1pexp(eta) */
+                    const float sg = eta[i] >= 0.0f ? iw[i] : ex[i] * iw[i];                    /* sigmoid(eta)  */
+                    llt += fmaf(ys[i], eta[i], -l1p);
+                    rv[i] = ys[i] - sg;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    const __nv_bfloat162 hh = __floats2bfloat162_rn(rv[i], rv[i + 1]);
+                    const float2 hf = __bfloat1622float2(hh);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(rv[i] - hf.x, rv[i + 1] - hf.y);
+                    rh[(c0 + i) >> 1] = *reinterpret_cast<const unsigned*>(&hh);
+                    rl[(c0 + i) >> 1] = *reinterpret_cast<const unsigned*>(&l2);
+                }
             }
             /* only now does R have to be free: GEMM2 of the previous tile ran under the arithmetic above */
             t_mbar_wait(bars + BAR_REMPTY, (unsigned)((t & 1) ^ 1));
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < CW / 8; ++g) {
                 const unsigned eh[4] = {rh[4 * g], rh[4 * g + 1], rh[4 * g + 2], rh[4 * g + 3]};
                 const unsigned el[4] = {rl[4 * g], rl[4 * g + 1], rl[4 * g + 2], rl[4 * g + 3]};
-                store_chunk(tsm + kOffR, m, 4 * h + g, eh);
-                store_chunk(tsm + kOffR + 16384, m, 4 * h + g, el);
+                store_chunk(tsm + kOffR, m, CW / 8 * h + g, eh);
+                store_chunk(tsm + kOffR + 16384, m, CW / 8 * h + g, el);
             }
-            ll += (double)llt;
+            const int npad = min(CW, max(0, CW - nlive));
+            ll += (double)llt + (double)npad * 0.6931471805599453;
             t_fence_before();                            /* this thread's TMEM reads of the accumulator are done */
             t_fence_async_smem();                        /* its R rows are visible to the tensor core */
             __syncwarp();
             if (lane == 0) { t_mbar_arrive(bars + BAR_A1EMPTY + s); t_mbar_arrive(bars + BAR_RFULL); }
         }
-        /* ---- tail of the step (fp64): gradient, Hastings terms, accept  (MALA.jl:73-93); dimensions 64h .. 64h+63 ---- */
+        /* ---- tail of the step (fp64): gradient, Hastings terms, accept  (MALA.jl:73-93); dimensions DW h .. DW h + DW - 1 ---- */
         t_mbar_wait(bars + BAR_A2FULL, 0u);              /* every MMA has completed: R's shared memory is free too */
         t_fence_after();
         double q = 0.0, A = 0.0, Bq = 0.0;
 #pragma unroll 1
-        for (int cc = 0; cc < 64; cc += 16) {
-            const int c0 = 64 * h + cc;
+        for (int cc = 0; cc < DW; cc += 16) {
+            const int c0 = DW * h + cc;
             float gg[16];
             t_ld16(tmem + ((unsigned)(32 * lg) << 16) + (unsigned)(128 + c0), gg);
             if (active) {
@@ -356,17 +378,22 @@ mala_tensor_kernel(const __grid_constant__ MalaTArgs a, const __grid_constant__ 
             }
         }
         t_fence_before();
-        /* the two halves of a chain meet in shared memory (R's region is free now) */
-        double* part = reinterpret_cast<double*>(tsm + kOffR);          /* [128 chains][4]: ll, q, A, B of half 1 */
-        int* verdict = reinterpret_cast<int*>(tsm + kOffR + 8192);       /* [128 chains] */
-        if (h == 1) { part[4 * m] = ll; part[4 * m + 1] = q; part[4 * m + 2] = A; part[4 * m + 3] = Bq; }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        /* the parts of a chain meet in shared memory (R's region is free now) */
+        double* part = reinterpret_cast<double*>(tsm + kOffR);          /* [NQ - 1][128 chains][4]: ll, q, A, B of parts 1.. */
+        int* verdict = reinterpret_cast<int*>(tsm + kOffR + (NQ - 1) * 4096);       /* [128 chains] */
+        if (h >= 1) { double* pp = part + (size_t)(h - 1) * 512 + 4 * m; pp[0] = ll; pp[1] = q; pp[2] = A; pp[3] = Bq; }
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * NQ) : "memory");
         double lp = 0.0, lp_c = 0.0;
         bool acc = false;
         if (h == 0) {
             if (active) {
                 lp = a.st.lp[ch];
-                const double llf = ll + part[4 * m], qf = q + part[4 * m + 1], Af = A + part[4 * m + 2], Bf = Bq + part[4 * m + 3];
+                double llf = ll, qf = q, Af = A, Bf = Bq;
+#pragma unroll
+                for (int k = 0; k < NQ - 1; ++k) {
+                    const double* pp = part + (size_t)k * 512 + 4 * m;
+                    llf += pp[0]; qf += pp[1]; Af += pp[2]; Bf += pp[3];
+                }
                 lp_c = llf - qf * a.inv2tau2;
                 const double logratio = (-0.5 * (Af / a.sigma2)) - (-0.5 * (Bf / a.sigma2));
                 const double loga = (lp_c - lp) + logratio;
@@ -375,18 +402,18 @@ mala_tensor_kernel(const __grid_constant__ MalaTArgs a, const __grid_constant__ 
             }
             verdict[m] = acc ? 1 : 0;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * NQ) : "memory");
         acc = verdict[m] != 0;
         if (active) {
             if (acc) {
-                for (int j = 64 * h; j < 64 * h + 64; ++j) {
+                for (int j = DW * h; j < DW * h + DW; ++j) {
                     const long long o = (long long)j * pitch + ch;
                     a.st.X[o] = a.Xc[o];
                     a.st.G[o] = a.Gc[o];
                 }
             }
             if (a.sv.out || a.sv.sum) {
-                for (int j = 64 * h; j < 64 * h + 64; ++j) {
+                for (int j = DW * h; j < DW * h + DW; ++j) {
                     const long long o = (long long)j * pitch + ch;
                     const double v = a.st.X[o];
                     if (a.sv.out) a.sv.out[(long long)j * a.sv.out_pitch + ch] = v;
@@ -499,7 +526,8 @@ int launch_mala_tensor(amh_run& r, int nsteps, const SaveArgs& sv) {
         if (!rc) rc = make_map(&st->maps[2], XThi, st->rows_pad, kTD, kTD);
         if (!rc) rc = make_map(&st->maps[3], XTlo, st->rows_pad, kTD, kTD);
         if (rc) { delete st; return rc; }
-        AMH_CUDA_TRY(cudaFuncSetAttribute(mala_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemT));
+        AMH_CUDA_TRY(cudaFuncSetAttribute(mala_tensor_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemT));
+        AMH_CUDA_TRY(cudaFuncSetAttribute(mala_tensor_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemT));
         r.tensor_state = st;
     }
     MalaTensorState& st = *(MalaTensorState*)r.tensor_state;
@@ -511,12 +539,14 @@ int launch_mala_tensor(amh_run& r, int nsteps, const SaveArgs& sv) {
     a.nrows = nrows; a.ntiles = st.rows_pad / kTRows;
     a.y = st.y32; a.Xc = st.Xc; a.Gc = st.Gc;
     const unsigned grid = (unsigned)((r.n + 127) / 128);
+    static const int nq = [] { const char* ev = std::getenv("AMH_K3T_NQ"); return (ev && std::atoi(ev) == 2) ? 2 : 4; }();   /* A/B switch */
     SaveArgs none;
     std::memset(&none, 0, sizeof(none));
     for (int k = 0; k < nsteps; ++k) {
         a.step = (unsigned long long)(r.step + k + 1);
         a.sv = (k == nsteps - 1) ? sv : none;
-        mala_tensor_kernel<<<grid, 320, kSmemT, r.ctx->stream>>>(a, st.maps[0], st.maps[1], st.maps[2], st.maps[3]);
+        if (nq == 4) mala_tensor_kernel<4><<<grid, 576, kSmemT, r.ctx->stream>>>(a, st.maps[0], st.maps[1], st.maps[2], st.maps[3]);
+        else mala_tensor_kernel<2><<<grid, 320, kSmemT, r.ctx->stream>>>(a, st.maps[0], st.maps[1], st.maps[2], st.maps[3]);
         AMH_CUDA_TRY(cudaGetLastError());
         r.launches += 1;
         r.pending_launches += 1;
