@@ -76,13 +76,13 @@ def main():
             report(f"C2 RWMH MvNormal d={d} {kind} proposal", n * 500, ms, 2 * (d + 1) * 8, f"accept={st['naccept'].sum() / (n * st['step']):.3f}")
             run.close()
     if "c3" in which:
-        d, nw, ne = 10, int(os.environ.get("AMH_C3_NW", "4096")), int(os.environ.get("AMH_C3_NE", "64"))
-        t = amh.RosenbrockTarget(d)
+        d, nw, ne = int(os.environ.get("AMH_C3_D", "10")), int(os.environ.get("AMH_C3_NW", "4096")), int(os.environ.get("AMH_C3_NE", "64"))
+        t = amh.MvNormalTarget(None, spd(d, 3, 0.5, 2.0)) if os.environ.get("AMH_C3_TARGET") == "mvn" else amh.RosenbrockTarget(d)
         s = amh.Ensemble(nw, amh.StretchProposal(amh.MvNormal(np.zeros(d), amh.I)))
         run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), nw * ne, seeds(ne, 2))
         ms = timed(run, 64, spl=16)
         st = run.state()
-        report(f"C3 stretch Rosenbrock d=10 {ne}x{nw}", nw * ne * 64, ms, 2 * (d + 1) * 8, f"accept={st['naccept'].sum() / (nw * ne * st['step']):.3f}")
+        report(f"C3 stretch {os.environ.get('AMH_C3_TARGET', 'Rosenbrock')} d={d} {ne}x{nw}", nw * ne * 64, ms, 2 * (d + 1) * 8, f"accept={st['naccept'].sum() / (nw * ne * st['step']):.3f}")
         run.close()
     if "c4" in which:
         d, nrows = 128, 10000
