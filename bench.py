@@ -427,6 +427,7 @@ def main():
     achieved = B * float(n) * spl / (ms / max(1, nl) * 1e-3) / 1e9
     # DRAM bytes of one launch: only quoted when the committed ncu --set full capture is of THIS launch shape
     # (same chains, same fused steps); anything else is not a measurement of the timed launch -> null
+    cv = run.contract()
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic_mh_step.json")
     if os.path.exists(tpath):
@@ -435,12 +436,11 @@ def main():
             if (int(tj.get("mcmc_steps_in_captured_launch", -1)) == spl and int(tj.get("chains", 65536)) == n and int(tj.get("dim", 32)) == d
                     and int(tj.get("contract_version", 1)) == cv):
                 traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("capture")
-        except Exception:
+        except (OSError, ValueError, TypeError):
             traffic = None
     # what really bounds the kernel: the shared FP64 datapath.  Pipe cycles one 16-chain warp-step needs, from the
     # instruction mix of the kernel (ncu source page) x the per-instruction pipe costs measured with tools/ubench/issue_probe.cu
     # (profiles/r1_issue_probe_b200.txt: DMMA 16.2, DFMA-class 2.07, IMAD.WIDE/HI 4.1 cycles of a scheduler's FP64 pipe)
-    cv = run.contract()
     mix = PIPE_MIX.get(cv) if d == 32 else None
     pipe_cycles_per_warp_step = None if mix is None else sum(m * c for m, c in zip(mix, PIPE_COST))
     fp64_pipe = None
