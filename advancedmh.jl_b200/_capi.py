@@ -174,6 +174,24 @@ def sampler_desc(*, kind, dim, symmetric=False, cov_kind=COV_SCALAR, mean=None, 
     return d, keep
 
 
+def _point_at_bundled_nccl():
+    """The library dlopen()s NCCL lazily (multi-GPU jobs with an NCCL broadcast only).  If the NCCL wheel PyTorch was built
+    against is installed, make that the copy it loads (AMH_NCCL_LIB, unless the caller set it): the loader keys libraries by
+    soname, so an older system libnccl.so.2 loaded first would be handed to a later `import torch` and break it."""
+    if os.environ.get("AMH_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for loc in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(loc, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["AMH_NCCL_LIB"] = cand
+                return
+    except (ImportError, ValueError, AttributeError):
+        pass
+
+
 class Engine:
     """One library + one device context."""
 
@@ -185,6 +203,7 @@ class Engine:
                 "advancedmh.jl_b200 has no CPU fallback.")
         self.path = path
         self.prefix = prefix
+        _point_at_bundled_nccl()
         self.lib = C.CDLL(path)
         self._bind()
         ctx = C.c_void_p()

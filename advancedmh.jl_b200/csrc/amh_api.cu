@@ -53,6 +53,18 @@ static int sample_steps_per_launch(const amh_run& r, long long interval) {
     }
 }
 
+cudaError_t sync_stream(amh_ctx* ctx, cudaStream_t st) {
+    if (!ctx->blocking_wait) return cudaStreamSynchronize(st);
+    if (!ctx->wait_ev) {
+        const cudaError_t e = cudaEventCreateWithFlags(&ctx->wait_ev, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    const cudaError_t e = cudaEventRecord(ctx->wait_ev, st);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ctx->wait_ev);
+}
+void ctx_set_blocking_wait(amh_ctx* ctx, bool on) { if (ctx) ctx->blocking_wait = on; }
+
 int dmalloc(amh_ctx* ctx, void** p, size_t bytes) {
     *p = nullptr;
     if (bytes == 0) return AMH_OK;
@@ -221,6 +233,7 @@ int32_t amh_ctx_destroy(amh_ctx* c) {
     if (!c) return AMH_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->wait_ev) cudaEventDestroy(c->wait_ev);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
     if (c->pool) cudaMemPoolDestroy(c->pool);
@@ -527,7 +540,7 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
         r->S = Ssave;
         if (!rc) rc = ramw_init_S(*r);
     } else if (!rc) rc = launch_init(*r, mode);
-    cu(cudaStreamSynchronize(st), "init sync");       /* host buffers are only read during the call */
+    cu(amhh::sync_stream(ctx, st), "init sync");      /* host buffers are only read during the call */
     if (rc) { free_run(r); return rc; }
     *out = r;
     return AMH_OK;
@@ -546,7 +559,7 @@ int32_t amh_run_steps(amh_run* run, int64_t nsteps, int32_t warmup, int32_t step
 int32_t amh_run_sync(amh_run* run) {
     if (!run) return fail(AMH_ERR_INVALID, "run is NULL");
     AMH_CUDA_TRY(cudaSetDevice(run->ctx->device));
-    AMH_CUDA_TRY(cudaStreamSynchronize(run->ctx->stream));
+    AMH_CUDA_TRY(amhh::sync_stream(run->ctx, run->ctx->stream));
     return AMH_OK;
 }
 
@@ -570,9 +583,10 @@ int32_t amh_run_sample_ld(amh_run* run, int64_t N, int64_t discard_initial, int6
     static const bool trace = std::getenv("AMH_TRACE") != nullptr;
     const auto tr0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) {
-        if (trace) std::fprintf(stderr, "[amh] run_sample %-22s %8.3f ms\n", what,
+        if (trace) std::fprintf(stderr, "[amh] dev %d run_sample %-22s %8.3f ms\n", r.ctx->device, what,
                                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count());
     };
+    if (trace) r.timing = true;                  /* the trace also reports the device time of the stepping kernels */
     AMH_CUDA_TRY(cudaSetDevice(r.ctx->device));
     AMH_CUDA_TRY(cudaMemsetAsync(r.sum, 0, sizeof(double) * d * np, st));
     AMH_CUDA_TRY(cudaMemsetAsync(r.sumsq, 0, sizeof(double) * d * np, st));
@@ -599,7 +613,7 @@ int32_t amh_run_sample_ld(amh_run* run, int64_t N, int64_t discard_initial, int6
         }
     }
     auto cleanup = [&]() {
-        cudaStreamSynchronize(cs);
+        amhh::sync_stream(r.ctx, cs);
         for (int b = 0; b < 2; ++b) {
             dfree(r.ctx, dsamp[b]);
             dfree(r.ctx, dacc[b]);
@@ -621,6 +635,8 @@ int32_t amh_run_sample_ld(amh_run* run, int64_t N, int64_t discard_initial, int6
         return AMH_OK;
     };
     lap("setup done");
+    cudaEvent_t tr_ev = nullptr;
+    if (trace && cudaEventCreateWithFlags(&tr_ev, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(tr_ev, st);
     for (long long i = 0; i < N && !rc; ++i) {
         long long k = (i == 0) ? discard_initial : thinning;
         const int b = chunk ? (int)((i / chunk) % nbuf) : 0;
@@ -650,16 +666,25 @@ int32_t amh_run_sample_ld(amh_run* run, int64_t N, int64_t discard_initial, int6
         if (chunk && !rc && (slot == chunk - 1 || i == N - 1)) rc = drain(b, i - slot, slot + 1);
     }
     lap("all enqueued");
-    if (trace) { cudaStreamSynchronize(st); lap("step stream idle"); }
+    if (trace) {
+        if (tr_ev) { cudaEventSynchronize(tr_ev); cudaEventDestroy(tr_ev); lap("stream reached run_sample (run_create's copies and init kernel done)"); }
+        if (std::getenv("AMH_TRACE_POLL")) { while (cudaStreamQuery(st) == cudaErrorNotReady) {} }   /* spin instead of the driver's wait */
+        cudaStreamSynchronize(st);
+        lap("step stream idle");
+        double kms = 0;
+        int64_t kl = 0;
+        amh_run_kernel_time_ms(run, 0, &kms, &kl);
+        std::fprintf(stderr, "[amh] dev %d run_sample stepping kernels: %.3f ms in %lld launches (CUDA events)\n", r.ctx->device, kms, (long long)kl);
+    }
     if (!rc) {
-        cudaError_t e = cudaStreamSynchronize(cs);
+        cudaError_t e = amhh::sync_stream(r.ctx, cs);
         if (e != cudaSuccess) rc = cuda_fail(e, "copy stream sync");
     }
     lap("copies done");
     cleanup();
     lap("cleanup done");
     if (rc) return rc;
-    AMH_CUDA_TRY(cudaStreamSynchronize(st));
+    AMH_CUDA_TRY(amhh::sync_stream(r.ctx, st));
     if (summary) {
         std::vector<double> hs((size_t)d * np), hq((size_t)d * np);
         std::vector<unsigned long long> ha((size_t)np);

@@ -15,6 +15,12 @@ struct amh_ctx {
     cudaMemPool_t pool = nullptr;         /* this context's stream-ordered memory pool */
     int sm_count = 0;
     std::set<const void*> configured;     /* kernels whose function attributes were set on this device */
+    /* How host threads wait for this context's streams.  false (default): cudaStreamSynchronize -- the driver spins,
+     * lowest latency.  true: sleep on an event created with cudaEventBlockingSync (AMH_JOB_BLOCKING=1 sets it for the
+     * contexts of a multi-device job: for hosts with fewer free cores than devices; ~0.3 ms of wake-up latency per wait
+     * on the 2 x B200 box, profiles/r2_job_fanout_2gpu.txt). */
+    bool blocking_wait = false;
+    cudaEvent_t wait_ev = nullptr;
 };
 
 namespace amhh { struct RtcState; }
@@ -114,6 +120,9 @@ int cuda_fail(cudaError_t e, const char* what);
         if (_e != cudaSuccess) return amhh::cuda_fail(_e, #expr); \
     } while (0)
 
+/* host wait for everything enqueued on `st` so far, spinning or sleeping as the context says */
+cudaError_t sync_stream(amh_ctx* ctx, cudaStream_t st);
+void ctx_set_blocking_wait(amh_ctx* ctx, bool on);
 amhd::ChainState chain_state(amh_run& r);
 int target_create_impl(amh_ctx* ctx, int32_t kind, int32_t dim, const double* blob, int64_t nblob, amh_target** out, bool upload_data);
 int target_create_empty(amh_ctx* ctx, int32_t kind, int32_t dim, const double* blob, int64_t nblob, amh_target** out);

@@ -36,11 +36,18 @@ struct NcclApi {
 NcclApi& nccl_api() {
     static NcclApi api = [] {
         NcclApi a;
+        /* 1. a copy this process already holds (PyTorch's, the host application's): the loader would hand it out under the
+         *    soname anyway, and two NCCLs in one process is what must not happen;
+         * 2. AMH_NCCL_LIB (the Python host points it at the NCCL wheel next to PyTorch, so that a later `import torch`
+         *    finds the version it was built against -- an older system libnccl loaded first made that import fail with an
+         *    undefined ncclDevCommCreate);
+         * 3. the system's. */
+        a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL | RTLD_NOLOAD);
         const char* names[] = {std::getenv("AMH_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
         for (const char* nm : names) {
+            if (a.lib) break;
             if (!nm || !*nm) continue;
             a.lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
-            if (a.lib) break;
         }
         if (a.lib) {
             a.CommInitAll = (decltype(a.CommInitAll))dlsym(a.lib, "ncclCommInitAll");
@@ -95,6 +102,12 @@ struct CudaBackend {
         const char* ev = std::getenv("AMH_JOB_BCAST");
         std::string want = ev ? ev : "";
         if (j.ngpus == 1) { sh.mode = "h2d"; return AMH_OK; }
+        /* AMH_JOB_BLOCKING=1: the worker threads SLEEP while they wait for their devices (amh_host.h, amh_ctx::blocking_wait)
+         * instead of spinning inside the driver -- for hosts with fewer free cores than devices; costs wake-up latency
+         * (~0.9 ms per sample() call on the 2 x B200 box, profiles/r2_job_fanout_2gpu.txt), so it is not the default */
+        if (const char* bw = std::getenv("AMH_JOB_BLOCKING"))
+            if (bw[0] == '1')
+                for (int k = 0; k < j.ngpus; ++k) amhh::ctx_set_blocking_wait(j.ctx[k], true);
         /* peer access 0 <-> k: lets cudaMemcpyPeer go over NVLink without staging (harmless if already enabled) */
         for (int k = 1; k < j.ngpus; ++k) {
             int can = 0;

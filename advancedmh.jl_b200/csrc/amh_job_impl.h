@@ -15,9 +15,12 @@
  * same code under its own symbol prefix and the sharding logic is testable without a GPU. */
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -36,47 +39,96 @@ inline void shard_bounds(long long nunits, int k, int world, long long& lo, long
 }
 
 /* one persistent host thread per device: a phase of a job call (create, sample, read state ...) is posted to all of
- * them at once and joined; no thread is created per call (8 thread creations per phase were ~1 ms of a 10 ms call) */
+ * them at once and joined; no thread is created per call (8 thread creations per phase were ~1 ms of a 10 ms call).
+ *
+ * Waiting is spin-then-sleep on both sides: a worker that has finished a phase polls for the next one for `spin_us`
+ * (AMH_JOB_SPIN_US, default 4000; 0 = sleep at once) before it sleeps on the condition variable, and the caller polls
+ * for the join (the devices have equal shares and finish within microseconds of each other).  The phases of one
+ * `sample` call, and the calls of a loop, follow each other within a millisecond, so inside a burst no thread is ever
+ * woken: 6.62 against 6.74-6.9 ms per 2-GPU call with sleeping workers (profiles/r2_job_fanout_2gpu.txt), and a
+ * sleeping worker's wake-up can take a scheduler time slice (~4 ms) when every core is busy -- seen when the host
+ * program's BLAS threads were still spinning after a matrix product (the same file; what looked like "one device starts
+ * 4.7 ms late" in tools/job_check.py was that).  Workers fall asleep a few milliseconds after the last call. */
 class Workers {
 public:
-    explicit Workers(int n) : n_(n), done_(0), gen_(0), stop_(false) {
+    explicit Workers(int n) : n_(n) {
+        if (const char* ev = std::getenv("AMH_JOB_SPIN_US")) spin_us_ = std::max(0l, std::atol(ev));
         for (int k = 1; k < n; ++k) th_.emplace_back([this, k] { loop(k); });      /* worker 0 is the calling thread */
     }
     ~Workers() {
-        { std::lock_guard<std::mutex> g(m_); stop_ = true; ++gen_; }
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; gen_.fetch_add(1, std::memory_order_release); }
         cv_.notify_all();
         for (auto& t : th_) t.join();
     }
     void run(const std::function<void(int)>& f) {
         if (n_ == 1) { f(0); return; }
-        { std::lock_guard<std::mutex> g(m_); task_ = &f; done_ = 0; ++gen_; }
-        cv_.notify_all();
+        {
+            std::lock_guard<std::mutex> g(m_);             /* the lock orders the post against a worker that is about to sleep */
+            task_ = &f;
+            done_.store(0, std::memory_order_relaxed);
+            gen_.fetch_add(1, std::memory_order_release);
+        }
+        if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
         f(0);
-        std::unique_lock<std::mutex> lk(m_);
-        cvd_.wait(lk, [this] { return done_ == n_ - 1; });
+        /* join: the other devices finish within microseconds of this one (equal shares), so poll first */
+        const auto t0 = std::chrono::steady_clock::now();
+        unsigned spins = 0;
+        while (done_.load(std::memory_order_acquire) != n_ - 1) {
+            relax();
+            if ((++spins & 1023u) == 0 &&
+                std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() >= spin_us_) {
+                std::unique_lock<std::mutex> lk(m_);
+                joiner_sleeps_.store(true, std::memory_order_release);
+                cvd_.wait(lk, [&] { return done_.load(std::memory_order_acquire) == n_ - 1; });
+                joiner_sleeps_.store(false, std::memory_order_release);
+            }
+        }
         task_ = nullptr;
     }
 private:
+    static void relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
     void loop(int k) {
         unsigned long long seen = 0;
         for (;;) {
-            const std::function<void(int)>* f;
-            {
-                std::unique_lock<std::mutex> lk(m_);
-                cv_.wait(lk, [&] { return gen_ != seen; });
-                seen = gen_;
-                if (stop_) return;
-                f = task_;
+            /* poll for the next phase, then sleep */
+            const auto t0 = std::chrono::steady_clock::now();
+            unsigned spins = 0;
+            while (gen_.load(std::memory_order_acquire) == seen) {
+                relax();
+                if ((++spins & 1023u) == 0 &&
+                    std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() >= spin_us_) {
+                    std::unique_lock<std::mutex> lk(m_);
+                    sleepers_.fetch_add(1, std::memory_order_acq_rel);
+                    cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen; });
+                    sleepers_.fetch_sub(1, std::memory_order_acq_rel);
+                    break;
+                }
             }
+            seen = gen_.load(std::memory_order_acquire);
+            if (stop_) return;
+            const std::function<void(int)>* f = task_;
             (*f)(k);
-            { std::lock_guard<std::mutex> g(m_); ++done_; }
-            cvd_.notify_one();
+            done_.fetch_add(1, std::memory_order_release);
+            /* pass through the mutex: either this comes before the joiner's critical section (then its predicate sees
+             * done_) or after it has entered wait() (then the flag is visible here and it is woken) */
+            { std::lock_guard<std::mutex> g(m_); }
+            if (joiner_sleeps_.load(std::memory_order_acquire)) cvd_.notify_one();
         }
     }
-    int n_, done_;
-    unsigned long long gen_;
-    bool stop_;
+    int n_;
+    long spin_us_ = 4000;
+    std::atomic<int> done_{0};
+    std::atomic<int> sleepers_{0};
+    std::atomic<unsigned long long> gen_{0};
+    std::atomic<bool> stop_{false};
     const std::function<void(int)>* task_ = nullptr;
+    std::atomic<bool> joiner_sleeps_{false};
     std::mutex m_;
     std::condition_variable cv_, cvd_;
     std::vector<std::thread> th_;
@@ -103,13 +155,24 @@ struct Job {
     int each(F f, bool only_with_run = false) {
         std::vector<int> rc(ngpus, AMH_OK);
         std::vector<std::string> msg(ngpus);
+        static const bool trace = std::getenv("AMH_TRACE") != nullptr;        /* absolute times of the fan-out, per worker */
+        const auto t0 = std::chrono::steady_clock::now();
+        auto ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+        std::vector<double> ta(ngpus, 0.0), tb(ngpus, 0.0);
         const std::function<void(int)> body = [&](int k) {
             if (only_with_run && !run[k]) return;
+            ta[k] = ms();
             rc[k] = f(k);
             if (rc[k] != AMH_OK) msg[k] = B::last_error();
+            tb[k] = ms();
         };
         if (!workers) workers.reset(new Workers(ngpus));
         workers->run(body);
+        if (trace) {
+            std::string line = "[amh] job fan-out: joined at " + std::to_string(ms()) + " ms; worker start/end";
+            for (int k = 0; k < ngpus; ++k) line += "  [" + std::to_string(k) + "] " + std::to_string(ta[k]) + " / " + std::to_string(tb[k]);
+            std::fprintf(stderr, "%s\n", line.c_str());
+        }
         for (int k = 0; k < ngpus; ++k)
             if (rc[k] != AMH_OK) return B::fail(rc[k], "device " + std::to_string(devices[k]) + ": " + msg[k]);
         return AMH_OK;

@@ -530,7 +530,7 @@ static int launch_mh_tc_t(amh_run& r, int nsteps, const SaveArgs& sv) {
             all.push_back(s.d.cov_kind == AMH_COV_DIAG ? s.scale[i] : s.d.cov_kind == AMH_COV_SCALAR ? s.scale[0] : 0.0);
         { const int rca = dmalloc(r.ctx, &r.scratch, all.size() * sizeof(double)); if (rca) return rca; }
         AMH_CUDA_TRY(cudaMemcpyAsync(r.scratch, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice, r.ctx->stream));
-        AMH_CUDA_TRY(cudaStreamSynchronize(r.ctx->stream));     /* `all` is a stack temporary */
+        AMH_CUDA_TRY(sync_stream(r.ctx, r.ctx->stream));        /* `all` is a stack temporary */
     }
     constexpr int NT = (D / 8) * (D / 8 + 1);
     MhTcArgs a;

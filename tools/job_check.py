@@ -14,6 +14,7 @@ import sys
 import time
 
 import numpy as np
+from threadpoolctl import threadpool_limits
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -93,10 +94,18 @@ def e2e(eng, ngpus, out, per_gpu=65536, spl=500, reps=5):
     for k in sorted({1, ngpus}):
         n = per_gpu * k
         hinit = eng.pinned_empty((d, n))
-        hinit[...] = L @ np.random.default_rng(100).normal(size=(d, n))
+        # one BLAS thread for the set-up product: numpy's OpenBLAS workers keep spinning on every core for ~100 ms after a
+        # threaded GEMM, and a timed region that starts inside that window measures them, not the library (that was the
+        # "0.57 efficiency at 2 GPUs" of the first version of this script: profiles/r2_job_fanout_2gpu.txt)
+        with threadpool_limits(limits=1):
+            hinit[...] = L @ np.random.default_rng(100).normal(size=(d, n))
         pout = eng.pinned_empty((2, d + 1, n)); pacc = eng.pinned_empty((2, n), dtype=np.uint8)
         par = amh.MCMCB200(ngpus=k)
-        amh.sample(model, s, par, 2, n, initial_params=hinit, thinning=spl, chain_type=amh.Chains, seed=99, out=(pout, pacc))
+        if os.environ.get("AMH_TRACE"):
+            print("threads in the process:", [l.split()[1] for l in open("/proc/self/status") if l.startswith("Threads")], "cpus", os.cpu_count(),
+                  "affinity", len(os.sched_getaffinity(0)), file=sys.stderr, flush=True)
+        for w in range(3):
+            amh.sample(model, s, par, 2, n, initial_params=hinit, thinning=spl, chain_type=amh.Chains, seed=99 + w, out=(pout, pacc))
         t0 = time.perf_counter()
         for i in range(reps):
             amh.sample(model, s, par, 2, n, initial_params=hinit, thinning=spl, chain_type=amh.Chains, seed=i, out=(pout, pacc))
