@@ -36,7 +36,7 @@ amhd::ChainState chain_state(amh_run& r) {
 
 int default_steps_per_launch(const amh_run& r) {
     switch (r.sampler->d.kind) {
-    case AMH_SAMPLER_STRETCH: return 16;
+    case AMH_SAMPLER_STRETCH: return stretch_default_steps_per_launch(r);
     case AMH_SAMPLER_RAM: return r.ram_warp ? 16 : 1;   /* K4W keeps the factor in shared memory across fused steps */
     default: return 64;
     }

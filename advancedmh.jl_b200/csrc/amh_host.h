@@ -147,6 +147,8 @@ bool mala_logistic_eligible(const amh_run& r);
 int launch_mala_logistic(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_ram(amh_run& r, int nsteps, bool warmup, const amhd::SaveArgs& sv);
 int launch_stretch(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
+/* exact-dimension stretch kernels of the second translation unit (amh_launch_stretch_dims.cu); taken = false: not one of its dimensions */
+int launch_stretch_more_dims(amh_run& r, int nsteps, const amhd::SaveArgs& sv, bool& taken);
 int launch_init(amh_run& r, int mode);
 int ram_gather_S(amh_run& r, double* dst);
 int ram_scatter_S(amh_run& r, const double* src);   /* [tri][pitch] device buffer -> current factor of every chain */
@@ -158,6 +160,7 @@ int ramw_init_S(amh_run& r);
 int ramw_import_S(amh_run& r, const double* src);
 int ramw_export_S(amh_run& r, double* dst);   /* current factor of every chain -> dst [tri][pitch] */
 int default_steps_per_launch(const amh_run& r);
+int stretch_default_steps_per_launch(const amh_run& r);   /* amh_launch_stretch.cu */
 /* user-supplied targets: kernels compiled at run time by NVRTC (amh_rtc.cu) */
 enum RtcKernel { RK_INIT = 0, RK_MH, RK_COMP, RK_MALA, RK_RAM128, RK_RAM64, RK_RAM32, RK_STRETCH, RK_FLOW512, RK_FLOW768,
                  RK_FLOW1024, RK_COUNT };

@@ -15,6 +15,8 @@
  * that owns the walker as soon as its partner is available; __syncthreads()
  * between wavefronts orders the global writes inside the CTA.
  */
+#include <initializer_list>
+#include <type_traits>
 #include "amh_params.cuh"
 
 namespace amhh {
@@ -867,9 +869,25 @@ int launch_stretch_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     return AMH_OK;
 }
 
+#ifndef AMH_STRETCH_EXTRA_TU
+/* Sweeps per launch when the caller does not say: 16, and for the K2R shapes as many of 64 / 32 as keep the two plan
+ * buffers under 2 GiB -- a launch ends with the deepest dependency chain of its slowest ensemble while the other SMs
+ * idle, so longer launches pay: config 3 at 8 / 16 / 32 / 64 sweeps per launch 1.05 / 1.13 / 1.15 / 1.18e10 moves/s
+ * (profiles/r2_c3_shape_sweep.txt); 64 sweeps of 64 x 4 096 walkers are 2 x 0.8 GB of plan entries. */
+int stretch_default_steps_per_launch(const amh_run& r) {
+    const long long nw = r.sampler->d.n_walkers;
+    if (nw < 1 || r.n % nw) return 16;
+    const long long nens = r.n / nw;
+    if (!stretch_res_shape(nw, nens, r.ctx->sm_count) || std::getenv("AMH_STRETCH_RES")) return 16;
+    const double per_sweep = (double)nens * 2.0 * ((double)res_nwp(nw) * 4 * sizeof(double) + kResMeta * sizeof(int));
+    for (int spl : {64, 32})
+        if (2.0 * spl * per_sweep <= 2147483648.0) return spl;
+    return 16;
+}
+
 template <class T>
 int launch_stretch_dim(amh_run& r, int nsteps, const SaveArgs& sv) {
-    switch (r.dim) {          /* exact-dimension instantiations; everything else is generic */
+    switch (r.dim) {          /* exact-dimension instantiations; more of them in amh_launch_stretch_dims.cu; everything else is generic */
     case 2: return launch_stretch_t<2, T>(r, nsteps, sv);
     case 3: return launch_stretch_t<3, T>(r, nsteps, sv);
     case 4: return launch_stretch_t<4, T>(r, nsteps, sv);
@@ -882,6 +900,11 @@ int launch_stretch_dim(amh_run& r, int nsteps, const SaveArgs& sv) {
 }
 
 int launch_stretch(amh_run& r, int nsteps, const SaveArgs& sv) {
+    {   /* the second translation unit's exact-dimension instantiations (compiled in parallel with this one) */
+        bool taken = false;
+        const int rc = launch_stretch_more_dims(r, nsteps, sv, taken);
+        if (taken) return rc;
+    }
     switch (r.target->kind) {
     case AMH_TARGET_MVNORMAL: return launch_stretch_dim<TMvNormal>(r, nsteps, sv);
     case AMH_TARGET_GAUSS_PREC: return launch_stretch_dim<TGaussPrec>(r, nsteps, sv);
@@ -894,5 +917,6 @@ int launch_stretch(amh_run& r, int nsteps, const SaveArgs& sv) {
     }
     return fail(AMH_ERR_INVALID, "unknown target kind");
 }
+#endif  /* AMH_STRETCH_EXTRA_TU */
 
 }  // namespace amhh

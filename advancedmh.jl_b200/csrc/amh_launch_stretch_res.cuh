@@ -63,6 +63,9 @@ __device__ __forceinline__ ResEntry res_entry_load(const double* __restrict__ en
     return r;
 }
 
+/* the shapes K2R is chosen for: few, large ensembles (two SMs each) */
+inline bool stretch_res_shape(long long nw, long long nens, int sm_count) { return 2 * nens <= sm_count && nw >= 1024 && nw <= 16384; }
+
 __host__ __device__ inline long long res_nwp(long long nw) { return (((nw + 1) / 2 + 31) & ~31ll) + 32 * (kStretchLevels + 1); }
 
 template <int BLOCK>
@@ -618,7 +621,11 @@ bool launch_stretch_res_t(amh_run& r, int nsteps, const StretchArgs& a, const ty
     const long long nens = r.n / nw;
     /* two SMs per ensemble pay when the ensembles are few and large (BASELINE config 3: 64 x 4 096 -> 128 of 148 SMs);
      * many small ensembles are faster one CTA each (K2F): measured in profiles/r2_k2r_vs_k2f_shapes.txt */
-    if (res_env ? std::atoi(res_env) == 0 : !(2 * nens <= r.ctx->sm_count && nw >= 1024)) return false;
+    /* ... and when the target is cheap next to the hand-offs: with a dense quadratic form of d >= 12 per move (MvNormal /
+     * GaussPrec) the 2 x 384 threads of a cluster lose to K2F's wider CTA (d = 12 / 16, 64 x 2 048 walkers: 5.6 vs 6.1 and
+     * 4.0 vs 4.6e9 moves/s, profiles/r2_c3_shape_sweep.txt) */
+    constexpr bool dense_target = std::is_same<T, TMvNormal>::value || std::is_same<T, TGaussPrec>::value;
+    if (res_env ? std::atoi(res_env) == 0 : !(stretch_res_shape(nw, nens, r.ctx->sm_count) && !(dense_target && DMAX >= 12))) return false;
     const size_t nwl = (size_t)(nw + 1) / 2;
     const size_t rec_b = ((nwl * (DMAX + 1) + 1) & ~(size_t)1) * sizeof(double);
     const size_t fixed_b = rec_b + nwl * (sizeof(unsigned) + sizeof(unsigned short)) + 64;

@@ -169,12 +169,12 @@ def bench_c3(amh, eng, peak, seed=2):
     s = amh.Ensemble(nw, amh.StretchProposal(amh.MvNormal(np.zeros(d), amh.I)))
     sd = np.random.default_rng(seed).integers(0, 2 ** 64, size=ne, dtype=np.uint64)
     run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), nw * ne, sd)
-    ms = _timed(run, 64, spl=16)
+    ms = _timed(run, 128, spl=0)          # 0 = the library's choice: 64 sweeps per launch for this shape (2 x 0.8 GB of plan entries)
     st = run.state()
-    out = _rec(nw * ne * 64, ms, 2 * (d + 1) * 8, peak, workload=f"C3: Ensemble(4096, StretchProposal) Rosenbrock d=10, {ne} ensembles per GPU, exact sequential sweep",
+    out = _rec(nw * ne * 128, ms, 2 * (d + 1) * 8, peak, workload=f"C3: Ensemble(4096, StretchProposal) Rosenbrock d=10, {ne} ensembles per GPU, exact sequential sweep",
                kernel="stretch_plan_res_kernel + stretch_sweep_res_kernel (K2R: ensemble resident in the shared memory of a 2-CTA cluster, "
                       "in-place records, st.async + mbarrier hand-off; plan made ahead on a second stream)",
-               accept_rate=float(st["naccept"].sum() / (nw * ne * st["step"])), sweeps_timed=64 * 3)
+               accept_rate=float(st["naccept"].sum() / (nw * ne * st["step"])), sweeps_timed=128 * 3, sweeps_per_launch=64)
     run.close()
     return out
 

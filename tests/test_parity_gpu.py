@@ -265,7 +265,12 @@ def test_ram_sample_schedule_warmup_bit_exact(amh, cuda, oracle):
 
 # -------------------------------------------------------------------------- stretch (K2)
 @pytest.mark.parametrize("kind,d,nw,ne", [("rosenbrock", 10, 64, 3), ("nig", 2, 100, 2), ("niglog", 2, 37, 2),
-                                          ("mvnormal", 5, 1024, 2), ("rosenbrock", 10, 4096, 1), ("mvnormal", 20, 50, 2)])
+                                          ("mvnormal", 5, 1024, 2), ("rosenbrock", 10, 4096, 1), ("mvnormal", 20, 50, 2),
+                                          # the second translation unit's exact dimensions (amh_launch_stretch_dims.cu) and
+                                          # two dimensions that stay on the generic kernels
+                                          ("rosenbrock", 6, 200, 2), ("mvnormal", 7, 333, 2), ("rosenbrock", 9, 1024, 1),
+                                          ("rosenbrock", 12, 777, 2), ("rosenbrock", 20, 130, 2), ("mvnormal", 24, 96, 2),
+                                          ("gaussprec", 12, 150, 2), ("rosenbrock", 11, 64, 2), ("mvnormal", 33, 40, 2)])
 def test_stretch_bit_exact_sequential_sweep(amh, cuda, oracle, kind, d, nw, ne):
     if kind == "rosenbrock":
         target = amh.RosenbrockTarget(d)
@@ -273,6 +278,8 @@ def test_stretch_bit_exact_sequential_sweep(amh, cuda, oracle, kind, d, nw, ne):
         target = amh.NormalInverseGammaToy()
     elif kind == "niglog":
         target = amh.NormalInverseGammaToy(log_space=True)
+    elif kind == "gaussprec":
+        target = amh.GaussianPrecisionTarget(np.linalg.inv(make_spd(d, seed=d, lo=0.5, hi=4.0)))
     else:
         target = amh.MvNormalTarget(None, make_spd(d, seed=d, lo=0.5, hi=4.0))
     spl = amh.Ensemble(nw, amh.StretchProposal(amh.MvNormal(np.zeros(d), amh.I)))
@@ -557,7 +564,7 @@ def test_stretch_level_schedule_configs_and_overflow_bucket(amh, cuda, oracle, m
     assert np.array_equal(out_g, out_o) and np.array_equal(acc_g, acc_o)
 
 
-@pytest.mark.parametrize("d,nw,ne", [(10, 333, 3), (3, 256, 2), (16, 130, 2)])
+@pytest.mark.parametrize("d,nw,ne", [(10, 333, 3), (3, 256, 2), (16, 130, 2), (12, 301, 2), (7, 129, 2), (24, 70, 2)])
 @pytest.mark.parametrize("win,fwd,levels", [(None, None, None), ("7", None, None), ("100", "0", None), (None, "20", "4"),
                                               ("33", "5", "3")])
 def test_stretch_resident_cluster_sweep_paths(amh, cuda, oracle, monkeypatch, d, nw, ne, win, fwd, levels):

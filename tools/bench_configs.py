@@ -80,9 +80,17 @@ def main():
         t = amh.MvNormalTarget(None, spd(d, 3, 0.5, 2.0)) if os.environ.get("AMH_C3_TARGET") == "mvn" else amh.RosenbrockTarget(d)
         s = amh.Ensemble(nw, amh.StretchProposal(amh.MvNormal(np.zeros(d), amh.I)))
         run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), nw * ne, seeds(ne, 2))
-        ms = timed(run, 64, spl=16)
+        c3spl = int(os.environ.get("AMH_C3_SPL", "0"))   # 0 = the library's choice
+        c3n = max(128, 2 * c3spl)
+        ms = timed(run, c3n, spl=c3spl)
+        import time as _time                     # the same by the host's clock: the plan kernels run on a second stream
+        t0 = _time.perf_counter()
+        for _ in range(3):
+            run.steps(c3n, steps_per_launch=c3spl)
+        run.sync()
+        wall_ms = (_time.perf_counter() - t0) * 1e3 / 3
         st = run.state()
-        report(f"C3 stretch {os.environ.get('AMH_C3_TARGET', 'Rosenbrock')} d={d} {ne}x{nw}", nw * ne * 64, ms, 2 * (d + 1) * 8, f"accept={st['naccept'].sum() / (nw * ne * st['step']):.3f}")
+        report(f"C3 stretch {os.environ.get('AMH_C3_TARGET', 'Rosenbrock')} d={d} {ne}x{nw} spl={c3spl}", nw * ne * c3n, ms, 2 * (d + 1) * 8, f"accept={st['naccept'].sum() / (nw * ne * st['step']):.3f} events {ms:.3f} ms, host clock {wall_ms:.3f} ms")
         run.close()
     if "c4" in which:
         d, nrows = 128, 10000
