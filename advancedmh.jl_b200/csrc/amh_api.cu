@@ -478,7 +478,8 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
     const size_t nt = (size_t)d * (d + 1) / 2;
     int rc = AMH_OK;
     auto chk = [&](int c) { if (!rc) rc = c; };
-    chk(dev_alloc(ctx, &r->X, (size_t)d * np));
+    r->x_rows = (d + 7) & ~7;               /* padding rows for the padded tensor-core MH kernels (amh_launch_mh_tcp.cu) */
+    chk(dev_alloc(ctx, &r->X, (size_t)r->x_rows * np));
     chk(dev_alloc(ctx, &r->lp, np));
     chk(dev_alloc(ctx, &r->lq, np));
     chk(dev_alloc(ctx, &r->acc, np));
@@ -512,7 +513,7 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
     if (rc) { free_run(r); return rc; }
     cudaStream_t st = ctx->stream;
     auto cu = [&](cudaError_t e, const char* w) { if (!rc && e != cudaSuccess) rc = cuda_fail(e, w); };
-    cu(cudaMemsetAsync(r->X, 0, sizeof(double) * d * np, st), "memset X");
+    cu(cudaMemsetAsync(r->X, 0, sizeof(double) * r->x_rows * np, st), "memset X");
     cu(cudaMemsetAsync(r->lp, 0, sizeof(double) * np, st), "memset lp");
     cu(cudaMemsetAsync(r->lq, 0, sizeof(double) * np, st), "memset lq");
     cu(cudaMemsetAsync(r->acc, 0, np, st), "memset acc");

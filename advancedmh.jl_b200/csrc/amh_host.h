@@ -63,6 +63,7 @@ struct amh_run {
     amh_sampler* sampler = nullptr;
     long long n = 0, off = 0, pitch = 0;
     int dim = 0;
+    int x_rows = 0;                /* rows X was allocated with: dim rounded up to a multiple of 8, the extra rows stay 0 */
     long long nseeds = 0;
     /* device state */
     double* X = nullptr;
@@ -137,6 +138,9 @@ int launch_mh(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_mh_comp(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 bool mh_tc_eligible(const amh_run& r);        /* K1T: both mat-vecs on the FP64 tensor cores */
 int launch_mh_tc(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
+/* the same kernels for the dimensions in between, padded to a multiple of 8, d <= 64 (amh_launch_mh_tcp.cu) */
+bool mh_tc_padded_eligible(const amh_run& r);
+int launch_mh_tc_padded(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_mala(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 /* K3T: the same on the tcgen05 tensor cores as split-bf16 GEMMs, opt-in (amh_launch_mala_tensor.cu) */
 bool mala_tensor_eligible(const amh_run& r);

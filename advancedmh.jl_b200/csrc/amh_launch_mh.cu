@@ -89,6 +89,7 @@ int launch_mh_d2(amh_run& r, int nsteps, const SaveArgs& sv) {
 
 int launch_mh(amh_run& r, int nsteps, const SaveArgs& sv) {
     if (r.mh_path != 1 && mh_tc_eligible(r)) return launch_mh_tc(r, nsteps, sv);
+    if (r.mh_path != 1 && mh_tc_padded_eligible(r)) return launch_mh_tc_padded(r, nsteps, sv);
     if (r.dim > kGenericCap) return fail(AMH_ERR_UNSUPPORTED, "StaticMH/RWMH on the device supports dim <= 128");
     switch (r.target->kind) {
     case AMH_TARGET_MVNORMAL: return launch_mh_full<TMvNormal>(r, nsteps, sv);

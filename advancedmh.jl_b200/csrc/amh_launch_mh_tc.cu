@@ -41,6 +41,10 @@ struct MhTcArgs {
     double c0;
     const double* dscale;      /* [D] standard deviations of a diagonal / isotropic proposal (COVD variants) */
     int pace;                  /* nanoseconds of optional pause per step (see the step loop of K1T16) */
+    /* PAD variants (amh_launch_mh_tcp.cu): the run's dimension d <= D, its noise blocks per step and the offset of the
+     * exponential's block inside a step (contract v2: ceil(d/4) + 1 and ceil(d/4)) */
+    int d_real;
+    unsigned long long blocks_per_step, exp_block;
 };
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
@@ -263,11 +267,19 @@ __host__ __device__ constexpr int tc16_smem_doubles_per_warp() { return D * kPZ1
  * end-of-launch tail and LOSES throughput for every k (5.28e9 at k <= 16). */
 /* COVD: the proposal covariance is diagonal (ScalMat / PDiagMat): v_i = sigma_i z_i needs no mat-vec, phase 1 is
  * c = x + sigma_i z_i on the chain lanes (the contract's two roundings, proposal.jl:41-56 with a diagonal factor). */
-template <int D, int WARPS, bool MU_ZERO, bool IS_RW, bool COVD = false, int CV = 1>
+/* PAD (amh_launch_mh_tcp.cu, contract v2): the run's dimension is a.d_real <= D.  L, U, mu and the scales are padded with
+ * zeros (rows / columns d_real..D-1), the state has D rows on the device (the padding rows stay 0), and the noise blocks
+ * are indexed with the real dimension's blocks per step, so every real coordinate sees exactly the contract's arithmetic:
+ * a padding column adds fma(0, z, acc) = acc to a row's dot product -- what the zeros above the diagonal inside the
+ * diagonal tiles do already -- and a padding row contributes fma(0, 0, q) = q to the quadratic form.  The normals the
+ * lanes draw for padding rows come from blocks of the chain's stream outside this step's range; they are finite and only
+ * ever multiply zeros.  D up to 64 (fewer warps per SM: the Z / C tile grows with D). */
+template <int D, int WARPS, bool MU_ZERO, bool IS_RW, bool COVD = false, int CV = 1, bool PAD = false>
 __global__ void __launch_bounds__(32 * WARPS, 28 / WARPS)
 mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
 
-    static_assert(D % 8 == 0 && D >= 8 && D <= 32, "row blocks of 8; D/4 (v1) or D/8 (v2) noise blocks per lane half");
+    static_assert(D % 8 == 0 && D >= 8 && (D <= 32 || (PAD && D <= 64)), "row blocks of 8; D/4 (v1) or D/8 (v2) noise blocks per lane half");
+    static_assert(!PAD || CV == 2, "padded dimensions: contract v2 only");
     constexpr int NB = D / 8;
     constexpr int NPB = (CV == 2) ? 4 : 2;     /* normals per Philox block (contract v1 / v2) */
     constexpr int NPH = D / (2 * NPB);         /* Philox blocks per half-chain lane */
@@ -290,7 +302,8 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
     double lp = active ? a.st.lp[ch] : 0.0;
     unsigned nacc = 0u;                         /* accepted moves of this launch */
     unsigned char accepted = active ? a.st.acc[ch] : (unsigned char)0;
-    constexpr unsigned long long B = (unsigned long long)(D / NPB + 1);
+    const unsigned long long B = PAD ? a.blocks_per_step : (unsigned long long)(D / NPB + 1);
+    const unsigned long long EB = PAD ? a.exp_block : (unsigned long long)(D / NPB);      /* the exponential's block within a step */
     double e_next = 0.0;
 
     for (int s = 0; s < a.nsteps; ++s) {
@@ -305,7 +318,34 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
             if (a.pace > 0) __nanosleep((unsigned)a.pace);
         }
         double e;
-        {
+        if constexpr (PAD) {
+            /* groups of at most two blocks (four Box-Muller pairs in lock-step), the last one carries the exponential */
+            const unsigned long long b0 = k * B + (unsigned long long)(NPH * half);
+            double* zt = ZC + (HR * half) * kPZ16 + cl;
+            constexpr int NG = (NPH + 1) / 2;
+            double eh = 0.0;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const bool last = g == NG - 1;
+                if (!last) {
+                    double dmy;
+                    noise_group<2, false, CV>(seed, b0 + 2 * g, 0ull, zt + NPB * 2 * g * kPZ16, dmy, amh::amh_log_tab_dev, kPZ16);
+                } else if ((s & 1) == 0) {
+                    noise_group<NPH - 2 * (NG - 1), true, CV>(seed, b0 + 2 * (NG - 1), (k + (unsigned long long)half) * B + EB,
+                                                              zt + NPB * 2 * (NG - 1) * kPZ16, eh, amh::amh_log_tab_dev, kPZ16);
+                } else {
+                    double dmy;
+                    noise_group<NPH - 2 * (NG - 1), false, CV>(seed, b0 + 2 * (NG - 1), 0ull, zt + NPB * 2 * (NG - 1) * kPZ16, dmy,
+                                                               amh::amh_log_tab_dev, kPZ16);
+                }
+            }
+            if ((s & 1) == 0) {
+                e = __shfl_sync(0xffffffffu, eh, cl);
+                e_next = __shfl_sync(0xffffffffu, eh, cl + 16);
+            } else {
+                e = e_next;
+            }
+        } else {
             const unsigned long long b0 = k * B + (unsigned long long)(NPH * half);
             double* zt = ZC + (HR * half) * kPZ16 + cl;            /* Z[HR half + j][cl] */
             /* two lock-step batches when there are >= 6 pairs (v2, d = 32: 2 + 2 blocks; one batch of 4 blocks measured 2.5 % slower) */
@@ -315,7 +355,7 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
              * h draws the exponential of step k + h, and odd steps draw none */
             if ((s & 1) == 0) {
                 double eh;
-                noise_group<NPH - G1, true, CV>(seed, b0 + G1, (k + (unsigned long long)half) * B + (unsigned long long)(D / NPB),
+                noise_group<NPH - G1, true, CV>(seed, b0 + G1, (k + (unsigned long long)half) * B + EB,
                                                 zt + NPB * G1 * kPZ16, eh, amh::amh_log_tab_dev, kPZ16);
                 e = __shfl_sync(0xffffffffu, eh, cl);
                 e_next = __shfl_sync(0xffffffffu, eh, cl + 16);
@@ -470,6 +510,7 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
 #pragma unroll 4
         for (int ii = 0; ii < HR; ++ii) {
             const int i = HR * half + ii;
+            if (PAD && i >= a.d_real) break;                       /* padding rows are not part of the sample */
             const long long o = (long long)i * pitch + ch;
             const double v = X[o];
             if (a.sv.out) a.sv.out[(long long)i * a.sv.out_pitch + ch] = v;
@@ -482,22 +523,25 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
         a.st.lp[ch] = lp;
         a.st.nacc[ch] = a.st.nacc[ch] + (unsigned long long)nacc;
         a.st.acc[ch] = accepted;
-        if (a.sv.out) a.sv.out[(long long)D * a.sv.out_pitch + ch] = lp;
+        if (a.sv.out) a.sv.out[(long long)(PAD ? a.d_real : D) * a.sv.out_pitch + ch] = lp;
         if (a.sv.acc_out) a.sv.acc_out[ch] = accepted;
     }
 }
 
 /* A fragments of a packed lower-triangular factor: frag[tile(mb,kb)][lane] = M[8mb + lane/4][4kb + lane%4] */
-static void build_frags(const double* tri_packed, int d, std::vector<double>& out) {
-    const int nb = d / 8;
+/* dpad >= d: the factor padded with zero rows / columns to a multiple of 8 (PAD kernels) */
+static void build_frags(const double* tri_packed, int d, std::vector<double>& out, int dpad = 0) {
+    const int nb = (dpad ? dpad : d) / 8;
     out.assign((size_t)nb * (nb + 1) * 32, 0.0);
     for (int mb = 0; mb < nb; ++mb)
         for (int kb = 0; kb <= 2 * mb + 1; ++kb)
             for (int lane = 0; lane < 32; ++lane) {
                 const int row = 8 * mb + lane / 4, col = 4 * kb + lane % 4;
-                if (col <= row) out[((size_t)(mb * (mb + 1) + kb)) * 32 + lane] = tri_packed[tri_h(row, col)];
+                if (col <= row && row < d) out[((size_t)(mb * (mb + 1) + kb)) * 32 + lane] = tri_packed[tri_h(row, col)];
             }
 }
+
+#ifndef AMH_MHTC_EXTRA_TU
 
 bool mh_tc_eligible(const amh_run& r) {
     const amh_sampler& s = *r.sampler;
@@ -675,5 +719,6 @@ int launch_mh_tc(amh_run& r, int nsteps, const SaveArgs& sv) {
     }
     return fail(AMH_ERR_INVALID, "tensor-core MH path: unsupported dimension");
 }
+#endif  /* AMH_MHTC_EXTRA_TU */
 
 }  // namespace amhh

@@ -32,7 +32,11 @@ def _seeds(n, s=0):
 
 @pytest.mark.parametrize("d,cov", [(1, "scalar"), (2, "scalar"), (2, "diag"), (3, "full"), (8, "full"), (8, "diag"), (13, "full"),
                                    (16, "full"), (24, "full"), (32, "full"), (32, "scalar"), (40, "full"),
-                                   (8, "scalar"), (16, "diag"), (24, "scalar"), (32, "diag")])
+                                   (8, "scalar"), (16, "diag"), (24, "scalar"), (32, "diag"),
+                                   # dimensions padded to a multiple of 8 on the tensor-core kernels (amh_launch_mh_tcp.cu)
+                                   (7, "full"), (9, "full"), (11, "diag"), (14, "full"), (15, "scalar"), (17, "full"), (18, "full"),
+                                   (19, "diag"), (21, "full"), (23, "full"), (25, "full"), (27, "scalar"), (28, "full"), (29, "full"),
+                                   (31, "full"), (31, "diag"), (48, "full")])
 def test_rwmh_mvnormal_bit_exact(amh, cuda, oracle, d, cov):
     Sigma = make_spd(d, seed=d)
     target = amh.MvNormalTarget(np.linspace(-1, 1, d), Sigma)
@@ -306,6 +310,28 @@ def test_stretch_sample_bit_exact(amh, cuda, oracle):
     oo, ao, so = ro.sample(13, discard_initial=5, thinning=2)
     assert np.array_equal(og, oo) and np.array_equal(ag, ao)
     assert np.array_equal(sg["mean"], so["mean"])
+
+
+@pytest.mark.parametrize("d,zero_mean", [(7, True), (13, False), (22, True), (30, False)])
+def test_padded_tensor_core_path_static_symmetric_sample_and_resume(amh, cuda, oracle, d, zero_mean):
+    """the padded K1T16 kernels (amh_launch_mh_tcp.cu): symmetric StaticProposal and RWMH through the sample schedule (the
+    save epilogue must skip the padding rows), summaries, zero / non-zero target mean, 1 001 chains (a ragged last warp),
+    and a state round trip in the middle (the padding rows of the device state must stay zero)"""
+    Sigma = make_spd(d, seed=70 + d, lo=0.5, hi=4.0)
+    target = amh.MvNormalTarget(None if zero_mean else np.linspace(0.5, -0.5, d), Sigma)
+    n = 1001
+    for spl in (amh.MetropolisHastings(amh.SymmetricStaticProposal(amh.MvNormal(np.zeros(d), 1.2 * Sigma))),
+                amh.RWMH(amh.MvNormal(np.zeros(d), (2.38 ** 2 / d) * Sigma))):
+        rg, ro = _pair(amh, cuda, oracle, target, spl, n, _seeds(n, 78 + d))
+        og, ag, sg = rg.sample(9, discard_initial=3, thinning=5, chain_means=True)
+        oo, ao, so = ro.sample(9, discard_initial=3, thinning=5, chain_means=True)
+        assert np.array_equal(og, oo) and np.array_equal(ag, ao)
+        assert np.array_equal(sg["mean"], so["mean"]) and np.array_equal(sg["var"], so["var"])
+        _assert_same_state(rg, ro)
+        st = rg.state()
+        rg.set_state(st); ro.set_state(ro.state())
+        rg.steps(33, steps_per_launch=0); ro.steps(33)
+        _assert_same_state(rg, ro)
 
 
 def test_tensor_core_path_static_symmetric_and_sample(amh, cuda, oracle):
