@@ -109,6 +109,21 @@ __host__ __device__ constexpr int psched(int nb, int t, bool desc, int what) {
     return -1;
 }
 
+/* the same schedule as compile-time tables: for more than four row blocks (padded dimensions above 32) folding the psched()
+ * calls of the unrolled tile loops costs the compiler tens of minutes */
+template <int NB, bool DESC>
+struct PSchedTab {
+    static constexpr int NT = NB * (NB + 1);
+    int mb[NT], kb[NT], last[NT];
+    constexpr PSchedTab() : mb{}, kb{}, last{} {
+        for (int t = 0; t < NT; ++t) {
+            mb[t] = psched(NB, t, DESC, 0);
+            kb[t] = psched(NB, t, DESC, 1);
+            last[t] = psched(NB, t, DESC, 2);
+        }
+    }
+};
+
 constexpr int kPZ = 36;        /* row pitch (doubles) of the Z/C tile: conflict-free B-fragment loads */
 constexpr int kPW = 40;        /* row pitch of the W staging tile: conflict-free 128-bit stores       */
 
@@ -284,6 +299,13 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
     constexpr int NPB = (CV == 2) ? 4 : 2;     /* normals per Philox block (contract v1 / v2) */
     constexpr int NPH = D / (2 * NPB);         /* Philox blocks per half-chain lane */
     constexpr int HR = D / 2;                  /* rows of Z / X owned by a half      */
+    /* tile schedule of the two mat-vecs: psched() folded by the optimiser up to D = 32 (the kernels bench.py times keep the
+     * code they were tuned with), compile-time tables above */
+    constexpr bool WIDE = D > 32;
+    constexpr PSchedTab<(WIDE ? NB : 1), true> pst1{};
+    constexpr PSchedTab<(WIDE ? NB : 1), false> pst2{};
+#define PS1(t_, w_) (WIDE ? ((w_) == 0 ? pst1.mb[(WIDE ? (t_) : 0)] : (w_) == 1 ? pst1.kb[(WIDE ? (t_) : 0)] : pst1.last[(WIDE ? (t_) : 0)]) : psched(NB, (t_), true, (w_)))
+#define PS2(t_, w_) (WIDE ? ((w_) == 0 ? pst2.mb[(WIDE ? (t_) : 0)] : (w_) == 1 ? pst2.kb[(WIDE ? (t_) : 0)] : pst2.last[(WIDE ? (t_) : 0)]) : psched(NB, (t_), false, (w_)))
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -393,14 +415,14 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
             double acc[NB][2][2];
 #pragma unroll
             for (int j = 0; j < P && j < NT; ++j) {
-                const int mbj = psched(NB, j, true, 0), kbj = psched(NB, j, true, 1);
+                const int mbj = PS1(j, 0), kbj = PS1(j, 1);
                 aq[j] = ld_a_frag(a.Lf + (mbj * (mbj + 1) + kbj) * 32 + lane);
             }
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
-                const int mb = psched(NB, t, true, 0), kb = psched(NB, t, true, 1);
+                const int mb = PS1(t, 0), kb = PS1(t, 1);
                 if (t + P < NT) {
-                    const int mbj = psched(NB, t + P, true, 0), kbj = psched(NB, t + P, true, 1);
+                    const int mbj = PS1(t + P, 0), kbj = PS1(t + P, 1);
                     aq[t + P] = ld_a_frag(a.Lf + (mbj * (mbj + 1) + kbj) * 32 + lane);
                 }
                 if (kb == 0) { acc[mb][0][0] = 0.0; acc[mb][0][1] = 0.0; acc[mb][1][0] = 0.0; acc[mb][1][1] = 0.0; }
@@ -409,7 +431,7 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
                     const double bf = ZC[(4 * kb + fc) * kPZ16 + 8 * nb + fr];
                     dmma(acc[mb][nb][0], acc[mb][nb][1], aq[t], bf);
                 }
-                if (psched(NB, t, true, 2) == 1) {
+                if (PS1(t, 2) == 1) {
                     /* both row blocks of the pair have read Z: their rows of C may now replace it.  The reads feed
                      * mma.sync.aligned instructions that every lane has executed before it gets here, so they have
                      * completed warp-wide; the explicit warp barrier states that ordering for the memory model and for
@@ -450,14 +472,14 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
             double acc[NB][2][2];
 #pragma unroll
             for (int j = 0; j < P && j < NT; ++j) {
-                const int mbj = psched(NB, j, false, 0), kbj = psched(NB, j, false, 1);
+                const int mbj = PS2(j, 0), kbj = PS2(j, 1);
                 aq[j] = ld_a_frag(a.Uf + (mbj * (mbj + 1) + kbj) * 32 + lane);
             }
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
-                const int mb = psched(NB, t, false, 0), kb = psched(NB, t, false, 1);
+                const int mb = PS2(t, 0), kb = PS2(t, 1);
                 if (t + P < NT) {
-                    const int mbj = psched(NB, t + P, false, 0), kbj = psched(NB, t + P, false, 1);
+                    const int mbj = PS2(t + P, 0), kbj = PS2(t + P, 1);
                     aq[t + P] = ld_a_frag(a.Uf + (mbj * (mbj + 1) + kbj) * 32 + lane);
                 }
                 if (kb == 0) { acc[mb][0][0] = 0.0; acc[mb][0][1] = 0.0; acc[mb][1][0] = 0.0; acc[mb][1][1] = 0.0; }
@@ -469,7 +491,7 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
                     if (!MU_ZERO) bf = bf - muk;
                     dmma(acc[mb][nb][0], acc[mb][nb][1], aq[t], bf);
                 }
-                if (psched(NB, t, false, 2) == 1) {
+                if (PS2(t, 2) == 1) {
                     /* the pair is complete: hand its rows of W to the chain lanes in ascending row order */
                     const int pa = mb / 2;
 #pragma unroll
@@ -527,6 +549,9 @@ mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
         if (a.sv.acc_out) a.sv.acc_out[ch] = accepted;
     }
 }
+
+#undef PS1
+#undef PS2
 
 /* A fragments of a packed lower-triangular factor: frag[tile(mb,kb)][lane] = M[8mb + lane/4][4kb + lane%4] */
 /* dpad >= d: the factor padded with zero rows / columns to a multiple of 8 (PAD kernels) */

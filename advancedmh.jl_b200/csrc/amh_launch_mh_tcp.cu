@@ -3,8 +3,8 @@
  *
  * Why: the exact-dimension kernels cover d = 1..6, 8, 10, 12, 16, 20, 24, 32; every other dimension fell to the generic
  * per-thread kernel (run-time dimension, vectors in local memory), which is 4-100 x slower -- measured on 65 536 chains
- * (profiles/r2_c2_dims.txt): d = 7 -> 7.1e9 chain-steps/s next to 3.0e10 at d = 8, d = 14 -> 2.7e9 (16: 1.45e10),
- * d = 28 -> 8.4e8 (32: 6.3e9), d = 48 -> 1.5e8, d = 64 -> 4.6e7.  The tensor-core step does not care whether a row of
+ * (profiles/r2_c2_dims.txt, before -> after): d = 7 -> 7.1e9 chain-steps/s next to 3.0e10 at d = 8 (now 2.8e10), d = 14 -> 2.7e9 (now 1.5e10; 16: 1.45e10),
+ * d = 28 -> 8.4e8 (now 6.2e9; 32: 6.3e9), d = 48 -> 1.5e8 (now 2.5e9), d = 64 -> 4.6e7 (now 1.95e9).  The tensor-core step does not care whether a row of
  * L or U is zero, so the same kernel template runs these dimensions bit-exactly (see the PAD note at the kernel:
  * amh_launch_mh_tc.cu) -- contract v2 only.  A second translation unit so that the two halves compile in parallel. */
 #define AMH_MHTC_EXTRA_TU
@@ -18,11 +18,7 @@ bool mh_tc_padded_eligible(const amh_run& r) {
     const amh_sampler& s = *r.sampler;
     const int d = r.dim;
     if (r.cv != AMH_CONTRACT_V2 || r.target->kind != AMH_TARGET_MVNORMAL) return false;
-#ifdef AMH_TCP_WIDE
     if (d < 7 || d > 64) return false;
-#else
-    if (d < 7 || d > 32) return false;
-#endif
     switch (d) {          /* dimensions with an exact kernel of their own (K1T16 or the per-thread K1) */
     case 8: case 10: case 12: case 16: case 20: case 24: case 32: return false;
     }
@@ -106,12 +102,10 @@ int launch_mh_tc_padded(amh_run& r, int nsteps, const SaveArgs& sv) {
     case 16: return launch_padded_t<16, 28>(r, nsteps, sv);
     case 24: return launch_padded_t<24, 28>(r, nsteps, sv);
     case 32: return launch_padded_t<32, 28>(r, nsteps, sv);
-#ifdef AMH_TCP_WIDE
     case 40: return launch_padded_t<40, 24>(r, nsteps, sv);
     case 48: return launch_padded_t<48, 20>(r, nsteps, sv);
     case 56: return launch_padded_t<56, 16>(r, nsteps, sv);
     case 64: return launch_padded_t<64, 16>(r, nsteps, sv);
-#endif
     }
     return fail(AMH_ERR_INVALID, "padded tensor-core MH path: unsupported dimension");
 }
