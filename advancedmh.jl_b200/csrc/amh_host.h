@@ -134,6 +134,7 @@ void dfree(amh_ctx* ctx, void* p);
 
 /* per-sampler launchers; each enqueues kernels on r.ctx->stream and bumps r.launches */
 int launch_mh(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
+int launch_mh_more_dims(amh_run& r, int nsteps, const amhd::SaveArgs& sv, bool& taken);   /* amh_launch_mh_dims.cu */
 /* K1C: arrays of univariate proposal laws / arrays of proposals (amh_launch_mh_comp.cu) */
 int launch_mh_comp(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 bool mh_tc_eligible(const amh_run& r);        /* K1T: both mat-vecs on the FP64 tensor cores */
@@ -142,6 +143,7 @@ int launch_mh_tc(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 bool mh_tc_padded_eligible(const amh_run& r);
 int launch_mh_tc_padded(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_mala(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
+int launch_mala_more_dims(amh_run& r, int nsteps, const amhd::SaveArgs& sv, bool& taken);   /* amh_launch_mala_dims.cu */
 /* K3T: the same on the tcgen05 tensor cores as split-bf16 GEMMs, opt-in (amh_launch_mala_tensor.cu) */
 bool mala_tensor_eligible(const amh_run& r);
 int launch_mala_tensor(amh_run& r, int nsteps, const amhd::SaveArgs& sv);

@@ -146,8 +146,14 @@ int launch_mala_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     return AMH_OK;
 }
 
+#ifndef AMH_MALA_EXTRA_TU
 template <class T>
 int launch_mala_dim(amh_run& r, int nsteps, const SaveArgs& sv) {
+    {   /* the second translation unit's exact dimensions (amh_launch_mala_dims.cu) */
+        bool taken = false;
+        const int rc = launch_mala_more_dims(r, nsteps, sv, taken);
+        if (taken) return rc;
+    }
     switch (r.dim) {          /* exact-dimension instantiations; everything else is generic */
     case 2: return launch_mala_t<2, T>(r, nsteps, sv);
     case 3: return launch_mala_t<3, T>(r, nsteps, sv);
@@ -176,5 +182,6 @@ int launch_mala(amh_run& r, int nsteps, const SaveArgs& sv) {
     }
     return fail(AMH_ERR_INVALID, "The gradient of the log density function is not defined");
 }
+#endif  /* AMH_MALA_EXTRA_TU */
 
 }  // namespace amhh

@@ -60,9 +60,15 @@ static bool needs_generic(const amh_run& r) {
     return false;
 }
 
+#ifndef AMH_MH_EXTRA_TU
 template <class T>
 int launch_mh_full(amh_run& r, int nsteps, const SaveArgs& sv) {
     if (needs_generic(r)) return launch_mh_t<0, T>(r, nsteps, sv);
+    {   /* the second translation unit's exact dimensions (amh_launch_mh_dims.cu) */
+        bool taken = false;
+        const int rc = launch_mh_more_dims(r, nsteps, sv, taken);
+        if (taken) return rc;
+    }
     switch (r.dim) {          /* exact-dimension instantiations; everything else is generic */
     case 1: return launch_mh_t<1, T>(r, nsteps, sv);
     case 2: return launch_mh_t<2, T>(r, nsteps, sv);
@@ -168,5 +174,7 @@ int launch_init(amh_run& r, int mode) {
     }
     return fail(AMH_ERR_INVALID, "unknown target kind");
 }
+
+#endif  /* AMH_MH_EXTRA_TU */
 
 }  // namespace amhh

@@ -131,6 +131,32 @@ def test_other_targets_bit_exact(amh, cuda, oracle, kind):
     _assert_same_state(rg, ro)
 
 
+@pytest.mark.parametrize("kind,d,cov", [("gaussprec", 7, "full"), ("rosenbrock", 9, "scalar"), ("gaussprec", 11, "diag"),
+                                        ("rosenbrock", 14, "full"), ("gaussprec", 18, "scalar"), ("gaussprec", 28, "full"),
+                                        ("rosenbrock", 28, "diag"), ("gaussprec", 13, "full")])
+def test_rwmh_other_targets_more_exact_dimensions(amh, cuda, oracle, kind, d, cov):
+    """amh_launch_mh_dims.cu: the per-thread MH kernel instantiated for d = 7, 9, 11, 14, 18, 28 (d = 13 stays generic)"""
+    Sigma = make_spd(d, seed=d, lo=0.5, hi=4.0)
+    target = amh.RosenbrockTarget(d) if kind == "rosenbrock" else amh.GaussianPrecisionTarget(np.linalg.inv(Sigma))
+    scale = 0.05 if kind == "rosenbrock" else 1.0
+    if cov == "scalar":
+        prop = amh.MvNormal(np.zeros(d), (0.3 * scale) ** 2 * amh.I)
+    elif cov == "diag":
+        prop = [amh.Normal(0, scale * (0.2 + 0.01 * i)) for i in range(d)]
+    else:
+        prop = amh.MvNormal(np.zeros(d), scale * (2.38 ** 2 / d) * Sigma)
+    n = 700
+    rg, ro = _pair(amh, cuda, oracle, target, amh.RWMH(prop), n, _seeds(n, 300 + d))
+    _assert_same_state(rg, ro)
+    for k, spl_ in [(1, 1), (7, 3), (40, 0)]:
+        rg.steps(k, steps_per_launch=spl_)
+        ro.steps(k)
+        _assert_same_state(rg, ro)
+    og, ag, _ = rg.sample(4, 1, 3)
+    oo, ao, _ = ro.sample(4, 1, 3)
+    assert np.array_equal(og, oo) and np.array_equal(ag, ao)
+
+
 def test_sample_schedule_and_outputs_bit_exact(amh, cuda, oracle):
     d = 5
     Sigma = make_spd(d, seed=2, lo=0.5, hi=4.0)
@@ -176,14 +202,18 @@ def test_large_config2_shape_bit_exact_and_moments(amh, cuda, oracle):
 
 # ----------------------------------------------------------------------------- MALA (K3)
 @pytest.mark.parametrize("kind,d", [("gaussprec", 2), ("mvnormal", 5), ("mvnormal", 16), ("mvnormal", 24),
-                                    ("rosenbrock", 10), ("iid", 2), ("logistic", 7)])
+                                    ("rosenbrock", 10), ("iid", 2), ("logistic", 7),
+                                    # amh_launch_mala_dims.cu (exact) and two dimensions that stay generic
+                                    ("mvnormal", 6), ("mvnormal", 7), ("gaussprec", 9), ("mvnormal", 12), ("rosenbrock", 14),
+                                    ("mvnormal", 20), ("gaussprec", 24), ("mvnormal", 32), ("rosenbrock", 32), ("mvnormal", 11),
+                                    ("mvnormal", 40)])
 def test_mala_bit_exact(amh, cuda, oracle, kind, d):
     rng = np.random.default_rng(5)
     sigma2 = 0.05
     if kind == "gaussprec":
         # TheNormalLogDensity of test/runtests.jl:335-365
-        target = amh.GaussianPrecisionTarget(np.linalg.inv(np.array([[1.5, 0.35], [0.35, 1.0]])))
-        sigma2 = 0.5
+        target = amh.GaussianPrecisionTarget(np.linalg.inv(np.array([[1.5, 0.35], [0.35, 1.0]]) if d == 2 else make_spd(d, seed=d, lo=0.5, hi=4.0)))
+        sigma2 = 0.5 if d == 2 else 0.05
     elif kind == "mvnormal":
         target = amh.MvNormalTarget(np.linspace(-0.5, 0.5, d), make_spd(d, seed=d, lo=0.5, hi=4.0))
     elif kind == "rosenbrock":
