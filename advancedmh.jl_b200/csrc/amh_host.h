@@ -134,6 +134,7 @@ void dfree(amh_ctx* ctx, void* p);
 
 /* per-sampler launchers; each enqueues kernels on r.ctx->stream and bumps r.launches */
 int launch_mh(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
+int launch_mh_hast(amh_run& r, int nsteps, const amhd::SaveArgs& sv, bool& taken);        /* amh_launch_mh_hast.cu */
 int launch_mh_more_dims(amh_run& r, int nsteps, const amhd::SaveArgs& sv, bool& taken);   /* amh_launch_mh_dims.cu */
 /* K1C: arrays of univariate proposal laws / arrays of proposals (amh_launch_mh_comp.cu) */
 int launch_mh_comp(amh_run& r, int nsteps, const amhd::SaveArgs& sv);

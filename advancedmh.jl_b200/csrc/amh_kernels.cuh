@@ -34,7 +34,9 @@ struct MhArgs {
  * Hastings correction -> exponential draw -> accept/reject.  The current state
  * lives in shared memory ([i][thread], conflict free), the candidate in
  * registers. */
-template <int DMAX, class T, int BLOCK, int MINB>
+/* HAST1 (exact dimensions, amh_launch_mh_hast.cu): StaticProposal with issymmetric = false -- the Hastings term
+ * logq(state) - logq(candidate) with logq(state) cached per chain */
+template <int DMAX, class T, int BLOCK, int MINB, bool HAST1 = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
 mh_step_kernel(const __grid_constant__ MhArgs<DMAX> a,
                const __grid_constant__ typename T::template Params<DMAX> tp) {
@@ -94,6 +96,9 @@ mh_step_kernel(const __grid_constant__ MhArgs<DMAX> a,
                 }
                 logratio = logq<DMAX>(t1, d, a.prop) - logq<DMAX>(t2, d, a.prop);
             }
+        } else if constexpr (HAST1) {
+            lq_c = logq_fixed<DMAX>(z, a.prop);
+            logratio = lq - lq_c;
         }
         const double loga = (lp_c - lp) + logratio;
         if (-e < loga) {

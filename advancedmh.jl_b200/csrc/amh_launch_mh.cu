@@ -59,6 +59,12 @@ static bool needs_generic(const amh_run& r) {
     if (!s.d.symmetric && (s.d.kind == AMH_SAMPLER_STATIC || s.has_mean)) return true;
     return false;
 }
+/* StaticProposal with issymmetric = false (the reference's default for StaticMH): exact-dimension kernels with the
+ * Hastings term live in amh_launch_mh_hast.cu */
+static bool wants_hast1(const amh_run& r) {
+    const amh_sampler& s = *r.sampler;
+    return r.dim <= 32 && !s.d.symmetric && s.d.kind == AMH_SAMPLER_STATIC && !s.by_components();
+}
 
 #ifndef AMH_MH_EXTRA_TU
 template <class T>
@@ -94,6 +100,11 @@ int launch_mh_d2(amh_run& r, int nsteps, const SaveArgs& sv) {
 }
 
 int launch_mh(amh_run& r, int nsteps, const SaveArgs& sv) {
+    if (wants_hast1(r)) {
+        bool taken = false;
+        const int rc = launch_mh_hast(r, nsteps, sv, taken);
+        if (taken) return rc;
+    }
     if (r.mh_path != 1 && mh_tc_eligible(r)) return launch_mh_tc(r, nsteps, sv);
     if (r.mh_path != 1 && mh_tc_padded_eligible(r)) return launch_mh_tc_padded(r, nsteps, sv);
     if (r.dim > kGenericCap) return fail(AMH_ERR_UNSUPPORTED, "StaticMH/RWMH on the device supports dim <= 128");

@@ -83,6 +83,45 @@ def test_static_mh_bit_exact(amh, cuda, oracle, sym, cov):
         _assert_same_state(rg, ro)
 
 
+@pytest.mark.parametrize("kind,d,cov", [("mvnormal", 1, "scalar"), ("mvnormal", 2, "full"), ("mvnormal", 5, "diag"), ("mvnormal", 8, "full"),
+                                        ("gaussprec", 9, "full"), ("rosenbrock", 10, "scalar"), ("mvnormal", 14, "full"),
+                                        ("mvnormal", 16, "full"), ("gaussprec", 20, "diag"), ("mvnormal", 24, "full"),
+                                        ("rosenbrock", 28, "full"), ("mvnormal", 32, "full"), ("mvnormal", 13, "full"),
+                                        ("mvnormal", 40, "full")])
+def test_static_mh_default_asymmetric_exact_dimension_kernels(amh, cuda, oracle, kind, d, cov):
+    """`StaticMH(dist)` as the reference builds it (StaticProposal{false}: the Hastings term logq(state) - logq(cand) is
+    evaluated every step, mh-core.jl:119-123) on the exact-dimension kernels of amh_launch_mh_hast.cu; d = 13 and 40 stay
+    on the generic kernel.  States, cached logq (through the accept decisions), samples and a state round trip."""
+    Sigma = make_spd(d, seed=20 + d, lo=0.5, hi=2.0)
+    if kind == "mvnormal":
+        target = amh.MvNormalTarget(np.linspace(0.2, -0.1, d), Sigma)
+    elif kind == "gaussprec":
+        target = amh.GaussianPrecisionTarget(np.linalg.inv(Sigma))
+    else:
+        target = amh.RosenbrockTarget(d)
+    mean = np.linspace(0.1, -0.2, d) if kind != "rosenbrock" else np.ones(d)
+    if cov == "scalar":
+        dist = amh.MvNormal(mean, (0.3 if kind == "rosenbrock" else 2.0) * amh.I)
+    elif cov == "diag":
+        dist = [amh.Normal(m, 1.5) for m in mean]
+    else:
+        dist = amh.MvNormal(mean, (0.05 if kind == "rosenbrock" else 1.5) * Sigma)
+    spl = amh.StaticMH(dist)
+    n = 600
+    rg, ro = _pair(amh, cuda, oracle, target, spl, n, _seeds(n, 500 + d))
+    _assert_same_state(rg, ro)
+    for k, spl_ in [(1, 1), (9, 4), (40, 0)]:
+        rg.steps(k, steps_per_launch=spl_)
+        ro.steps(k)
+        _assert_same_state(rg, ro)
+    og, ag, _ = rg.sample(5, 2, 3)
+    oo, ao, _ = ro.sample(5, 2, 3)
+    assert np.array_equal(og, oo) and np.array_equal(ag, ao)
+    rg.set_state(rg.state()); ro.set_state(ro.state())        # logq(state) is recomputed on restore
+    rg.steps(11); ro.steps(11)
+    _assert_same_state(rg, ro)
+
+
 def test_rw_nonzero_mean_hastings_bit_exact(amh, cuda, oracle):
     d = 4
     Sigma = make_spd(d, seed=9, lo=0.5, hi=2.0)

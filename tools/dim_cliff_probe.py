@@ -29,6 +29,14 @@ if "rwgp" in which:
     for d in (5, 7, 8, 9, 12, 14, 16, 24, 28, 32):
         Sg = spd(d, 32, 1.0, 100.0)
         go("RWMH x GaussianPrecision", amh.GaussianPrecisionTarget(np.linalg.inv(Sg)), amh.RWMH(amh.MvNormal(np.zeros(d), (2.38 ** 2 / d) * Sg)), d, 65536, 200, 100)
+if "static" in which:
+    # StaticMH(MvNormal) as the reference constructs it: issymmetric = false, the Hastings term needs logq(state) and logq(cand)
+    for d in (2, 4, 8, 10, 16, 24, 32):
+        Sg = spd(d, 32, 1.0, 100.0)
+        go("StaticMH x MvNormal", amh.MvNormalTarget(None, Sg), amh.StaticMH(amh.MvNormal(np.zeros(d), 1.3 * Sg)), d, 65536, 200, 100)
+    for d in (2, 8, 16, 32):
+        Sg = spd(d, 32, 1.0, 100.0)
+        go("RWMH nonzero-mean proposal", amh.MvNormalTarget(None, Sg), amh.RWMH(amh.MvNormal(0.01 * np.ones(d), (2.38 ** 2 / d) * Sg)), d, 65536, 200, 100)
 if "mala" in which:
     for d in (4, 5, 6, 7, 8, 9, 10, 12, 14, 16, 20, 24, 32):
         Sg = spd(d, 32, 0.5, 2.0)
