@@ -478,7 +478,7 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
     const size_t nt = (size_t)d * (d + 1) / 2;
     int rc = AMH_OK;
     auto chk = [&](int c) { if (!rc) rc = c; };
-    r->x_rows = (d + 7) & ~7;               /* padding rows for the padded tensor-core MH kernels (amh_launch_mh_tcp.cu) */
+    r->x_rows = d <= 64 ? (d + 7) & ~7 : (d + 15) & ~15;   /* padding rows for the padded tensor-core MH kernels (amh_launch_mh_tcp.cu) */
     chk(dev_alloc(ctx, &r->X, (size_t)r->x_rows * np));
     chk(dev_alloc(ctx, &r->lp, np));
     chk(dev_alloc(ctx, &r->lq, np));

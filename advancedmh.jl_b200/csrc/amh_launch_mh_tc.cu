@@ -290,10 +290,10 @@ __host__ __device__ constexpr int tc16_smem_doubles_per_warp() { return D * kPZ1
  * lanes draw for padding rows come from blocks of the chain's stream outside this step's range; they are finite and only
  * ever multiply zeros.  D up to 64 (fewer warps per SM: the Z / C tile grows with D). */
 template <int D, int WARPS, bool MU_ZERO, bool IS_RW, bool COVD = false, int CV = 1, bool PAD = false>
-__global__ void __launch_bounds__(32 * WARPS, 28 / WARPS)
+__global__ void __launch_bounds__(32 * WARPS, (WARPS <= 7 ? 28 / WARPS : 1))
 mh_step_tc16_kernel(const __grid_constant__ MhTcArgs a) {
 
-    static_assert(D % 8 == 0 && D >= 8 && (D <= 32 || (PAD && D <= 64)), "row blocks of 8; D/4 (v1) or D/8 (v2) noise blocks per lane half");
+    static_assert(D % 8 == 0 && D >= 8 && (D <= 32 || (PAD && D <= 128)), "row blocks of 8; D/4 (v1) or D/8 (v2) noise blocks per lane half");
     static_assert(!PAD || CV == 2, "padded dimensions: contract v2 only");
     constexpr int NB = D / 8;
     constexpr int NPB = (CV == 2) ? 4 : 2;     /* normals per Philox block (contract v1 / v2) */

@@ -12,13 +12,14 @@
 
 namespace amhh {
 
-static int padded_dim(int d) { return (d + 7) & ~7; }
+/* multiples of 8 up to 64, of 16 above (fewer instantiations of the large kernels) */
+static int padded_dim(int d) { return d <= 64 ? (d + 7) & ~7 : (d + 15) & ~15; }
 
 bool mh_tc_padded_eligible(const amh_run& r) {
     const amh_sampler& s = *r.sampler;
     const int d = r.dim;
     if (r.cv != AMH_CONTRACT_V2 || r.target->kind != AMH_TARGET_MVNORMAL) return false;
-    if (d < 7 || d > 64) return false;
+    if (d < 7 || d > 128) return false;
     switch (d) {          /* dimensions with an exact kernel of their own (K1T16 or the per-thread K1) */
     case 8: case 10: case 12: case 16: case 20: case 24: case 32: return false;
     }
@@ -31,7 +32,9 @@ bool mh_tc_padded_eligible(const amh_run& r) {
     return !off;
 }
 
-template <int D, int W>
+/* FEW: only the general-mean variants are instantiated (a zero mean then costs a subtraction of 0 per operand -- the
+ * same bits -- instead of a kernel of its own; the kernels above 64 are large) */
+template <int D, int W, bool FEW = false>
 static int launch_padded_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     const amh_sampler& s = *r.sampler;
     const amh_target& t = *r.target;
@@ -57,7 +60,7 @@ static int launch_padded_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     a.sv = sv;
     a.nsteps = nsteps;
     a.is_rw = s.d.kind == AMH_SAMPLER_RW;
-    a.mu_zero = 1;
+    a.mu_zero = FEW ? 0 : 1;
     for (int i = 0; i < d; ++i)
         if (t.blob[1 + i] != 0.0) a.mu_zero = 0;
     a.step0 = (unsigned long long)r.step;
@@ -72,16 +75,21 @@ static int launch_padded_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     const bool covd = s.d.cov_kind != AMH_COV_FULL;
     const size_t smem = (size_t)W * tc16_smem_doubles_per_warp<D>() * sizeof(double);
     const unsigned grid = (unsigned)((r.n + 16 * W - 1) / (16 * W));
-    const void* key = (const void*)mh_step_tc16_kernel<D, W, true, true, false, 2, true>;
+    const void* key = (const void*)mh_step_tc16_kernel<D, W, false, true, false, 2, true>;
     if (!r.ctx->configured.count(key)) {
 #define AMH_TCP_ATTR(...) AMH_CUDA_TRY(cudaFuncSetAttribute(mh_step_tc16_kernel<D, W, __VA_ARGS__, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
-        AMH_TCP_ATTR(true, true, false); AMH_TCP_ATTR(false, true, false); AMH_TCP_ATTR(true, false, false); AMH_TCP_ATTR(false, false, false);
-        AMH_TCP_ATTR(true, true, true); AMH_TCP_ATTR(false, true, true); AMH_TCP_ATTR(true, false, true); AMH_TCP_ATTR(false, false, true);
+        if constexpr (!FEW) {
+            AMH_TCP_ATTR(true, true, false); AMH_TCP_ATTR(true, false, false); AMH_TCP_ATTR(true, true, true); AMH_TCP_ATTR(true, false, true);
+        }
+        AMH_TCP_ATTR(false, true, false); AMH_TCP_ATTR(false, false, false); AMH_TCP_ATTR(false, true, true); AMH_TCP_ATTR(false, false, true);
 #undef AMH_TCP_ATTR
         r.ctx->configured.insert(key);
     }
 #define AMH_TCP_GO(...) mh_step_tc16_kernel<D, W, __VA_ARGS__, 2, true><<<grid, 32 * W, smem, r.ctx->stream>>>(a)
-    if (covd) {
+    if constexpr (FEW) {
+        if (covd) { if (a.is_rw) AMH_TCP_GO(false, true, true); else AMH_TCP_GO(false, false, true); }
+        else { if (a.is_rw) AMH_TCP_GO(false, true, false); else AMH_TCP_GO(false, false, false); }
+    } else if (covd) {
         if (a.is_rw) { if (a.mu_zero) AMH_TCP_GO(true, true, true); else AMH_TCP_GO(false, true, true); }
         else { if (a.mu_zero) AMH_TCP_GO(true, false, true); else AMH_TCP_GO(false, false, true); }
     } else {
@@ -106,6 +114,10 @@ int launch_mh_tc_padded(amh_run& r, int nsteps, const SaveArgs& sv) {
     case 48: return launch_padded_t<48, 20>(r, nsteps, sv);
     case 56: return launch_padded_t<56, 16>(r, nsteps, sv);
     case 64: return launch_padded_t<64, 16>(r, nsteps, sv);
+    case 80: return launch_padded_t<80, 14, true>(r, nsteps, sv);
+    case 96: return launch_padded_t<96, 12, true>(r, nsteps, sv);
+    case 112: return launch_padded_t<112, 10, true>(r, nsteps, sv);
+    case 128: return launch_padded_t<128, 10, true>(r, nsteps, sv);
     }
     return fail(AMH_ERR_INVALID, "padded tensor-core MH path: unsupported dimension");
 }

@@ -37,7 +37,8 @@ def _seeds(n, s=0):
                                    (7, "full"), (9, "full"), (11, "diag"), (14, "full"), (15, "scalar"), (17, "full"), (18, "full"),
                                    (19, "diag"), (21, "full"), (23, "full"), (25, "full"), (27, "scalar"), (28, "full"), (29, "full"),
                                    (31, "full"), (31, "diag"), (33, "full"), (37, "scalar"), (47, "diag"), (48, "full"), (50, "full"),
-                                   (56, "full"), (63, "full"), (64, "full"), (64, "scalar"), (65, "full")])
+                                   (56, "full"), (63, "full"), (64, "full"), (64, "scalar"), (65, "full"), (72, "scalar"), (77, "full"), (80, "full"), (90, "full"),
+                                   (100, "full"), (112, "scalar"), (127, "full"), (128, "full")])
 def test_rwmh_mvnormal_bit_exact(amh, cuda, oracle, d, cov):
     Sigma = make_spd(d, seed=d)
     target = amh.MvNormalTarget(np.linspace(-1, 1, d), Sigma)
@@ -382,7 +383,8 @@ def test_stretch_sample_bit_exact(amh, cuda, oracle):
     assert np.array_equal(sg["mean"], so["mean"])
 
 
-@pytest.mark.parametrize("d,zero_mean", [(7, True), (13, False), (22, True), (30, False), (41, True), (60, False)])
+@pytest.mark.parametrize("d,zero_mean", [(7, True), (13, False), (22, True), (30, False), (41, True), (60, False), (70, True),
+                                         (101, False)])
 def test_padded_tensor_core_path_static_symmetric_sample_and_resume(amh, cuda, oracle, d, zero_mean):
     """the padded K1T16 kernels (amh_launch_mh_tcp.cu): symmetric StaticProposal and RWMH through the sample schedule (the
     save epilogue must skip the padding rows), summaries, zero / non-zero target mean, 1 001 chains (a ragged last warp),
