@@ -480,6 +480,29 @@ def main():
                     dist.all_reduce(tm, op=dist.ReduceOp.MIN)
                     rec["tensor_bf16x2"]["value"] = float(tm.item()) * world
             configs[name] = rec
+        # config 2 in the reference's default output mode: EVERY step is a sample (thinning = 1), i.e. one launch per MCMC
+        # step with the save epilogue (device ring), and in between: 16 steps per launch.  Per rank; wall clock around the
+        # launches + sync beside the event-timed kernel durations shows what the launch cadence costs.
+        barrier()
+        c2s = {"workload": f"C2 with one launch per MCMC step / 16 steps per launch ({n} chains per GPU, d = {d})"}
+        for k_per in (1, 16):
+            nst = 256
+            run.steps(nst, steps_per_launch=k_per)
+            run.sync()
+            run.kernel_time_ms(reset=True)
+            t0 = time.perf_counter()
+            run.steps(nst, steps_per_launch=k_per)
+            run.sync()
+            wall = (time.perf_counter() - t0) * 1e3
+            kms, knl = run.kernel_time_ms(reset=True)
+            c2s[f"steps_per_launch_{k_per}"] = {
+                "value": float(n) * nst / (wall * 1e-3) * world, "unit": UNIT, "us_per_mcmc_step_wall": wall * 1e3 / nst,
+                "us_per_mcmc_step_kernels": kms * 1e3 / nst, "launches": int(knl),
+                "frac": B * float(n) * nst / (wall * 1e-3) / 1e9 / peak}
+        c2s["note"] = ("not CUDA-graphed: the launches are already back to back on one stream (wall ~ sum of the kernel durations); what a 1-step "
+                       "launch costs is the kernel's own prologue / epilogue (seeds, lp, counters, the state round trip through L2) and the "
+                       "end-of-launch tail of a single-wave kernel, which a graph does not remove")
+        configs["c2_launch_cadence"] = c2s
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
