@@ -142,6 +142,7 @@ bool mh_tc_eligible(const amh_run& r);        /* K1T: both mat-vecs on the FP64 
 int launch_mh_tc(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 /* the same kernels for the dimensions in between, padded to a multiple of 8, d <= 64 (amh_launch_mh_tcp.cu) */
 bool mh_tc_padded_eligible(const amh_run& r);
+bool mh_tc_small_eligible(const amh_run& r);     /* few chains: the 4-warp CTA shape, served by launch_mh_tc_padded too */
 int launch_mh_tc_padded(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_mala(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_mala_more_dims(amh_run& r, int nsteps, const amhd::SaveArgs& sv, bool& taken);   /* amh_launch_mala_dims.cu */

@@ -34,6 +34,12 @@ bool mh_tc_padded_eligible(const amh_run& r) {
 
 /* FEW: only the general-mean variants are instantiated (a zero mean then costs a subtraction of 0 per operand -- the
  * same bits -- instead of a kernel of its own; the kernels above 64 are large) */
+/* Below this many chains the 4-warp CTA shape (64 chains per CTA, up to seven CTAs per SM) beats one 28-warp CTA per SM:
+ * 448 chains per CTA leave most SMs idle when there are few chains, and a lone CTA is latency-bound at ~6.6 us per step
+ * whatever its size.  Measured at d = 32 (profiles/r2_c2_nchains.txt): 1 024 chains 8.8e7 -> 2.5e8, 4 096 3.5e8 -> 1.0e9,
+ * 16 384 1.4e9 -> 2.7e9, 32 768 2.8e9 -> 4.2e9 chain-steps/s; at 65 536 the 28-warp CTA wins. */
+constexpr long long kSmallRunChains = 49152;
+
 template <int D, int W, bool FEW = false>
 static int launch_padded_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     const amh_sampler& s = *r.sampler;
@@ -83,6 +89,15 @@ static int launch_padded_t(amh_run& r, int nsteps, const SaveArgs& sv) {
         }
         AMH_TCP_ATTR(false, true, false); AMH_TCP_ATTR(false, false, false); AMH_TCP_ATTR(false, true, true); AMH_TCP_ATTR(false, false, true);
 #undef AMH_TCP_ATTR
+        if constexpr (W <= 7) {
+            /* shared memory actually needed by the 28 / W resident CTAs; the rest of the 256 KB stays L1 for the L / U fragments */
+            const int need_kb = (int)(((28 / W) * (smem + 1024) + 1023) / 1024);
+            const int carve = std::min(100, (need_kb * 100 + 227) / 228 + 1);
+#define AMH_TCP_CARVE(...) AMH_CUDA_TRY(cudaFuncSetAttribute(mh_step_tc16_kernel<D, W, __VA_ARGS__, 2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve))
+            AMH_TCP_CARVE(true, true, false); AMH_TCP_CARVE(true, false, false); AMH_TCP_CARVE(true, true, true); AMH_TCP_CARVE(true, false, true);
+            AMH_TCP_CARVE(false, true, false); AMH_TCP_CARVE(false, false, false); AMH_TCP_CARVE(false, true, true); AMH_TCP_CARVE(false, false, true);
+#undef AMH_TCP_CARVE
+        }
         r.ctx->configured.insert(key);
     }
 #define AMH_TCP_GO(...) mh_step_tc16_kernel<D, W, __VA_ARGS__, 2, true><<<grid, 32 * W, smem, r.ctx->stream>>>(a)
@@ -103,8 +118,32 @@ static int launch_padded_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     return AMH_OK;
 }
 
+/* fewer chains than kSmallRunChains, d <= 32 (exact tensor-core dimensions included): the 4-warp CTA shape */
+bool mh_tc_small_eligible(const amh_run& r) {
+    const amh_sampler& s = *r.sampler;
+    const int d = r.dim;
+    if (r.cv != AMH_CONTRACT_V2 || r.target->kind != AMH_TARGET_MVNORMAL) return false;
+    if (r.n >= kSmallRunChains || d < 7 || d > 32) return false;
+    switch (d) {          /* the per-thread kernel K1 has these and spreads its 128-thread CTAs over the SMs already */
+    case 10: case 12: case 20: return false;
+    }
+    if (s.has_mean || s.by_components()) return false;
+    if (s.d.cov_kind != AMH_COV_FULL && s.d.cov_kind != AMH_COV_DIAG && s.d.cov_kind != AMH_COV_SCALAR) return false;
+    if (s.d.kind == AMH_SAMPLER_STATIC && !s.d.symmetric) return false;
+    if (r.pitch % 32 || r.mh_path == 2 || r.x_rows < padded_dim(d)) return false;
+    return std::getenv("AMH_TC_NO_SMALL") == nullptr;                         /* A/B / test switch: always the 28-warp CTA */
+}
+
 /* warps per CTA (one CTA per SM) by padded dimension: the per-warp Z / C tile is 160 D + 1 536 bytes */
 int launch_mh_tc_padded(amh_run& r, int nsteps, const SaveArgs& sv) {
+    if (mh_tc_small_eligible(r)) {
+        switch (padded_dim(r.dim)) {
+        case 8: return launch_padded_t<8, 4>(r, nsteps, sv);
+        case 16: return launch_padded_t<16, 4>(r, nsteps, sv);
+        case 24: return launch_padded_t<24, 4>(r, nsteps, sv);
+        case 32: return launch_padded_t<32, 4>(r, nsteps, sv);
+        }
+    }
     switch (padded_dim(r.dim)) {
     case 8: return launch_padded_t<8, 28>(r, nsteps, sv);
     case 16: return launch_padded_t<16, 28>(r, nsteps, sv);

@@ -406,6 +406,31 @@ def test_padded_tensor_core_path_static_symmetric_sample_and_resume(amh, cuda, o
         _assert_same_state(rg, ro)
 
 
+@pytest.mark.parametrize("d,cov", [(8, "full"), (13, "full"), (16, "diag"), (24, "full"), (29, "full"), (32, "full"), (32, "scalar")])
+def test_tensor_core_kernels_one_cta_per_sm_shape_with_few_chains(amh, cuda, oracle, monkeypatch, d, cov):
+    """runs with few chains take the 4-warp CTA shape (amh_launch_mh_tcp.cu, kSmallRunChains); AMH_TC_NO_SMALL keeps them on
+    the 28-warp kernels (exact and padded), which large runs use -- both must reproduce the oracle"""
+    monkeypatch.setenv("AMH_TC_NO_SMALL", "1")
+    Sigma = make_spd(d, seed=d)
+    target = amh.MvNormalTarget(np.linspace(-1, 1, d), Sigma)
+    if cov == "scalar":
+        prop = amh.MvNormal(np.zeros(d), 0.3 * amh.I)
+    elif cov == "diag":
+        prop = [amh.Normal(0, 0.2 + 0.02 * i) for i in range(d)]
+    else:
+        prop = amh.MvNormal(np.zeros(d), (2.38 ** 2 / d) * Sigma)
+    n = 1500
+    rg, ro = _pair(amh, cuda, oracle, target, amh.RWMH(prop), n, _seeds(n, 900 + d))
+    _assert_same_state(rg, ro)
+    for k, spl_ in [(1, 1), (7, 3), (30, 0)]:
+        rg.steps(k, steps_per_launch=spl_)
+        ro.steps(k)
+        _assert_same_state(rg, ro)
+    og, ag, _ = rg.sample(4, 1, 3)
+    oo, ao, _ = ro.sample(4, 1, 3)
+    assert np.array_equal(og, oo) and np.array_equal(ag, ao)
+
+
 def test_tensor_core_path_static_symmetric_and_sample(amh, cuda, oracle):
     """K1T (DMMA mat-vecs) with a symmetric StaticProposal and through the sample schedule / save epilogue"""
     d = 16
