@@ -153,6 +153,9 @@ void mala_tensor_release(amh_run& r);
 /* K3L: MALA on the many-row logistic target as two chained DMMA GEMMs (amh_launch_mala_logistic.cu) */
 bool mala_logistic_eligible(const amh_run& r);
 int launch_mala_logistic(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
+/* the same kernel without the gradient: RWMH with an isotropic / diagonal proposal on the many-row logistic target */
+bool mh_logistic_eligible(const amh_run& r);
+int launch_mh_logistic(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 int launch_ram(amh_run& r, int nsteps, bool warmup, const amhd::SaveArgs& sv);
 int launch_stretch(amh_run& r, int nsteps, const amhd::SaveArgs& sv);
 /* exact-dimension stretch kernels of the second translation unit (amh_launch_stretch_dims.cu); taken = false: not one of its dimensions */

@@ -38,6 +38,7 @@ struct MalaLArgs {
     double inv2tau2, invtau2;
     double* Xc;                /* [D][pitch] candidate             */
     double* Gc;                /* [D][pitch] gradient at candidate */
+    const double* dscale;      /* RW variant: [D] standard deviations of the isotropic / diagonal random-walk proposal */
 };
 
 __device__ __forceinline__ unsigned l_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -98,7 +99,11 @@ __device__ __forceinline__ void logistic_terms(double eta, double y, double& t, 
     r = y - sg;
 }
 
-template <int D>
+/* RW = true: the random-walk MH step (mh-core.jl:92-117) on the same target with an isotropic or diagonal zero-mean
+ * proposal -- the same kernel without the gradient: candidate = x + sigma_j z_j (the per-thread kernel's two roundings),
+ * GEMM1 + the log-likelihood terms only, Hastings term exactly 0.  RWMH on a logistic regression ran the generic
+ * per-thread kernel before: 4.6e5 chain-steps/s on config 4's model, 9 x SLOWER than MALA on it (profiles/r2_dim_cliffs.txt). */
+template <int D, bool RW = false>
 __global__ void __launch_bounds__(512)
 mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
     static_assert(D % 32 == 0 && D <= 128, "D/4 dims per lane part, D/8 noise blocks per part");
@@ -185,8 +190,12 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
                 const long long o = (long long)j * pitch + ch;
                 double c = 0.0;
                 if (active) {
-                    c = a.st.X[o] + (a.sigma * z[i] + a.drift * a.st.G[o]);
-                    a.Xc[o] = c;
+                    if constexpr (RW) {
+                        c = a.st.X[o] + __ldg(a.dscale + j) * z[i];
+                    } else {
+                        c = a.st.X[o] + (a.sigma * z[i] + a.drift * a.st.G[o]);
+                        a.Xc[o] = c;
+                    }
                 }
                 Bs[j * kLPB + cl] = c;
             }
@@ -223,6 +232,7 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
                 logistic_terms(e11, y1, t11, r11);
                 if (row0 < a.nrows) { ll0 = ll0 + t00; ll1 = ll1 + t01; }
                 if (row0 + 8 < a.nrows) { ll0 = ll0 + t10; ll1 = ll1 + t11; }
+                if constexpr (!RW) {
                 *reinterpret_cast<double2*>(Rs + fr * kLPR + 2 * fc) = make_double2(r00, r01);
                 *reinterpret_cast<double2*>(Rs + (8 + fr) * kLPR + 2 * fc) = make_double2(r10, r11);
                 __syncwarp();
@@ -241,6 +251,7 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
                     l_dmma(gg[m][0], gg[m][1], a2, rb2);
                     l_dmma(gg[m][0], gg[m][1], a3, rb3);
                 }
+                }
             }
             __syncwarp();
             if (lane == 0) { l_mbar_arrive(empty + st0); l_mbar_arrive(empty + st1); }
@@ -252,7 +263,7 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
             ll1 = ll1 + __shfl_xor_sync(0xffffffffu, ll1, m);
         }
         /* gradient at the candidate in fragment layout: features 8m+fr, chains cbase + 2fc + {0,1} */
-        if (warp_active) {
+        if (!RW && warp_active) {
 #pragma unroll
             for (int m = 0; m < MT2; ++m) {
                 const int j = 8 * m + fr;
@@ -269,6 +280,12 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
         const double ll = (cl & 1) ? llsel1 : llsel0;
         double q = 0.0, A = 0.0, Bq = 0.0;
         if (active) {
+            if constexpr (RW) {
+                for (int j = 0; j < D; ++j) {
+                    const double c = Bs[j * kLPB + cl];
+                    q = (j == 0) ? c * c : fma(c, c, q);
+                }
+            } else {
             for (int j = 0; j < D; ++j) {
                 const long long o = (long long)j * pitch + ch;
                 const double c = Bs[j * kLPB + cl];
@@ -279,9 +296,10 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
                 A = (j == 0) ? da * da : fma(da, da, A);
                 Bq = (j == 0) ? db * db : fma(db, db, Bq);
             }
+            }
         }
         const double lp_c = ll - q * a.inv2tau2;
-        const double logratio = (-0.5 * (A / a.sigma2)) - (-0.5 * (Bq / a.sigma2));
+        const double logratio = RW ? 0.0 : (-0.5 * (A / a.sigma2)) - (-0.5 * (Bq / a.sigma2));
         const double loga = (lp_c - lp) + logratio;
         if (active && -e < loga) {                                   /* MALA.jl:86 */
 #pragma unroll 4
@@ -289,7 +307,7 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
                 const int j = 2 * NPP * part + i;
                 const long long o = (long long)j * pitch + ch;
                 a.st.X[o] = Bs[j * kLPB + cl];
-                a.st.G[o] = __ldcg(a.Gc + o);
+                if constexpr (!RW) a.st.G[o] = __ldcg(a.Gc + o);
             }
             lp = lp_c;
             accepted = 1;
@@ -327,7 +345,7 @@ bool mala_logistic_eligible(const amh_run& r) {
            r.target->ndata >= 64 && r.pitch % 32 == 0;
 }
 
-template <int D>
+template <int D, bool RW = false>
 static int launch_mala_logistic_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     const amh_sampler& s = *r.sampler;
     const amh_target& t = *r.target;
@@ -335,14 +353,21 @@ static int launch_mala_logistic_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     const int nblk = (int)((n + 15) / 16) * 2;          /* 8-row blocks, consumed in pairs */
     const size_t np = (size_t)r.pitch;
     if (!r.scratch) {
-        /* [Xpad | ypad | Xc | Gc] */
+        /* MALA: [Xpad | ypad | Xc | Gc]    RW: [Xpad | ypad | proposal scales] */
         const size_t nx = (size_t)nblk * 8 * D, ny = (size_t)nblk * 8;
-        const int rca = dmalloc(r.ctx, &r.scratch, sizeof(double) * (nx + ny + 2 * (size_t)D * np));
+        const size_t tail = RW ? (size_t)D : 2 * (size_t)D * np;
+        const int rca = dmalloc(r.ctx, &r.scratch, sizeof(double) * (nx + ny + tail));
         if (rca) return rca;
         double* base = (double*)r.scratch;
-        AMH_CUDA_TRY(cudaMemsetAsync(base, 0, sizeof(double) * (nx + ny + 2 * (size_t)D * np), r.ctx->stream));
+        AMH_CUDA_TRY(cudaMemsetAsync(base, 0, sizeof(double) * (nx + ny + tail), r.ctx->stream));
         AMH_CUDA_TRY(cudaMemcpyAsync(base, t.dblob + 1, sizeof(double) * (size_t)n * D, cudaMemcpyDeviceToDevice, r.ctx->stream));
         AMH_CUDA_TRY(cudaMemcpyAsync(base + nx, t.dblob + 1 + (size_t)n * D, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, r.ctx->stream));
+        if (RW) {
+            std::vector<double> sc(D);
+            for (int i = 0; i < D; ++i) sc[i] = s.d.cov_kind == AMH_COV_DIAG ? s.scale[i] : s.scale[0];
+            AMH_CUDA_TRY(cudaMemcpyAsync(base + nx + ny, sc.data(), sizeof(double) * D, cudaMemcpyHostToDevice, r.ctx->stream));
+            AMH_CUDA_TRY(sync_stream(r.ctx, r.ctx->stream));        /* `sc` is a stack temporary */
+        }
     }
     MalaLArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -356,6 +381,7 @@ static int launch_mala_logistic_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     a.yp = base + (size_t)nblk * 8 * D;
     a.Xc = base + (size_t)nblk * 8 * D + (size_t)nblk * 8;
     a.Gc = a.Xc + (size_t)D * np;
+    if (RW) { a.dscale = a.Xc; a.Xc = nullptr; a.Gc = nullptr; }
     a.nrows = n;
     a.nblk = nblk;
     a.inv2tau2 = t.inv2tau2; a.invtau2 = t.invtau2;
@@ -378,7 +404,7 @@ static int launch_mala_logistic_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     while (nst + 2 <= 16 && l_smem_bytes<D>(warps, nst + 2) + 1024 <= 227 * 1024) nst += 2;
     a.nst = nst;
     const size_t smem = l_smem_bytes<D>(warps, nst);
-    auto kern = mala_logistic_kernel<D>;
+    auto kern = mala_logistic_kernel<D, RW>;
     AMH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((groups + warps - 1) / warps);
     kern<<<grid, 32 * (warps + 1), smem, r.ctx->stream>>>(a);
@@ -395,6 +421,25 @@ int launch_mala_logistic(amh_run& r, int nsteps, const SaveArgs& sv) {
     case 128: return launch_mala_logistic_t<128>(r, nsteps, sv);
     }
     return fail(AMH_ERR_INVALID, "tiled logistic MALA: unsupported dimension");
+}
+
+/* RWMH on the many-row logistic target with an isotropic / diagonal zero-mean proposal: the RW variant of the kernel */
+bool mh_logistic_eligible(const amh_run& r) {
+    const amh_sampler& s = *r.sampler;
+    const int d = r.dim;
+    if (s.d.kind != AMH_SAMPLER_RW || r.target->kind != AMH_TARGET_LOGISTIC) return false;
+    if (!(d == 32 || d == 64 || d == 128) || r.target->ndata < 64 || r.pitch % 32) return false;
+    if (s.has_mean || s.by_components()) return false;
+    if (s.d.cov_kind != AMH_COV_DIAG && s.d.cov_kind != AMH_COV_SCALAR) return false;
+    return std::getenv("AMH_MH_NO_LOGISTIC") == nullptr;             /* A/B switch: the generic per-thread kernel */
+}
+int launch_mh_logistic(amh_run& r, int nsteps, const SaveArgs& sv) {
+    switch (r.dim) {
+    case 32: return launch_mala_logistic_t<32, true>(r, nsteps, sv);
+    case 64: return launch_mala_logistic_t<64, true>(r, nsteps, sv);
+    case 128: return launch_mala_logistic_t<128, true>(r, nsteps, sv);
+    }
+    return fail(AMH_ERR_INVALID, "tiled logistic RWMH: unsupported dimension");
 }
 
 }  // namespace amhh

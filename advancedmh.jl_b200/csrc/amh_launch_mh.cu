@@ -105,6 +105,7 @@ int launch_mh(amh_run& r, int nsteps, const SaveArgs& sv) {
         const int rc = launch_mh_hast(r, nsteps, sv, taken);
         if (taken) return rc;
     }
+    if (r.mh_path != 1 && mh_logistic_eligible(r)) return launch_mh_logistic(r, nsteps, sv);
     if (r.mh_path != 1 && mh_tc_small_eligible(r)) return launch_mh_tc_padded(r, nsteps, sv);
     if (r.mh_path != 1 && mh_tc_eligible(r)) return launch_mh_tc(r, nsteps, sv);
     if (r.mh_path != 1 && mh_tc_padded_eligible(r)) return launch_mh_tc_padded(r, nsteps, sv);

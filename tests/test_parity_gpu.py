@@ -495,6 +495,38 @@ def test_mala_logistic_tiled_tensor_core_kernel_bit_exact(amh, cuda, oracle, d, 
     assert np.array_equal(og, oo) and np.array_equal(ag, ao)
 
 
+@pytest.mark.parametrize("d,rows,n,cov", [(32, 100, 50, "scalar"), (64, 64, 24, "diag"), (128, 203, 70, "scalar"), (128, 1000, 33, "diag"),
+                                          (32, 77, 40, "int")])
+def test_rwmh_logistic_tiled_tensor_core_kernel_bit_exact(amh, cuda, oracle, d, rows, n, cov):
+    """the RW variant of K3L (amh_launch_mala_logistic.cu, RW = true): RWMH with an isotropic / diagonal proposal on the
+    many-row logistic target -- GEMM1 and the log-likelihood terms on the FP64 tensor cores, no gradient -- against the
+    oracle's scalar row loop, incl. `RWMH(d::Int)`, ragged rows / chains, the sample schedule and a state round trip"""
+    rng = np.random.default_rng(1000 + d)
+    X = rng.normal(size=(rows, d)) / np.sqrt(d)
+    beta = rng.normal(size=d)
+    y = (rng.random(rows) < 1 / (1 + np.exp(-X @ beta))).astype(float)
+    target = amh.LogisticRegressionTarget(X, y, tau=5.0)
+    if cov == "scalar":
+        spl = amh.RWMH(amh.MvNormal(np.zeros(d), (0.08 ** 2) * amh.I))
+    elif cov == "diag":
+        spl = amh.RWMH([amh.Normal(0, 0.05 + 0.0005 * i) for i in range(d)])
+    else:
+        spl = amh.RWMH(d)                                       # MvNormal(Zeros(d), I): mh-core.jl:51
+    init = 0.1 * rng.normal(size=(d, n))
+    rg, ro = _pair(amh, cuda, oracle, target, spl, n, _seeds(n, 700 + d), init)
+    _assert_same_state(rg, ro)
+    for k, spl_ in [(1, 1), (5, 2), (12, 0)]:
+        rg.steps(k, steps_per_launch=spl_)
+        ro.steps(k)
+        _assert_same_state(rg, ro)
+    og, ag, sg = rg.sample(5, discard_initial=2, thinning=2)
+    oo, ao, so = ro.sample(5, discard_initial=2, thinning=2)
+    assert np.array_equal(og, oo) and np.array_equal(ag, ao)
+    rg.set_state(rg.state()); ro.set_state(ro.state())
+    rg.steps(7); ro.steps(7)
+    _assert_same_state(rg, ro)
+
+
 def test_sample_pipelined_copy_many_chunks_and_pinned_buffers(amh, cuda, oracle):
     """amh_run_sample drains the device sample ring through the copy stream in chunks (two buffers): force many
     chunks (N large, small slabs) and use caller-owned pinned buffers; results must equal the oracle's"""

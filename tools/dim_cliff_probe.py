@@ -37,6 +37,16 @@ if "static" in which:
     for d in (2, 8, 16, 32):
         Sg = spd(d, 32, 1.0, 100.0)
         go("RWMH nonzero-mean proposal", amh.MvNormalTarget(None, Sg), amh.RWMH(amh.MvNormal(0.01 * np.ones(d), (2.38 ** 2 / d) * Sg)), d, 65536, 200, 100)
+if "logistic" in which:
+    # RWMH / MALA / RAM on the logistic-regression target (BASELINE config 4's model): only MALA has a dedicated kernel (K3L)
+    for d, nrows, n in ((128, 10000, 16384), (32, 2000, 16384), (8, 500, 65536)):
+        rng = np.random.default_rng(128)
+        X = rng.normal(size=(nrows, d)) / np.sqrt(d)
+        y = (rng.random(nrows) < 1 / (1 + np.exp(-X @ rng.normal(size=d)))).astype(float)
+        t = amh.LogisticRegressionTarget(X, y, tau=10.0)
+        go(f"RWMH x logistic {nrows} rows", t, amh.RWMH(amh.MvNormal(np.zeros(d), (0.05 ** 2) * amh.I)), d, n, 8, 4, init=np.zeros((d, n)))
+        sg2 = 0.002
+        go(f"MALA x logistic {nrows} rows", t, amh.MALA(lambda g: amh.MvNormal(0.5 * sg2 * g, sg2 * amh.I)), d, n, 8, 4, init=np.zeros((d, n)))
 if "mala" in which:
     for d in (4, 5, 6, 7, 8, 9, 10, 12, 14, 16, 20, 24, 32):
         Sg = spd(d, 32, 0.5, 2.0)
