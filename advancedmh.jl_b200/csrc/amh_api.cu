@@ -479,6 +479,8 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
     int rc = AMH_OK;
     auto chk = [&](int c) { if (!rc) rc = c; };
     r->x_rows = d <= 64 ? (d + 7) & ~7 : (d + 15) & ~15;   /* padding rows for the padded tensor-core MH kernels (amh_launch_mh_tcp.cu) */
+    if (target->kind == AMH_TARGET_LOGISTIC && d <= 128)     /* ... and of the tiled logistic kernels: features padded to 32 / 64 / 128 */
+        r->x_rows = d <= 32 ? 32 : d <= 64 ? 64 : 128;
     chk(dev_alloc(ctx, &r->X, (size_t)r->x_rows * np));
     chk(dev_alloc(ctx, &r->lp, np));
     chk(dev_alloc(ctx, &r->lq, np));
@@ -488,7 +490,7 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
     chk(dev_alloc(ctx, &r->seeds, (size_t)nseeds));
     chk(dev_alloc(ctx, &r->sum, (size_t)d * np));
     chk(dev_alloc(ctx, &r->sumsq, (size_t)d * np));
-    if (kind == AMH_SAMPLER_MALA) chk(dev_alloc(ctx, &r->G, (size_t)d * np));
+    if (kind == AMH_SAMPLER_MALA) chk(dev_alloc(ctx, &r->G, (size_t)r->x_rows * np));
     if (kind == AMH_SAMPLER_STRETCH) {
         chk(dev_alloc(ctx, &r->X2, (size_t)d * np));
         chk(dev_alloc(ctx, &r->lp2, np));
@@ -514,6 +516,7 @@ int32_t amh_run_create(amh_ctx* ctx, amh_target* target, amh_sampler* sampler, i
     cudaStream_t st = ctx->stream;
     auto cu = [&](cudaError_t e, const char* w) { if (!rc && e != cudaSuccess) rc = cuda_fail(e, w); };
     cu(cudaMemsetAsync(r->X, 0, sizeof(double) * r->x_rows * np, st), "memset X");
+    if (r->G) cu(cudaMemsetAsync(r->G, 0, sizeof(double) * r->x_rows * np, st), "memset G");      /* the padding rows must be 0 */
     cu(cudaMemsetAsync(r->lp, 0, sizeof(double) * np, st), "memset lp");
     cu(cudaMemsetAsync(r->lq, 0, sizeof(double) * np, st), "memset lq");
     cu(cudaMemsetAsync(r->acc, 0, np, st), "memset acc");

@@ -38,7 +38,11 @@ struct MalaLArgs {
     double inv2tau2, invtau2;
     double* Xc;                /* [D][pitch] candidate             */
     double* Gc;                /* [D][pitch] gradient at candidate */
-    const double* dscale;      /* RW variant: [D] standard deviations of the isotropic / diagonal random-walk proposal */
+    const double* dscale;      /* [D] per-coordinate noise scale: RW: the proposal's standard deviations; MALA: sigma; 0 in the padding */
+    /* the run's dimension d <= D (features d..D-1 are padding: zero columns of X, zero scale, zero state) and its noise
+     * blocks per step / the exponential's block within a step under the run's contract version */
+    int d_real;
+    unsigned long long blocks_per_step, exp_block;
 };
 
 __device__ __forceinline__ unsigned l_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -127,7 +131,6 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
     const bool warp_active = cbase < a.st.n;                        /* idle warps still take part in the ring */
     const long long ch = cbase + cl;
     const bool active = ch < a.st.n;
-    constexpr unsigned long long B = (unsigned long long)(D / 2 + 1);
     constexpr unsigned stage_bytes = (unsigned)(8 * D * sizeof(double) + 8 * sizeof(double));
 
     if (threadIdx.x == 0) {
@@ -167,21 +170,22 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
             if (a.st.cv == AMH_CONTRACT_V2) {
                 /* contract v2: four normals per block -> D/16 blocks per lane part, the exponential in block D/4 */
                 constexpr int NB2 = D / 16;
-                constexpr unsigned long long B2 = (unsigned long long)(D / 4 + 1);
+                const unsigned long long B2 = a.blocks_per_step;
                 const unsigned long long b0 = k * B2 + (unsigned long long)(NB2 * part);
                 if constexpr (NB2 > 4) {
                     noise_group<4, false, 2>(seed, b0, 0ull, z, e);
-                    noise_group<NB2 - 4, true, 2>(seed, b0 + 4, k * B2 + (unsigned long long)(D / 4), z + 16, e);
+                    noise_group<NB2 - 4, true, 2>(seed, b0 + 4, k * B2 + a.exp_block, z + 16, e);
                 } else {
-                    noise_group<NB2, true, 2>(seed, b0, k * B2 + (unsigned long long)(D / 4), z, e);
+                    noise_group<NB2, true, 2>(seed, b0, k * B2 + a.exp_block, z, e);
                 }
             } else {
-            const unsigned long long b0 = k * B + (unsigned long long)(NPP * part);
+            const unsigned long long Bv1 = a.blocks_per_step;
+            const unsigned long long b0 = k * Bv1 + (unsigned long long)(NPP * part);
             if constexpr (NPP > 8) {
                 noise_group<8, false>(seed, b0, 0ull, z, e);
-                noise_group<NPP - 8, true>(seed, b0 + 8, k * B + (unsigned long long)(D / 2), z + 16, e);
+                noise_group<NPP - 8, true>(seed, b0 + 8, k * Bv1 + a.exp_block, z + 16, e);
             } else {
-                noise_group<NPP, true>(seed, b0, k * B + (unsigned long long)(D / 2), z, e);
+                noise_group<NPP, true>(seed, b0, k * Bv1 + a.exp_block, z, e);
             }
             }
 #pragma unroll
@@ -190,10 +194,11 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
                 const long long o = (long long)j * pitch + ch;
                 double c = 0.0;
                 if (active) {
+                    /* the scale is 0 in the padding rows (and x, grad stay 0 there): c = 0 */
                     if constexpr (RW) {
                         c = a.st.X[o] + __ldg(a.dscale + j) * z[i];
                     } else {
-                        c = a.st.X[o] + (a.sigma * z[i] + a.drift * a.st.G[o]);
+                        c = a.st.X[o] + (__ldg(a.dscale + j) * z[i] + a.drift * a.st.G[o]);
                         a.Xc[o] = c;
                     }
                 }
@@ -322,6 +327,7 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
     if (a.sv.out || a.sv.sum) {
         for (int i = 0; i < 2 * NPP; ++i) {
             const int j = 2 * NPP * part + i;
+            if (j >= a.d_real) break;                                  /* padding rows are not part of the sample */
             const long long o = (long long)j * pitch + ch;
             const double v = a.st.X[o];
             if (a.sv.out) a.sv.out[(long long)j * a.sv.out_pitch + ch] = v;
@@ -334,15 +340,19 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
         a.st.lp[ch] = lp;
         a.st.nacc[ch] = a.st.nacc[ch] + (unsigned long long)nacc;
         a.st.acc[ch] = accepted;
-        if (a.sv.out) a.sv.out[(long long)D * a.sv.out_pitch + ch] = lp;
+        if (a.sv.out) a.sv.out[(long long)a.d_real * a.sv.out_pitch + ch] = lp;
         if (a.sv.acc_out) a.sv.acc_out[ch] = accepted;
     }
 }
 
+/* any dimension up to 128: the features are padded to 32 / 64 / 128 with zero columns of X (an exact no-op in every dot
+ * product), zero noise scale and zero state rows, and the noise blocks are indexed with the real dimension's count */
+static int logistic_padded_dim(int d) { return d <= 32 ? 32 : d <= 64 ? 64 : 128; }
 bool mala_logistic_eligible(const amh_run& r) {
     const int d = r.dim;
-    return r.sampler->d.kind == AMH_SAMPLER_MALA && r.target->kind == AMH_TARGET_LOGISTIC && (d == 32 || d == 64 || d == 128) &&
-           r.target->ndata >= 64 && r.pitch % 32 == 0;
+    return r.sampler->d.kind == AMH_SAMPLER_MALA && r.target->kind == AMH_TARGET_LOGISTIC && d >= 1 && d <= 128 &&
+           r.x_rows >= logistic_padded_dim(d) && r.target->ndata >= 64 && r.pitch % 32 == 0 &&
+           (d % 32 == 0 || std::getenv("AMH_LOGISTIC_NO_PAD") == nullptr);
 }
 
 template <int D, bool RW = false>
@@ -350,24 +360,24 @@ static int launch_mala_logistic_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     const amh_sampler& s = *r.sampler;
     const amh_target& t = *r.target;
     const long long n = t.ndata;
+    const int d = r.dim;                                /* <= D: features d..D-1 are padding */
     const int nblk = (int)((n + 15) / 16) * 2;          /* 8-row blocks, consumed in pairs */
     const size_t np = (size_t)r.pitch;
     if (!r.scratch) {
-        /* MALA: [Xpad | ypad | Xc | Gc]    RW: [Xpad | ypad | proposal scales] */
+        /* [Xpad | ypad | noise scales | MALA only: Xc | Gc] */
         const size_t nx = (size_t)nblk * 8 * D, ny = (size_t)nblk * 8;
-        const size_t tail = RW ? (size_t)D : 2 * (size_t)D * np;
+        const size_t tail = (size_t)D + (RW ? 0 : 2 * (size_t)D * np);
         const int rca = dmalloc(r.ctx, &r.scratch, sizeof(double) * (nx + ny + tail));
         if (rca) return rca;
         double* base = (double*)r.scratch;
         AMH_CUDA_TRY(cudaMemsetAsync(base, 0, sizeof(double) * (nx + ny + tail), r.ctx->stream));
-        AMH_CUDA_TRY(cudaMemcpyAsync(base, t.dblob + 1, sizeof(double) * (size_t)n * D, cudaMemcpyDeviceToDevice, r.ctx->stream));
-        AMH_CUDA_TRY(cudaMemcpyAsync(base + nx, t.dblob + 1 + (size_t)n * D, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, r.ctx->stream));
-        if (RW) {
-            std::vector<double> sc(D);
-            for (int i = 0; i < D; ++i) sc[i] = s.d.cov_kind == AMH_COV_DIAG ? s.scale[i] : s.scale[0];
-            AMH_CUDA_TRY(cudaMemcpyAsync(base + nx + ny, sc.data(), sizeof(double) * D, cudaMemcpyHostToDevice, r.ctx->stream));
-            AMH_CUDA_TRY(sync_stream(r.ctx, r.ctx->stream));        /* `sc` is a stack temporary */
-        }
+        AMH_CUDA_TRY(cudaMemcpy2DAsync(base, sizeof(double) * D, t.dblob + 1, sizeof(double) * d, sizeof(double) * d, (size_t)n,
+                                       cudaMemcpyDeviceToDevice, r.ctx->stream));
+        AMH_CUDA_TRY(cudaMemcpyAsync(base + nx, t.dblob + 1 + (size_t)n * d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, r.ctx->stream));
+        std::vector<double> sc(D, 0.0);
+        for (int i = 0; i < d; ++i) sc[i] = !RW ? s.mala_sigma : s.d.cov_kind == AMH_COV_DIAG ? s.scale[i] : s.scale[0];
+        AMH_CUDA_TRY(cudaMemcpyAsync(base + nx + ny, sc.data(), sizeof(double) * D, cudaMemcpyHostToDevice, r.ctx->stream));
+        AMH_CUDA_TRY(sync_stream(r.ctx, r.ctx->stream));        /* `sc` is a stack temporary */
     }
     MalaLArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -379,9 +389,12 @@ static int launch_mala_logistic_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     double* base = (double*)r.scratch;
     a.Xp = base;
     a.yp = base + (size_t)nblk * 8 * D;
-    a.Xc = base + (size_t)nblk * 8 * D + (size_t)nblk * 8;
-    a.Gc = a.Xc + (size_t)D * np;
-    if (RW) { a.dscale = a.Xc; a.Xc = nullptr; a.Gc = nullptr; }
+    a.dscale = base + (size_t)nblk * 8 * D + (size_t)nblk * 8;
+    a.Xc = RW ? nullptr : const_cast<double*>(a.dscale) + D;
+    a.Gc = RW ? nullptr : a.Xc + (size_t)D * np;
+    a.d_real = d;
+    a.exp_block = (unsigned long long)(r.cv == AMH_CONTRACT_V2 ? (d + 3) / 4 : (d + 1) / 2);
+    a.blocks_per_step = a.exp_block + 1ull;
     a.nrows = n;
     a.nblk = nblk;
     a.inv2tau2 = t.inv2tau2; a.invtau2 = t.invtau2;
@@ -415,7 +428,7 @@ static int launch_mala_logistic_t(amh_run& r, int nsteps, const SaveArgs& sv) {
 }
 
 int launch_mala_logistic(amh_run& r, int nsteps, const SaveArgs& sv) {
-    switch (r.dim) {
+    switch (logistic_padded_dim(r.dim)) {
     case 32: return launch_mala_logistic_t<32>(r, nsteps, sv);
     case 64: return launch_mala_logistic_t<64>(r, nsteps, sv);
     case 128: return launch_mala_logistic_t<128>(r, nsteps, sv);
@@ -428,13 +441,14 @@ bool mh_logistic_eligible(const amh_run& r) {
     const amh_sampler& s = *r.sampler;
     const int d = r.dim;
     if (s.d.kind != AMH_SAMPLER_RW || r.target->kind != AMH_TARGET_LOGISTIC) return false;
-    if (!(d == 32 || d == 64 || d == 128) || r.target->ndata < 64 || r.pitch % 32) return false;
+    if (d < 1 || d > 128 || r.x_rows < logistic_padded_dim(d) || r.target->ndata < 64 || r.pitch % 32) return false;
+    if (d % 32 != 0 && std::getenv("AMH_LOGISTIC_NO_PAD")) return false;
     if (s.has_mean || s.by_components()) return false;
     if (s.d.cov_kind != AMH_COV_DIAG && s.d.cov_kind != AMH_COV_SCALAR) return false;
     return std::getenv("AMH_MH_NO_LOGISTIC") == nullptr;             /* A/B switch: the generic per-thread kernel */
 }
 int launch_mh_logistic(amh_run& r, int nsteps, const SaveArgs& sv) {
-    switch (r.dim) {
+    switch (logistic_padded_dim(r.dim)) {
     case 32: return launch_mala_logistic_t<32, true>(r, nsteps, sv);
     case 64: return launch_mala_logistic_t<64, true>(r, nsteps, sv);
     case 128: return launch_mala_logistic_t<128, true>(r, nsteps, sv);

@@ -469,7 +469,7 @@ def test_ram_warp_kernel_user_S_fused_steps_and_sample(amh, cuda, oracle):
     _assert_same_state(rg, ro, S=True)
 
 
-@pytest.mark.parametrize("d,rows,n", [(32, 100, 50), (64, 64, 24), (128, 203, 70)])
+@pytest.mark.parametrize("d,rows,n", [(32, 100, 50), (64, 64, 24), (128, 203, 70), (5, 80, 30), (20, 333, 41), (48, 100, 22), (90, 130, 13), (127, 99, 9)])
 def test_mala_logistic_tiled_tensor_core_kernel_bit_exact(amh, cuda, oracle, d, rows, n):
     """K3L: the many-row logistic target as two chained DMMA GEMMs (TMA-staged design matrix), against the oracle's
     scalar row loop: candidate, gradient, log-density and accept decisions bit-for-bit; rows % 8 != 0 and
@@ -496,7 +496,10 @@ def test_mala_logistic_tiled_tensor_core_kernel_bit_exact(amh, cuda, oracle, d, 
 
 
 @pytest.mark.parametrize("d,rows,n,cov", [(32, 100, 50, "scalar"), (64, 64, 24, "diag"), (128, 203, 70, "scalar"), (128, 1000, 33, "diag"),
-                                          (32, 77, 40, "int")])
+                                          (32, 77, 40, "int"),
+                                          # features padded to 32 / 64 / 128 with zero columns of the design matrix
+                                          (3, 90, 30, "scalar"), (7, 64, 25, "diag"), (20, 333, 41, "scalar"), (33, 100, 20, "diag"),
+                                          (50, 150, 26, "scalar"), (100, 120, 17, "diag"), (127, 99, 9, "scalar")])
 def test_rwmh_logistic_tiled_tensor_core_kernel_bit_exact(amh, cuda, oracle, d, rows, n, cov):
     """the RW variant of K3L (amh_launch_mala_logistic.cu, RW = true): RWMH with an isotropic / diagonal proposal on the
     many-row logistic target -- GEMM1 and the log-likelihood terms on the FP64 tensor cores, no gradient -- against the
