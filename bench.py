@@ -255,6 +255,44 @@ def bench_c5(amh, eng, peak, seed=4, n=32768):
     return out
 
 
+def bench_off_shape(amh, eng, peak, seed=7):
+    """The same samplers OFF the hand-sized shapes of configs 2-5 ("The dimensions in between"): dimensions without
+    an exact kernel, few chains, the reference's default StaticMH (issymmetric = false), RWMH / MALA on a logistic regression whose
+    feature count is not 32 / 64 / 128.  Short runs; each entry: chain-steps/s and the fraction of the algorithmic HBM roofline."""
+    out = {"workload": "off-shape cases: padded tensor-core MH kernels, small-run CTA shape, Hastings-term kernels, exact-dimension MALA, padded tiled logistic kernels"}
+    sd = lambda n, k: np.random.default_rng(seed + k).integers(0, 2 ** 64, size=n, dtype=np.uint64)
+
+    def one(tag, t, s, d, n, nsteps, spl, bytes_per, init=None):
+        run = eng.run(eng.target(t.kind, d, t.blob()), s.lower(eng, d), n, sd(n, d), init)
+        ms = _timed(run, nsteps, spl=spl)
+        out[tag] = _rec(n * nsteps, ms, bytes_per, peak)
+        run.close()
+
+    for d, n in ((28, 65536), (48, 65536), (100, 65536), (32, 16384), (32, 4096)):
+        Sg = _spd(d, 32, 1.0, 100.0)
+        one(f"rwmh_mvnormal_d{d}_n{n}", amh.MvNormalTarget(None, Sg), amh.RWMH(amh.MvNormal(np.zeros(d), (2.38 ** 2 / d) * Sg)), d, n, 200, 100,
+            2 * (d + 1) * 8)
+    d = 32
+    Sg = _spd(d, 32, 1.0, 100.0)
+    one("staticmh_default_asymmetric_mvnormal_d32", amh.MvNormalTarget(None, Sg), amh.StaticMH(amh.MvNormal(np.zeros(d), 1.3 * Sg)), d, 65536, 200, 100,
+        2 * (d + 1) * 8)
+    d = 20
+    Sg = _spd(d, 32, 0.5, 2.0)
+    sg2 = (0.3 / d ** (1 / 3)) ** 2
+    one("mala_mvnormal_d20", amh.MvNormalTarget(None, Sg), amh.MALA(lambda g: amh.MvNormal(0.5 * sg2 * g, sg2 * amh.I)), d, 65536, 100, 50,
+        2 * (2 * d + 1) * 8, init=np.zeros((d, 65536)))
+    d, nrows, n = 20, 2000, 16384
+    rng = np.random.default_rng(128)
+    X = rng.normal(size=(nrows, d)) / np.sqrt(d)
+    y = (rng.random(nrows) < 1 / (1 + np.exp(-X @ rng.normal(size=d)))).astype(float)
+    t = amh.LogisticRegressionTarget(X, y, tau=10.0)
+    one("rwmh_logistic_d20_2000rows", t, amh.RWMH(amh.MvNormal(np.zeros(d), (0.05 ** 2) * amh.I)), d, n, 8, 4, 2 * (d + 1) * 8, init=np.zeros((d, n)))
+    s2 = 0.002
+    one("mala_logistic_d20_2000rows", t, amh.MALA(lambda g: amh.MvNormal(0.5 * s2 * g, s2 * amh.I)), d, n, 8, 4, 2 * (2 * d + 1) * 8, init=np.zeros((d, n)))
+    out.update(value=out["rwmh_mvnormal_d28_n65536"]["value"], unit=UNIT, frac=out["rwmh_mvnormal_d28_n65536"]["frac"])
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path.  Julia cannot run here, so this is the oracle port
     with all host threads, on the same config/metric; each step is a bounded sample."""
@@ -465,7 +503,7 @@ def main():
     configs = None
     if not args.no_configs:
         configs = {}
-        for name, fn in (("c3", bench_c3), ("c4", bench_c4), ("c5", bench_c5)):
+        for name, fn in (("c3", bench_c3), ("c4", bench_c4), ("c5", bench_c5), ("off_shape", bench_off_shape)):
             barrier()
             rec = fn(amh, eng, peak, seed=10 * (rank + 1) + len(configs), **({"bf16_peak": float(peaks.get("bf16_tflops_sustained", 1403.9))} if name == "c4" else {}))
             if dist is not None:
