@@ -5,7 +5,7 @@ tag=${1:-r2}
 mkdir -p gpurun_out
 sum=gpurun_out/sanitizer_${tag}_summary.txt
 : > $sum
-for tool in memcheck racecheck synccheck; do
+for tool in ${SAN_TOOLS:-memcheck racecheck synccheck}; do
   for c in ${SAN_CASES:-c2 c3 c3cl c3r c3rs c4 c4t c5 c5redo}; do
     log=gpurun_out/sanitizer_${tag}_${tool}_${c}.log
     start=$(date +%s)

@@ -10,6 +10,9 @@ parity run.  Usage: python tools/sanitize_cases.py <case> ; cases:
   c4     K3L    MALA logistic d=32, 200 rows                    (TMA producer warp + 10-stage mbarrier ring, wraps)
   c5     K4W    RAM warm-up d=32                                (bulk load / store of the factor, roll-back)
   c5redo K4W    same with the IEEE redo path forced on every step
+  c2pad / c2pad60 / c2big  K1T16 zero-padded (d = 13 on 4-warp CTAs, d = 60 as D = 64, d = 29 on the 28-warp CTA)
+  c2hast K1     StaticMH with issymmetric = false, exact-dimension kernel with the Hastings term
+  c4rw / c4pad  K3L  RWMH (RW variant) / MALA on a logistic regression with 20 features padded to 32
   c4t    K3T    MALA logistic d=128 on the opt-in split-bf16 tcgen05 path (TMA ring, TMEM accumulators, 8 epilogue warps);
                 compared with the oracle within the path's stated tolerance instead of bit for bit
 """
@@ -46,6 +49,8 @@ def main():
         os.environ["AMH_STRETCH_LEVELS"] = "4"
     if case == "c5redo":
         os.environ["AMH_RAMW_FORCE_REDO"] = "1"
+    if case == "c2big":
+        os.environ["AMH_TC_NO_SMALL"] = "1"
     import amh_b200 as amh
     gpu = amh.default_engine(0)
     orc = amh.Engine(lib_path=os.path.join(ROOT, "oracle", "libamh_oracle.so"), prefix="amho_")
@@ -55,6 +60,30 @@ def main():
         d, n = 32, 1024
         Sg = spd(d, 32, 1.0, 100.0)
         t, s, sd = amh.MvNormalTarget(None, Sg), amh.RWMH(amh.MvNormal(np.zeros(d), (2.38 ** 2 / d) * Sg)), seeds(n, 1)
+    elif case in ("c2pad", "c2pad60", "c2big"):
+        # the zero-padded tensor-core kernels (amh_launch_mh_tcp.cu): d = 13 on 4-warp CTAs (few chains), d = 60 as D = 64 on
+        # 16-warp CTAs, and d = 29 with AMH_TC_NO_SMALL: the 28-warp padded kernel; ragged chain counts
+        d, n = {"c2pad": (13, 1001), "c2pad60": (60, 777), "c2big": (29, 1501)}[case]
+        Sg = spd(d, 32, 1.0, 100.0)
+        t, s, sd = amh.MvNormalTarget(np.linspace(-1, 1, d), Sg), amh.RWMH(amh.MvNormal(np.zeros(d), (2.38 ** 2 / d) * Sg)), seeds(n, 1)
+    elif case == "c2hast":
+        # StaticMH with the reference's default issymmetric = false on an exact-dimension kernel (amh_launch_mh_hast.cu)
+        d, n = 9, 700
+        Sg = spd(d, 32, 0.5, 2.0)
+        t, s, sd = amh.MvNormalTarget(None, Sg), amh.StaticMH(amh.MvNormal(np.linspace(0.1, -0.2, d), 1.5 * Sg)), seeds(n, 1)
+    elif case in ("c4rw", "c4pad"):
+        # RWMH (RW variant of K3L) and MALA on a logistic regression with 20 features padded to 32, ragged rows
+        d, rows, n = 20, 203, 70
+        rng = np.random.default_rng(5)
+        X = rng.normal(size=(rows, d)) / np.sqrt(d)
+        y = (rng.random(rows) < 0.5).astype(float)
+        t = amh.LogisticRegressionTarget(X, y, tau=10.0)
+        if case == "c4rw":
+            s = amh.RWMH(amh.MvNormal(np.zeros(d), (0.1 ** 2) * amh.I))
+        else:
+            s = amh.MALA(lambda g: amh.MvNormal((0.05 / 2) * g, 0.05 * amh.I))
+            keys = keys + ["grad"]
+        sd, init, nsteps, spl = seeds(n, 3), np.zeros((d, n)), 4, 2
     elif case in ("c3", "c3cl", "c3r", "c3rs"):
         d, nw, ne = 10, 1024, 2
         t = amh.RosenbrockTarget(d)
