@@ -144,6 +144,24 @@ int launch_mh_tc_padded(amh_run& r, int nsteps, const SaveArgs& sv) {
         case 32: return launch_padded_t<32, 4>(r, nsteps, sv);
         }
     }
+    /* D = 40 ... 64 with so few chains that the large CTAs would cover less than half of the SMs: 8-warp CTAs (128 chains) */
+    if (r.dim > 32 && r.dim <= 64 && !std::getenv("AMH_TC_NO_SMALL")) {
+        const int D = padded_dim(r.dim);
+        const int wbig = D == 40 ? 24 : D == 48 ? 20 : 16;
+        /* measured (profiles/r2_c2_nchains.txt): D = 40 is faster on 8-warp CTAs at every size tried (65 536 chains: 3.6e9 vs
+         * 2.7e9 -- 171 CTAs of 384 chains are 1.15 waves), D = 48 up to ~100 000 chains (2.75e9 vs 2.5e9), D = 56 / 64 only
+         * while the large CTAs would leave SMs idle */
+        long long small_max = D == 40 ? (1ll << 62) : D == 48 ? 100000 : 74ll * 16 * wbig;
+        if (const char* ev = std::getenv("AMH_TC_SMALL_MAX")) small_max = std::atoll(ev);      /* A/B switch */
+        if (r.n < small_max) {
+            switch (D) {
+            case 40: return launch_padded_t<40, 8, true>(r, nsteps, sv);
+            case 48: return launch_padded_t<48, 8, true>(r, nsteps, sv);
+            case 56: return launch_padded_t<56, 8, true>(r, nsteps, sv);
+            case 64: return launch_padded_t<64, 8, true>(r, nsteps, sv);
+            }
+        }
+    }
     switch (padded_dim(r.dim)) {
     case 8: return launch_padded_t<8, 28>(r, nsteps, sv);
     case 16: return launch_padded_t<16, 28>(r, nsteps, sv);

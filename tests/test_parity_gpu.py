@@ -431,6 +431,25 @@ def test_tensor_core_kernels_one_cta_per_sm_shape_with_few_chains(amh, cuda, ora
     assert np.array_equal(og, oo) and np.array_equal(ag, ao)
 
 
+@pytest.mark.parametrize("d", [37, 48, 55, 64])
+@pytest.mark.parametrize("small", [True, False])
+def test_padded_tensor_core_kernels_above_32_both_cta_shapes(amh, cuda, oracle, monkeypatch, d, small):
+    """d = 33 ... 64: few chains take 8-warp CTAs, AMH_TC_NO_SMALL keeps the large (24 / 20 / 16-warp) CTAs -- both bit-exact"""
+    if not small:
+        monkeypatch.setenv("AMH_TC_NO_SMALL", "1")
+    Sigma = make_spd(d, seed=d)
+    target = amh.MvNormalTarget(np.linspace(-1, 1, d), Sigma)
+    n = 900
+    rg, ro = _pair(amh, cuda, oracle, target, amh.RWMH(amh.MvNormal(np.zeros(d), (2.38 ** 2 / d) * Sigma)), n, _seeds(n, 1200 + d))
+    for k, spl_ in [(1, 1), (7, 3), (20, 0)]:
+        rg.steps(k, steps_per_launch=spl_)
+        ro.steps(k)
+        _assert_same_state(rg, ro)
+    og, ag, _ = rg.sample(3, 1, 2)
+    oo, ao, _ = ro.sample(3, 1, 2)
+    assert np.array_equal(og, oo) and np.array_equal(ag, ao)
+
+
 def test_tensor_core_path_static_symmetric_and_sample(amh, cuda, oracle):
     """K1T (DMMA mat-vecs) with a symmetric StaticProposal and through the sample schedule / save epilogue"""
     d = 16
