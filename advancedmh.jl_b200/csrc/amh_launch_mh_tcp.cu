@@ -39,6 +39,8 @@ bool mh_tc_padded_eligible(const amh_run& r) {
  * whatever its size.  Measured at d = 32 (profiles/r2_c2_nchains.txt): 1 024 chains 8.8e7 -> 2.5e8, 4 096 3.5e8 -> 1.0e9,
  * 16 384 1.4e9 -> 2.7e9, 32 768 2.8e9 -> 4.2e9 chain-steps/s; at 65 536 the 28-warp CTA wins. */
 constexpr long long kSmallRunChains = 49152;
+/* (at 65 536 chains, d = 32: one 28-warp CTA per SM 6.34e9 chain-steps/s -- 6.17e9 for this file's padded variant of it --,
+ * two 14-warp CTAs 5.49e9, four 7-warp CTAs 5.56e9: profiles/r2_c2_nchains.txt) */
 
 template <int D, int W, bool FEW = false>
 static int launch_padded_t(amh_run& r, int nsteps, const SaveArgs& sv) {
