@@ -43,6 +43,9 @@ struct MalaLArgs {
      * blocks per step / the exponential's block within a step under the run's contract version */
     int d_real;
     unsigned long long blocks_per_step, exp_block;
+    /* RW variant with a FULL-covariance proposal: DMMA A fragments of its lower Cholesky factor, padded to D x D
+     * (frag[tile(mb, kb)][lane] = L[8 mb + lane / 4][4 kb + lane % 4], tiles kb = 0 .. 2 mb + 1 of row block mb); else NULL */
+    const double* Lf;
 };
 
 __device__ __forceinline__ unsigned l_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -103,8 +106,9 @@ __device__ __forceinline__ void logistic_terms(double eta, double y, double& t, 
     r = y - sg;
 }
 
-/* RW = true: the random-walk MH step (mh-core.jl:92-117) on the same target with an isotropic or diagonal zero-mean
- * proposal -- the same kernel without the gradient: candidate = x + sigma_j z_j (the per-thread kernel's two roundings),
+/* RW = true: the random-walk MH step (mh-core.jl:92-117) on the same target with a zero-mean proposal -- isotropic,
+ * diagonal, or full covariance (candidate = x + L z as a small DMMA mat-vec, see phase A) -- the same kernel without the
+ * gradient: candidate = x + sigma_j z_j (the per-thread kernel's two roundings),
  * GEMM1 + the log-likelihood terms only, Hastings term exactly 0.  RWMH on a logistic regression ran the generic
  * per-thread kernel before: 4.6e5 chain-steps/s on config 4's model, 9 x SLOWER than MALA on it (profiles/r2_dim_cliffs.txt). */
 template <int D, bool RW = false>
@@ -188,6 +192,35 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
                 noise_group<NPP, true>(seed, b0, k * Bv1 + a.exp_block, z, e);
             }
             }
+            bool drawn = false;
+            if constexpr (RW) {
+                if (a.Lf) {
+                    /* full-covariance proposal (proposal.jl:41-56 with MvNormal(0, Sigma)): candidate = x + L z as a DMMA
+                     * mat-vec for the warp's 8 chains.  z goes into the candidate tile, the row blocks are produced from the
+                     * last to the first and overwrite it in place (block mb reads rows <= 8 mb + 7 only); the accumulation over
+                     * a row's tiles is the per-thread kernel's fma chain (the first product onto 0, zeros above the diagonal) */
+                    drawn = true;
+#pragma unroll
+                    for (int i = 0; i < 2 * NPP; ++i) Bs[(2 * NPP * part + i) * kLPB + cl] = z[i];
+                    __syncwarp();
+                    const long long c0 = cbase + 2 * fc;
+                    for (int mb = D / 8 - 1; mb >= 0; --mb) {
+                        double y0 = 0.0, y1 = 0.0;
+                        for (int kb = 0; kb <= 2 * mb + 1; ++kb) {
+                            const double af = __ldg(a.Lf + ((size_t)(mb * (mb + 1) + kb)) * 32 + lane);
+                            const double bf = Bs[(4 * kb + fc) * kLPB + fr];
+                            l_dmma(y0, y1, af, bf);
+                        }
+                        __syncwarp();
+                        const long long o = (long long)(8 * mb + fr) * pitch + c0;
+                        const double x0 = (c0 < a.st.n) ? a.st.X[o] : 0.0;
+                        const double x1 = (c0 + 1 < a.st.n) ? a.st.X[o + 1] : 0.0;
+                        *reinterpret_cast<double2*>(Bs + (8 * mb + fr) * kLPB + 2 * fc) = make_double2(x0 + y0, x1 + y1);
+                        __syncwarp();
+                    }
+                }
+            }
+            if (!drawn) {
 #pragma unroll
             for (int i = 0; i < 2 * NPP; ++i) {
                 const int j = 2 * NPP * part + i;
@@ -203,6 +236,7 @@ mala_logistic_kernel(const __grid_constant__ MalaLArgs a) {
                     }
                 }
                 Bs[j * kLPB + cl] = c;
+            }
             }
         }
         __syncwarp();
@@ -375,9 +409,25 @@ static int launch_mala_logistic_t(amh_run& r, int nsteps, const SaveArgs& sv) {
                                        cudaMemcpyDeviceToDevice, r.ctx->stream));
         AMH_CUDA_TRY(cudaMemcpyAsync(base + nx, t.dblob + 1 + (size_t)n * d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, r.ctx->stream));
         std::vector<double> sc(D, 0.0);
-        for (int i = 0; i < d; ++i) sc[i] = !RW ? s.mala_sigma : s.d.cov_kind == AMH_COV_DIAG ? s.scale[i] : s.scale[0];
+        const bool fullcov = RW && s.d.cov_kind == AMH_COV_FULL;
+        for (int i = 0; i < d && !fullcov; ++i) sc[i] = !RW ? s.mala_sigma : s.d.cov_kind == AMH_COV_DIAG ? s.scale[i] : s.scale[0];
         AMH_CUDA_TRY(cudaMemcpyAsync(base + nx + ny, sc.data(), sizeof(double) * D, cudaMemcpyHostToDevice, r.ctx->stream));
-        AMH_CUDA_TRY(sync_stream(r.ctx, r.ctx->stream));        /* `sc` is a stack temporary */
+        std::vector<double> lf;
+        if (fullcov) {
+            /* A fragments of the proposal's factor, zero-padded to D x D (the layout of amh_launch_mh_tc.cu's build_frags) */
+            constexpr int NBL = D / 8;
+            lf.assign((size_t)NBL * (NBL + 1) * 32, 0.0);
+            for (int mb = 0; mb < NBL; ++mb)
+                for (int kb = 0; kb <= 2 * mb + 1; ++kb)
+                    for (int ln = 0; ln < 32; ++ln) {
+                        const int row = 8 * mb + ln / 4, col = 4 * kb + ln % 4;
+                        if (col <= row && row < d) lf[((size_t)(mb * (mb + 1) + kb)) * 32 + ln] = s.scale[tri_h(row, col)];
+                    }
+            const int rcb = dmalloc(r.ctx, &r.scratch2, sizeof(double) * lf.size());
+            if (rcb) return rcb;
+            AMH_CUDA_TRY(cudaMemcpyAsync(r.scratch2, lf.data(), sizeof(double) * lf.size(), cudaMemcpyHostToDevice, r.ctx->stream));
+        }
+        AMH_CUDA_TRY(sync_stream(r.ctx, r.ctx->stream));        /* `sc`, `lf` are stack temporaries */
     }
     MalaLArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -393,6 +443,7 @@ static int launch_mala_logistic_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     a.Xc = RW ? nullptr : const_cast<double*>(a.dscale) + D;
     a.Gc = RW ? nullptr : a.Xc + (size_t)D * np;
     a.d_real = d;
+    a.Lf = (RW && s.d.cov_kind == AMH_COV_FULL) ? (const double*)r.scratch2 : nullptr;
     a.exp_block = (unsigned long long)(r.cv == AMH_CONTRACT_V2 ? (d + 3) / 4 : (d + 1) / 2);
     a.blocks_per_step = a.exp_block + 1ull;
     a.nrows = n;
@@ -444,7 +495,7 @@ bool mh_logistic_eligible(const amh_run& r) {
     if (d < 1 || d > 128 || r.x_rows < logistic_padded_dim(d) || r.target->ndata < 64 || r.pitch % 32) return false;
     if (d % 32 != 0 && std::getenv("AMH_LOGISTIC_NO_PAD")) return false;
     if (s.has_mean || s.by_components()) return false;
-    if (s.d.cov_kind != AMH_COV_DIAG && s.d.cov_kind != AMH_COV_SCALAR) return false;
+    if (s.d.cov_kind != AMH_COV_DIAG && s.d.cov_kind != AMH_COV_SCALAR && s.d.cov_kind != AMH_COV_FULL) return false;
     return std::getenv("AMH_MH_NO_LOGISTIC") == nullptr;             /* A/B switch: the generic per-thread kernel */
 }
 int launch_mh_logistic(amh_run& r, int nsteps, const SaveArgs& sv) {

@@ -518,7 +518,10 @@ def test_mala_logistic_tiled_tensor_core_kernel_bit_exact(amh, cuda, oracle, d, 
                                           (32, 77, 40, "int"),
                                           # features padded to 32 / 64 / 128 with zero columns of the design matrix
                                           (3, 90, 30, "scalar"), (7, 64, 25, "diag"), (20, 333, 41, "scalar"), (33, 100, 20, "diag"),
-                                          (50, 150, 26, "scalar"), (100, 120, 17, "diag"), (127, 99, 9, "scalar")])
+                                          (50, 150, 26, "scalar"), (100, 120, 17, "diag"), (127, 99, 9, "scalar"),
+                                          # full-covariance proposal: candidate = x + L z as a DMMA mat-vec inside the kernel
+                                          (32, 100, 50, "full"), (20, 203, 41, "full"), (64, 80, 13, "full"), (77, 90, 9, "full"),
+                                          (128, 150, 21, "full")])
 def test_rwmh_logistic_tiled_tensor_core_kernel_bit_exact(amh, cuda, oracle, d, rows, n, cov):
     """the RW variant of K3L (amh_launch_mala_logistic.cu, RW = true): RWMH with an isotropic / diagonal proposal on the
     many-row logistic target -- GEMM1 and the log-likelihood terms on the FP64 tensor cores, no gradient -- against the
@@ -532,6 +535,8 @@ def test_rwmh_logistic_tiled_tensor_core_kernel_bit_exact(amh, cuda, oracle, d, 
         spl = amh.RWMH(amh.MvNormal(np.zeros(d), (0.08 ** 2) * amh.I))
     elif cov == "diag":
         spl = amh.RWMH([amh.Normal(0, 0.05 + 0.0005 * i) for i in range(d)])
+    elif cov == "full":
+        spl = amh.RWMH(amh.MvNormal(np.zeros(d), (0.1 ** 2 / d) * make_spd(d, seed=3 * d, lo=0.5, hi=4.0)))
     else:
         spl = amh.RWMH(d)                                       # MvNormal(Zeros(d), I): mh-core.jl:51
     init = 0.1 * rng.normal(size=(d, n))
