@@ -12,7 +12,7 @@ parity run.  Usage: python tools/sanitize_cases.py <case> ; cases:
   c5redo K4W    same with the IEEE redo path forced on every step
   c2pad / c2pad60 / c2big  K1T16 zero-padded (d = 13 on 4-warp CTAs, d = 60 as D = 64, d = 29 on the 28-warp CTA)
   c2hast K1     StaticMH with issymmetric = false, exact-dimension kernel with the Hastings term
-  c4rw / c4pad  K3L  RWMH (RW variant) / MALA on a logistic regression with 20 features padded to 32
+  c4rw / c4pad / c4rwf  K3L  RWMH (RW variant; c4rwf: full-covariance proposal) / MALA on a logistic regression with 20 features padded to 32
   c4t    K3T    MALA logistic d=128 on the opt-in split-bf16 tcgen05 path (TMA ring, TMEM accumulators, 8 epilogue warps);
                 compared with the oracle within the path's stated tolerance instead of bit for bit
 """
@@ -71,7 +71,7 @@ def main():
         d, n = 9, 700
         Sg = spd(d, 32, 0.5, 2.0)
         t, s, sd = amh.MvNormalTarget(None, Sg), amh.StaticMH(amh.MvNormal(np.linspace(0.1, -0.2, d), 1.5 * Sg)), seeds(n, 1)
-    elif case in ("c4rw", "c4pad"):
+    elif case in ("c4rw", "c4pad", "c4rwf"):
         # RWMH (RW variant of K3L) and MALA on a logistic regression with 20 features padded to 32, ragged rows
         d, rows, n = 20, 203, 70
         rng = np.random.default_rng(5)
@@ -80,6 +80,8 @@ def main():
         t = amh.LogisticRegressionTarget(X, y, tau=10.0)
         if case == "c4rw":
             s = amh.RWMH(amh.MvNormal(np.zeros(d), (0.1 ** 2) * amh.I))
+        elif case == "c4rwf":                                   # full-covariance proposal: x + L z by DMMA, in-place tile
+            s = amh.RWMH(amh.MvNormal(np.zeros(d), (0.1 ** 2 / d) * spd(d, 9, 0.5, 4.0)))
         else:
             s = amh.MALA(lambda g: amh.MvNormal((0.05 / 2) * g, 0.05 * amh.I))
             keys = keys + ["grad"]
