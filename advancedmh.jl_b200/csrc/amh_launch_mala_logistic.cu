@@ -455,13 +455,20 @@ static int launch_mala_logistic_t(amh_run& r, int nsteps, const SaveArgs& sv) {
     const int sms = r.ctx->sm_count;
     int warps = 14;
     {
+        /* the largest W among the most even fillings; runs with few chains end up with small CTAs on many SMs (1 024 chains
+         * of config 4's model: 9 CTAs of 15 warps before, 128 CTAs of one consumer warp now -- every CTA streams X for
+         * itself, from L2) */
         double best_eff = 0;
-        for (int w = 8; w <= 15; ++w) {
+        for (int w = 15; w >= 1; --w) {
             if (l_smem_bytes<D>(w, 4) + 1024 > 227 * 1024) continue;
             const long long ctas = (groups + w - 1) / w;
             const long long waves = (ctas + sms - 1) / sms;
             const double eff = (double)groups / ((double)waves * sms * w);
             if (eff > best_eff + 1e-9) { best_eff = eff; warps = w; }
+        }
+        if (const char* ev = std::getenv("AMH_K3L_WARPS")) {                          /* A/B and test switch */
+            const int w = std::atoi(ev);
+            if (w >= 1 && w <= 15 && l_smem_bytes<D>(w, 4) + 1024 <= 227 * 1024) warps = w;
         }
     }
     int nst = 4;

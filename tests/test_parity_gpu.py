@@ -554,6 +554,26 @@ def test_rwmh_logistic_tiled_tensor_core_kernel_bit_exact(amh, cuda, oracle, d, 
     _assert_same_state(rg, ro)
 
 
+@pytest.mark.parametrize("warps", ["3", "8", "14"])
+@pytest.mark.parametrize("sampler", ["mala", "rwmh"])
+def test_logistic_tiled_kernels_multi_warp_ctas(amh, cuda, oracle, monkeypatch, warps, sampler):
+    """runs with few chains get one consumer warp per CTA (the chain groups are spread over the SMs); AMH_K3L_WARPS forces the
+    CTA shapes large runs use (several consumer warps sharing one TMA ring of X) -- same bits"""
+    monkeypatch.setenv("AMH_K3L_WARPS", warps)
+    d, rows, n = 32, 150, 8 * 14 * 2 + 5
+    rng = np.random.default_rng(77)
+    X = rng.normal(size=(rows, d)) / np.sqrt(d)
+    y = (rng.random(rows) < 1 / (1 + np.exp(-X @ rng.normal(size=d)))).astype(float)
+    target = amh.LogisticRegressionTarget(X, y, tau=5.0)
+    s2 = 0.02
+    spl = amh.MALA(lambda g: amh.MvNormal((s2 / 2) * g, s2 * amh.I)) if sampler == "mala" else amh.RWMH(amh.MvNormal(np.zeros(d), (0.08 ** 2) * amh.I))
+    rg, ro = _pair(amh, cuda, oracle, target, spl, n, _seeds(n, 333), 0.1 * rng.normal(size=(d, n)))
+    for k, spl_ in [(1, 1), (6, 2)]:
+        rg.steps(k, steps_per_launch=spl_)
+        ro.steps(k)
+        _assert_same_state(rg, ro, grad=sampler == "mala")
+
+
 def test_sample_pipelined_copy_many_chunks_and_pinned_buffers(amh, cuda, oracle):
     """amh_run_sample drains the device sample ring through the copy stream in chunks (two buffers): force many
     chunks (N large, small slabs) and use caller-owned pinned buffers; results must equal the oracle's"""
