@@ -4,7 +4,7 @@
  * instantiation runs the generic (run-time dimension, local-memory) variant, which is 4-8 x slower: Rosenbrock,
  * 64 x 4 096 walkers, d = 10 -> 1.13e10 moves/s, d = 12 (generic) -> 3.0e9, d = 20 (generic, 64 x 2 048) -> 1.36e9
  * (profiles/r2_c3_shape_sweep.txt).  amh_launch_stretch.cu holds d = 2, 3, 4, 5, 8, 10, 16; this translation unit adds
- * the dimensions below for the three catalogue targets that take any dimension.  It is a second translation unit only so
+ * the dimensions below (6, 7, 9, 12, 14, 20, 24, 32) for the three catalogue targets that take any dimension.  It is a second translation unit only so
  * that the two halves compile in parallel (the kernels are the same templates: the source file is included). */
 #define AMH_STRETCH_EXTRA_TU
 #include "amh_launch_stretch.cu"
@@ -19,8 +19,10 @@ static int more_dims(amh_run& r, int nsteps, const SaveArgs& sv, bool& taken) {
     case 7: return launch_stretch_t<7, T>(r, nsteps, sv);
     case 9: return launch_stretch_t<9, T>(r, nsteps, sv);
     case 12: return launch_stretch_t<12, T>(r, nsteps, sv);
+    case 14: return launch_stretch_t<14, T>(r, nsteps, sv);
     case 20: return launch_stretch_t<20, T>(r, nsteps, sv);
     case 24: return launch_stretch_t<24, T>(r, nsteps, sv);
+    case 32: return launch_stretch_t<32, T>(r, nsteps, sv);
     }
     taken = false;
     return AMH_OK;

@@ -345,7 +345,8 @@ def test_ram_sample_schedule_warmup_bit_exact(amh, cuda, oracle):
                                           # two dimensions that stay on the generic kernels
                                           ("rosenbrock", 6, 200, 2), ("mvnormal", 7, 333, 2), ("rosenbrock", 9, 1024, 1),
                                           ("rosenbrock", 12, 777, 2), ("rosenbrock", 20, 130, 2), ("mvnormal", 24, 96, 2),
-                                          ("gaussprec", 12, 150, 2), ("rosenbrock", 11, 64, 2), ("mvnormal", 33, 40, 2)])
+                                          ("gaussprec", 12, 150, 2), ("rosenbrock", 11, 64, 2), ("mvnormal", 33, 40, 2),
+                                          ("rosenbrock", 14, 300, 2), ("mvnormal", 32, 1100, 1), ("rosenbrock", 32, 96, 2)])
 def test_stretch_bit_exact_sequential_sweep(amh, cuda, oracle, kind, d, nw, ne):
     if kind == "rosenbrock":
         target = amh.RosenbrockTarget(d)
