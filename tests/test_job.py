@@ -146,3 +146,28 @@ def test_job_on_the_devices_of_this_box_equals_one_device_and_the_oracle(amh, cu
     job = amh.sampling._job_for(cuda, ndev)
     mode, ms, init_ms = job.broadcast_info()
     assert mode in ("nccl", "peer", "h2d") and (ndev > 1 or mode == "h2d")
+
+
+@pytest.mark.parametrize("spin_us", ["0", "300", None])
+def test_job_worker_threads_spin_then_sleep_hand_off(amh, oracle, monkeypatch, spin_us):
+    """The job's worker threads poll for the next phase for AMH_JOB_SPIN_US and then sleep (csrc/amh_job_impl.h): many short
+    phases with pauses on both sides of that window must neither lose a wake-up nor change a result (0 = sleep at once,
+    300 us = both regimes inside one test, default = mostly polling)."""
+    import time
+    if spin_us is not None:
+        monkeypatch.setenv("AMH_JOB_SPIN_US", spin_us)
+    target = amh.MvNormalTarget(None, np.array([[2.0, 0.3], [0.3, 1.0]]))
+    spl = amh.RWMH(2)
+    n = 23
+    job = oracle.job(4)                      # the workers are created with the job's first fan-out and read the variable then
+    a, b = _run_pair(oracle, job, target, spl, n, _seeds(n, 9))
+    rng = np.random.default_rng(0)
+    for i in range(120):
+        k = int(rng.integers(1, 4))
+        a.steps(k); b.steps(k)
+        if i % 3 == 0:
+            time.sleep(float(rng.choice([0.0, 0.0002, 0.002, 0.008])))       # shorter and longer than the polling window
+        if i % 10 == 9:
+            sa, sb = a.state(), b.state()
+            assert np.array_equal(sa["x"], sb["x"]) and np.array_equal(sa["naccept"], sb["naccept"])
+    a.close(); b.close(); job.close()
