@@ -279,3 +279,25 @@ def test_run_sample_ld_rejects_a_leading_dimension_smaller_than_the_shard(amh, o
     assert np.all(big[:, :, :n] == 0) and np.any(big[:, :, n:] != 0)
     with pytest.raises(amh.AMHArgumentError):
         run.sample(3, out=np.zeros((3, d + 1, n))[:, :, ::2], summary=False)        # not unit stride along chains
+
+
+def test_python_host_points_the_job_layer_at_the_nccl_next_to_pytorch(monkeypatch):
+    """_capi._point_at_bundled_nccl: without AMH_NCCL_LIB the library would dlopen the system libnccl.so.2 under its soname, and a
+    later `import torch` would be handed that (older) copy and fail; the host names the wheel's copy instead, never overriding
+    a caller's choice"""
+    import importlib.util
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import amh_b200  # noqa: F401
+    import advancedmh_jl_b200._capi as K
+    monkeypatch.delenv("AMH_NCCL_LIB", raising=False)
+    K._point_at_bundled_nccl()
+    spec = importlib.util.find_spec("nvidia.nccl")
+    if spec is not None and any(os.path.exists(os.path.join(p, "lib", "libnccl.so.2")) for p in spec.submodule_search_locations):
+        assert os.environ["AMH_NCCL_LIB"].endswith(os.path.join("nvidia", "nccl", "lib", "libnccl.so.2"))
+    else:
+        assert "AMH_NCCL_LIB" not in os.environ
+    monkeypatch.setenv("AMH_NCCL_LIB", "/somewhere/else/libnccl.so.2")
+    K._point_at_bundled_nccl()
+    assert os.environ["AMH_NCCL_LIB"] == "/somewhere/else/libnccl.so.2"
