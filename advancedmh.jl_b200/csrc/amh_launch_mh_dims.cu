@@ -26,8 +26,22 @@ static int more_dims(amh_run& r, int nsteps, const SaveArgs& sv, bool& taken) {
     return AMH_OK;
 }
 
+/* MvNormal targets: only where the per-thread kernel beats the padded tensor-core one -- d = 9 and 11 would be padded to 16
+ * (3 x / 2 x the mat-vec work: 1.5e10 chain-steps/s against 2.2e10 for the per-thread kernel at d = 10), d = 18 to 24 */
+static int mvnormal_dims(amh_run& r, int nsteps, const SaveArgs& sv, bool& taken) {
+    taken = true;
+    switch (r.dim) {
+    case 9: return launch_mh_t<9, TMvNormal>(r, nsteps, sv);
+    case 11: return launch_mh_t<11, TMvNormal>(r, nsteps, sv);
+    case 18: return launch_mh_t<18, TMvNormal>(r, nsteps, sv);
+    }
+    taken = false;
+    return AMH_OK;
+}
+
 int launch_mh_more_dims(amh_run& r, int nsteps, const SaveArgs& sv, bool& taken) {
     switch (r.target->kind) {
+    case AMH_TARGET_MVNORMAL: return mvnormal_dims(r, nsteps, sv, taken);
     case AMH_TARGET_GAUSS_PREC: return more_dims<TGaussPrec>(r, nsteps, sv, taken);
     case AMH_TARGET_ROSENBROCK: return more_dims<TRosenbrock>(r, nsteps, sv, taken);
     }
