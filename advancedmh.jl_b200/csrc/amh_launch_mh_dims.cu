@@ -27,13 +27,16 @@ static int more_dims(amh_run& r, int nsteps, const SaveArgs& sv, bool& taken) {
 }
 
 /* MvNormal targets: only where the per-thread kernel beats the padded tensor-core one -- d = 9 and 11 would be padded to 16
- * (3 x / 2 x the mat-vec work: 1.5e10 chain-steps/s against 2.2e10 for the per-thread kernel at d = 10), d = 18 to 24 */
+ * (3 x / 2 x the mat-vec work: 1.5e10 chain-steps/s against 2.2e10 for the per-thread kernel at d = 10), d = 17 ... 19 to 24
+ * (8.9e9 against 1.0-1.2e10; with few chains those three stay on the tensor-core kernels' 4-warp CTAs, which spread better) */
 static int mvnormal_dims(amh_run& r, int nsteps, const SaveArgs& sv, bool& taken) {
     taken = true;
     switch (r.dim) {
     case 9: return launch_mh_t<9, TMvNormal>(r, nsteps, sv);
     case 11: return launch_mh_t<11, TMvNormal>(r, nsteps, sv);
+    case 17: return launch_mh_t<17, TMvNormal>(r, nsteps, sv);
     case 18: return launch_mh_t<18, TMvNormal>(r, nsteps, sv);
+    case 19: return launch_mh_t<19, TMvNormal>(r, nsteps, sv);
     }
     taken = false;
     return AMH_OK;

@@ -22,7 +22,7 @@ bool mh_tc_padded_eligible(const amh_run& r) {
     if (d < 7 || d > 128) return false;
     switch (d) {          /* dimensions with an exact kernel of their own (K1T16 or the per-thread K1) */
     case 8: case 10: case 12: case 16: case 20: case 24: case 32: return false;
-    case 9: case 11: case 18: return false;      /* per-thread kernel (amh_launch_mh_dims.cu): padding to 16 / 24 costs more */
+    case 9: case 11: case 17: case 18: case 19: return false;      /* per-thread kernel (amh_launch_mh_dims.cu): padding to 16 / 24 costs more */
     }
     if (s.has_mean || s.by_components()) return false;
     if (s.d.cov_kind != AMH_COV_FULL && s.d.cov_kind != AMH_COV_DIAG && s.d.cov_kind != AMH_COV_SCALAR) return false;
@@ -128,7 +128,7 @@ bool mh_tc_small_eligible(const amh_run& r) {
     if (r.cv != AMH_CONTRACT_V2 || r.target->kind != AMH_TARGET_MVNORMAL) return false;
     if (r.n >= kSmallRunChains || d < 7 || d > 32) return false;
     switch (d) {          /* the per-thread kernel K1 has these and spreads its 128-thread CTAs over the SMs already */
-    case 9: case 10: case 11: case 12: case 18: case 20: return false;
+    case 9: case 10: case 11: case 12: case 20: return false;      /* (17 ... 19 take the 4-warp tensor-core CTAs when the chains are few) */
     }
     if (s.has_mean || s.by_components()) return false;
     if (s.d.cov_kind != AMH_COV_FULL && s.d.cov_kind != AMH_COV_DIAG && s.d.cov_kind != AMH_COV_SCALAR) return false;
